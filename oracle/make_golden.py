@@ -1,0 +1,169 @@
+"""TEST INFRASTRUCTURE ONLY.  Generate tests/golden/*.npz from the UNMODIFIED reference modules.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+Inputs and weights are never stored: they are regenerated from ``oracle/synth.py`` seeds by the
+tests; only reference OUTPUTS (and compact summaries of big gradient sets) are committed.
+"""
+import argparse
+import os
+
+import numpy as np
+import torch
+
+from . import ref_import, synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+WARP_CASES = [
+    # name, N, C, h, w, H0, W0, seed
+    ("warp_sq_full", 2, 8, 32, 32, 32, 32, 1),
+    ("warp_sq_div4", 2, 16, 16, 16, 64, 64, 2),
+    ("warp_nonsq_div2", 3, 8, 64, 32, 128, 64, 3),   # H != W quirk (pose_transform.py:52,56,72-73)
+    ("warp_224_div8", 2, 4, 28, 28, 224, 224, 4),
+]
+
+
+def sample_idx(numel, count=24):
+    return (np.arange(count, dtype=np.int64) * 2654435761 % max(numel, 1)).astype(np.int64)
+
+
+def summarize(t, count=24):
+    f = t.detach().reshape(-1).double()
+    idx = sample_idx(f.numel(), count)
+    return np.concatenate([[f.norm().item(), f.sum().item()], f[torch.from_numpy(idx)].numpy()])
+
+
+def warp_inputs(N, C, h, w, H0, W0, seed):
+    b = synth.make_batch(N, H0, W0, 2, seed=seed)
+    g = torch.Generator().manual_seed(4242 + seed)
+    x = torch.randn(N, C, h, w, generator=g)
+    gy = torch.randn(N, C, h, w, generator=g)
+    return x, b["warps"], b["masks"], gy
+
+
+def gen_warp(ns):
+    for name, N, C, h, w, H0, W0, seed in WARP_CASES:
+        x, warps, masks, gy = warp_inputs(N, C, h, w, H0, W0, seed)
+        x = x.clone().requires_grad_(True)
+        layer = ns.pose_transform.AffineTransformLayer(10, (H0, W0), "mask")
+        y = layer(x, warps.clone(), masks.clone())
+        y.backward(gy)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), y=y.detach().numpy(), dx=x.grad.numpy())
+        print(name, tuple(y.shape), float(y.abs().mean()))
+
+
+class _DropPatch:
+    """Feed explicit Dropout2d noise to the reference (it draws from global RNG, networks.py:161)."""
+
+    def __init__(self, masks):
+        self.masks = list(masks)
+        self.i = 0
+
+    def __enter__(self):
+        self.old = torch.nn.Dropout2d.forward
+        patch = self
+
+        def fwd(mod, x):
+            m = patch.masks[patch.i % len(patch.masks)]
+            patch.i += 1
+            return x * m
+        torch.nn.Dropout2d.forward = fwd
+        return self
+
+    def __exit__(self, *a):
+        torch.nn.Dropout2d.forward = self.old
+
+
+def gen_networks(ns, H, W, P, N, seed, tag):
+    image_size = (H, W)
+    big = max(image_size) >= 256
+    enc = (64, 128, 256, 512, 512, 512, 512) if big else (64, 128, 256, 512, 512, 512)
+    dec = (512, 512, 512, 512, 256, 128, 3) if big else (512, 512, 512, 256, 128, 3)
+    G = ns.networks.Deformable_Generator(3 + 2 * P, P, image_size, enc, dec, "mask")
+    D = ns.networks.Discriminator(3 + 2 * P + 3)
+    gshapes = {k: tuple(v.shape) for k, v in G.state_dict().items()}
+    dshapes = {k: tuple(v.shape) for k, v in D.state_dict().items()}
+    assert gshapes == synth.generator_shapes(P, image_size), "generator_shapes() drifted from reference"
+    assert dshapes == synth.discriminator_shapes(3 + 2 * P + 3)
+    G.load_state_dict(synth.fill_state_dict(gshapes, seed))
+    D.load_state_dict(synth.fill_state_dict(dshapes, seed + 1))
+    b = synth.make_batch(N, H, W, P, seed=seed)
+    drop = synth.dropout_masks(N, 512, 3, seed=seed)
+    with _DropPatch(drop):
+        out = G(b["input"], b["warps"].clone(), b["masks"].clone())
+    img, src, tgt = ns.pose_utils.get_imgpose(b["input"], True, P)
+    d_in = torch.cat([img, src, out.detach(), tgt], 1)
+    d_out = D(d_in)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "net_%s.npz" % tag), out_gen=out.detach().numpy(),
+                        d_out=d_out.detach().numpy(),
+                        n_params_g=np.int64(sum(p.numel() for p in G.parameters())),
+                        n_params_d=np.int64(sum(p.numel() for p in D.parameters())))
+    print("net", tag, tuple(out.shape), tuple(d_out.shape), float(out.abs().mean()), float(d_out.mean()))
+
+
+def gen_step(ns, H, W, P, N, seed, tag, content="block1_conv2", area=5, l1_w=0.01, steps=2):
+    import argparse as ap
+    import torchvision
+    image_size = (H, W)
+    opt = ap.Namespace(image_size=image_size, use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=4,
+                       gen_type="baseline", warp_skip="mask", dataset="fasion", learning_rate=2e-4,
+                       content_loss_layer=content, nn_loss_area_size=area, gan_penalty_weight=1.0,
+                       l1_penalty_weight=l1_w)
+    dsd = synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1)
+    vgg = torchvision.models.vgg19(weights=None)
+    vw, vb = synth.vgg_conv1_1(seed)
+    with torch.no_grad():
+        vgg.features[0].weight.copy_(vw)
+        vgg.features[0].bias.copy_(vb)
+    model = ref_import.make_reference_gan(opt, dsd, vgg)
+    model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, image_size), seed))
+    od = vars(opt)
+    rec = {}
+    for s in range(steps):
+        b = synth.make_batch(N, H, W, P, seed=seed + 10 * s)
+        r = synth.make_batch(N, H, W, P, seed=seed + 10 * s + 1)
+        b2 = synth.make_batch(N, H, W, P, seed=seed + 10 * s + 2)
+        drop_d = synth.dropout_masks(N, 512, 3, seed=seed + 10 * s)
+        drop_g = synth.dropout_masks(N, 512, 3, seed=seed + 10 * s + 2)
+        with _DropPatch(drop_d):
+            dl = model.dis_update(b["input"], b["target"], {"warps": b["warps"].clone(), "masks": b["masks"].clone()},
+                                  r["input"], r["target"], od)
+        rec["d_loss_%d" % s] = np.array(dl)
+        rec["d_grad_%d" % s] = np.stack([summarize(p.grad) for _, p in sorted(model.disc.named_parameters())])
+        with _DropPatch(drop_g):
+            out, _, gl = model.gen_update(b2["input"], b2["target"], {"warps": b2["warps"].clone(), "masks": b2["masks"].clone()}, od)
+        rec["g_loss_%d" % s] = np.array(gl)
+        rec["out_gen_%d" % s] = out.detach().numpy()
+        rec["g_grad_%d" % s] = np.stack([summarize(p.grad) for _, p in sorted(model.gen.named_parameters())])
+        rec["g_param_%d" % s] = np.stack([summarize(p) for _, p in sorted(model.gen.named_parameters())])
+        rec["d_param_%d" % s] = np.stack([summarize(p) for _, p in sorted(model.disc.named_parameters())])
+        print("step", tag, s, dl, gl)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "step_%s.npz" % tag), **rec)
+
+
+def main():
+    apx = argparse.ArgumentParser()
+    apx.add_argument("--only", default="")
+    a = apx.parse_args()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.manual_seed(0)
+    ns = ref_import.load()
+    if a.only in ("", "warp"):
+        gen_warp(ns)
+    if a.only in ("", "net"):
+        gen_networks(ns, 64, 64, 18, 2, 0, "64x64_p18")
+        gen_networks(ns, 128, 64, 16, 3, 1, "128x64_p16")
+    if a.only in ("", "step"):
+        gen_step(ns, 64, 64, 18, 2, 0, "64x64_p18_nn5")
+        gen_step(ns, 64, 64, 18, 2, 3, "64x64_p18_l1", content="none", area=1, l1_w=100.0, steps=1)
+    if a.only in ("", "params"):
+        # known answers from the reference logs (gen_full_fasion:158,193 ; gen_full_h36m:136,171)
+        for (H, P, ng, nd) in ((256, 18, 82080611, 2803782), (224, 16, 61106781, 2799686)):
+            g = sum(int(np.prod(s)) for s in synth.generator_shapes(P, (H, H)).values())
+            d = sum(int(np.prod(s)) for s in synth.discriminator_shapes(3 + 2 * P + 3).values())
+            assert (g, d) == (ng, nd), (g, d)
+        print("param counts OK")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,101 @@
+"""TEST INFRASTRUCTURE ONLY.  Import the unmodified reference modules.
+
+The reference tree (``/root/reference/src_deformable``) only exists in the build container, never on
+the GPU box, so everything here is used to *generate* fixtures (``oracle/make_golden.py``) and to pin
+``oracle/restate.py`` in the CPU test-suite (tests skip when the tree is absent).
+
+Shims (none of them touches arithmetic):
+  * stub modules for dead/unavailable imports: keras (networks.py:9), skimage (pose_transform.py:3-6,
+    pose_utils.py:5,13), matplotlib/pylab (pose_utils.py:8-11, pose_transform.py:1);
+  * ``.cuda()`` is hard-coded (pose_transform.py:74,84; pose_utils.py:321,327; pose_gan.py:59-60) so
+    on a CPU-only host ``Tensor.cuda``/``Module.cuda`` become identity;
+  * ``DeformablePose_GAN.__init__`` unconditionally loads ``disc_090.pkl`` (pose_gan.py:40-42) and
+    ``vgg19(pretrained=True)`` (pose_gan.py:56): both are patched to seeded in-memory objects.
+"""
+import os
+import sys
+import types
+
+import torch
+
+REFERENCE_ROOT = os.environ.get("PTK_REFERENCE_ROOT", "/root/reference/src_deformable")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "networks.py"))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+_loaded = None
+
+
+def load():
+    """Returns a namespace with the reference modules: networks, pose_gan, pose_transform, pose_utils."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    saved = {k: sys.modules.get(k) for k in ("models", "utils", "models.networks", "models.pose_gan",
+                                             "utils.pose_transform", "utils.pose_utils")}
+    if "keras" not in sys.modules:
+        _stub("keras")
+        _stub("keras.optimizers", Adam=object)
+    if "skimage" not in sys.modules:
+        sk = _stub("skimage")
+        sk.io = _stub("skimage.io", imread=None)
+        sk.transform = _stub("skimage.transform", warp_coords=None, estimate_transform=None)
+        sk.measure = _stub("skimage.measure")
+        sk.draw = _stub("skimage.draw", circle=None, line_aa=None, polygon=None)
+    if "matplotlib" not in sys.modules:
+        mpl = _stub("matplotlib", use=lambda *a, **k: None)
+        mpl.pyplot = _stub("matplotlib.pyplot")
+        mpl.patches = _stub("matplotlib.patches")
+    if "pylab" not in sys.modules:
+        _stub("pylab")
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+    for k in list(saved):
+        sys.modules.pop(k, None)
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        from models import networks, pose_gan          # noqa
+        from utils import pose_transform, pose_utils   # noqa
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+    ns = types.SimpleNamespace(networks=networks, pose_gan=pose_gan,
+                               pose_transform=pose_transform, pose_utils=pose_utils)
+    # keep the reference modules reachable under private names only, so that they never shadow the
+    # product's own `models` / `utils` drop-in packages.
+    for k in ("models", "utils", "models.networks", "models.pose_gan", "utils.pose_transform",
+              "utils.pose_utils"):
+        mod = sys.modules.pop(k, None)
+        if mod is not None:
+            sys.modules["_ptk_reference." + k] = mod
+        if saved[k] is not None:
+            sys.modules[k] = saved[k]
+    _loaded = ns
+    return ns
+
+
+def make_reference_gan(opt, disc_state, vgg):
+    """Instantiate the reference DeformablePose_GAN with the two file loads patched."""
+    ns = load()
+    pg = ns.pose_gan
+    old_load, old_vgg = pg.torch.load, pg.vgg19
+    pg.torch.load = lambda path, *a, **k: disc_state
+    pg.vgg19 = lambda pretrained=True: vgg
+    try:
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = pg.DeformablePose_GAN(opt)
+    finally:
+        pg.torch.load, pg.vgg19 = old_load, old_vgg
+    return model
