@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the deformable-GAN training step (BASELINE.json metric: training images/sec at 256x256,
+warp_skip=mask; warp-kernel HBM GB/s).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (hand-written sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+
+One "step" = one main.py iteration = dis_update + gen_update (training_ratio = 1, src_deformable/main.py:78-108)
+on one synthetic batch (oracle/synth.py).  `value` = whole-job images/s with the batch resident in
+HBM; `e2e.value` = the same through DeformablePose_GAN's public methods with the batch in pinned HOST memory
+(H2D copies of input/target/warps/masks and the D2H loss read inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H = W = 256
+P = 18
+KPARTS = 10
+PER_GPU_BATCH = 8
+# SURVEY 8d work model (256^2, P=18): necessary conv FLOPs per image per iteration and warp bytes per image
+CONV_GFLOP_PER_IMG = 582.3
+WARP_FWD_BYTES_PER_IMG = 66.40e6
+
+
+def make_opt(N, content="block1_conv2", area=5, l1_w=0.01):
+    return argparse.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=4,
+                              gen_type="baseline", warp_skip="mask", dataset="fasion", learning_rate=2e-4,
+                              content_loss_layer=content, nn_loss_area_size=area, gan_penalty_weight=1.0,
+                              l1_penalty_weight=l1_w)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_info():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_iteration(model, batches, N):
+    from oracle import synth
+    b, r, b2 = batches
+    t0 = time.perf_counter()
+    model.dis_update(b["input"], b["target"], b["warps"], b["masks"], r["input"], r["target"], 1.0,
+                     synth.dropout_masks(N, 512, 3, seed=0))
+    model.gen_update(b2["input"], b2["target"], b2["warps"], b2["masks"], 1.0, 0.01, synth.dropout_masks(N, 512, 3, seed=1))
+    return time.perf_counter() - t0
+
+
+def make_cpu_reference(N):
+    from oracle import restate, synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    vw, vb = synth.vgg_conv1_1(0)
+    model = restate.OracleGAN(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), 0),
+                              synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), 1), vw, vb, (H, W), P, N,
+                              faithful_waste=True)
+    batches = [synth.make_batch(N, H, W, P, seed=s) for s in (0, 1, 2)]
+    return model, batches
+
+
+def run_reference(args):
+    """The reference algorithm (oracle/restate.py: the reference's own torch CPU op sequence, incl. its wasted
+    generator backward in dis_update) on the host cores.  Each step is a bounded sample: one iteration at N=2
+    (the smallest batch the reference supports, models/networks.py:169) of the 256x256 workload."""
+    rank, world, _ = dist_info()
+    if rank != 0:
+        return
+    N = 2
+    model, batches = make_cpu_reference(N)
+    for _ in range(args.warmup):
+        cpu_reference_iteration(model, batches, N)
+    times = [cpu_reference_iteration(model, batches, N) for _ in range(args.steps)]
+    total = sum(times)
+    v = N * args.steps / total
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": "training images/sec at 256x256 warp_skip=mask", "value": v, "unit": "img/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "src_deformable warp_skip=mask, fasion 256x256, 18 kpts (BASELINE configs[1])",
+                       "per_step_sample": "1 iteration (dis_update+gen_update) at batch 2"},
+            "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
+                             "sample": "%d iterations at batch 2, 256x256, torch CPU fp32, %d threads" % (args.steps, cores)},
+            "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- our arm (B200)
+def run_ours(args):
+    import torch.distributed as dist
+    rank, world, local = dist_info()
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device -- there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import pose_transfer_b200  # noqa: F401
+    from pose_transfer_b200 import _lib, kernels as K
+    from pose_transfer_b200.models import pose_gan
+    from oracle import synth
+
+    N = args.batch
+    opt = make_opt(N)
+    model = pose_gan.DeformablePose_GAN(opt).cuda()
+    model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), 0))
+    model.disc.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), 1))
+    vw, vb = synth.vgg_conv1_1(0)
+    with torch.no_grad():
+        model.content_model.features[0].weight.copy_(vw)
+        model.content_model.features[0].bias.copy_(vb)
+    od = vars(opt)
+
+    # three distinct synthetic batches per step (D-fake, D-real, G), as in main.py:81-82,105; rank-dependent seeds
+    host = [synth.make_batch(N, H, W, P, seed=100 * rank + s) for s in range(3)]
+    pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    resident = [dict(b, warps=b["warps"].float()) for b in resident]
+    h2d_bytes = sum(b[k].numel() * b[k].element_size() for b in pinned for k in ("input", "warps", "masks"))
+    h2d_bytes += pinned[1]["target"].numel() * 4 + pinned[2]["target"].numel() * 4
+    d2h_bytes = 2 * 4 * 4   # two 4-float loss buffers per step
+
+    def step_resident():
+        b, r, b2 = resident
+        model.dis_update(b["input"], b["target"], {"warps": b["warps"], "masks": b["masks"]}, r["input"], r["target"], od)
+        model.gen_update(b2["input"], b2["target"], {"warps": b2["warps"], "masks": b2["masks"]}, od)
+
+    def step_e2e():
+        # what main.py does per iteration (main.py:81-86,105-107): host batch -> .cuda() -> update -> .item()
+        b, r, b2 = pinned
+        cu = lambda t: t.to(dev, non_blocking=True)  # noqa: E731
+        model.dis_update(cu(b["input"]), cu(b["target"]), {"warps": cu(b["warps"]).float(), "masks": cu(b["masks"])},
+                         cu(r["input"]), cu(r["target"]), od)
+        model.gen_update(cu(b2["input"]), cu(b2["target"]), {"warps": cu(b2["warps"]).float(), "masks": cu(b2["masks"])}, od)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-kernel-family device times (CUDA events on the launching stream) over a few more steps
+    prof_steps = min(args.steps, 3)
+    barrier()
+    K.profile_start()
+    for _ in range(prof_steps):
+        step_resident()
+    prof = K.profile_stop()
+    hbm_peak, tf_peak, peak_src = measured_peaks()
+    wl, wms = prof.get("warp_forward", (0, 0.0))
+    # 2 generator forwards per step (dis_update + gen_update), 4 warped levels each
+    warp_bytes_per_launch_set = WARP_FWD_BYTES_PER_IMG * N
+    warp_sets = max(wl // 4, 1)
+    warp_gbs = warp_bytes_per_launch_set * warp_sets / (wms * 1e-3) / 1e9 if wms > 0 else 0.0
+    conv_ms = sum(prof.get(k, (0, 0.0))[1] for k in ("conv_forward", "conv_wgrad")) / prof_steps
+    conv_tflops = CONV_GFLOP_PER_IMG * N / (conv_ms * 1e-3) / 1e3 if conv_ms > 0 else 0.0
+
+    value = world * N * args.steps / (ms * 1e-3)
+    e2e_value = world * N * args.steps / (ms_e2e * 1e-3)
+    line = {"metric": "training images/sec at 256x256 warp_skip=mask", "value": value, "unit": "img/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "src_deformable warp_skip=mask, fasion 256x256, 18 kpts, batch %d/GPU (BASELINE configs[1])" % N,
+                       "global_batch": N * world, "parallelism": "dp%d" % world, "step": "dis_update + gen_update",
+                       "content_loss_layer": "block1_conv2", "nn_loss_area_size": 5,
+                       "l2": "working set per step (>10 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "warp_forward_kernel (4 levels)", "achieved": warp_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": warp_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch_set": warp_bytes_per_launch_set,
+                         "ms_per_launch_set": wms / warp_sets if warp_sets else None},
+            "conv_roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": tf_peak / 2, "unit": "TFLOP/s",
+                              "frac": conv_tflops / (tf_peak / 2), "peak_source": peak_src + " bf16 sustained / 2 (tf32)",
+                              "algorithmic_gflop_per_img": CONV_GFLOP_PER_IMG, "conv_ms_per_step": conv_ms},
+            "kernel_ms_per_step": {k: v[1] / prof_steps for k, v in sorted(prof.items())}}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            torch.cuda.synchronize()
+            cm, cb = make_cpu_reference(2)
+            t = cpu_reference_iteration(cm, cb, 2)
+            line["cpu_baseline"] = {"value": 2 / t, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "1 iteration (dis_update+gen_update) at batch 2, 256x256, torch CPU fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE configs[1]: 8)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,165 @@
+/*
+ * ptk.h -- C ABI of the B200 (sm_100a) kernel library for the deformable-GAN training step.
+ *
+ * The reference (saurabhsharma1993/pose-transfer, src_deformable/) ships no native code: every
+ * entry point below replaces a torch/cuDNN/cv2 LIBRARY CALL SITE of the reference, cited per
+ * function as path:line relative to /root/reference/src_deformable/.
+ *
+ * Conventions
+ *   - All activations are fp32 NHWC with an explicit pixel stride `ld` (floats): element (n,y,x,c) of a
+ *     tensor lives at base[((n*H + y)*W + x)*ld + c].  `ld >= C` lets producers write straight into a
+ *     channel slice of a wider concat buffer (this replaces the reference's torch.cat call sites,
+ *     models/networks.py:241,245,284,286 and models/pose_gan.py:86,133-136).
+ *   - Caller (PyTorch) owns every buffer, including scratch; the library never allocates or frees.
+ *   - Every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns immediately.
+ *   - Return value: 0 = OK, otherwise an error code; ptk_last_error() gives the (thread-local) message.
+ *   - Activation codes: 0 = identity, 1 = LeakyReLU(0.2), 2 = ReLU, 3 = tanh, 4 = sigmoid.
+ */
+#ifndef PTK_H_
+#define PTK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTK_ACT_NONE 0
+#define PTK_ACT_LEAKY 1
+#define PTK_ACT_RELU 2
+#define PTK_ACT_TANH 3
+#define PTK_ACT_SIGMOID 4
+
+#define PTK_IMPL_AUTO 0
+#define PTK_IMPL_SIMT 1 /* fp32 CUDA-core implicit GEMM (exact-fp32 path) */
+#define PTK_IMPL_TC 2   /* tcgen05 TF32 tensor-core implicit GEMM        */
+
+int ptk_version(void);
+const char* ptk_last_error(void);
+
+/* ---------------------------------------------------------------- layout (replaces torch.cat / views) */
+/* dst[n,y,x,c_dst0+c] = act(src[n,c_src0+c,y,x]); src NCHW with C_src channels, dst NHWC (ld_dst).
+ * utils/pose_utils.py:227-233 (get_imgpose slices) + models/networks.py:271, models/pose_gan.py:86,133-136 */
+int ptk_nchw_to_nhwc(const float* src, int C_src, int c_src0, float* dst, int ld_dst, int c_dst0,
+                     int N, int C, int H, int W, int act, void* stream);
+/* dst[n,c,y,x] = src[n,y,x,c_src0+c]  (NHWC slice -> dense NCHW, e.g. out_gen for the caller) */
+int ptk_nhwc_to_nchw(const float* src, int ld_src, int c_src0, float* dst, int N, int C, int H, int W,
+                     void* stream);
+/* Weight repack.  src is the torch layout [A][B][k][k] (Conv2d: A=Cout,B=Cin; ConvTranspose2d: A=Cin,
+ * B=Cout; models/networks.py:154,156).  transpose==0: dst[tap][a][b_pad]; transpose==1: dst[tap][b][a_pad].
+ * Padding entries are written as zero. */
+int ptk_pack_weight(const float* src, float* dst, int A, int B, int taps, int A_pad, int B_pad,
+                    int transpose, void* stream);
+/* grad[a][b][tap] (+)= src[tap][a][b_pad]  (inverse of transpose==0 packing, drops padding) */
+int ptk_unpack_weight_grad(const float* src, float* grad, int A, int B, int taps, int B_pad,
+                           int accumulate, void* stream);
+int ptk_fill(float* dst, int64_t n, float value, void* stream);
+
+/* ---------------------------------------------------------------- convolutions
+ * One geometry struct describes Conv2d and ConvTranspose2d(+Cropping2D) fprop/dgrad/wgrad
+ * (models/networks.py:154 Conv k4 s2 p1, :156-157 ConvT k4 s2 p0 + crop 1 == p1, :186 stem k3 s1 p1,
+ *  :232 final k3, :341 D stem k4 s2 p0; torchvision vgg19.features[0] is fused in ptk_nnloss_*). */
+typedef struct {
+  int N;            /* batch                                                          */
+  int H, W;         /* spatial extent of the SMALL-stride side input (see transposed) */
+  int Cin, ldx;     /* channels consumed from x, pixel stride of x                    */
+  int OH, OW;       /* spatial extent of y                                            */
+  int Cout, ldy;    /* channels produced, pixel stride of y                           */
+  int k, stride, pad;
+  int transposed;   /* 0: y = conv(x): iy = oy*stride - pad + kh.  1: y = conv_transpose(x): oy = iy*stride - pad + kh
+                       (pad = torch padding; ConvT(p=0)+Cropping2D(1) is pad = 1).  dgrad of one kind is the
+                       forward of the other kind with the weight roles swapped. */
+  int impl;         /* PTK_IMPL_*                                                     */
+} ptk_conv_geom;
+
+/* y = epilogue(conv(x, w) + bias).  w is packed [tap][Cin_pad][Cout_pad] ("WT": transpose==1 packing of
+ * a Conv2d weight, transpose==0 packing of a ConvTranspose2d weight) for the SIMT path, and
+ * [tap][Cout][Cin] ("WK") for the tensor-core path; pass both (either may be NULL if that path is
+ * never selected).  `stats` (may be NULL) receives per-sample {sum, sum of squares} of the conv output
+ * (double[N][2], must be zeroed by the caller) -- the first half of the reference's
+ * InstanceNorm3d (models/networks.py:159).  If y2 != NULL the NCHW copy of the result is also written
+ * (only supported for Cout <= 4). */
+/* 1 if the tcgen05 path can serve this geometry */
+int ptk_conv_tc_supported(const ptk_conv_geom* g);
+int ptk_conv_forward(const ptk_conv_geom* g, const float* x, const float* w_t, const float* w_k,
+                     const float* bias, int act, float* y, float* y_nchw, double* stats, void* stream);
+/* dw[tap][A][B_pad] (+)= sum_pixels small[m][a] * big[m*stride+off(tap)][b]; for Conv2d small=dy,big=x
+ * (result [tap][Cout][Cin]); for ConvTranspose2d small=x,big=dy (result [tap][Cin][Cout]).  dw must be
+ * zeroed by the caller when accumulate==0 semantics are wanted (the kernel always atomically adds). */
+int ptk_conv_wgrad(const ptk_conv_geom* g, const float* x, const float* dy, float* dw, void* stream);
+/* dbias[c] += sum_pixels dy[pixel][c] */
+int ptk_bias_grad(const float* dy, int ld, int64_t pixels, int C, float* dbias, void* stream);
+
+/* ---------------------------------------------------------------- norm (models/networks.py:159,164-172) */
+/* stats[n] = {sum, sumsq} over HW*C elements of sample n (double, caller zeroes). */
+int ptk_gn_stats(const float* z, int ld, int N, int64_t HW, int C, double* stats, void* stream);
+/* y = ((z-mean)*rstd*gamma+beta) * drop[n,c];  out1 = act1(y) [, out2 = act2(y)].  gamma/beta are device
+ * scalars (NULL => identity affine AND no normalisation: y = z, used by the bn=False blocks).
+ * drop is [N][C] (values 0 or 2, models/networks.py:161) or NULL. eps = 1e-3, biased variance. */
+int ptk_gn_apply(const float* z, int ldz, const double* stats, const float* gamma, const float* beta,
+                 const float* drop, int N, int64_t HW, int C, float* out1, int ld1, int act1,
+                 float* out2, int ld2, int act2, void* stream);
+/* Backward.  dy = sum_i g_i * act_i'(a_i) * drop  (i = 1,2; a_i = the stored activated output, NULL =>
+ * identity).  Writes dy dense (ld = C) and, when gamma != NULL, sums[n] += {sum dy, sum dy*xhat}. */
+int ptk_gn_bwd_reduce(const float* g1, int ldg1, const float* a1, int lda1, int act1,
+                      const float* g2, int ldg2, const float* a2, int lda2, int act2,
+                      const float* drop, const float* z, int ldz, const double* stats,
+                      int N, int64_t HW, int C, float* dy, double* sums, void* stream);
+/* dz = gamma*rstd*(dy - mean(dy) - xhat*mean(dy*xhat)) in place over dy; dgamma += sum_n S2_n,
+ * dbeta += sum_n S1_n. */
+int ptk_gn_bwd_apply(float* dy, const float* z, int ldz, const double* stats, const double* sums,
+                     const float* gamma, int N, int64_t HW, int C, float* dgamma, float* dbeta,
+                     void* stream);
+
+/* ---------------------------------------------------------------- affine warp (utils/pose_transform.py:16-92) */
+/* cv2.resize(INTER_LINEAR) of the f64 masks [N,K,H0,W0] to f32 [N,h,w,K] (pose_transform.py:82-87). */
+int ptk_mask_pyramid(const double* masks, int N, int K, int H0, int W0, float* out, int h, int w,
+                     void* stream);
+/* y[n,y,x,c] = act(max_k m[n,y,x,k] * bilinear(x[n,:,:,c]; theta_k(y,x))).  warps = raw [N,K,8] rows
+ * (first 6 used, :28).  argk[n,y,x,c] = winning part (255 = zero winner).  H0,W0 = init_image_size. */
+int ptk_warp_forward(const float* x, int ldx, const float* warps, const float* mask_lvl, float* y, int ldy,
+                     uint8_t* argk, int N, int C, int h, int w, int K, int H0, int W0, int align_corners,
+                     int act, void* stream);
+/* dx (dense, ld = C, caller zeroes) += scatter of dy*act'(y)*m*bilinear weights through argk. */
+int ptk_warp_backward(const float* dy, int lddy, const float* y, int ldy, int act, const float* warps,
+                      const float* mask_lvl, const uint8_t* argk, float* dx, int N, int C, int h, int w,
+                      int K, int H0, int W0, int align_corners, void* stream);
+
+/* ---------------------------------------------------------------- losses (models/pose_gan.py:90-98,140-199) */
+/* logits [rows][J] (pre-sigmoid).  rows < n_true: -mean_j log(sig+1e-7); other rows: -mean_j log(1-sig+1e-7);
+ * both scaled by `scale`.  loss[0] += true part, loss[1] += fake part; if dlogits != NULL the gradient of
+ * element i is written to dlogits[i*ldd] (ldd = 4 gives the zero-padded 4-channel NHWC layout the dgrad reads). */
+int ptk_adv_loss(const float* logits, int rows, int J, int n_true, float scale, float* loss,
+                 float* dlogits, int ldd, void* stream);
+/* loss[0] += scale*mean|a-b| ; grad = scale*sign(a-b)/n (if non-NULL) */
+int ptk_l1_loss(const float* a, const float* b, int64_t n, float scale, float* loss, float* grad,
+                void* stream);
+/* Fused Feature_Extractor('block1_conv2') (utils/pose_utils.py:320-338, vgg features[0..1] incl. the
+ * view-based preprocessing) + nn_loss (models/pose_gan.py:173-199).  pred/target NCHW [N,3,H,W];
+ * vgg_w [64][3][3][3], vgg_b [64].  loss[0] += scale * mean_{n,y,x} min_shift sum_c |gt_shift - pred|;
+ * argmin[n,y,x] = winning shift (row-major in the area x area window). */
+int ptk_nnloss_forward(const float* pred, const float* target, const float* vgg_w, const float* vgg_b,
+                       int N, int H, int W, int area, float scale, float* loss, uint8_t* argmin,
+                       void* stream);
+/* dpred NCHW [N,3,H,W] = d(scale*nn_loss)/dpred (overwrites). */
+int ptk_nnloss_backward(const float* pred, const float* target, const float* vgg_w, const float* vgg_b,
+                        const uint8_t* argmin, int N, int H, int W, int area, float scale, float* dpred,
+                        void* stream);
+/* dz[n,y,x,c] (NHWC, ld) = (g_nchw[n,c,y,x] + g_nhwc[(n,y,x)*ldg + c]) * (1 - out[n,c,y,x]^2); either g may be NULL */
+int ptk_tanh_bwd_combine(const float* g_nchw, const float* g_nhwc, int ldg, const float* out_nchw,
+                         float* dz, int ld, int N, int C, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------- optimiser (models/pose_gan.py:49-51) */
+/* torch.optim.Adam (no weight decay, no amsgrad) on a flat fp32 arena. step >= 1. grad_scale multiplies g
+ * first (1/world for data-parallel averaging). */
+int ptk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------- diagnostics */
+/* number of kernels this process has launched through the library (for bench.py's gpu_launches) */
+int64_t ptk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTK_H_ */

@@ -1,0 +1,72 @@
+"""ctypes binding of csrc/libptk.so (the C ABI declared in include/ptk.h)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libptk.so")
+_lib = None
+
+i32, i64, f32, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class ConvGeom(ctypes.Structure):
+    """Mirror of ptk_conv_geom (include/ptk.h)."""
+    _fields_ = [(n, i32) for n in ("N", "H", "W", "Cin", "ldx", "OH", "OW", "Cout", "ldy", "k", "stride", "pad",
+                                   "transposed", "impl")]
+
+
+# name -> argtypes (everything returns int unless listed in _RESTYPES)
+SIGNATURES = {
+    "ptk_version": [],
+    "ptk_last_error": [],
+    "ptk_launch_count": [],
+    "ptk_nchw_to_nhwc": [vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "ptk_nhwc_to_nchw": [vp, i32, i32, vp, i32, i32, i32, i32, vp],
+    "ptk_pack_weight": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "ptk_unpack_weight_grad": [vp, vp, i32, i32, i32, i32, i32, vp],
+    "ptk_fill": [vp, i64, f32, vp],
+    "ptk_conv_tc_supported": [ctypes.POINTER(ConvGeom)],
+    "ptk_conv_forward": [ctypes.POINTER(ConvGeom), vp, vp, vp, vp, i32, vp, vp, vp, vp],
+    "ptk_conv_wgrad": [ctypes.POINTER(ConvGeom), vp, vp, vp, vp],
+    "ptk_bias_grad": [vp, i32, i64, i32, vp, vp],
+    "ptk_gn_stats": [vp, i32, i32, i64, i32, vp, vp],
+    "ptk_gn_apply": [vp, i32, vp, vp, vp, vp, i32, i64, i32, vp, i32, i32, vp, i32, i32, vp],
+    "ptk_gn_bwd_reduce": [vp, i32, vp, i32, i32, vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, i64, i32, vp, vp, vp],
+    "ptk_gn_bwd_apply": [vp, vp, i32, vp, vp, vp, i32, i64, i32, vp, vp, vp],
+    "ptk_mask_pyramid": [vp, i32, i32, i32, i32, vp, i32, i32, vp],
+    "ptk_warp_forward": [vp, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "ptk_warp_backward": [vp, i32, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "ptk_adv_loss": [vp, i32, i32, i32, f32, vp, vp, i32, vp],
+    "ptk_l1_loss": [vp, vp, i64, f32, vp, vp, vp],
+    "ptk_nnloss_forward": [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp],
+    "ptk_nnloss_backward": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp],
+    "ptk_tanh_bwd_combine": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp],
+    "ptk_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
+}
+_RESTYPES = {"ptk_last_error": ctypes.c_char_p, "ptk_launch_count": i64}
+
+
+def lib():
+    """Load libptk.so (once).  Raises if it was not built -- there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError("pose_transfer_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; "
+                               "g.build()'` (or `make -C pose-transfer_b200/csrc`) first; there is no CPU fallback"
+                               % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, i32)
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, lib().ptk_last_error().decode()))
+
+
+def launch_count():
+    return int(lib().ptk_launch_count())

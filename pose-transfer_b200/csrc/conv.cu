@@ -1,0 +1,48 @@
+// C-ABI dispatch for the convolution family: chooses the fp32 CUDA-core path or the tcgen05 TF32 path.
+#include "common.cuh"
+
+namespace ptk {
+int conv_forward_simt(const ptk_conv_geom& c, const float* x, const float* w_t, int cout_pad, const float* bias, int act,
+                      float* y, float* y_nchw, cudaStream_t st);
+int conv_wgrad_simt(const ptk_conv_geom& c, const float* x, const float* dy, float* dw, cudaStream_t st);
+bool conv_tc_supported(const ptk_conv_geom& c);
+int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, const float* bias, int act, float* y,
+                    double* stats, cudaStream_t st);
+}  // namespace ptk
+
+using namespace ptk;
+
+extern "C" int ptk_conv_tc_supported(const ptk_conv_geom* g) { return conv_tc_supported(*g) ? 1 : 0; }
+
+extern "C" int ptk_conv_forward(const ptk_conv_geom* g, const float* x, const float* w_t, const float* w_k,
+                                const float* bias, int act, float* y, float* y_nchw, double* stats, void* stream) {
+  PTK_REQUIRE(g && x && (y || y_nchw), "conv_forward: null argument");
+  PTK_REQUIRE(g->N > 0 && g->H > 0 && g->W > 0 && g->OH > 0 && g->OW > 0 && g->Cin > 0 && g->Cout > 0, "conv_forward: bad extents");
+  PTK_REQUIRE(g->ldx >= g->Cin && (!y || g->ldy >= g->Cout), "conv_forward: ld smaller than channel count");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool use_tc = false;
+  if (g->impl == PTK_IMPL_TC) {
+    PTK_REQUIRE(conv_tc_supported(*g), "conv_forward: geometry not supported by the tcgen05 path");
+    use_tc = true;
+  } else if (g->impl == PTK_IMPL_AUTO) {
+    use_tc = w_k != nullptr && conv_tc_supported(*g);
+  }
+  if (use_tc) {
+    PTK_REQUIRE(w_k != nullptr && y != nullptr && y_nchw == nullptr, "conv_forward(tc): needs w_k and an NHWC destination");
+    return conv_forward_tc(*g, x, w_k, bias, act, y, stats, st);
+  }
+  PTK_REQUIRE(w_t != nullptr, "conv_forward(simt): w_t is NULL");
+  const int cout_pad = (g->Cout + 3) & ~3;
+  int rc = conv_forward_simt(*g, x, w_t, cout_pad, bias, act, y, y_nchw, st);
+  if (rc) return rc;
+  if (stats) {
+    PTK_REQUIRE(y != nullptr && act == PTK_ACT_NONE, "conv_forward: stats need a raw NHWC output");
+    rc = ptk_gn_stats(y, g->ldy, g->N, (int64_t)g->OH * g->OW, g->Cout, stats, stream);
+  }
+  return rc;
+}
+
+extern "C" int ptk_conv_wgrad(const ptk_conv_geom* g, const float* x, const float* dy, float* dw, void* stream) {
+  PTK_REQUIRE(g && x && dy && dw, "conv_wgrad: null argument");
+  return conv_wgrad_simt(*g, x, dy, dw, (cudaStream_t)stream);
+}

@@ -1,0 +1,134 @@
+// Layout kernels: NCHW <-> NHWC channel-slice copies (the reference's torch.cat / get_imgpose call sites,
+// utils/pose_utils.py:227-233, models/networks.py:271, models/pose_gan.py:86,133-136) and weight repacking
+// between the torch checkpoint layout and the GEMM layouts.
+#include "common.cuh"
+
+namespace ptk {
+
+// src NCHW plane-major -> dst NHWC slice.  Tile: 32 pixels x 32 channels through shared memory.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C_src, int c_src0, float* __restrict__ dst,
+                                    int ld_dst, int c_dst0, int C, int64_t HW, int act) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i;
+    const int64_t p = p0 + tx;
+    tile[i][tx] = (c < C && p < HW) ? src[((int64_t)n * C_src + c_src0 + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t p = p0 + i;
+    const int c = c0 + tx;
+    if (c < C && p < HW) dst[((int64_t)n * HW + p) * ld_dst + c_dst0 + c] = apply_act(tile[tx][i], act);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int ld_src, int c_src0, float* __restrict__ dst,
+                                    int C, int64_t HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t p = p0 + i;
+    const int c = c0 + tx;
+    tile[i][tx] = (c < C && p < HW) ? src[((int64_t)n * HW + p) * ld_src + c_src0 + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i;
+    const int64_t p = p0 + tx;
+    if (c < C && p < HW) dst[((int64_t)n * C + c) * HW + p] = tile[tx][i];
+  }
+}
+
+// src [A][B][taps] -> dst[tap][a][b_pad] (transpose=0) or dst[tap][b][a_pad] (transpose=1); zero padding.
+__global__ void pack_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int A, int B, int taps,
+                                   int A_pad, int B_pad, int transpose) {
+  const int64_t rows = transpose ? B_pad : A_pad, cols = transpose ? A_pad : B_pad;
+  const int64_t total = (int64_t)taps * rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % cols;
+    const int64_t r = (i / cols) % rows;
+    const int t = (int)(i / (cols * rows));
+    const int64_t a = transpose ? c : r, b = transpose ? r : c;
+    dst[i] = (a < A && b < B) ? src[(a * B + b) * taps + t] : 0.f;
+  }
+}
+
+__global__ void unpack_weight_grad_kernel(const float* __restrict__ src, float* __restrict__ grad, int A, int B,
+                                          int taps, int B_pad, int accumulate) {
+  const int64_t total = (int64_t)A * B * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const int64_t b = (i / taps) % B;
+    const int64_t a = i / ((int64_t)taps * B);
+    const float v = src[((int64_t)t * A + a) * B_pad + b];
+    grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ dst, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = v;
+}
+
+static inline int grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace ptk
+
+using namespace ptk;
+
+extern "C" int ptk_nchw_to_nhwc(const float* src, int C_src, int c_src0, float* dst, int ld_dst, int c_dst0,
+                                int N, int C, int H, int W, int act, void* stream) {
+  PTK_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && N <= 65535, "nchw_to_nhwc: bad extents");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, C_src, c_src0, dst, ld_dst, c_dst0, C, HW, act);
+  PTK_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return 0;
+}
+
+extern "C" int ptk_nhwc_to_nchw(const float* src, int ld_src, int c_src0, float* dst, int N, int C, int H, int W,
+                                void* stream) {
+  PTK_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && N <= 65535, "nhwc_to_nchw: bad extents");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, ld_src, c_src0, dst, C, HW);
+  PTK_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return 0;
+}
+
+extern "C" int ptk_pack_weight(const float* src, float* dst, int A, int B, int taps, int A_pad, int B_pad,
+                               int transpose, void* stream) {
+  PTK_REQUIRE(A_pad >= A && B_pad >= B && taps > 0, "pack_weight: bad extents");
+  const int64_t total = (int64_t)taps * A_pad * B_pad;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, A, B, taps, A_pad, B_pad, transpose);
+  PTK_LAUNCH_CHECK("pack_weight_kernel");
+  return 0;
+}
+
+extern "C" int ptk_unpack_weight_grad(const float* src, float* grad, int A, int B, int taps, int B_pad,
+                                      int accumulate, void* stream) {
+  const int64_t total = (int64_t)A * B * taps;
+  unpack_weight_grad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, grad, A, B, taps, B_pad, accumulate);
+  PTK_LAUNCH_CHECK("unpack_weight_grad_kernel");
+  return 0;
+}
+
+extern "C" int ptk_fill(float* dst, int64_t n, float value, void* stream) {
+  if (n <= 0) return 0;
+  fill_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dst, n, value);
+  PTK_LAUNCH_CHECK("fill_kernel");
+  return 0;
+}

@@ -1,0 +1,238 @@
+// Fused per-body-part affine warp of an encoder skip tensor (AffineTransformLayer + AffineLayer,
+// utils/pose_transform.py:16-92 of the reference).  The reference materialises K=10 replicas of the
+// feature map, an affine grid, the sampled replicas and the masked product before a max over parts, and
+// round-trips the masks through the CPU (cv2.resize) once per level.  Here: one pass, coordinates in
+// registers, masks from a device-side pyramid, zero-mask parts skipped, output written (optionally through
+// the consumer's ReLU) straight into its slice of the decoder's concat buffer.  HBM-bound gather.
+#include "common.cuh"
+
+namespace ptk {
+
+struct Theta { float a, b, tx, c, d, ty; };
+
+// AffineTransformLayer.forward :72-76 followed by AffineLayer.normalize_transforms :48-58 (sequential
+// in-place updates: tx' sees the rescaled b, ty' the rescaled c; tx is scaled with the HEIGHT ratio).
+__device__ __forceinline__ Theta normalized_theta(const float* __restrict__ wp, int h, int w, int H0, int W0) {
+  Theta t;
+  const float mul_x = (float)H0 / (float)h, mul_y = (float)W0 / (float)w;
+  t.a = wp[0];
+  t.b = wp[1] * (float)w / (float)h;
+  t.tx = (wp[2] / mul_x) * 2.f / (float)h + t.a + t.b - 1.f;
+  t.c = wp[3] * (float)h / (float)w;
+  t.d = wp[4];
+  t.ty = (wp[5] / mul_y) * 2.f / (float)w + t.c + t.d - 1.f;
+  return t;
+}
+
+struct Footprint { int x0, y0; float w00, w01, w10, w11; bool any; };
+
+// F.affine_grid + grid_sample(bilinear, zeros) coordinates for output pixel (i, j) (pose_transform.py:37-39)
+__device__ __forceinline__ Footprint footprint(const Theta& t, int i, int j, int h, int w, int align_corners) {
+  float gx, gy;
+  if (align_corners) {
+    gx = w > 1 ? (float)j * 2.f / (float)(w - 1) - 1.f : 0.f;
+    gy = h > 1 ? (float)i * 2.f / (float)(h - 1) - 1.f : 0.f;
+  } else {
+    gx = (2.f * (float)j + 1.f) / (float)w - 1.f;
+    gy = (2.f * (float)i + 1.f) / (float)h - 1.f;
+  }
+  const float sx = t.a * gx + t.b * gy + t.tx;
+  const float sy = t.c * gx + t.d * gy + t.ty;
+  float px, py;
+  if (align_corners) {
+    px = (sx + 1.f) * 0.5f * (float)(w - 1);
+    py = (sy + 1.f) * 0.5f * (float)(h - 1);
+  } else {
+    px = ((sx + 1.f) * (float)w - 1.f) * 0.5f;
+    py = ((sy + 1.f) * (float)h - 1.f) * 0.5f;
+  }
+  Footprint f;
+  const float fx0 = floorf(px), fy0 = floorf(py);
+  const float fx = px - fx0, fy = py - fy0;
+  // keep the integer conversion safe for the 1000-pixel "missing part" translations
+  f.x0 = (int)fminf(fmaxf(fx0, -2.f), (float)w);
+  f.y0 = (int)fminf(fmaxf(fy0, -2.f), (float)h);
+  const bool xin0 = f.x0 >= 0 && f.x0 < w, xin1 = f.x0 + 1 >= 0 && f.x0 + 1 < w;
+  const bool yin0 = f.y0 >= 0 && f.y0 < h, yin1 = f.y0 + 1 >= 0 && f.y0 + 1 < h;
+  f.w00 = (yin0 && xin0) ? (1.f - fy) * (1.f - fx) : 0.f;
+  f.w01 = (yin0 && xin1) ? (1.f - fy) * fx : 0.f;
+  f.w10 = (yin1 && xin0) ? fy * (1.f - fx) : 0.f;
+  f.w11 = (yin1 && xin1) ? fy * fx : 0.f;
+  f.any = (xin0 || xin1) && (yin0 || yin1);
+  return f;
+}
+
+constexpr int kMaxParts = 16;
+
+// grid (chunks, N); thread -> (pixel, 4 channels)
+__global__ void __launch_bounds__(256)
+warp_forward_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ warps,
+                    const float* __restrict__ mask_lvl, float* __restrict__ y, int ldy, uint8_t* __restrict__ argk,
+                    int C, int h, int w, int K, int H0, int W0, int align_corners, int act) {
+  __shared__ Theta s_theta[kMaxParts];
+  const int n = blockIdx.y;
+  if (threadIdx.x < K) s_theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * K + threadIdx.x) * 8, h, w, H0, W0);
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int64_t HW = (int64_t)h * w;
+  const int64_t total = HW * C4;
+  const float* xb = x + (int64_t)n * HW * ldx;
+  const float* mb = mask_lvl + (int64_t)n * HW * K;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = idx / C4;
+    const int c = (int)(idx - p * C4) << 2;
+    const int i = (int)(p / w), j = (int)(p - (int64_t)i * w);
+    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    uchar4 arg = make_uchar4(255, 255, 255, 255);
+    for (int k = 0; k < K; ++k) {
+      const float m = __ldg(mb + p * K + k);
+      float4 cand = make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned char tag = 255;
+      if (m != 0.f) {
+        const Footprint f = footprint(s_theta[k], i, j, h, w, align_corners);
+        if (f.any) {
+          tag = (unsigned char)k;
+          const float* r0 = xb + ((int64_t)f.y0 * w + f.x0) * ldx + c;
+          const float* r1 = r0 + (int64_t)w * ldx;
+          if (f.w00 != 0.f) { const float4 v = __ldg(reinterpret_cast<const float4*>(r0)); cand.x += f.w00 * v.x; cand.y += f.w00 * v.y; cand.z += f.w00 * v.z; cand.w += f.w00 * v.w; }
+          if (f.w01 != 0.f) { const float4 v = __ldg(reinterpret_cast<const float4*>(r0 + ldx)); cand.x += f.w01 * v.x; cand.y += f.w01 * v.y; cand.z += f.w01 * v.z; cand.w += f.w01 * v.w; }
+          if (f.w10 != 0.f) { const float4 v = __ldg(reinterpret_cast<const float4*>(r1)); cand.x += f.w10 * v.x; cand.y += f.w10 * v.y; cand.z += f.w10 * v.z; cand.w += f.w10 * v.w; }
+          if (f.w11 != 0.f) { const float4 v = __ldg(reinterpret_cast<const float4*>(r1 + ldx)); cand.x += f.w11 * v.x; cand.y += f.w11 * v.y; cand.z += f.w11 * v.z; cand.w += f.w11 * v.w; }
+          cand.x *= m; cand.y *= m; cand.z *= m; cand.w *= m;
+        }
+      }
+      // torch.max(dim=1): first maximum wins (pose_transform.py:89)
+      if (cand.x > best.x) { best.x = cand.x; arg.x = tag; }
+      if (cand.y > best.y) { best.y = cand.y; arg.y = tag; }
+      if (cand.z > best.z) { best.z = cand.z; arg.z = tag; }
+      if (cand.w > best.w) { best.w = cand.w; arg.w = tag; }
+    }
+    const float4 o = make_float4(apply_act(best.x, act), apply_act(best.y, act), apply_act(best.z, act), apply_act(best.w, act));
+    *reinterpret_cast<float4*>(y + ((int64_t)n * HW + p) * ldy + c) = o;
+    *reinterpret_cast<uchar4*>(argk + ((int64_t)n * HW + p) * C + c) = arg;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+warp_backward_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, int act,
+                     const float* __restrict__ warps, const float* __restrict__ mask_lvl,
+                     const uint8_t* __restrict__ argk, float* __restrict__ dx, int C, int h, int w, int K, int H0,
+                     int W0, int align_corners) {
+  __shared__ Theta s_theta[kMaxParts];
+  const int n = blockIdx.y;
+  if (threadIdx.x < K) s_theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * K + threadIdx.x) * 8, h, w, H0, W0);
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int64_t HW = (int64_t)h * w;
+  const int64_t total = HW * C4;
+  const float* mb = mask_lvl + (int64_t)n * HW * K;
+  float* dxb = dx + (int64_t)n * HW * C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = idx / C4;
+    const int c = (int)(idx - p * C4) << 2;
+    const uchar4 arg4 = *reinterpret_cast<const uchar4*>(argk + ((int64_t)n * HW + p) * C + c);
+    if (arg4.x == 255 && arg4.y == 255 && arg4.z == 255 && arg4.w == 255) continue;
+    const int i = (int)(p / w), j = (int)(p - (int64_t)i * w);
+    float4 g = __ldg(reinterpret_cast<const float4*>(dy + ((int64_t)n * HW + p) * lddy + c));
+    if (act != PTK_ACT_NONE) {
+      const float4 yv = __ldg(reinterpret_cast<const float4*>(y + ((int64_t)n * HW + p) * ldy + c));
+      g.x *= act_grad_from_output(yv.x, act); g.y *= act_grad_from_output(yv.y, act);
+      g.z *= act_grad_from_output(yv.z, act); g.w *= act_grad_from_output(yv.w, act);
+    }
+    const float gs[4] = {g.x, g.y, g.z, g.w};
+    const unsigned char as[4] = {arg4.x, arg4.y, arg4.z, arg4.w};
+    int prev = -1;
+    Footprint f;
+    float m = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = as[q];
+      if (k == 255 || gs[q] == 0.f) continue;
+      if (k != prev) {
+        f = footprint(s_theta[k], i, j, h, w, align_corners);
+        m = __ldg(mb + p * K + k);
+        prev = k;
+      }
+      const float gm = gs[q] * m;
+      float* r0 = dxb + ((int64_t)f.y0 * w + f.x0) * C + c + q;
+      float* r1 = r0 + (int64_t)w * C;
+      if (f.w00 != 0.f) atomicAdd(r0, gm * f.w00);
+      if (f.w01 != 0.f) atomicAdd(r0 + C, gm * f.w01);
+      if (f.w10 != 0.f) atomicAdd(r1, gm * f.w10);
+      if (f.w11 != 0.f) atomicAdd(r1 + C, gm * f.w11);
+    }
+  }
+}
+
+// cv2.resize(INTER_LINEAR) == half-pixel bilinear; computed in double like the reference (masks are f64).
+__global__ void mask_pyramid_kernel(const double* __restrict__ masks, int K, int H0, int W0,
+                                    float* __restrict__ out, int h, int w, int64_t total) {
+  const double sy = (double)H0 / h, sx = (double)W0 / w;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    // idx = ((n*K + k)*h + i)*w + j  (read-coalesced); written to [n][i][j][k]
+    const int j = (int)(idx % w);
+    const int i = (int)((idx / w) % h);
+    const int k = (int)((idx / ((int64_t)w * h)) % K);
+    const int64_t n = idx / ((int64_t)w * h * K);
+    double fy = (i + 0.5) * sy - 0.5, fx = (j + 0.5) * sx - 0.5;
+    if (fy < 0) fy = 0;
+    if (fx < 0) fx = 0;
+    int y0 = (int)fy, x0 = (int)fx;
+    if (y0 > H0 - 1) y0 = H0 - 1;
+    if (x0 > W0 - 1) x0 = W0 - 1;
+    const int y1 = y0 + 1 < H0 ? y0 + 1 : H0 - 1, x1 = x0 + 1 < W0 ? x0 + 1 : W0 - 1;
+    const double ly = fy - y0, lx = fx - x0;
+    const double* src = masks + (n * K + k) * (int64_t)H0 * W0;
+    const double v = (1 - ly) * ((1 - lx) * src[(int64_t)y0 * W0 + x0] + lx * src[(int64_t)y0 * W0 + x1]) +
+                     ly * ((1 - lx) * src[(int64_t)y1 * W0 + x0] + lx * src[(int64_t)y1 * W0 + x1]);
+    out[((n * h + i) * (int64_t)w + j) * K + k] = (float)v;
+  }
+}
+
+}  // namespace ptk
+
+using namespace ptk;
+
+static inline dim3 warp_grid(int64_t work, int N) {
+  int64_t b = (work + 255) / 256;
+  int64_t cap = ((int64_t)num_sms() * 8 + N - 1) / N;
+  if (cap < 1) cap = 1;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return dim3((unsigned)b, (unsigned)N);
+}
+
+extern "C" int ptk_mask_pyramid(const double* masks, int N, int K, int H0, int W0, float* out, int h, int w,
+                                void* stream) {
+  PTK_REQUIRE(N > 0 && K > 0 && h > 0 && w > 0, "mask_pyramid: bad extents");
+  const int64_t total = (int64_t)N * K * h * w;
+  int64_t b = (total + 255) / 256;
+  if (b > (int64_t)num_sms() * 16) b = (int64_t)num_sms() * 16;
+  mask_pyramid_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(masks, K, H0, W0, out, h, w, total);
+  PTK_LAUNCH_CHECK("mask_pyramid_kernel");
+  return 0;
+}
+
+extern "C" int ptk_warp_forward(const float* x, int ldx, const float* warps, const float* mask_lvl, float* y,
+                                int ldy, uint8_t* argk, int N, int C, int h, int w, int K, int H0, int W0,
+                                int align_corners, int act, void* stream) {
+  PTK_REQUIRE(N > 0 && N <= 65535 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "warp_forward: C/ld must be multiples of 4");
+  PTK_REQUIRE(K > 0 && K <= kMaxParts, "warp_forward: K must be in [1,%d]", kMaxParts);
+  PTK_REQUIRE(act == PTK_ACT_NONE || act == PTK_ACT_RELU || act == PTK_ACT_LEAKY, "warp_forward: bad act");
+  warp_forward_kernel<<<warp_grid((int64_t)h * w * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(
+      x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, K, H0, W0, align_corners, act);
+  PTK_LAUNCH_CHECK("warp_forward_kernel");
+  return 0;
+}
+
+extern "C" int ptk_warp_backward(const float* dy, int lddy, const float* y, int ldy, int act, const float* warps,
+                                 const float* mask_lvl, const uint8_t* argk, float* dx, int N, int C, int h, int w,
+                                 int K, int H0, int W0, int align_corners, void* stream) {
+  PTK_REQUIRE(N > 0 && N <= 65535 && C > 0 && C % 4 == 0 && lddy % 4 == 0, "warp_backward: C/ld must be multiples of 4");
+  PTK_REQUIRE(K > 0 && K <= kMaxParts, "warp_backward: K must be in [1,%d]", kMaxParts);
+  PTK_REQUIRE(act == PTK_ACT_NONE || (y != nullptr && ldy % 4 == 0), "warp_backward: y required for act backward");
+  warp_backward_kernel<<<warp_grid((int64_t)h * w * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(
+      dy, lddy, y, ldy, act, warps, mask_lvl, argk, dx, C, h, w, K, H0, W0, align_corners);
+  PTK_LAUNCH_CHECK("warp_backward_kernel");
+  return 0;
+}

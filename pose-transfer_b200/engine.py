@@ -1,0 +1,531 @@
+"""Explicit forward/backward schedules of the generator and the discriminator on the ptk kernels.
+
+This is the "autograd glue" of the product: instead of recording a torch graph, the fixed U-Net / PatchGAN
+topology of the reference (models/networks.py:175-288,329-357) is executed as a hand-scheduled sequence of
+kernel launches over pre-allocated NHWC workspaces, with the backward pass written out explicitly.  All
+concatenations of the reference are replaced by channel-slice writes into shared buffers, every activation
+is applied by the producer of a tensor, and the affine warp runs fused (utils/pose_transform.py:16-92).
+"""
+import torch
+
+from . import kernels as K
+from .kernels import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, Slice
+
+
+def ceil4(x):
+    return (x + 3) // 4 * 4
+
+
+class ConvLayer:
+    """A Conv2d / ConvTranspose2d bound to its parameters.  Keeps GEMM-layout copies of the weight."""
+
+    def __init__(self, weight, bias, transposed, k, stride, pad):
+        self.weight, self.bias = weight, bias
+        self.transposed, self.k, self.stride, self.pad = transposed, k, stride, pad
+        if transposed:
+            self.cin, self.cout = weight.shape[0], weight.shape[1]
+        else:
+            self.cout, self.cin = weight.shape[0], weight.shape[1]
+        self.cin_pad, self.cout_pad = ceil4(self.cin), ceil4(self.cout)
+        self.taps = k * k
+        self.w_fwd = None    # [taps][cin_pad][cout_pad]
+        self.w_bwd = None    # [taps][cout_pad][cin_pad]  (weights of the dgrad gather-conv)
+        self.impl = K.IMPL_AUTO
+
+    def _alloc(self):
+        if self.w_fwd is None or self.w_fwd.device != self.weight.device:
+            dev = self.weight.device
+            self.w_fwd = torch.empty(self.taps * self.cin_pad * self.cout_pad, device=dev)
+            self.w_bwd = torch.empty(self.taps * self.cin_pad * self.cout_pad, device=dev)
+
+    def pack_forward(self):
+        self._alloc()
+        w = self.weight.detach()
+        if self.transposed:   # torch layout [Cin][Cout][k][k]
+            K.pack_weight(w, self.w_fwd, self.cin, self.cout, self.taps, self.cin_pad, self.cout_pad, 0)
+        else:                 # torch layout [Cout][Cin][k][k]
+            K.pack_weight(w, self.w_fwd, self.cout, self.cin, self.taps, self.cout_pad, self.cin_pad, 1)
+
+    def pack_backward(self):
+        self._alloc()
+        w = self.weight.detach()
+        if self.transposed:
+            K.pack_weight(w, self.w_bwd, self.cin, self.cout, self.taps, self.cin_pad, self.cout_pad, 1)
+        else:
+            K.pack_weight(w, self.w_bwd, self.cout, self.cin, self.taps, self.cout_pad, self.cin_pad, 0)
+
+    def out_hw(self, H, W):
+        if self.transposed:
+            return (H - 1) * self.stride - 2 * self.pad + self.k, (W - 1) * self.stride - 2 * self.pad + self.k
+        return (H + 2 * self.pad - self.k) // self.stride + 1, (W + 2 * self.pad - self.k) // self.stride + 1
+
+    def forward(self, x, N, H, W, y, act=ACT_NONE, stats=None, y_nchw=None):
+        """x: Slice with cin_pad readable channels; y: Slice (cout channels) or None."""
+        OH, OW = self.out_hw(H, W)
+        g = K.conv_geom(N, H, W, self.cin_pad, x.ld, OH, OW, self.cout, y.ld if y is not None else self.cout, self.k,
+                        self.stride, self.pad, self.transposed, self.impl)
+        K.conv_forward(g, x, self.w_fwd, None, self.bias.detach() if self.bias is not None else None, act, y, y_nchw, stats)
+        return OH, OW
+
+    def dgrad(self, dy, N, H, W, dx, dx_channels=None):
+        """dy: Slice over the OUTPUT grid (cout_pad readable channels); dx: Slice over the input grid (H, W)."""
+        OH, OW = self.out_hw(H, W)
+        cout_dx = self.cin if dx_channels is None else dx_channels
+        g = K.conv_geom(N, OH, OW, self.cout_pad, dy.ld, H, W, cout_dx, dx.ld, self.k, self.stride, self.pad,
+                        not self.transposed, self.impl)
+        # the dgrad weights are [taps][cout_pad][cin_pad]; the kernel's inner extent is ceil4(Cout')
+        assert ceil4(cout_dx) == self.cin_pad
+        K.conv_forward(g, dy, self.w_bwd, None, None, ACT_NONE, dx, None, None)
+
+    def wgrad(self, x, dy, N, H, W, scratch, grad_w):
+        """grad_w (torch layout, fp32 view into the gradient arena) += dW."""
+        OH, OW = self.out_hw(H, W)
+        g = K.conv_geom(N, H, W, self.cin_pad, x.ld, OH, OW, self.cout if self.cout <= 4 else self.cout_pad, dy.ld, self.k,
+                        self.stride, self.pad, self.transposed, self.impl)
+        if self.transposed:
+            A, B, B_pad = self.cin, self.cout, self.cout_pad
+            a_rows = self.cin_pad
+        else:
+            A, B, B_pad = self.cout, self.cin, self.cin_pad
+            a_rows = self.cout if self.cout <= 4 else self.cout_pad
+        n = self.taps * a_rows * B_pad
+        dw = scratch[:n]
+        K.fill(dw, 0.0)
+        K.conv_wgrad(g, x, dy, dw)
+        if a_rows == A:
+            K.unpack_weight_grad(dw, grad_w, A, B, self.taps, B_pad, True)
+        else:  # padded row count (never hit for this network: every wide channel count is a multiple of 4)
+            raise RuntimeError("wgrad: padded A rows unsupported")
+
+
+class NormLayer:
+    """Scalar-affine per-sample norm (InstanceNorm3d(1) on unsqueeze(1), models/networks.py:159,164-169)."""
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
+class _Workspace:
+    """Named, lazily allocated device buffers that persist across steps (PyTorch owns the memory)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, shape, dtype=torch.float32, zero=False):
+        t = self.bufs.get(name)
+        shape = tuple(int(s) for s in shape)
+        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        elif zero:
+            t.zero_()
+        return t
+
+
+class GeneratorEngine:
+    """Deformable_Generator.forward / backward (models/networks.py:269-288 + encoder/decoder :193-250)."""
+
+    def __init__(self, module):
+        self.m = module
+        self.P = module.pose_dim
+        self.enc = list(module.nfilters_enc)
+        self.dec = list(module.nfilters_dec)
+        self.L = len(self.enc)
+        self.image_size = tuple(module.image_size)
+        self.ws = None
+        self.layers_built = False
+        self.saved = None
+
+    # ------------------------------------------------------------------ parameter binding
+    def _build_layers(self):
+        m = self.m
+        self.enc_conv = {}
+        self.enc_norm = {}
+        for name, e in (("app", m.encoder_app), ("pose", m.encoder_pose)):
+            convs, norms = [], []
+            for i, mod in enumerate(e.net):
+                if i == 0:
+                    convs.append(ConvLayer(mod.weight, mod.bias, False, 3, 1, 1))
+                    norms.append(None)
+                else:
+                    conv = mod.net[1]
+                    convs.append(ConvLayer(conv.weight, None, False, 4, 2, 1))
+                    norms.append(NormLayer(mod.net[2].weight, mod.net[2].bias) if len(mod.net) > 2 else None)
+            self.enc_conv[name], self.enc_norm[name] = convs, norms
+        self.dec_conv, self.dec_norm = [], []
+        for j in range(self.L - 1):
+            blk = m.decoder.net[j]
+            self.dec_conv.append(ConvLayer(blk.net[1].weight, None, True, 4, 2, 1))
+            self.dec_norm.append(NormLayer(blk.net[3].weight, blk.net[3].bias))
+        fin = m.decoder.net[self.L]
+        self.final_conv = ConvLayer(fin.weight, fin.bias, False, 3, 1, 1)
+        self.all_convs = self.enc_conv["app"] + self.enc_conv["pose"] + self.dec_conv + [self.final_conv]
+        self.layers_built = True
+
+    def _ensure(self, device):
+        if not self.layers_built or self.final_conv.weight is not self.m.decoder.net[self.L].weight:
+            self._build_layers()
+        if self.ws is None or self.ws.device != device:
+            self.ws = _Workspace(device)
+
+    def pack_weights(self, backward=False):
+        for c in self.all_convs:
+            c.pack_forward()
+            if backward:
+                c.pack_backward()
+
+    def pack_weights_backward(self):
+        for c in self.all_convs:
+            c.pack_backward()
+
+    # ------------------------------------------------------------------ geometry helpers
+    def _sizes(self, H, W):
+        hs, wsz = [H], [W]
+        for _ in range(1, self.L):
+            hs.append((hs[-1] + 2 - 4) // 2 + 1)
+            wsz.append((wsz[-1] + 2 - 4) // 2 + 1)
+        return hs, wsz
+
+    def _cat_layout(self, j):
+        """Channel layout of decoder level j's input: (dec_prev, enc_i) with i = L-1-j."""
+        i = self.L - 1 - j
+        dprev = 0 if j == 0 else self.dec[j - 1]
+        return i, dprev, dprev + 2 * self.enc[i]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, inp, warps, masks, drop=None, repack=True, d_input=None):
+        """inp [N,3+2P,H,W] f32, warps [N,K,8] f32, masks [N,K,H,W] f64 -> out_gen [N,3,H,W] (fresh tensor).
+        `drop`: list of three [N,512] (or [N,512,1,1]) Dropout2d noise tensors or None (=> drawn here).
+        `d_input`: optional Slice of a discriminator input buffer that also receives out_gen (NHWC)."""
+        assert inp.dtype == torch.float32 and inp.dim() == 4   # device is enforced by the kernel wrappers
+        N, Ct, H, W = inp.shape
+        assert N >= 2, "the reference's .squeeze() (models/networks.py:169) makes N=1 unsupported"
+        P, L = self.P, self.L
+        assert Ct == 3 + 2 * P
+        self._ensure(inp.device)
+        ws = self.ws
+        inp = inp.contiguous()
+        warps = warps.contiguous().float()
+        masks = masks.contiguous()
+        if masks.dtype != torch.float64:
+            masks = masks.double()
+        Kp = warps.shape[1]
+        H0, W0 = self.image_size
+        if repack:
+            self.pack_weights()
+        hs, wsz = self._sizes(H, W)
+        tag = "%d_%d_%d" % (N, H, W)
+        n_norm = 2 * (L - 2) + (L - 1)
+        stats = ws.get("stats" + tag, (n_norm, N, 2), torch.float64, zero=True)
+        st_idx = {}
+
+        def stat_for(key):
+            if key not in st_idx:
+                st_idx[key] = len(st_idx)
+            return stats[st_idx[key]]
+
+        # dropout noise (Dropout2d(0.5), models/networks.py:161; active in every forward of the reference)
+        drops = []
+        for j in range(min(3, L - 1)):
+            if drop is None:
+                d = torch.empty(N, self.dec[j], 1, 1, device=inp.device).bernoulli_(0.5).div_(0.5)
+            else:
+                d = drop[j].to(inp.device, torch.float32)
+            drops.append(d.reshape(N, self.dec[j]).contiguous())
+
+        # concat buffers (decoder inputs), everything stored post-ReLU
+        cats = []
+        for j in range(L):
+            i, dprev, width = self._cat_layout(j)
+            cats.append(ws.get("cat%d_%s" % (j, tag), (N, hs[i], wsz[i], width)))
+
+        # mask pyramid for the 4 warped levels
+        mlv = []
+        for i in range(min(4, L)):
+            mk = ws.get("mask%d_%s" % (i, tag), (N, hs[i], wsz[i], Kp))
+            K.mask_pyramid(masks, mk)
+            mlv.append(mk)
+
+        sv = {"N": N, "H": H, "W": W, "hs": hs, "ws": wsz, "tag": tag, "stats": stats, "st_idx": st_idx, "drops": drops,
+              "cats": cats, "mlv": mlv, "warps": warps, "K": Kp, "z": {}, "act": {}, "yraw": {}, "argk": {}, "xin": {}}
+
+        for name, c_src0, cin in (("app", 0, 3 + P), ("pose", 3 + P, P)):
+            convs, norms = self.enc_conv[name], self.enc_norm[name]
+            xin = ws.get("xin_%s_%s" % (name, tag), (N, H, W, ceil4(cin)))
+            K.nchw_to_nhwc(inp, c_src0, cin, Slice(xin, 0, cin))
+            sv["xin"][name] = xin
+            for i in range(L):
+                j = L - 1 - i
+                _, dprev, _ = self._cat_layout(j)
+                c = self.enc[i]
+                cat_slice = Slice(cats[j], dprev + (0 if name == "app" else c), c)
+                z = ws.get("z_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
+                src = Slice(xin) if i == 0 else Slice(sv["act"][(name, i - 1)])
+                norm = norms[i]
+                st = stat_for((name, i)) if norm is not None else None
+                convs[i].forward(src, N, hs[i - 1] if i else H, wsz[i - 1] if i else W, Slice(z), ACT_NONE, st)
+                sv["z"][(name, i)] = z
+                HW = hs[i] * wsz[i]
+                gam = norm.weight.detach() if norm is not None else None
+                bet = norm.bias.detach() if norm is not None else None
+                warped = name == "app" and i < 4
+                if i < L - 1:
+                    act = ws.get("act_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
+                    sv["act"][(name, i)] = act
+                    if warped:
+                        if norm is not None:
+                            yraw = ws.get("yraw_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
+                            K.gn_apply(z, st, gam, bet, None, N, HW, c, act, ACT_LEAKY, yraw, ACT_NONE)
+                        else:
+                            yraw = z
+                            K.gn_apply(z, None, None, None, None, N, HW, c, act, ACT_LEAKY)
+                        sv["yraw"][i] = yraw
+                    else:
+                        K.gn_apply(z, st, gam, bet, None, N, HW, c, act, ACT_LEAKY, cat_slice, ACT_RELU)
+                else:
+                    K.gn_apply(z, st, gam, bet, None, N, HW, c, cat_slice, ACT_RELU)
+                if warped:
+                    argk = ws.get("argk%d_%s" % (i, tag), (N, hs[i], wsz[i], c), torch.uint8)
+                    K.warp_forward(sv["yraw"][i], warps, mlv[i], cat_slice, argk, N, c, hs[i], wsz[i], Kp, H0, W0, ACT_RELU)
+                    sv["argk"][i] = argk
+
+        # decoder
+        zd = []
+        for j in range(L - 1):
+            i, dprev, width = self._cat_layout(j)
+            co = self.dec[j]
+            oh, ow = hs[i - 1], wsz[i - 1]
+            z = ws.get("zd%d_%s" % (j, tag), (N, oh, ow, co))
+            st = stat_for(("dec", j))
+            self.dec_conv[j].forward(Slice(cats[j]), N, hs[i], wsz[i], Slice(z), ACT_NONE, st)
+            nl = self.dec_norm[j]
+            K.gn_apply(z, st, nl.weight.detach(), nl.bias.detach(), drops[j] if j < 3 else None, N, oh * ow, co,
+                       Slice(cats[j + 1], 0, co), ACT_RELU)
+            zd.append(z)
+        sv["zd"] = zd
+        out = torch.empty(N, 3, H, W, device=inp.device)
+        self.final_conv.forward(Slice(cats[L - 1]), N, H, W, d_input, ACT_TANH, None, out)
+        sv["out"] = out
+        self.saved = sv
+        return out
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, grads, dout_nchw=None, dout_nhwc=None, repack=True):
+        """Accumulate parameter gradients into `grads` (dict: parameter -> fp32 tensor of the same shape).
+        dout_nchw [N,3,H,W] and/or dout_nhwc (Slice over [N,H,W,*]) are gradients w.r.t. out_gen."""
+        sv = self.saved
+        assert sv is not None, "forward() must run before backward()"
+        ws, L = self.ws, self.L
+        N, H, W, hs, wsz, tag = sv["N"], sv["H"], sv["W"], sv["hs"], sv["ws"], sv["tag"]
+        cats, stats, st_idx, drops = sv["cats"], sv["stats"], sv["st_idx"], sv["drops"]
+        H0, W0 = self.image_size
+        if repack:
+            self.pack_weights_backward()
+        max_w = max(c.taps * c.cin_pad * c.cout_pad for c in self.all_convs)
+        scratch = ws.get("wgrad_scratch", (max_w,))
+        sums = ws.get("sums" + tag, tuple(stats.shape), torch.float64, zero=True)
+
+        # final conv: tanh' then wgrad / bias grad / dgrad
+        dzf = ws.get("dzf" + tag, (N, H, W, 4))
+        K.tanh_bwd_combine(dout_nchw, dout_nhwc, sv["out"], dzf, 4, N, 3, H, W)
+        fc = self.final_conv
+        fc.wgrad(Slice(cats[L - 1]), Slice(dzf), N, H, W, scratch, grads[fc.weight])
+        K.bias_grad(dzf, 4, N * H * W, 3, grads[fc.bias])
+        dcat = ws.get("dcat%d_%s" % (L - 1, tag), tuple(cats[L - 1].shape))
+        fc.dgrad(Slice(dzf), N, H, W, Slice(dcat))
+        dcats = {L - 1: dcat}
+
+        # decoder blocks, last to first
+        for j in range(L - 2, -1, -1):
+            i, dprev, width = self._cat_layout(j)
+            co = self.dec[j]
+            oh, ow = hs[i - 1], wsz[i - 1]
+            nl = self.dec_norm[j]
+            si = st_idx[("dec", j)]
+            dy = ws.get("dyd%d_%s" % (j, tag), (N, oh, ow, co))
+            K.gn_bwd_reduce(Slice(dcats[j + 1], 0, co), Slice(cats[j + 1], 0, co), ACT_RELU, None, None, ACT_NONE,
+                            drops[j] if j < 3 else None, sv["zd"][j], stats[si], N, oh * ow, co, dy, sums[si])
+            K.gn_bwd_apply(dy, sv["zd"][j], stats[si], sums[si], nl.weight.detach(), N, oh * ow, co, grads[nl.weight],
+                           grads[nl.bias])
+            cv = self.dec_conv[j]
+            cv.wgrad(Slice(cats[j]), Slice(dy), N, hs[i], wsz[i], scratch, grads[cv.weight])
+            dc = ws.get("dcat%d_%s" % (j, tag), tuple(cats[j].shape))
+            cv.dgrad(Slice(dy), N, hs[i], wsz[i], Slice(dc))
+            dcats[j] = dc
+
+        # encoders, deepest level first
+        for name in ("app", "pose"):
+            convs, norms = self.enc_conv[name], self.enc_norm[name]
+            dact_next = None
+            for i in range(L - 1, -1, -1):
+                j = L - 1 - i
+                _, dprev, _ = self._cat_layout(j)
+                c = self.enc[i]
+                HW = hs[i] * wsz[i]
+                off = dprev + (0 if name == "app" else c)
+                warped = name == "app" and i < 4
+                if warped:
+                    dwarp = ws.get("dwarp%d_%s" % (i, tag), (N, hs[i], wsz[i], c))
+                    K.fill(dwarp, 0.0)
+                    K.warp_backward(Slice(dcats[j], off, c), Slice(cats[j], off, c), ACT_RELU, sv["warps"], sv["mlv"][i],
+                                    sv["argk"][i], dwarp, N, c, hs[i], wsz[i], sv["K"], H0, W0)
+                    skip_g, skip_a, skip_act = Slice(dwarp), None, ACT_NONE
+                else:
+                    skip_g, skip_a, skip_act = Slice(dcats[j], off, c), Slice(cats[j], off, c), ACT_RELU
+                norm = norms[i]
+                z = sv["z"][(name, i)]
+                dy = ws.get("dye_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
+                si = st_idx[(name, i)] if norm is not None else None
+                st = stats[si] if norm is not None else None
+                sm = sums[si] if norm is not None else None
+                if dact_next is not None:
+                    K.gn_bwd_reduce(Slice(dact_next), Slice(sv["act"][(name, i)]), ACT_LEAKY, skip_g, skip_a, skip_act,
+                                    None, z if norm is not None else None, st, N, HW, c, dy, sm)
+                else:
+                    K.gn_bwd_reduce(skip_g, skip_a, skip_act, None, None, ACT_NONE, None, z if norm is not None else None,
+                                    st, N, HW, c, dy, sm)
+                if norm is not None:
+                    K.gn_bwd_apply(dy, z, st, sm, norm.weight.detach(), N, HW, c, grads[norm.weight], grads[norm.bias])
+                cv = convs[i]
+                if i == 0:
+                    cv.wgrad(Slice(sv["xin"][name]), Slice(dy), N, H, W, scratch, grads[cv.weight])
+                    K.bias_grad(dy, c, N * HW, c, grads[cv.bias])
+                else:
+                    cv.wgrad(Slice(sv["act"][(name, i - 1)]), Slice(dy), N, hs[i - 1], wsz[i - 1], scratch, grads[cv.weight])
+                    dact = ws.get("dact_%s%d_%s" % (name, i - 1, tag), (N, hs[i - 1], wsz[i - 1], self.enc[i - 1]))
+                    cv.dgrad(Slice(dy), N, hs[i - 1], wsz[i - 1], Slice(dact))
+                    dact_next = dact
+
+
+class DiscriminatorEngine:
+    """Discriminator.forward / backward (models/networks.py:338-357): Conv(k4,s2,p0)+bias -> 3 normed
+    Blocks -> Block(512,1,bn=False) -> Sigmoid -> Flatten."""
+
+    def __init__(self, module):
+        self.m = module
+        self.ws = None
+        self.layers_built = False
+        self.saved = None
+
+    def _build_layers(self):
+        net = self.m.net
+        self.convs = [ConvLayer(net[0].weight, net[0].bias, False, 4, 2, 0)]
+        self.norms = [None]
+        i = 1
+        while hasattr(net[i], "net"):
+            blk = net[i]
+            self.convs.append(ConvLayer(blk.net[1].weight, None, False, 4, 2, 1))
+            self.norms.append(NormLayer(blk.net[2].weight, blk.net[2].bias) if len(blk.net) > 2 else None)
+            i += 1
+        self.layers_built = True
+
+    def _ensure(self, device):
+        if not self.layers_built or self.convs[0].weight is not self.m.net[0].weight:
+            self._build_layers()
+        if self.ws is None or self.ws.device != device:
+            self.ws = _Workspace(device)
+
+    def input_buffer(self, M, H, W, device):
+        """NHWC input buffer [M,H,W,ceil4(input_nc)] (zero padded channels) the caller fills by slices."""
+        self._ensure(device)
+        return self.ws.get("din_%d_%d_%d" % (M, H, W), (M, H, W, ceil4(self.m.input_nc)))
+
+    def pack_weights(self, backward=False):
+        for c in self.convs:
+            c.pack_forward()
+            if backward:
+                c.pack_backward()
+
+    def pack_weights_backward(self):
+        for c in self.convs:
+            c.pack_backward()
+
+    def forward(self, din, repack=True, probs=False):
+        """din = input_buffer() filled by the caller.  Returns logits [M, OH*OW] (pre-sigmoid), or the sigmoid
+        probabilities if probs=True (what Discriminator.forward returns in the reference)."""
+        M, H, W, _ = din.shape
+        self._ensure(din.device)
+        ws = self.ws
+        if repack:
+            self.pack_weights()
+        tag = "%d_%d_%d" % (M, H, W)
+        nl = len(self.convs)
+        stats = ws.get("dstats" + tag, (nl, M, 2), torch.float64, zero=True)
+        sv = {"M": M, "H": H, "W": W, "tag": tag, "din": din, "stats": stats, "z": [], "act": [], "hw": []}
+        x, h, w = din, H, W
+        for i, cv in enumerate(self.convs):
+            oh, ow = cv.out_hw(h, w)
+            last = i == nl - 1
+            if i == 0:
+                act = ws.get("dact0_" + tag, (M, oh, ow, cv.cout))
+                cv.forward(Slice(x), M, h, w, Slice(act), ACT_LEAKY)
+                sv["z"].append(None)
+                sv["act"].append(act)
+            elif not last:
+                z = ws.get("dz%d_%s" % (i, tag), (M, oh, ow, cv.cout))
+                cv.forward(Slice(x), M, h, w, Slice(z), ACT_NONE, stats[i])
+                act = ws.get("dact%d_%s" % (i, tag), (M, oh, ow, cv.cout))
+                nm = self.norms[i]
+                K.gn_apply(z, stats[i], nm.weight.detach(), nm.bias.detach(), None, M, oh * ow, cv.cout, act, ACT_LEAKY)
+                sv["z"].append(z)
+                sv["act"].append(act)
+            else:
+                logits = torch.empty(M, oh * ow * cv.cout, device=din.device)
+                cv.forward(Slice(x), M, h, w, Slice(logits.view(M, oh, ow, cv.cout)), ACT_SIGMOID if probs else ACT_NONE)
+                sv["logits_hw"] = (oh, ow)
+                act = logits
+            sv["hw"].append((h, w))
+            x, h, w = act, oh, ow
+        self.saved = sv
+        return x
+
+    def backward(self, dlogits4, grads=None, need_input_grad=False, repack=True):
+        """dlogits4: [M*J, 4] (gradient w.r.t. the logits in channel 0, zero padding in 1..3).
+        grads: dict parameter -> gradient tensor (None => no weight gradients, G-step use).
+        Returns the gradient w.r.t. the NHWC input buffer if need_input_grad."""
+        sv = self.saved
+        ws = self.ws
+        M, tag = sv["M"], sv["tag"]
+        if repack:
+            self.pack_weights_backward()
+        nl = len(self.convs)
+        stats = sv["stats"]
+        sums = ws.get("dsums" + tag, tuple(stats.shape), torch.float64, zero=True)
+        max_w = max(c.taps * c.cin_pad * c.cout_pad for c in self.convs)
+        scratch = ws.get("wgrad_scratch", (max_w,)) if grads is not None else None
+        dummy = ws.get("dummy_gb", (2,))
+        dy = dlogits4
+        din_grad = None
+        for i in range(nl - 1, -1, -1):
+            cv = self.convs[i]
+            h, w = sv["hw"][i]
+            oh, ow = cv.out_hw(h, w)
+            x = sv["din"] if i == 0 else sv["act"][i - 1]
+            dy_s = Slice(dy.view(M, oh, ow, -1))
+            if grads is not None:
+                cv.wgrad(Slice(x), dy_s, M, h, w, scratch, grads[cv.weight])
+                if cv.bias is not None:
+                    K.bias_grad(dy, dy_s.ld, M * oh * ow, cv.cout, grads[cv.bias])
+            if i == 0:
+                if need_input_grad:
+                    din_grad = ws.get("din_grad" + tag, tuple(sv["din"].shape))
+                    cv.dgrad(dy_s, M, h, w, Slice(din_grad), dx_channels=cv.cin_pad)
+                break
+            # gradient w.r.t. the previous block's activated output, then through its activation / norm
+            pc = self.convs[i - 1]
+            dact = ws.get("ddact%d_%s" % (i - 1, tag), (M, h, w, pc.cout))
+            cv.dgrad(dy_s, M, h, w, Slice(dact))
+            dprev = ws.get("ddy%d_%s" % (i - 1, tag), (M, h, w, pc.cout))
+            nm = self.norms[i - 1]
+            if nm is not None:
+                K.gn_bwd_reduce(Slice(dact), Slice(sv["act"][i - 1]), ACT_LEAKY, None, None, ACT_NONE, None, sv["z"][i - 1],
+                                stats[i - 1], M, h * w, pc.cout, dprev, sums[i - 1])
+                K.gn_bwd_apply(dprev, sv["z"][i - 1], stats[i - 1], sums[i - 1], nm.weight.detach(), M, h * w, pc.cout,
+                               grads[nm.weight] if grads is not None else dummy[0:1],
+                               grads[nm.bias] if grads is not None else dummy[1:2])
+            else:
+                K.gn_bwd_reduce(Slice(dact), Slice(sv["act"][i - 1]), ACT_LEAKY, None, None, ACT_NONE, None, None, None, M,
+                                h * w, pc.cout, dprev, None)
+            dy = dprev
+        return din_grad

@@ -1,0 +1,225 @@
+"""Thin typed wrappers over the C ABI (include/ptk.h).  Inputs are CUDA torch tensors (memory owners);
+every call enqueues on torch's current stream.  No arithmetic happens in Python."""
+import torch
+
+from . import _lib
+from ._lib import ConvGeom, check
+
+ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+
+
+class Slice:
+    """A channel slice [c0, c0+C) of an NHWC buffer `t` ([..., ld])."""
+    __slots__ = ("t", "c0", "C")
+
+    def __init__(self, t, c0=0, C=None):
+        self.t, self.c0 = t, c0
+        self.C = t.shape[-1] - c0 if C is None else C
+
+    @property
+    def ld(self):
+        return self.t.shape[-1]
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() + 4 * self.c0
+
+
+def _p(x):
+    if x is None:
+        return None
+    if isinstance(x, Slice):
+        return x.ptr
+    assert x.is_cuda and x.is_contiguous(), "kernel operands must be contiguous CUDA tensors"
+    return x.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# Optional per-kernel-family timing with CUDA events on the launching stream (used by bench.py for the
+# roofline numbers; disabled => zero overhead beyond one `is None` test).
+PROFILE = None
+
+
+def profile_start():
+    global PROFILE
+    PROFILE = {}
+
+
+def profile_stop():
+    """Returns {family: (launches, total_ms)}; synchronises."""
+    global PROFILE
+    prof, PROFILE = PROFILE, None
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (prof or {}).items()}
+
+
+def _timed(name):
+    def deco(fn):
+        def wrapper(*a, **kw):
+            if PROFILE is None:
+                return fn(*a, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **kw)
+            e1.record()
+            PROFILE.setdefault(name, []).append((e0, e1))
+            return r
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
+
+def _as_slice(x):
+    return x if isinstance(x, Slice) else Slice(x)
+
+
+def nchw_to_nhwc(src, c_src0, C, dst, act=ACT_NONE):
+    """dst slice <- act(src[:, c_src0:c_src0+C]) ; src [N,Cs,H,W] fp32, dst Slice of [N,H,W,ld]."""
+    N, Cs, H, W = src.shape
+    dst = _as_slice(dst)
+    check(_lib.lib().ptk_nchw_to_nhwc(_p(src), Cs, c_src0, dst.t.data_ptr(), dst.ld, dst.c0, N, C, H, W, act, _stream()),
+          "ptk_nchw_to_nhwc")
+
+
+def nhwc_to_nchw(src, dst):
+    """dst [N,C,H,W] <- src slice."""
+    src = _as_slice(src)
+    N, C, H, W = dst.shape
+    check(_lib.lib().ptk_nhwc_to_nchw(src.t.data_ptr(), src.ld, src.c0, _p(dst), N, C, H, W, _stream()), "ptk_nhwc_to_nchw")
+
+
+@_timed("pack")
+def pack_weight(src, dst, A, B, taps, A_pad, B_pad, transpose):
+    check(_lib.lib().ptk_pack_weight(_p(src), _p(dst), A, B, taps, A_pad, B_pad, int(transpose), _stream()), "ptk_pack_weight")
+
+
+@_timed("pack")
+def unpack_weight_grad(src, grad, A, B, taps, B_pad, accumulate=True):
+    check(_lib.lib().ptk_unpack_weight_grad(_p(src), _p(grad), A, B, taps, B_pad, int(accumulate), _stream()),
+          "ptk_unpack_weight_grad")
+
+
+def fill(dst, value=0.0):
+    check(_lib.lib().ptk_fill(_p(dst), dst.numel(), float(value), _stream()), "ptk_fill")
+
+
+def conv_geom(N, H, W, Cin, ldx, OH, OW, Cout, ldy, k, stride, pad, transposed=False, impl=IMPL_AUTO):
+    return ConvGeom(N, H, W, Cin, ldx, OH, OW, Cout, ldy, k, stride, pad, int(transposed), impl)
+
+
+def conv_tc_supported(g):
+    return bool(_lib.lib().ptk_conv_tc_supported(g))
+
+
+@_timed("conv_forward")
+def conv_forward(g, x, w_t, w_k, bias, act, y, y_nchw=None, stats=None):
+    check(_lib.lib().ptk_conv_forward(g, _p(x), _p(w_t), _p(w_k), _p(bias), act, _p(y), _p(y_nchw), _p(stats), _stream()),
+          "ptk_conv_forward")
+
+
+@_timed("conv_wgrad")
+def conv_wgrad(g, x, dy, dw):
+    check(_lib.lib().ptk_conv_wgrad(g, _p(x), _p(dy), _p(dw), _stream()), "ptk_conv_wgrad")
+
+
+def bias_grad(dy, ld, pixels, C, dbias):
+    check(_lib.lib().ptk_bias_grad(_p(dy), ld, pixels, C, _p(dbias), _stream()), "ptk_bias_grad")
+
+
+@_timed("gn")
+def gn_stats(z, N, HW, C, stats):
+    z = _as_slice(z)
+    check(_lib.lib().ptk_gn_stats(z.ptr, z.ld, N, HW, C, _p(stats), _stream()), "ptk_gn_stats")
+
+
+@_timed("gn")
+def gn_apply(z, stats, gamma, beta, drop, N, HW, C, out1, act1, out2=None, act2=ACT_NONE):
+    z, out1 = _as_slice(z), _as_slice(out1)
+    o2 = _as_slice(out2) if out2 is not None else None
+    check(_lib.lib().ptk_gn_apply(z.ptr, z.ld, _p(stats), _p(gamma), _p(beta), _p(drop), N, HW, C, out1.ptr, out1.ld, act1,
+                                  o2.ptr if o2 else None, o2.ld if o2 else 0, act2, _stream()), "ptk_gn_apply")
+
+
+@_timed("gn")
+def gn_bwd_reduce(g1, a1, act1, g2, a2, act2, drop, z, stats, N, HW, C, dy, sums):
+    g1 = _as_slice(g1)
+    a1 = _as_slice(a1) if a1 is not None else None
+    g2 = _as_slice(g2) if g2 is not None else None
+    a2 = _as_slice(a2) if a2 is not None else None
+    zz = _as_slice(z) if z is not None else None
+    check(_lib.lib().ptk_gn_bwd_reduce(g1.ptr, g1.ld, a1.ptr if a1 else None, a1.ld if a1 else 0, act1,
+                                       g2.ptr if g2 else None, g2.ld if g2 else 0, a2.ptr if a2 else None,
+                                       a2.ld if a2 else 0, act2, _p(drop), zz.ptr if zz else None, zz.ld if zz else 0,
+                                       _p(stats), N, HW, C, _p(dy), _p(sums), _stream()), "ptk_gn_bwd_reduce")
+
+
+@_timed("gn")
+def gn_bwd_apply(dy, z, stats, sums, gamma, N, HW, C, dgamma, dbeta):
+    z = _as_slice(z)
+    check(_lib.lib().ptk_gn_bwd_apply(_p(dy), z.ptr, z.ld, _p(stats), _p(sums), _p(gamma), N, HW, C, _p(dgamma), _p(dbeta),
+                                      _stream()), "ptk_gn_bwd_apply")
+
+
+@_timed("mask_pyramid")
+def mask_pyramid(masks, out):
+    """masks [N,K,H0,W0] f64 -> out [N,h,w,K] f32."""
+    N, K, H0, W0 = masks.shape
+    _, h, w, _ = out.shape
+    assert masks.dtype == torch.float64 and out.dtype == torch.float32
+    check(_lib.lib().ptk_mask_pyramid(_p(masks), N, K, H0, W0, _p(out), h, w, _stream()), "ptk_mask_pyramid")
+
+
+@_timed("warp_forward")
+def warp_forward(x, warps, mask_lvl, y, argk, N, C, h, w, K, H0, W0, act=ACT_NONE, align_corners=False):
+    x, y = _as_slice(x), _as_slice(y)
+    check(_lib.lib().ptk_warp_forward(x.ptr, x.ld, _p(warps), _p(mask_lvl), y.ptr, y.ld, _p(argk), N, C, h, w, K, H0, W0,
+                                      int(align_corners), act, _stream()), "ptk_warp_forward")
+
+
+@_timed("warp_backward")
+def warp_backward(dy, y, act, warps, mask_lvl, argk, dx, N, C, h, w, K, H0, W0, align_corners=False):
+    dy = _as_slice(dy)
+    yy = _as_slice(y) if y is not None else None
+    check(_lib.lib().ptk_warp_backward(dy.ptr, dy.ld, yy.ptr if yy else None, yy.ld if yy else 0, act, _p(warps),
+                                       _p(mask_lvl), _p(argk), _p(dx), N, C, h, w, K, H0, W0, int(align_corners), _stream()),
+          "ptk_warp_backward")
+
+
+def adv_loss(logits, rows, J, n_true, scale, loss, dlogits=None, ldd=1):
+    check(_lib.lib().ptk_adv_loss(_p(logits), rows, J, n_true, float(scale), _p(loss), _p(dlogits), ldd, _stream()),
+          "ptk_adv_loss")
+
+
+def l1_loss(a, b, scale, loss, grad=None):
+    check(_lib.lib().ptk_l1_loss(_p(a), _p(b), a.numel(), float(scale), _p(loss), _p(grad), _stream()), "ptk_l1_loss")
+
+
+@_timed("nnloss")
+def nnloss_forward(pred, target, vgg_w, vgg_b, area, scale, loss, argmin):
+    N, _, H, W = pred.shape
+    check(_lib.lib().ptk_nnloss_forward(_p(pred), _p(target), _p(vgg_w), _p(vgg_b), N, H, W, area, float(scale), _p(loss),
+                                        _p(argmin), _stream()), "ptk_nnloss_forward")
+
+
+@_timed("nnloss")
+def nnloss_backward(pred, target, vgg_w, vgg_b, argmin, area, scale, dpred):
+    N, _, H, W = pred.shape
+    check(_lib.lib().ptk_nnloss_backward(_p(pred), _p(target), _p(vgg_w), _p(vgg_b), _p(argmin), N, H, W, area,
+                                         float(scale), _p(dpred), _stream()), "ptk_nnloss_backward")
+
+
+def tanh_bwd_combine(g_nchw, g_nhwc, out_nchw, dz, ld, N, C, H, W):
+    g2 = _as_slice(g_nhwc) if g_nhwc is not None else None
+    check(_lib.lib().ptk_tanh_bwd_combine(_p(g_nchw), g2.ptr if g2 else None, g2.ld if g2 else 0, _p(out_nchw), _p(dz), ld,
+                                          N, C, H, W, _stream()), "ptk_tanh_bwd_combine")
+
+
+@_timed("adam")
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    check(_lib.lib().ptk_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale,
+                                   _stream()), "ptk_adam_step")

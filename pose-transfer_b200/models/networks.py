@@ -1,0 +1,290 @@
+"""Drop-in for the reference's ``models/networks.py`` (src_deformable/models/networks.py:130-357).
+
+Same class names, constructor signatures, sub-module tree and therefore the same ``state_dict`` keys and
+shapes (checkpoint ABI), but ``forward`` runs the hand-written sm_100a kernels through
+``engine.GeneratorEngine`` / ``engine.DiscriminatorEngine``.  The leaf ``nn.Conv2d`` / ``nn.InstanceNorm3d``
+objects only OWN parameters; their own forward is never called.  There is no eager fallback: CPU tensors
+raise.
+"""
+import torch
+import torch.nn as nn
+
+from ..engine import DiscriminatorEngine, GeneratorEngine
+from ..kernels import Slice
+from ..utils import pose_utils
+from ..utils.pose_transform import AffineTransformLayer  # noqa: F401  (re-exported like the reference)
+
+
+def print_network(net):
+    """models/networks.py:18-24."""
+    num_params = sum(p.numel() for p in net.parameters())
+    print(net)
+    print('Total number of parameters: %d' % num_params)
+
+
+def xavier_weights_init(m):
+    """models/networks.py:26-31 (not applied by DeformablePose_GAN, pose_gan.py:62-65)."""
+    classname = m.__class__.__name__
+    if classname.find('Conv') == 0 and hasattr(m, 'weight'):
+        nn.init.xavier_uniform_(m.weight.data, gain=1)
+
+
+def gaussian_weights_init(m):
+    classname = m.__class__.__name__
+    if classname.find('Conv') == 0 and hasattr(m, 'weight'):
+        m.weight.data.normal_(0.0, 0.02)
+
+
+class Flatten(nn.Module):
+    def forward(self, input):
+        return input.view(input.size(0), -1)
+
+
+class Cropping2D(nn.Module):
+    def __init__(self, crop_size):
+        super(Cropping2D, self).__init__()
+        self.crop_size = crop_size
+
+    def forward(self, input):
+        return input[:, :, self.crop_size:-self.crop_size, self.crop_size:-self.crop_size]
+
+
+def _no_eager(name):
+    raise RuntimeError("%s.forward: this module only owns parameters; the computation runs inside the fused "
+                       "CUDA schedule of its parent network (no eager fallback)" % name)
+
+
+class Block(nn.Module):
+    """Parameter container mirroring models/networks.py:142-172 (module indices = state_dict keys)."""
+
+    def __init__(self, input_nc, output_nc, down=True, bn=True, dropout=False, leaky=True):
+        super(Block, self).__init__()
+        self.net = self.build_net(input_nc, output_nc, down, bn, dropout, leaky)
+
+    def build_net(self, input_nc, output_nc, down=True, bn=True, dropout=False, leaky=True):
+        model = [nn.LeakyReLU(0.2) if leaky else nn.ReLU()]
+        if down:
+            model.append(nn.Conv2d(input_nc, output_nc, kernel_size=4, stride=2, padding=1, bias=False))
+        else:
+            model.append(nn.ConvTranspose2d(input_nc, output_nc, kernel_size=4, stride=2, bias=False))
+            model.append(Cropping2D(1))
+        if bn:
+            model.append(nn.InstanceNorm3d(1, eps=1e-3, affine=True, track_running_stats=False))
+        if dropout:
+            model.append(nn.Dropout2d())
+        return nn.ModuleList(model)
+
+    def forward(self, input):
+        _no_eager("Block")
+
+
+class encoder(nn.Module):
+    """models/networks.py:175-202."""
+
+    def __init__(self, input_nc, nfilters_enc):
+        super(encoder, self).__init__()
+        self.input_nc = input_nc
+        self.nfilters_enc = nfilters_enc
+        self.net = self.build_net(input_nc, nfilters_enc)
+
+    def build_net(self, input_nc, nfilters_enc):
+        model = []
+        for i, nf in enumerate(nfilters_enc):
+            if i == 0:
+                model.append(nn.Conv2d(input_nc, nf, kernel_size=3, padding=1, bias=True))
+            elif i == len(nfilters_enc) - 1:
+                model.append(Block(nfilters_enc[i - 1], nf, bn=False))
+            else:
+                model.append(Block(nfilters_enc[i - 1], nf))
+        return nn.ModuleList(model)
+
+    def forward(self, input):
+        _no_eager("encoder")
+
+
+class decoder(nn.Module):
+    """models/networks.py:204-250."""
+
+    def __init__(self, nfilters_dec, nfilters_enc, num_skips=1):
+        super(decoder, self).__init__()
+        self.num_skips = num_skips
+        self.nfilters_dec = nfilters_dec
+        self.nfilters_enc = nfilters_enc
+        self.net = self.build_net(nfilters_dec)
+
+    def build_net(self, nfilters_dec):
+        model_dec = []
+        for i, nf in enumerate(nfilters_dec):
+            if i == 0:
+                model_dec.append(Block(self.num_skips * self.nfilters_enc[-1], nf, down=False, leaky=False, dropout=True))
+            elif 0 < i < 3:
+                model_dec.append(Block(self.num_skips * self.nfilters_enc[-(i + 1)] + nfilters_dec[i - 1], nf, down=False,
+                                       leaky=False, dropout=True))
+            elif i == len(nfilters_dec) - 1:
+                model_dec.append(nn.ReLU())
+                model_dec.append(nn.Conv2d(self.num_skips * self.nfilters_enc[-(i + 1)] + nfilters_dec[i - 1], nf,
+                                           kernel_size=3, padding=1, bias=True))
+            else:
+                model_dec.append(Block(self.num_skips * self.nfilters_enc[-(i + 1)] + nfilters_dec[i - 1], nf, down=False,
+                                       leaky=False))
+        model_dec.append(nn.Tanh())
+        return nn.ModuleList(model_dec)
+
+    def forward(self, skips):
+        _no_eager("decoder")
+
+
+class _GeneratorFn(torch.autograd.Function):
+    """Makes the fused schedule differentiable for external callers (main.py / test.py style use)."""
+
+    @staticmethod
+    def forward(ctx, gen, inp, warps, masks, *params):
+        ctx.gen = gen
+        ctx.params = params
+        out = gen.engine.forward(inp, warps, masks, drop=gen._next_drop())
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        gen = ctx.gen
+        grads = {p: torch.zeros_like(p) for p in ctx.params}
+        gen.engine.backward(grads, dout_nchw=dout.contiguous())
+        return (None, None, None, None) + tuple(grads[p] if p.requires_grad else None for p in ctx.params)
+
+
+class Deformable_Generator(nn.Module):
+    """models/networks.py:252-288."""
+
+    def __init__(self, input_nc, pose_dim, image_size, nfilters_enc, nfilters_dec, warp_skip, use_input_pose=True):
+        super(Deformable_Generator, self).__init__()
+        self.input_nc = input_nc
+        # 'none' (opts.py:60) never equals 'None' (networks.py:257): num_skips is always 2 in the reference
+        self.num_skips = 1 if warp_skip == 'None' else 2
+        self.warp_skip = warp_skip
+        self.pose_dim = pose_dim
+        self.nfilters_dec = nfilters_dec
+        self.nfilters_enc = nfilters_enc
+        self.image_size = image_size
+        self.use_input_pose = use_input_pose
+        if warp_skip != 'mask' or not use_input_pose:
+            raise NotImplementedError("only warp_skip='mask' with use_input_pose=True is on the B200 hot path")
+        self.encoder_app = encoder(input_nc - self.pose_dim, nfilters_enc)
+        self.encoder_pose = encoder(self.pose_dim, nfilters_enc)
+        self.decoder = decoder(nfilters_dec, nfilters_enc, self.num_skips)
+        self.engine = GeneratorEngine(self)
+        self._drop_queue = None
+
+    def set_dropout_noise(self, drops):
+        """Test hook: the next forward uses these three [N,512,1,1] noise tensors instead of drawing."""
+        self._drop_queue = drops
+
+    def _next_drop(self):
+        d, self._drop_queue = self._drop_queue, None
+        return d
+
+    def forward(self, input, warps, masks):
+        if not input.is_cuda:
+            raise RuntimeError("Deformable_Generator: CUDA tensors required (no CPU fallback)")
+        params = tuple(self.parameters())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _GeneratorFn.apply(self, input, warps, masks, *params)
+        return self.engine.forward(input, warps, masks, drop=self._next_drop())
+
+
+class Stacked_Generator(nn.Module):
+    """models/networks.py:290-327 -- pure composition of Deformable_Generator."""
+
+    def __init__(self, input_nc, num_stacks, image_size, pose_dim, nfilters_enc, nfilters_dec, warp_skip=False,
+                 use_input_pose=True):
+        super(Stacked_Generator, self).__init__()
+        self.input_nc = input_nc
+        self.num_stacks = num_stacks
+        self.nfilters_dec = nfilters_dec
+        self.nfilters_enc = nfilters_enc
+        self.use_input_pose = use_input_pose
+        self.pose_dim = pose_dim
+        self.image_size = image_size
+        self.generator = Deformable_Generator(input_nc, pose_dim, image_size, nfilters_enc, nfilters_dec, warp_skip,
+                                              use_input_pose)
+
+    def forward(self, input, target_pose, target_warps, target_masks):
+        init_input, init_pose, _ = pose_utils.get_imgpose(input, self.use_input_pose, self.pose_dim)
+        outputs = []
+        P = self.pose_dim
+        for i in range(self.num_stacks):
+            if i == 0:
+                inp = torch.cat([init_input, init_pose, target_pose[:, i * P:(i + 1) * P]], dim=1)
+            else:
+                inp = torch.cat([out, target_pose[:, (i - 1) * P:i * P], target_pose[:, i * P:(i + 1) * P]], dim=1)
+            out = self.generator(inp, target_warps[:, i].contiguous(), target_masks[:, i].contiguous())
+            outputs.append(out)
+        return outputs
+
+
+class _DiscriminatorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disc, x, *params):
+        ctx.disc, ctx.params = disc, params
+        probs = disc._run(x)
+        ctx.save_for_backward(probs)
+        ctx.x_shape = x.shape
+        return probs
+
+    @staticmethod
+    def backward(ctx, dprobs):
+        from .. import kernels as K
+        disc = ctx.disc
+        probs, = ctx.saved_tensors
+        M, J = probs.shape
+        # sigmoid' (tiny [M,J] tensor; part of the autograd glue, not of the step's hot path)
+        dlog = (dprobs * probs * (1 - probs)).reshape(M * J, 1)
+        dlog4 = torch.zeros(M * J, 4, device=probs.device)
+        dlog4[:, :1] = dlog
+        grads = {p: torch.zeros_like(p) for p in ctx.params}
+        need_x = ctx.needs_input_grad[1]
+        din_grad = disc.engine.backward(dlog4, grads, need_input_grad=need_x)
+        dx = None
+        if need_x:
+            N, C, H, W = ctx.x_shape
+            dx = torch.empty(N, C, H, W, device=probs.device)
+            K.nhwc_to_nchw(Slice(din_grad, 0, C), dx)
+        return (None, dx) + tuple(grads[p] if p.requires_grad else None for p in ctx.params)
+
+
+class Discriminator(nn.Module):
+    """models/networks.py:329-357."""
+
+    def __init__(self, input_nc, warp_skip=False, use_input_pose=True, checkMode=0):
+        super(Discriminator, self).__init__()
+        self.input_nc = input_nc
+        self.use_input_pose = use_input_pose
+        self.warp_skip = warp_skip
+        self.checkMode = checkMode
+        self.net = self.build_net()
+        self.engine = DiscriminatorEngine(self)
+
+    def build_net(self):
+        model = [nn.Conv2d(self.input_nc, 64, kernel_size=4, stride=2), Block(64, 128), Block(128, 256)]
+        if self.checkMode == 0:
+            model.append(Block(256, 512))
+            model.append(Block(512, 1, bn=False))
+        else:
+            model.append(Block(256, 1, bn=False))
+        model.append(nn.Sigmoid())
+        model.append(Flatten())
+        return nn.Sequential(*model)
+
+    def _run(self, x):
+        from .. import kernels as K
+        M, C, H, W = x.shape
+        din = self.engine.input_buffer(M, H, W, x.device)
+        K.nchw_to_nhwc(x.contiguous(), 0, C, Slice(din, 0, C))
+        return self.engine.forward(din, probs=True)
+
+    def forward(self, input):
+        if not input.is_cuda:
+            raise RuntimeError("Discriminator: CUDA tensors required (no CPU fallback)")
+        params = tuple(self.parameters())
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params)):
+            return _DiscriminatorFn.apply(self, input, *params)
+        return self._run(input)

@@ -1,0 +1,286 @@
+"""Drop-in for the reference's ``models/pose_gan.py`` (src_deformable/models/pose_gan.py:11-224):
+``DeformablePose_GAN`` with the same constructor (an ``opts`` Namespace), attributes (``gen``, ``disc``,
+``gen_opt``, ``disc_opt``, ``content_model``) and methods (``gen_update``, ``dis_update``, ``nn_loss``,
+``resume``, ``save``), executing one D step / one G step as a hand-scheduled sequence of sm_100a kernels.
+
+Differences that do not change any returned value or parameter update:
+  * ``dis_update`` does not back-propagate into the generator (the reference's G gradients from that
+    backward are discarded by ``gen.zero_grad()`` before they are ever used);
+  * ``gen_update`` computes no discriminator / VGG weight gradients (never used by the reference);
+  * losses are reduced by one fused kernel each and read back with a single device->host copy.
+Data parallelism (absent from the reference): if ``torch.distributed`` is initialised, gradients are
+summed over ranks with NCCL on the flat gradient arena and the 1/world scale is folded into Adam;
+``opt.batch_size`` is the PER-RANK batch.
+"""
+import os
+
+import torch
+import torch.nn as nn
+from torchvision.models import vgg19
+
+from .. import kernels as K
+from ..kernels import Slice
+from ..utils import pose_utils
+from .networks import Deformable_Generator, Discriminator, Stacked_Generator  # noqa: F401
+
+
+class ParamArena:
+    """All parameters of a network as views into ONE flat fp32 buffer (plus flat grad / Adam state), so the
+    optimiser step is one kernel launch and the gradient all-reduce is one NCCL call."""
+
+    def __init__(self, module):
+        self.module = module
+        self.params = [p for p in module.parameters()]
+        self.bind()
+
+    def bind(self):
+        dev = self.params[0].device
+        total = 0
+        self.offsets = []
+        for p in self.params:
+            total = (total + 3) // 4 * 4          # keep every tensor 16-byte aligned
+            self.offsets.append(total)
+            total += p.numel()
+        self.total = (total + 3) // 4 * 4
+        self.flat = torch.zeros(self.total, device=dev)
+        self.grad = torch.zeros(self.total, device=dev)
+        self.exp_avg = torch.zeros(self.total, device=dev)
+        self.exp_avg_sq = torch.zeros(self.total, device=dev)
+        self.grads = {}
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                view = self.flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                g = self.grad[off:off + p.numel()].view(p.shape)
+                p.grad = g
+                self.grads[p] = g
+
+    def check(self):
+        """Re-flatten if some external code replaced parameter storage (e.g. module.to(...))."""
+        p0, pl = self.params[0], self.params[-1]
+        ok = (p0.data_ptr() == self.flat.data_ptr() + 4 * self.offsets[0] and
+              pl.data_ptr() == self.flat.data_ptr() + 4 * self.offsets[-1])
+        if not ok:
+            self.bind()
+        for p in self.params:     # someone may have set .grad = None (zero_grad(set_to_none=True))
+            if p.grad is None or p.grad.data_ptr() != self.grads[p].data_ptr():
+                p.grad = self.grads[p]
+
+    def zero_grad(self):
+        K.fill(self.grad, 0.0)
+
+
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(lr, betas=(0.5, 0.999)) semantics (pose_gan.py:49-51) on a ParamArena."""
+
+    def __init__(self, arena, lr, betas=(0.5, 0.999), eps=1e-8):
+        super().__init__(arena.params, dict(lr=lr, betas=betas, eps=eps))
+        self.arena = arena
+        self.steps = 0
+        self.grad_scale = 1.0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        g = self.param_groups[0]
+        self.steps += 1
+        a = self.arena
+        K.adam_step(a.flat, a.grad, a.exp_avg, a.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"], self.steps,
+                    self.grad_scale)
+
+    def zero_grad(self, set_to_none=False):
+        self.arena.zero_grad()
+
+
+class DeformablePose_GAN(nn.Module):
+    def __init__(self, opt):
+        super(DeformablePose_GAN, self).__init__()
+        # adding extra layers for larger image size (pose_gan.py:17-18)
+        nfilters_decoder = (512, 512, 512, 256, 128, 3) if max(opt.image_size) < 256 else (512, 512, 512, 512, 256, 128, 3)
+        nfilters_encoder = (64, 128, 256, 512, 512, 512) if max(opt.image_size) < 256 else (64, 128, 256, 512, 512, 512, 512)
+        input_nc = 3 + 2 * opt.pose_dim if opt.use_input_pose else 3 + opt.pose_dim
+        self.batch_size = opt.batch_size
+        self.num_stacks = opt.num_stacks
+        self.pose_dim = opt.pose_dim
+        self.image_size = tuple(opt.image_size)
+        if opt.gen_type == 'stacked':
+            raise NotImplementedError("gen_type='stacked' is outside the B200 hot path (SURVEY 8f-3)")
+        elif opt.gen_type == 'baseline':
+            self.gen = Deformable_Generator(input_nc, self.pose_dim, opt.image_size, nfilters_encoder, nfilters_decoder,
+                                            opt.warp_skip, use_input_pose=opt.use_input_pose)
+        else:
+            raise Exception('Invalid gen_type')
+        self.disc = Discriminator(input_nc + 3, use_input_pose=opt.use_input_pose)
+        # the reference unconditionally loads this checkpoint (pose_gan.py:40-42)
+        pretrained_disc_path = '../exp/' + 'full_' + opt.dataset + '/models/disc_090.pkl'
+        try:
+            self.disc.load_state_dict(torch.load(pretrained_disc_path))
+            print("Loaded discriminator from pretrained model ")
+        except (FileNotFoundError, OSError):
+            print("No pretrained discriminator at %s -- keeping default initialisation" % pretrained_disc_path)
+
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size()
+            self.rank = torch.distributed.get_rank()
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", self.rank % max(torch.cuda.device_count(), 1))))
+        else:
+            self.world, self.rank = 1, 0
+
+        self.content_loss_layer = opt.content_loss_layer
+        self.nn_loss_area_size = opt.nn_loss_area_size
+        if self.content_loss_layer != 'none':
+            try:
+                self.content_model = vgg19(pretrained=True)
+            except Exception as e:  # offline: no ImageNet weights reachable
+                print("vgg19(pretrained=True) unavailable (%s) -- using torchvision default init" % type(e).__name__)
+                self.content_model = vgg19(weights=None)
+        self.gen.cuda()
+        self.disc.cuda()
+        self._nn_loss_area_size = opt.nn_loss_area_size
+        self.ll_loss_criterion = torch.nn.L1Loss()
+
+        lr = opt.learning_rate
+        self.gen_arena = ParamArena(self.gen)
+        self.disc_arena = ParamArena(self.disc)
+        self.disc_opt = FlatAdam(self.disc_arena, lr=lr, betas=(0.5, 0.999))
+        self.gen_opt = FlatAdam(self.gen_arena, lr=lr, betas=(0.5, 0.999))
+        self.gen_opt.grad_scale = self.disc_opt.grad_scale = 1.0 / self.world
+        if self.world > 1:   # identical replicas: rank 0's weights win
+            torch.distributed.broadcast(self.gen_arena.flat, 0)
+            torch.distributed.broadcast(self.disc_arena.flat, 0)
+        self._vgg_dev = None
+        self._loss_buf = None
+
+    # ------------------------------------------------------------------ helpers
+    def _vgg_params(self, device):
+        if self._vgg_dev is None or self._vgg_dev[0].device != device:
+            conv = self.content_model.features[0]
+            self._vgg_dev = (conv.weight.detach().to(device, torch.float32).contiguous(),
+                             conv.bias.detach().to(device, torch.float32).contiguous())
+        return self._vgg_dev
+
+    def _allreduce(self, arena):
+        if self.world > 1:
+            torch.distributed.all_reduce(arena.grad)
+
+    def _fill_disc_input(self, din, inp, middle, P):
+        """din[..., :3+P] = (img, src pose); din[..., 3+P:6+P] = middle (or left to the generator);
+        din[..., 6+P:6+2P] = target pose   (pose_gan.py:84-86,131-135)."""
+        K.nchw_to_nhwc(inp, 0, 3 + P, Slice(din, 0, 3 + P))
+        if middle is not None:
+            K.nchw_to_nhwc(middle, 0, 3, Slice(din, 3 + P, 3))
+        K.nchw_to_nhwc(inp, 3 + P, P, Slice(din, 6 + P, P))
+
+    def _prep(self, t, dtype=torch.float32):
+        t = t.cuda() if not t.is_cuda else t
+        return t.to(dtype).contiguous() if t.dtype != dtype else t.contiguous()
+
+    # ------------------------------------------------------------------ updates
+    def gen_update(self, input, target, other_inputs, opt, drop=None):
+        if opt['gen_type'] != 'baseline':
+            raise NotImplementedError("gen_type='stacked' is outside the B200 hot path")
+        P = opt['pose_dim']
+        input, target = self._prep(input), self._prep(target)
+        warps, masks = other_inputs['warps'], other_inputs['masks']
+        N, _, H, W = input.shape
+        dev = input.device
+        self.gen_arena.check()
+        self.disc_arena.check()
+        self.gen_arena.zero_grad()                                       # self.gen.zero_grad()  (pose_gan.py:70)
+        loss = torch.zeros(4, device=dev)
+
+        din = self.disc.engine.input_buffer(N, H, W, dev)
+        self._fill_disc_input(din, input, None, P)
+        out_gen = self.gen.engine.forward(input, warps, masks, drop=drop if drop is not None else self.gen._next_drop(),
+                                          d_input=Slice(din, 3 + P, 3))
+        logits = self.disc.engine.forward(din)
+        J = logits.shape[1]
+        dlog4 = self.disc.engine.ws.get("dlog4_%d_%d" % (N, J), (N * J, 4))
+        # ad_loss = sum_n -mean_j log(out+1e-7), * gan_penalty_weight / batch_size   (pose_gan.py:90-98,107)
+        K.adv_loss(logits, N, J, N, opt['gan_penalty_weight'] / self.batch_size, loss[0:2], dlog4, 4)
+        din_grad = self.disc.engine.backward(dlog4, grads=None, need_input_grad=True)
+
+        dpred = self.gen.engine.ws.get("dpred_%d_%d_%d" % (N, H, W), (N, 3, H, W))
+        if self.content_loss_layer != 'none':
+            if pose_utils.get_layer_ind(self.content_loss_layer) != 1:
+                raise NotImplementedError("only content_loss_layer='block1_conv2' is on the B200 hot path")
+            vw, vb = self._vgg_params(dev)
+            area = self.nn_loss_area_size
+            argmin = self.gen.engine.ws.get("nn_argmin_%d_%d_%d" % (N, H, W), (N, H, W), torch.uint8)
+            K.nnloss_forward(out_gen, target, vw, vb, area, opt['l1_penalty_weight'], loss[2:3], argmin)
+            K.nnloss_backward(out_gen, target, vw, vb, argmin, area, opt['l1_penalty_weight'], dpred)
+        else:
+            K.l1_loss(out_gen, target, opt['l1_penalty_weight'], loss[2:3], dpred)
+
+        self.gen.engine.backward(self.gen_arena.grads, dout_nchw=dpred, dout_nhwc=Slice(din_grad, 3 + P, 3))
+        self._allreduce(self.gen_arena)
+        self.gen_opt.step()
+        host = loss.tolist()                                             # single device->host sync
+        self.gen_ad_loss, self.gen_ll_loss = host[0], host[2]
+        self.gen_total_loss = float(torch.tensor(host[0]) + torch.tensor(host[2]))
+        return out_gen, [], [self.gen_total_loss, self.gen_ll_loss, self.gen_ad_loss]
+
+    def dis_update(self, input, target, other_inputs, real_inp, real_target, opt, drop=None):
+        if opt['gen_type'] != 'baseline':
+            raise NotImplementedError("gen_type='stacked' is outside the B200 hot path")
+        P = opt['pose_dim']
+        input, real_inp, real_target = self._prep(input), self._prep(real_inp), self._prep(real_target)
+        warps, masks = other_inputs['warps'], other_inputs['masks']
+        N, _, H, W = input.shape
+        dev = input.device
+        self.gen_arena.check()
+        self.disc_arena.check()
+        self.disc_arena.zero_grad()                                      # self.disc.zero_grad() (pose_gan.py:118)
+        loss = torch.zeros(4, device=dev)
+
+        M = N + real_inp.shape[0]
+        din = self.disc.engine.input_buffer(M, H, W, dev)
+        nr = real_inp.shape[0]
+        self._fill_disc_input(din[:nr], real_inp, real_target, P)        # real rows first (pose_gan.py:136)
+        self._fill_disc_input(din[nr:], input, None, P)
+        self.gen.engine.forward(input, warps, masks, drop=drop if drop is not None else self.gen._next_drop(),
+                                d_input=Slice(din[nr:], 3 + P, 3))
+        logits = self.disc.engine.forward(din)
+        J = logits.shape[1]
+        dlog4 = self.disc.engine.ws.get("dlog4_%d_%d" % (M, J), (M * J, 4))
+        # rows < opt['batch_size'] are "true", the rest "fake"; both * gan_w / self.batch_size (pose_gan.py:140-163)
+        K.adv_loss(logits, M, J, opt['batch_size'], opt['gan_penalty_weight'] / self.batch_size, loss[0:2], dlog4, 4)
+        self.disc.engine.backward(dlog4, grads=self.disc_arena.grads, need_input_grad=False)
+        self._allreduce(self.disc_arena)
+        self.disc_opt.step()
+        host = loss.tolist()
+        self.dis_true_loss, self.dis_fake_loss = host[0], host[1]
+        self.dis_total_loss = float(torch.tensor(host[0]) + torch.tensor(host[1]))
+        return [self.dis_total_loss, self.dis_true_loss, self.dis_fake_loss]
+
+    def nn_loss(self, predicted, ground_truth, nh=3, nw=3):
+        """pose_gan.py:173-199 on feature tensors (API parity; the training step uses the fused kernels)."""
+        raise NotImplementedError("nn_loss on materialised features is fused into ptk_nnloss_* on the B200 path; "
+                                  "use DeformablePose_GAN.gen_update")
+
+    # ------------------------------------------------------------------ checkpoints (pose_gan.py:201-220)
+    def resume(self, save_dir):
+        last_model_name = pose_utils.get_model_list(save_dir, "gen")
+        if last_model_name is None:
+            return 1
+        self.gen.load_state_dict(torch.load(last_model_name))
+        epoch = int(last_model_name[-7:-4])
+        print('Resume gen from epoch %d' % epoch)
+        last_model_name = pose_utils.get_model_list(save_dir, "dis")
+        if last_model_name is None:
+            return 1
+        epoch = int(last_model_name[-7:-4])
+        self.disc.load_state_dict(torch.load(last_model_name))
+        print('Resume disc from epoch %d' % epoch)
+        return epoch
+
+    def save(self, save_dir, epoch):
+        if self.rank != 0:
+            return
+        gen_filename = os.path.join(save_dir, 'gen_{0:03d}.pkl'.format(epoch))
+        disc_filename = os.path.join(save_dir, 'disc_{0:03d}.pkl'.format(epoch))
+        torch.save(self.gen.state_dict(), gen_filename)
+        torch.save(self.disc.state_dict(), disc_filename)
+
+    def normalize_image(self, x):
+        return x[:, 0:3, :, :]

