@@ -1,8 +1,383 @@
-// tcgen05 TF32 implicit-GEMM convolutions (placeholder until the tensor-core kernels land).
+// tcgen05 (5th-gen tensor core) TF32 implicit-GEMM convolution for sm_100a.
+//
+//   D[m, n] = sum_taps sum_c A_tap[m, c] * B_tap[n, c]      (fp32 storage, TF32 operands, fp32 accumulate in TMEM)
+//
+// * A_tap tile = 128 output-grid pixels x 32 channels, fetched by ONE 4-D TMA box straight out of the NHWC
+//   activation tensor (the im2col matrix never exists): box (32 ch, BW, BH, BI images) at the tap's pixel offset,
+//   out-of-image taps zero-filled by TMA.  Stride-2 convs use four parity-split tensor maps (one per input
+//   row/column parity) so that every box is a dense unit-stride tile.
+// * B_tap tile = BLOCK_N output channels x 32 input channels of the K-major packed weight [tap][Cout][Cin].
+// * Both land in shared memory in the 128-byte-swizzled K-major layout that tcgen05.mma consumes directly.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2..5 = epilogue
+//   (tcgen05.ld -> registers -> global, plus the per-sample sum / sum-of-squares that the following
+//   InstanceNorm3d(1) needs, models/networks.py:159).
+// * Transposed convs (decoder, and the dgrad of every strided conv) run as 4 output-parity phases
+//   (blockIdx.z), each a 2x2-tap stride-1 gather.
+#include <cuda.h>
 #include "common.cuh"
+
 namespace ptk {
-bool conv_tc_supported(const ptk_conv_geom&) { return false; }
-int conv_forward_tc(const ptk_conv_geom&, const float*, const float*, const float*, int, float*, double*, cudaStream_t) {
-  return fail(4, "tcgen05 conv path not built");
+
+struct TcPhase {
+  int GH, GW, py, px, ntaps;
+  signed char cy[16], cx[16];
+  unsigned char wt[16], map[16];
+};
+
+struct TcGeom {
+  int N, OH, OW, ldy, so;
+  int BW, BH, BI, tiles_x, tiles_y, tiles_i;
+  int kchunks;
+  TcPhase ph[4];
+};
+
+struct TmapSet {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a trap (=> CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("ptk conv_tc: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, single CTA
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row atoms 1024 B apart).
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);   // start address           bits [0,14)
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset      bits [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, M x N tile
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192)
+conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcGeom g, float* __restrict__ y,
+               double* __restrict__ stats) {
+  constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BLOCK_N * 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + STAGES * A_BYTES, sBar = sB + STAGES * B_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full ; then the TMEM base-address slot
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_tmem = sBar + 16 * STAGES;
+  const uint32_t tmem_slot = bar_tmem + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const TcPhase ph = g.ph[blockIdx.z];
+  int t = blockIdx.x;
+  const int tx = t % g.tiles_x; t /= g.tiles_x;
+  const int ty = t % g.tiles_y;
+  const int ti = t / g.tiles_y;
+  const int gx0 = tx * g.BW, gy0 = ty * g.BH, n0 = ti * g.BI;
+  const int KB = ph.ntaps * g.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_tmem, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BLOCK_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t par = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(bar_empty + 8 * s, par ^ 1u);
+        const int tap = kb / g.kchunks;
+        const int c0 = (kb - tap * g.kchunks) * 32;
+        mbar_expect_tx(bar_full + 8 * s, A_BYTES + B_BYTES);
+        tma_load_4d(sA + s * A_BYTES, &maps.a[ph.map[tap]], bar_full + 8 * s, c0, gx0 + ph.cx[tap], gy0 + ph.cy[tap], n0);
+        tma_load_3d(sB + s * B_BYTES, &maps.b, bar_full + 8 * s, c0, blockIdx.y * BLOCK_N, ph.wt[tap]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(128, BLOCK_N);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t par = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(bar_full + 8 * s, par);
+        tc_fence_after();
+        const uint64_t da = smem_desc_k_sw128(sA + s * A_BYTES), db = smem_desc_k_sw128(sB + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzle row
+          tc_mma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        tc_commit(bar_empty + 8 * s);   // frees the smem stage once these MMAs have read it
+      }
+      tc_commit(bar_tmem);              // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int lg = warp & 3;            // TMEM lane group this warp may access
+    const int row = lg * 32 + lane;
+    const int x = row % g.BW;
+    const int yy = (row / g.BW) % g.BH;
+    const int ii = row / (g.BW * g.BH);
+    const int gx = gx0 + x, gy = gy0 + yy, n = n0 + ii;
+    const bool valid = gx < ph.GW && gy < ph.GH && n < g.N;
+    float* dst = nullptr;
+    if (valid) {
+      const int oy = gy * g.so + ph.py, ox = gx * g.so + ph.px;
+      dst = y + (((int64_t)n * g.OH + oy) * g.OW + ox) * g.ldy + blockIdx.y * BLOCK_N;
+    }
+    mbar_wait(bar_tmem, 0);
+    tc_fence_after();
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      float v[32];
+      tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), v);
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) { s1 += v[q]; s2 = fmaf(v[q], v[q], s2); }
+      }
+    }
+    if (stats != nullptr) {
+      if (g.BW * g.BH >= 32) {          // the warp's 32 rows belong to one image
+        const float a = warp_sum(s1), b = warp_sum(s2);
+        const int nw = n0 + (lg * 32) / (g.BW * g.BH);
+        if (lane == 0 && nw < g.N) { atomicAdd(stats + 2 * nw, (double)a); atomicAdd(stats + 2 * nw + 1, (double)b); }
+      } else if (valid) {
+        atomicAdd(stats + 2 * n, (double)s1);
+        atomicAdd(stats + 2 * n + 1, (double)s2);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(5, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(5, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u", (int)r, rank,
+                (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], box[2], rank > 3 ? box[3] : 0);
+  return 0;
+}
+
+static int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+static int floordiv2(int q) { return q >= 0 ? q / 2 : -((-q + 1) / 2); }
+
+bool conv_tc_supported(const ptk_conv_geom& c) {
+  if (c.Cin % 32 != 0 || c.Cout % 64 != 0) return false;
+  if (c.ldx % 4 != 0 || c.ldy % 4 != 0) return false;
+  if (!((c.k == 4 && c.stride == 2) || (c.k == 3 && c.stride == 1))) return false;
+  if (c.H < 4 || c.W < 4 || c.OH < 4 || c.OW < 4) return false;
+  if (c.N < 1 || c.N > 4096) return false;
+  return true;
+}
+
+int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, const float* bias, int act, float* y,
+                    double* stats, cudaStream_t st) {
+  PTK_REQUIRE(bias == nullptr && act == PTK_ACT_NONE, "conv_forward(tc): bias / activation epilogues are not implemented");
+  PTK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(w_k) & 15) == 0, "conv_forward(tc): pointers must be 16-byte aligned");
+  TcGeom g;
+  memset(&g, 0, sizeof(g));
+  TmapSet maps;
+  memset(&maps, 0, sizeof(maps));
+  g.N = c.N; g.OH = c.OH; g.OW = c.OW; g.ldy = c.ldy; g.kchunks = c.Cin / 32;
+  int nphases, maxGH = 0, maxGW = 0;
+  const int k = c.k, s = c.stride;
+  if (!c.transposed) {
+    nphases = 1; g.so = 1;
+    TcPhase& p = g.ph[0];
+    p.GH = c.OH; p.GW = c.OW; p.py = p.px = 0; p.ntaps = 0;
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) {
+        const int t = p.ntaps++;
+        const int qy = kh - c.pad, qx = kw - c.pad;
+        if (s == 2) {
+          p.map[t] = (unsigned char)((((qy % 2) + 2) % 2) * 2 + (((qx % 2) + 2) % 2));
+          p.cy[t] = (signed char)floordiv2(qy); p.cx[t] = (signed char)floordiv2(qx);
+        } else {
+          p.map[t] = 0; p.cy[t] = (signed char)qy; p.cx[t] = (signed char)qx;
+        }
+        p.wt[t] = (unsigned char)(kh * k + kw);
+      }
+  } else {
+    nphases = s * s; g.so = s;
+    for (int py = 0; py < s; ++py)
+      for (int px = 0; px < s; ++px) {
+        TcPhase& p = g.ph[py * s + px];
+        p.GH = (c.OH - py + s - 1) / s; p.GW = (c.OW - px + s - 1) / s; p.py = py; p.px = px; p.ntaps = 0;
+        for (int kh = 0; kh < k; ++kh) {
+          if ((py + c.pad - kh) % s != 0) continue;
+          for (int kw = 0; kw < k; ++kw) {
+            if ((px + c.pad - kw) % s != 0) continue;
+            const int t = p.ntaps++;
+            p.map[t] = 0;
+            p.cy[t] = (signed char)((py + c.pad - kh) / s); p.cx[t] = (signed char)((px + c.pad - kw) / s);
+            p.wt[t] = (unsigned char)(kh * k + kw);
+          }
+        }
+      }
+  }
+  for (int i = 0; i < nphases; ++i) { maxGH = g.ph[i].GH > maxGH ? g.ph[i].GH : maxGH; maxGW = g.ph[i].GW > maxGW ? g.ph[i].GW : maxGW; }
+  g.BW = pow2_ge(maxGW < 128 ? maxGW : 128);
+  g.BH = pow2_ge(maxGH < 128 / g.BW ? maxGH : 128 / g.BW);
+  g.BI = 128 / (g.BW * g.BH);
+  g.tiles_x = (maxGW + g.BW - 1) / g.BW; g.tiles_y = (maxGH + g.BH - 1) / g.BH; g.tiles_i = (c.N + g.BI - 1) / g.BI;
+
+  // activation tensor maps
+  const uint32_t boxA[4] = {32u, (uint32_t)g.BW, (uint32_t)g.BH, (uint32_t)g.BI};
+  if (!c.transposed && s == 2) {
+    for (int pyy = 0; pyy < 2; ++pyy)
+      for (int pxx = 0; pxx < 2; ++pxx) {
+        const uint64_t Hp = (uint64_t)(c.H - pyy + 1) / 2, Wp = (uint64_t)(c.W - pxx + 1) / 2;
+        const uint64_t dims[4] = {(uint64_t)c.Cin, Wp, Hp, (uint64_t)c.N};
+        const uint64_t str[3] = {(uint64_t)2 * c.ldx * 4, (uint64_t)2 * c.W * c.ldx * 4, (uint64_t)c.H * c.W * c.ldx * 4};
+        int rc = encode(&maps.a[pyy * 2 + pxx], x + ((int64_t)pyy * c.W + pxx) * c.ldx, 4, dims, str, boxA);
+        if (rc) return rc;
+      }
+  } else {
+    const uint64_t dims[4] = {(uint64_t)c.Cin, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.N};
+    const uint64_t str[3] = {(uint64_t)c.ldx * 4, (uint64_t)c.W * c.ldx * 4, (uint64_t)c.H * c.W * c.ldx * 4};
+    int rc = encode(&maps.a[0], x, 4, dims, str, boxA);
+    if (rc) return rc;
+  }
+  const int BN = (c.Cout % 128 == 0) ? 128 : 64;
+  {
+    const uint64_t dims[3] = {(uint64_t)c.Cin, (uint64_t)c.Cout, (uint64_t)(k * k)};
+    const uint64_t str[2] = {(uint64_t)c.Cin * 4, (uint64_t)c.Cin * c.Cout * 4};
+    const uint32_t boxB[3] = {32u, (uint32_t)BN, 1u};
+    int rc = encode(&maps.b, w_k, 3, dims, str, boxB);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)(g.tiles_x * g.tiles_y * g.tiles_i), (unsigned)(c.Cout / BN), (unsigned)nphases);
+  if (BN == 128) {
+    constexpr int STAGES = 3;
+    const size_t smem = STAGES * (128 * 128 + 128 * 128) + 16 * STAGES + 16 + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<128, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    conv_tc_kernel<128, STAGES><<<grid, 192, smem, st>>>(maps, g, y, stats);
+  } else {
+    constexpr int STAGES = 4;
+    const size_t smem = STAGES * (128 * 128 + 64 * 128) + 16 * STAGES + 16 + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<64, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    conv_tc_kernel<64, STAGES><<<grid, 192, smem, st>>>(maps, g, y, stats);
+  }
+  PTK_LAUNCH_CHECK("conv_tc_kernel");
+  return 0;
+}
+
 }  // namespace ptk

@@ -6,6 +6,8 @@ kernel launches over pre-allocated NHWC workspaces, with the backward pass writt
 concatenations of the reference are replaced by channel-slice writes into shared buffers, every activation
 is applied by the producer of a tensor, and the affine warp runs fused (utils/pose_transform.py:16-92).
 """
+import os
+
 import torch
 
 from . import kernels as K
@@ -30,7 +32,7 @@ class ConvLayer:
         self.taps = k * k
         self.w_fwd = None    # [taps][cin_pad][cout_pad]
         self.w_bwd = None    # [taps][cout_pad][cin_pad]  (weights of the dgrad gather-conv)
-        self.impl = K.IMPL_AUTO
+        self.impl = {"auto": K.IMPL_AUTO, "simt": K.IMPL_SIMT, "tc": K.IMPL_AUTO}[os.environ.get("PTK_CONV_IMPL", "auto")]
 
     def _alloc(self):
         if self.w_fwd is None or self.w_fwd.device != self.weight.device:
@@ -39,12 +41,15 @@ class ConvLayer:
             self.w_bwd = torch.empty(self.taps * self.cin_pad * self.cout_pad, device=dev)
 
     def pack_forward(self):
+        """Both GEMM layouts are refreshed: w_fwd = [tap][cin][cout] is the CUDA-core fprop operand AND the K-major
+        tensor-core operand of the dgrad; w_bwd = [tap][cout][cin] is the reverse."""
         self._alloc()
         w = self.weight.detach()
         if self.transposed:   # torch layout [Cin][Cout][k][k]
             K.pack_weight(w, self.w_fwd, self.cin, self.cout, self.taps, self.cin_pad, self.cout_pad, 0)
         else:                 # torch layout [Cout][Cin][k][k]
             K.pack_weight(w, self.w_fwd, self.cout, self.cin, self.taps, self.cout_pad, self.cin_pad, 1)
+        self.pack_backward()
 
     def pack_backward(self):
         self._alloc()
@@ -64,7 +69,7 @@ class ConvLayer:
         OH, OW = self.out_hw(H, W)
         g = K.conv_geom(N, H, W, self.cin_pad, x.ld, OH, OW, self.cout, y.ld if y is not None else self.cout, self.k,
                         self.stride, self.pad, self.transposed, self.impl)
-        K.conv_forward(g, x, self.w_fwd, None, self.bias.detach() if self.bias is not None else None, act, y, y_nchw, stats)
+        K.conv_forward(g, x, self.w_fwd, self.w_bwd, self.bias.detach() if self.bias is not None else None, act, y, y_nchw, stats)
         return OH, OW
 
     def dgrad(self, dy, N, H, W, dx, dx_channels=None):
@@ -75,7 +80,7 @@ class ConvLayer:
                         not self.transposed, self.impl)
         # the dgrad weights are [taps][cout_pad][cin_pad]; the kernel's inner extent is ceil4(Cout')
         assert ceil4(cout_dx) == self.cin_pad
-        K.conv_forward(g, dy, self.w_bwd, None, None, ACT_NONE, dx, None, None)
+        K.conv_forward(g, dy, self.w_bwd, self.w_fwd, None, ACT_NONE, dx, None, None)
 
     def wgrad(self, x, dy, N, H, W, scratch, grad_w):
         """grad_w (torch layout, fp32 view into the gradient arena) += dW."""

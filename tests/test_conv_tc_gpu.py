@@ -1,0 +1,103 @@
+"""GPU parity tests of the tcgen05 TF32 implicit-GEMM convolution path (csrc/conv_tc.cu) through the C ABI,
+against torch CPU fp32.  Tolerance: TF32 operands (10-bit mantissa) with fp32 accumulation => relative L2
+error <= 2e-3 per layer."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+TF32_TOL = 2e-3
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+TC_CASES = [
+    # name, transposed, k, s, p, Cin, Cout, N, H, W
+    ("down_64to128_16", False, 4, 2, 1, 64, 128, 2, 16, 16),
+    ("down_odd_128to256", False, 4, 2, 1, 128, 256, 3, 15, 31),
+    ("down_wide_64to128", False, 4, 2, 1, 64, 128, 2, 32, 256),
+    ("down_deep_512to512_8", False, 4, 2, 1, 512, 512, 2, 8, 8),
+    ("up_256to64", True, 4, 2, 1, 256, 64, 2, 6, 10),
+    ("up_1536to512_4", True, 4, 2, 1, 1536, 512, 2, 4, 4),
+    ("up_wide_512to128", True, 4, 2, 1, 512, 128, 2, 16, 128),
+    ("k3_128to128", False, 3, 1, 1, 128, 128, 2, 12, 20),
+]
+
+
+def describe(got, ref, what):
+    d = (got - ref).abs()
+    idx = torch.nonzero(d > 1e-2 * ref.abs().max())
+    return "%s rel_l2=%.3e max|d|=%.3e ref_max=%.3e bad=%d/%d first_bad=%s" % (
+        what, rel_l2(got, ref), float(d.max()), float(ref.abs().max()), idx.shape[0], d.numel(), idx[:6].tolist())
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv_tc_fprop_stats_dgrad(case):
+    import pose_transfer_b200  # noqa: F401
+    from pose_transfer_b200 import kernels as K
+    from pose_transfer_b200.engine import ConvLayer
+    name, tr, k, s, p, Cin, Cout, N, H, W = case
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    wshape = (Cin, Cout, k, k) if tr else (Cout, Cin, k, k)
+    w = (torch.rand(wshape, generator=g) * 2 - 1) / (Cin * k * k / (s * s if tr else 1)) ** 0.5
+    x = torch.randn(N, Cin, H, W, generator=g)
+    xr = x.clone().requires_grad_(True)
+    z = F.conv_transpose2d(xr, w, None, stride=s, padding=p) if tr else F.conv2d(xr, w, None, stride=s, padding=p)
+    dz = torch.randn(z.shape, generator=g)
+    z.backward(dz)
+    zd = z.detach()
+
+    layer = ConvLayer(torch.nn.Parameter(w.cuda()), None, tr, k, s, p)
+    layer.impl = K.IMPL_TC
+    layer.pack_forward()
+    xin = torch.zeros(N, H, W, Cin + 32, device="cuda")          # channel slice of a wider buffer
+    xin[..., 32:] = nhwc(x).cuda()
+    OH, OW = layer.out_hw(H, W)
+    y = torch.full((N, OH, OW, Cout + 64), 7.0, device="cuda")
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    layer.forward(K.Slice(xin, 32, Cin), N, H, W, K.Slice(y, 64, Cout), K.ACT_NONE, stats)
+    torch.cuda.synchronize()
+    got = nchw(y[..., 64:]).cpu()
+    assert rel_l2(got, zd) < TF32_TOL, describe(got, zd, "fprop")
+    assert float((y[..., :64] - 7.0).abs().max()) == 0, "wrote outside its channel slice"
+    ref_stats = torch.stack([zd.double().reshape(N, -1).sum(1), (zd.double() ** 2).reshape(N, -1).sum(1)], 1)
+    assert rel_l2(stats[:, 1], ref_stats[:, 1]) < 2e-3, (stats.cpu(), ref_stats)
+    rms = float(ref_stats[:, 1].max().sqrt())
+    assert float((stats[:, 0].cpu() - ref_stats[:, 0]).abs().max()) < 2e-3 * rms * (zd[0].numel() ** 0.5) + 1e-3
+
+    # dgrad (runs the other kind of gather on the tensor cores)
+    dzd = nhwc(dz).cuda()
+    dx = torch.zeros(N, H, W, Cin, device="cuda")
+    layer.dgrad(K.Slice(dzd), N, H, W, K.Slice(dx))
+    torch.cuda.synchronize()
+    gotdx = nchw(dx).cpu()
+    assert rel_l2(gotdx, xr.grad) < TF32_TOL, describe(gotdx, xr.grad, "dgrad")
+
+
+def test_conv_tc_matches_simt_full_size():
+    """Decoder level 5 geometry of BASELINE configs[1] (ConvT 512->128, 128x128 -> 256x256), N=2: tensor-core
+    result vs the fp32 CUDA-core path on the same device."""
+    import pose_transfer_b200  # noqa: F401
+    from pose_transfer_b200 import kernels as K
+    from pose_transfer_b200.engine import ConvLayer
+    g = torch.Generator().manual_seed(5)
+    w = ((torch.rand(512, 128, 4, 4, generator=g) * 2 - 1) / (512 * 4) ** 0.5).cuda()
+    x = torch.randn(2, 128, 128, 512, generator=g).cuda()
+    outs = []
+    for impl in (K.IMPL_SIMT, K.IMPL_TC):
+        layer = ConvLayer(torch.nn.Parameter(w), None, True, 4, 2, 1)
+        layer.impl = impl
+        layer.pack_forward()
+        y = torch.zeros(2, 256, 256, 128, device="cuda")
+        layer.forward(K.Slice(x), 2, 128, 128, K.Slice(y), K.ACT_NONE, None)
+        outs.append(y)
+    torch.cuda.synchronize()
+    assert rel_l2(outs[1], outs[0]) < TF32_TOL
