@@ -83,9 +83,11 @@ typedef struct {
 int ptk_conv_tc_supported(const ptk_conv_geom* g);
 int ptk_conv_forward(const ptk_conv_geom* g, const float* x, const float* w_t, const float* w_k,
                      const float* bias, int act, float* y, float* y_nchw, double* stats, void* stream);
-/* dw[tap][A][B_pad] (+)= sum_pixels small[m][a] * big[m*stride+off(tap)][b]; for Conv2d small=dy,big=x
- * (result [tap][Cout][Cin]); for ConvTranspose2d small=x,big=dy (result [tap][Cin][Cout]).  dw must be
- * zeroed by the caller when accumulate==0 semantics are wanted (the kernel always atomically adds). */
+/* dw[tap][A][B] = sum_pixels small[m][a] * big[m*stride+off(tap)][b]; for Conv2d small=dy,big=x
+ * (result [tap][Cout][Cin]); for ConvTranspose2d small=x,big=dy (result [tap][Cin][Cout]), with Cin/Cout as given in
+ * the geometry (i.e. including channel padding).  dw is scratch owned by the caller and is OVERWRITTEN (the library
+ * zero-fills it itself when it needs split-K accumulation).  tcgen05 TF32 path for k4 s2 layers with wide channels,
+ * fp32 CUDA-core path otherwise. */
 int ptk_conv_wgrad(const ptk_conv_geom* g, const float* x, const float* dy, float* dw, void* stream);
 /* dbias[c] += sum_pixels dy[pixel][c] */
 int ptk_bias_grad(const float* dy, int ld, int64_t pixels, int C, float* dbias, void* stream);

@@ -257,7 +257,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int encode(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box) {
+                  const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(5, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t gd[5], gs[4];
@@ -265,7 +265,7 @@ static int encode(CUtensorMap* m, const float* base, int rank, const uint64_t* d
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(5, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u", (int)r, rank,
                 (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
@@ -377,6 +377,219 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     conv_tc_kernel<64, STAGES><<<grid, 192, smem, st>>>(maps, g, y, stats);
   }
   PTK_LAUNCH_CHECK("conv_tc_kernel");
+  return 0;
+}
+
+
+// ============================================================================= weight gradient on tcgen05
+//   dW[t][a][b] = sum_pixels S[m][a] * Bg[2*m + q(t)][b]     (S: small grid, Bg: stride-2 addressed tensor)
+// Both operands are "MN-major" for the tensor core (channels contiguous, the GEMM-K index = pixel is the row).  For
+// 32-bit MN-major operands tcgen05 requires the "128B swizzle with 32B atoms" layout (UMMA layout type 1; TMA
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): a TMA box (32 channels x 32 pixels) lands as a column of 32x4 atoms
+// (4-pixel groups 512 B apart = SBO, next 32 channels = next box = LBO).  Split-K over pixel tiles across CTAs.
+struct WgTcGeom {
+  int N, GH, GW;                 // small grid
+  int BW, BH, BI, tiles_x, tiles_y, tiles_i, ntiles;
+  int Ca, Cb_pad;                // dw[t][Ca][Cb_pad]
+  int splits;
+  signed char cy[16], cx[16];
+  unsigned char map[16];
+};
+
+struct WgTmapSet {
+  CUtensorMap s;       // small tensor
+  CUtensorMap b[4];    // big tensor, one per (row parity, col parity)
+};
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between 32-channel (128 B) groups along M/N
+  d |= (uint64_t)(512 >> 4) << 32;                     // stride between 4-pixel groups along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                              // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192)
+wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ WgTcGeom g, float* __restrict__ dw) {
+  constexpr uint32_t KP = 32;                                    // pixels per stage
+  constexpr uint32_t A_BYTES = 128 * KP * 4, B_BYTES = BLOCK_N * KP * 4, BOX_BYTES = 32 * KP * 4;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + STAGES * A_BYTES, sBar = sB + STAGES * B_BYTES;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_tmem = sBar + 16 * STAGES;
+  const uint32_t tmem_slot = bar_tmem + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int btiles = g.Cb_pad / BLOCK_N;
+  const int at = blockIdx.x / btiles, bt = blockIdx.x - at * btiles;
+  const int tap = blockIdx.y, split = blockIdx.z;
+  const int per = (g.ntiles + g.splits - 1) / g.splits;
+  const int t_begin = split * per;
+  const int t_end = t_begin + per < g.ntiles ? t_begin + per : g.ntiles;
+  const int KB = t_end > t_begin ? t_end - t_begin : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_tmem, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BLOCK_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int cyt = g.cy[tap], cxt = g.cx[tap];
+      const CUtensorMap* mb = &maps.b[g.map[tap]];
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t par = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(bar_empty + 8 * s, par ^ 1u);
+        int t = t_begin + kb;
+        const int tx = t % g.tiles_x; t /= g.tiles_x;
+        const int ty = t % g.tiles_y;
+        const int ti = t / g.tiles_y;
+        const int gx0 = tx * g.BW, gy0 = ty * g.BH, n0 = ti * g.BI;
+        mbar_expect_tx(bar_full + 8 * s, A_BYTES + B_BYTES);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          tma_load_4d(sA + s * A_BYTES + j * BOX_BYTES, &maps.s, bar_full + 8 * s, at * 128 + j * 32, gx0, gy0, n0);
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 32; ++j)
+          tma_load_4d(sB + s * B_BYTES + j * BOX_BYTES, mb, bar_full + 8 * s, bt * BLOCK_N + j * 32, gx0 + cxt, gy0 + cyt, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // both operands MN-major: bits 15 (A) and 16 (B) of the instruction descriptor
+      constexpr uint32_t idesc = idesc_tf32(128, BLOCK_N) | (1u << 15) | (1u << 16);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t par = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(bar_full + 8 * s, par);
+        tc_fence_after();
+        const uint64_t da = smem_desc_mn_sw128_32b(sA + s * A_BYTES, BOX_BYTES), db = smem_desc_mn_sw128_32b(sB + s * B_BYTES, BOX_BYTES);
+#pragma unroll
+        for (int k = 0; k < (int)KP / 8; ++k)   // 8 pixels (one 1024-byte swizzle atom row-group) per MMA
+          tc_mma_tf32(tmem_base, da + (uint64_t)(k * (1024 >> 4)), db + (uint64_t)(k * (1024 >> 4)), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        tc_commit(bar_empty + 8 * s);
+      }
+      tc_commit(bar_tmem);
+    }
+    __syncwarp();
+  } else if (KB > 0) {
+    const int lg = warp & 3;
+    const int a = at * 128 + lg * 32 + lane;
+    float* dst = dw + ((int64_t)tap * g.Ca + a) * g.Cb_pad + bt * BLOCK_N;
+    mbar_wait(bar_tmem, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      float v[32];
+      tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), v);
+      if (g.splits == 1) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) atomicAdd(dst + c * 32 + q, v[q]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+  }
+}
+
+bool conv_wgrad_tc_supported(const ptk_conv_geom& c) {
+  if (c.k != 4 || c.stride != 2) return false;
+  const int Ca = c.transposed ? c.Cin : c.Cout, Cb = c.transposed ? c.Cout : c.Cin;
+  if (Ca % 128 != 0 || Cb % 64 != 0) return false;
+  if (c.ldx % 4 != 0 || c.ldy % 4 != 0) return false;
+  const int GH = c.transposed ? c.H : c.OH, GW = c.transposed ? c.W : c.OW;
+  if (GH < 2 || GW < 2) return false;
+  return true;
+}
+
+// dw must hold taps*Ca*Cb floats; it is fully overwritten when the launch uses a single split, otherwise the caller's
+// zero-fill is accumulated into (the function reports which via *overwrote).
+int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float* dw, cudaStream_t st) {
+  WgTcGeom g;
+  memset(&g, 0, sizeof(g));
+  WgTmapSet maps;
+  memset(&maps, 0, sizeof(maps));
+  const float *S, *Bg;
+  int lda, ldb, BHt, BWt, Cb;
+  if (!c.transposed) { S = dy; lda = c.ldy; g.Ca = c.Cout; g.GH = c.OH; g.GW = c.OW; Bg = x; ldb = c.ldx; Cb = c.Cin; BHt = c.H; BWt = c.W; }
+  else { S = x; lda = c.ldx; g.Ca = c.Cin; g.GH = c.H; g.GW = c.W; Bg = dy; ldb = c.ldy; Cb = c.Cout; BHt = c.OH; BWt = c.OW; }
+  PTK_REQUIRE((reinterpret_cast<uintptr_t>(S) & 15) == 0 && (reinterpret_cast<uintptr_t>(Bg) & 15) == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0,
+              "conv_wgrad(tc): pointers must be 16-byte aligned");
+  g.N = c.N; g.Cb_pad = Cb;
+  g.BW = pow2_ge(g.GW < 32 ? g.GW : 32);
+  g.BH = pow2_ge(g.GH < 32 / g.BW ? g.GH : 32 / g.BW);
+  g.BI = 32 / (g.BW * g.BH);
+  g.tiles_x = (g.GW + g.BW - 1) / g.BW; g.tiles_y = (g.GH + g.BH - 1) / g.BH; g.tiles_i = (c.N + g.BI - 1) / g.BI;
+  g.ntiles = g.tiles_x * g.tiles_y * g.tiles_i;
+  for (int kh = 0; kh < 4; ++kh)
+    for (int kw = 0; kw < 4; ++kw) {
+      const int t = kh * 4 + kw, qy = kh - c.pad, qx = kw - c.pad;
+      g.map[t] = (unsigned char)((((qy % 2) + 2) % 2) * 2 + (((qx % 2) + 2) % 2));
+      g.cy[t] = (signed char)floordiv2(qy); g.cx[t] = (signed char)floordiv2(qx);
+    }
+  const uint32_t box[4] = {32u, (uint32_t)g.BW, (uint32_t)g.BH, (uint32_t)g.BI};
+  {
+    const uint64_t dims[4] = {(uint64_t)g.Ca, (uint64_t)g.GW, (uint64_t)g.GH, (uint64_t)c.N};
+    const uint64_t str[3] = {(uint64_t)lda * 4, (uint64_t)g.GW * lda * 4, (uint64_t)g.GH * g.GW * lda * 4};
+    int rc = encode(&maps.s, S, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
+  for (int pyy = 0; pyy < 2; ++pyy)
+    for (int pxx = 0; pxx < 2; ++pxx) {
+      const uint64_t Hp = (uint64_t)(BHt - pyy + 1) / 2, Wp = (uint64_t)(BWt - pxx + 1) / 2;
+      const uint64_t dims[4] = {(uint64_t)Cb, Wp, Hp, (uint64_t)c.N};
+      const uint64_t str[3] = {(uint64_t)2 * ldb * 4, (uint64_t)2 * BWt * ldb * 4, (uint64_t)BHt * BWt * ldb * 4};
+      int rc = encode(&maps.b[pyy * 2 + pxx], Bg + ((int64_t)pyy * BWt + pxx) * ldb, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+      if (rc) return rc;
+    }
+  const int BN = (Cb % 128 == 0) ? 128 : 64;
+  const int base_ctas = (g.Ca / 128) * (Cb / BN) * 16;
+  int splits = (num_sms() * 4 + base_ctas - 1) / base_ctas;
+  if (splits > g.ntiles) splits = g.ntiles;
+  if (splits < 1) splits = 1;
+  // every split must own at least one pixel tile
+  while (splits > 1 && (g.ntiles + splits - 1) / splits * (splits - 1) >= g.ntiles) --splits;
+  g.splits = splits;
+  if (splits > 1) {
+    int rc = ptk_fill(dw, (int64_t)16 * g.Ca * Cb, 0.f, st);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)((g.Ca / 128) * (Cb / BN)), 16u, (unsigned)splits);
+  constexpr int STAGES = 3;
+  if (BN == 128) {
+    const size_t smem = STAGES * (128 * 128 + 128 * 128) + 16 * STAGES + 16 + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<128, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    wgrad_tc_kernel<128, STAGES><<<grid, 192, smem, st>>>(maps, g, dw);
+  } else {
+    const size_t smem = STAGES * (128 * 128 + 64 * 128) + 16 * STAGES + 16 + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<64, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    wgrad_tc_kernel<64, STAGES><<<grid, 192, smem, st>>>(maps, g, dw);
+  }
+  PTK_LAUNCH_CHECK("wgrad_tc_kernel");
   return 0;
 }
 

@@ -95,7 +95,6 @@ class ConvLayer:
             a_rows = self.cout if self.cout <= 4 else self.cout_pad
         n = self.taps * a_rows * B_pad
         dw = scratch[:n]
-        K.fill(dw, 0.0)
         K.conv_wgrad(g, x, dy, dw)
         if a_rows == A:
             K.unpack_weight_grad(dw, grad_w, A, B, self.taps, B_pad, True)

@@ -111,7 +111,7 @@ def install(K):
             z = F.conv2d(xs, w, None, stride=g.stride, padding=g.pad)
             gw, = torch.autograd.grad(z, w, dys)
             res = gw.permute(2, 3, 0, 1).reshape(k * k, g.Cout, g.Cin)       # [tap][Cout][Cin]
-        dw[:res.numel()].add_(res.reshape(-1))
+        dw[:res.numel()].copy_(res.reshape(-1))   # scratch is overwritten (include/ptk.h)
 
     def bias_grad(dy, ld, pixels, C, dbias):
         dbias.add_(dy.reshape(-1, ld)[:pixels, :C].sum(0))

@@ -50,7 +50,8 @@ def test_conv_tc_fprop_stats_dgrad(case):
     w = (torch.rand(wshape, generator=g) * 2 - 1) / (Cin * k * k / (s * s if tr else 1)) ** 0.5
     x = torch.randn(N, Cin, H, W, generator=g)
     xr = x.clone().requires_grad_(True)
-    z = F.conv_transpose2d(xr, w, None, stride=s, padding=p) if tr else F.conv2d(xr, w, None, stride=s, padding=p)
+    wr = w.clone().requires_grad_(True)
+    z = F.conv_transpose2d(xr, wr, None, stride=s, padding=p) if tr else F.conv2d(xr, wr, None, stride=s, padding=p)
     dz = torch.randn(z.shape, generator=g)
     z.backward(dz)
     zd = z.detach()
@@ -80,6 +81,14 @@ def test_conv_tc_fprop_stats_dgrad(case):
     torch.cuda.synchronize()
     gotdx = nchw(dx).cpu()
     assert rel_l2(gotdx, xr.grad) < TF32_TOL, describe(gotdx, xr.grad, "dgrad")
+
+    # wgrad on the tensor cores (MN-major operands, split-K over pixel tiles)
+    if k == 4:
+        gw = torch.zeros(wshape, device="cuda")
+        scratch = torch.full((layer.taps * layer.cin_pad * layer.cout_pad,), 3.0, device="cuda")
+        layer.wgrad(K.Slice(xin, 32, Cin), K.Slice(dzd), N, H, W, scratch, gw)
+        torch.cuda.synchronize()
+        assert rel_l2(gw, wr.grad) < TF32_TOL, describe(gw.cpu(), wr.grad, "wgrad")
 
 
 def test_conv_tc_matches_simt_full_size():

@@ -10,6 +10,25 @@ from helpers import assert_summary_close, golden, max_abs, rel_l2, summarize
 
 pytestmark = pytest.mark.gpu
 
+# Two arithmetic modes of the product are checked against the same fp32 reference goldens:
+#   "simt": every conv on the fp32 CUDA-core path (PTK_CONV_IMPL=simt)  -> tight, summation-order tolerances
+#   "auto": wide k4/s2 convs on the tcgen05 TF32 path (10-bit mantissa operands, fp32 accumulate) -> the TF32
+#           tolerances of SURVEY 8c: out_gen <= 1e-2 abs, losses <= 1e-2 rel, gradient tensors a few % in norm
+TOL = {
+    "simt": dict(out=2e-4, dout=2e-5, loss=1e-4, grad=dict(), param=dict(tol_norm=1e-4, tol_samp=2e-3, tol_scalar=2e-3),
+                 grad_rel=2e-3, grad_scalar=5e-2),
+    # (the scalar norm gains/biases have cancellation-dominated global-sum gradients: their tight check is the
+    #  "simt" mode; under TF32 they only get a sanity bound)
+    "auto": dict(out=1e-2, dout=2e-3, loss=1e-2, grad=dict(tol_norm=3e-2, tol_samp=0.15, tol_scalar=5.0),
+                 param=dict(tol_norm=1e-4, tol_samp=3e-2, tol_scalar=3e-2), grad_rel=3e-2, grad_scalar=5.0),
+}
+
+
+@pytest.fixture(params=["simt", "auto"])
+def impl(request, monkeypatch):
+    monkeypatch.setenv("PTK_CONV_IMPL", request.param)
+    return request.param
+
 
 def make_opt(H, W, P, N, content="block1_conv2", area=5, l1_w=0.01):
     return argparse.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=4,
@@ -32,7 +51,7 @@ def build_networks(H, W, P, seed):
 
 
 @pytest.mark.parametrize("tag,H,W,P,N,seed", [("64x64_p18", 64, 64, 18, 2, 0), ("128x64_p16", 128, 64, 16, 3, 1)])
-def test_networks_match_reference_golden(tag, H, W, P, N, seed):
+def test_networks_match_reference_golden(tag, H, W, P, N, seed, impl):
     from oracle import synth
     from pose_transfer_b200.utils import pose_utils
     g = golden("net_" + tag)
@@ -43,12 +62,11 @@ def test_networks_match_reference_golden(tag, H, W, P, N, seed):
         out = G(b["input"].cuda(), b["warps"].cuda(), b["masks"].cuda())
         img, src, tgt = pose_utils.get_imgpose(b["input"].cuda(), True, P)
         d_out = D(torch.cat([img, src, out, tgt], 1))
-    # fp32 CUDA-core convs: only summation-order differences vs the CPU reference
-    assert max_abs(out, g["out_gen"]) <= 2e-4
-    assert max_abs(d_out, g["d_out"]) <= 2e-5
+    assert max_abs(out, g["out_gen"]) <= TOL[impl]["out"]
+    assert max_abs(d_out, g["d_out"]) <= TOL[impl]["dout"]
 
 
-def test_module_autograd_surface():
+def test_module_autograd_surface(impl):
     """Deformable_Generator / Discriminator stay differentiable nn.Modules for external callers."""
     from oracle import restate, synth
     H = W = 64
@@ -67,9 +85,9 @@ def test_module_autograd_surface():
     for k in sorted(sd):
         assert got[k].grad is not None, k
         if sd[k].numel() == 1:
-            assert abs(float(got[k].grad) - float(sd[k].grad)) <= 5e-2 * abs(float(sd[k].grad)) + 1e-5, k
+            assert abs(float(got[k].grad) - float(sd[k].grad)) <= TOL[impl]["grad_scalar"] * abs(float(sd[k].grad)) + 1e-5, k
         else:
-            assert rel_l2(got[k].grad, sd[k].grad) <= 2e-3, k
+            assert rel_l2(got[k].grad, sd[k].grad) <= TOL[impl]["grad_rel"], k
     # discriminator through autograd, incl. gradient w.r.t. its input
     x = torch.randn(2, 42, 64, 64, generator=torch.Generator().manual_seed(2))
     xd = x.cuda().requires_grad_(True)
@@ -78,14 +96,14 @@ def test_module_autograd_surface():
     dsd = {k: v.clone().requires_grad_(True) for k, v in synth.fill_state_dict(synth.discriminator_shapes(42), seed + 1).items()}
     xr = x.clone().requires_grad_(True)
     restate.discriminator_forward(dsd, xr).sum().backward()
-    assert rel_l2(xd.grad, xr.grad) <= 2e-3
+    assert rel_l2(xd.grad, xr.grad) <= TOL[impl]["grad_rel"]
     gotd = dict(D.named_parameters())
     for k in sorted(dsd):
         if dsd[k].numel() > 1:
-            assert rel_l2(gotd[k].grad, dsd[k].grad) <= 2e-3, k
+            assert rel_l2(gotd[k].grad, dsd[k].grad) <= TOL[impl]["grad_rel"], k
 
 
-def _run_steps(tag, content, area, l1_w, steps, seed):
+def _run_steps(tag, content, area, l1_w, steps, seed, impl):
     from oracle import synth
     from pose_transfer_b200.models import pose_gan
     H = W = 64
@@ -105,8 +123,10 @@ def _run_steps(tag, content, area, l1_w, steps, seed):
         b = synth.make_batch(N, H, W, P, seed=seed + 10 * s)
         r = synth.make_batch(N, H, W, P, seed=seed + 10 * s + 1)
         b2 = synth.make_batch(N, H, W, P, seed=seed + 10 * s + 2)
-        rt = 1e-4 if s == 0 else 5e-3
-        loose = {} if s == 0 else dict(tol_norm=5e-2, tol_samp=0.6, tol_scalar=0.8)
+        T = TOL[impl]
+        rt = T["loss"] if s == 0 else max(5e-3, T["loss"])
+        loose = T["grad"] if s == 0 else dict(tol_norm=5e-2, tol_samp=0.6, tol_scalar=0.8)
+        ptol = T["param"] if s == 0 else dict(tol_norm=1e-3, tol_samp=5e-2, tol_scalar=5e-2)
         dl = model.dis_update(b["input"].cuda(), b["target"].cuda(), {"warps": b["warps"].cuda(), "masks": b["masks"].cuda()},
                               r["input"].cuda(), r["target"].cuda(), od, drop=synth.dropout_masks(N, 512, 3, seed=seed + 10 * s))
         np.testing.assert_allclose(dl, g["d_loss_%d" % s], rtol=rt)
@@ -117,24 +137,20 @@ def _run_steps(tag, content, area, l1_w, steps, seed):
                                       {"warps": b2["warps"].cuda(), "masks": b2["masks"].cuda()}, od,
                                       drop=synth.dropout_masks(N, 512, 3, seed=seed + 10 * s + 2))
         np.testing.assert_allclose(gl, g["g_loss_%d" % s], rtol=rt)
-        assert max_abs(out, g["out_gen_%d" % s]) <= (2e-4 if s == 0 else 5e-3)
+        assert max_abs(out, g["out_gen_%d" % s]) <= (T["out"] if s == 0 else max(5e-3, T["out"]))
         gnames = sorted(k for k, _ in model.gen.named_parameters())
         gpar = dict(model.gen.named_parameters())
         assert_summary_close(np.stack([summarize(gpar[k].grad) for k in gnames]), g["g_grad_%d" % s], what="g_grad", **loose)
-        assert_summary_close(np.stack([summarize(gpar[k]) for k in gnames]), g["g_param_%d" % s],
-                             tol_norm=1e-4 if s == 0 else 1e-3, tol_samp=2e-3 if s == 0 else 5e-2,
-                             tol_scalar=2e-3 if s == 0 else 5e-2, what="g_param")
-        assert_summary_close(np.stack([summarize(dpar[k]) for k in dnames]), g["d_param_%d" % s],
-                             tol_norm=1e-4 if s == 0 else 1e-3, tol_samp=2e-3 if s == 0 else 5e-2,
-                             tol_scalar=2e-3 if s == 0 else 5e-2, what="d_param")
+        assert_summary_close(np.stack([summarize(gpar[k]) for k in gnames]), g["g_param_%d" % s], what="g_param", **ptol)
+        assert_summary_close(np.stack([summarize(dpar[k]) for k in dnames]), g["d_param_%d" % s], what="d_param", **ptol)
 
 
-def test_train_step_nn_loss_matches_reference_golden():
-    _run_steps("64x64_p18_nn5", "block1_conv2", 5, 0.01, 2, 0)
+def test_train_step_nn_loss_matches_reference_golden(impl):
+    _run_steps("64x64_p18_nn5", "block1_conv2", 5, 0.01, 2, 0, impl)
 
 
-def test_train_step_l1_matches_reference_golden():
-    _run_steps("64x64_p18_l1", "none", 1, 100.0, 1, 3)
+def test_train_step_l1_matches_reference_golden(impl):
+    _run_steps("64x64_p18_l1", "none", 1, 100.0, 1, 3, impl)
 
 
 def test_checkpoint_roundtrip(tmp_path):
