@@ -216,6 +216,14 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    if args.ncu_step:
+        # for `ncu --profile-from-start off`: exactly one resident step inside the profiler range, nothing else
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -284,6 +292,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE configs[1]: 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true", help="profiling aid: warm up, then run ONE step inside "
+                    "cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off); prints no result line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

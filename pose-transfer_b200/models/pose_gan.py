@@ -122,7 +122,8 @@ class DeformablePose_GAN(nn.Module):
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
             self.rank = torch.distributed.get_rank()
-            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", self.rank % max(torch.cuda.device_count(), 1))))
+            if torch.cuda.is_available():
+                torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", self.rank % max(torch.cuda.device_count(), 1))))
         else:
             self.world, self.rank = 1, 0
 
