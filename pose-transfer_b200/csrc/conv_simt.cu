@@ -234,6 +234,126 @@ conv_narrow_fwd_kernel(TapGeom g, const float* __restrict__ x, const float* __re
   }
 }
 
+
+// ---------------------------------------------------------------- k3/s1/p1 narrow-N convolution (generator head)
+// Conv(256->3,k3,p1)+bias+tanh (models/networks.py:232 + Tanh): 3.6 GFMA per 8 images but only 3 output channels, so
+// it is scheduled as a stencil: 16x16-pixel tiles, 16-channel chunks staged in shared memory (halo 1), weights in
+// __constant__ memory so every FFMA takes its weight as a uniform constant operand (no load instruction).
+constexpr int kNarrowMaxW = 12288;                 // floats: taps(9) * Cin(<=256) * 4 fits with room to spare
+__constant__ float c_narrow_w[kNarrowMaxW];        // [tap][ci][4]
+
+__global__ void __launch_bounds__(256)
+conv_k3_narrow_fwd_kernel(const float* __restrict__ x, int ldx, int Cin, int H, int W, int Cout,
+                          const float* __restrict__ bias, int act, float* __restrict__ y, int ldy,
+                          float* __restrict__ y_nchw) {
+  constexpr int T = 16, R = T + 2, CH = 16, LD = 20;   // LD: padded pixel stride in floats (bank-conflict free float4 reads)
+  __shared__ __align__(16) float s_in[R * R * LD];
+  const int n = blockIdx.z, ty0 = blockIdx.y * T, tx0 = blockIdx.x * T;
+  const int tid = threadIdx.x, ly = tid / T, lx = tid % T;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* xb = x + (int64_t)n * H * W * ldx;
+  for (int c0 = 0; c0 < Cin; c0 += CH) {
+    __syncthreads();
+    for (int i = tid; i < R * R * (CH / 4); i += 256) {
+      const int p = i / (CH / 4), c4 = (i % (CH / 4)) * 4;
+      const int yy = ty0 - 1 + p / R, xx = tx0 - 1 + p % R;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = ldg4(xb + ((int64_t)yy * W + xx) * ldx + c0 + c4);
+      *reinterpret_cast<float4*>(&s_in[p * LD + c4]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* ip = &s_in[((ly + ky) * R + lx + kx) * LD];
+        const float* wp = &c_narrow_w[((ky * 3 + kx) * Cin + c0) * 4];
+#pragma unroll
+        for (int c4 = 0; c4 < CH; c4 += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(ip + c4);
+          const float in[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[0] = fmaf(in[j], wp[(c4 + j) * 4 + 0], acc[0]);
+            acc[1] = fmaf(in[j], wp[(c4 + j) * 4 + 1], acc[1]);
+            acc[2] = fmaf(in[j], wp[(c4 + j) * 4 + 2], acc[2]);
+            acc[3] = fmaf(in[j], wp[(c4 + j) * 4 + 3], acc[3]);
+          }
+        }
+      }
+  }
+  const int oy = ty0 + ly, ox = tx0 + lx;
+  if (oy < H && ox < W) {
+    for (int co = 0; co < Cout; ++co) {
+      float v = acc[co] + (bias ? __ldg(bias + co) : 0.f);
+      v = apply_act(v, act);
+      if (y) y[(((int64_t)n * H + oy) * W + ox) * ldy + co] = v;
+      if (y_nchw) y_nchw[(((int64_t)n * Cout + co) * H + oy) * W + ox] = v;
+    }
+  }
+}
+
+// Weight gradient of the same layer: dw[tap][co][ci] += sum_pixels dy[pix][co] * x[pix + tap][ci].
+// One thread per input channel, marching along input rows with a sliding 3x3 window of dy (float4 = 3 channels +
+// zero pad per pixel) kept in registers: per input pixel 1 coalesced load of x, 3 broadcast loads of dy, 27 FMAs.
+__global__ void __launch_bounds__(256)
+conv_k3_narrow_wgrad_kernel(const float* __restrict__ x, int ldx, int Cin, const float* __restrict__ dy, int lddy,
+                            int N, int H, int W, int Cout, int rows_per_block, float* __restrict__ dw) {
+  const int ci = blockIdx.y * 256 + threadIdx.x;
+  const bool live = ci < Cin;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t rows = (int64_t)N * H;
+  float acc[9][3];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = acc[t][2] = 0.f;
+  for (int64_t r = row0; r < row0 + rows_per_block && r < rows; ++r) {
+    const int n = (int)(r / H), yi = (int)(r - (int64_t)n * H);
+    const float* xrow = x + (((int64_t)n * H + yi) * W) * ldx + ci;
+    // dy rows oy = yi - ky + 1  (ky = 0,1,2)
+    const float* drow[3];
+    bool dok[3];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int oy = yi - ky + 1;
+      dok[ky] = oy >= 0 && oy < H;
+      drow[ky] = dy + (((int64_t)n * H + (dok[ky] ? oy : 0)) * W) * lddy;
+    }
+    // window columns: ox = xi - kx + 1 ; win[ky][j] holds dy at column (xi - 1 + j), j = 0..2  => kx = 2 - j
+    float4 win[3][3];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      win[ky][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      win[ky][1] = dok[ky] ? ldg4(drow[ky]) : make_float4(0.f, 0.f, 0.f, 0.f);            // column 0
+      win[ky][2] = (dok[ky] && W > 1) ? ldg4(drow[ky] + lddy) : make_float4(0.f, 0.f, 0.f, 0.f);  // column 1
+    }
+    // at step xi the window must hold columns xi-1, xi, xi+1: initial state is for xi = 0
+    for (int xi = 0; xi < W; ++xi) {
+      const float xv = live ? __ldg(xrow + (int64_t)xi * ldx) : 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int kx = 2 - j;
+          acc[ky * 3 + kx][0] = fmaf(win[ky][j].x, xv, acc[ky * 3 + kx][0]);
+          acc[ky * 3 + kx][1] = fmaf(win[ky][j].y, xv, acc[ky * 3 + kx][1]);
+          acc[ky * 3 + kx][2] = fmaf(win[ky][j].z, xv, acc[ky * 3 + kx][2]);
+        }
+      // slide: drop column xi-1, fetch column xi+2
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        win[ky][0] = win[ky][1];
+        win[ky][1] = win[ky][2];
+        win[ky][2] = (dok[ky] && xi + 2 < W) ? ldg4(drow[ky] + (int64_t)(xi + 2) * lddy) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      for (int co = 0; co < Cout; ++co) atomicAdd(dw + ((int64_t)t * Cout + co) * Cin + ci, acc[t][co]);
+  }
+}
+
 // ---------------------------------------------------------------- weight gradient
 // dw[t][a][b] += sum_m S[m][a] * Bg[pix(m,t)][b]  (S = "small-grid" tensor, Bg = strided-gather tensor).
 struct WgradGeom {
@@ -401,7 +521,16 @@ int conv_forward_simt(const ptk_conv_geom& c, const float* x, const float* w_t, 
       make_geom(c, py, px, cout_pad, &g);
       const int64_t M = (int64_t)g.N * g.GH * g.GW;
       if (M == 0) continue;
-      if (c.Cout <= 4) {
+      if (c.Cout <= 4 && !c.transposed && c.k == 3 && c.stride == 1 && c.pad == 1 && c.Cin % 16 == 0 &&
+          9 * c.Cin * 4 <= kNarrowMaxW && c.N <= 65535) {
+        // weights [tap][Cin][cout_pad(=4)] -> constant memory (device-to-device, stream ordered)
+        PTK_REQUIRE(cout_pad == 4, "k3 narrow conv: packed Cout must be 4");
+        cudaError_t ce = cudaMemcpyToSymbolAsync(c_narrow_w, w_t, sizeof(float) * 9 * c.Cin * 4, 0, cudaMemcpyDeviceToDevice, st);
+        if (ce != cudaSuccess) return fail(3, "cudaMemcpyToSymbolAsync: %s", cudaGetErrorString(ce));
+        dim3 grid((c.W + 15) / 16, (c.H + 15) / 16, c.N);
+        conv_k3_narrow_fwd_kernel<<<grid, 256, 0, st>>>(x, c.ldx, c.Cin, c.H, c.W, c.Cout, bias, act, y, c.ldy, y_nchw);
+        PTK_LAUNCH_CHECK("conv_k3_narrow_fwd_kernel");
+      } else if (c.Cout <= 4) {
         const int smem = g.ntaps * g.Cin * g.Cout * (int)sizeof(float);
         PTK_REQUIRE(smem <= 200 * 1024, "narrow conv: weights do not fit in shared memory");
         cudaFuncSetAttribute(conv_narrow_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -445,9 +574,19 @@ int conv_wgrad_simt(const ptk_conv_geom& c, const float* x, const float* dy, flo
       g.dx[kh * c.k + kw] = (signed char)(kw - c.pad);
     }
   const int64_t M = (int64_t)g.N * g.GH * g.GW;
+  if (g.Ca <= 3 && !c.transposed && c.k == 3 && c.stride == 1 && c.pad == 1 && c.ldy % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    const int64_t rows = (int64_t)c.N * c.H;
+    int rpb = (int)((rows + (int64_t)num_sms() * 4 - 1) / ((int64_t)num_sms() * 4));
+    if (rpb < 1) rpb = 1;
+    dim3 grid((unsigned)((rows + rpb - 1) / rpb), (c.Cin + 255) / 256);
+    conv_k3_narrow_wgrad_kernel<<<grid, 256, 0, st>>>(x, c.ldx, c.Cin, dy, c.ldy, c.N, c.H, c.W, c.Cout, rpb, dw);
+    PTK_LAUNCH_CHECK("conv_k3_narrow_wgrad_kernel");
+    return 0;
+  }
   if (g.Ca <= 4) {
     g.splits = 1;
-    int chunks = (int)((M + 255) / 256);
+    int chunks = (int)((M + 15) / 16);
     const int cap = num_sms() * 4;
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;

@@ -176,12 +176,19 @@ class GeneratorEngine:
     def pack_weights(self, backward=False):
         for c in self.all_convs:
             c.pack_forward()
-            if backward:
-                c.pack_backward()
+        self.packed_version = getattr(self.m, "_ptk_weights_version", None)
 
     def pack_weights_backward(self):
         for c in self.all_convs:
             c.pack_backward()
+
+    def _need_repack(self, repack):
+        """repack=True: always; None: only if the owning module's weight version moved since the last pack
+        (bumped by FlatAdam.step / load_state_dict / ParamArena.bind)."""
+        if repack is None:
+            v = getattr(self.m, "_ptk_weights_version", None)
+            return v is None or v != getattr(self, "packed_version", -1) or self.all_convs[0].w_fwd is None
+        return bool(repack)
 
     # ------------------------------------------------------------------ geometry helpers
     def _sizes(self, H, W):
@@ -216,7 +223,7 @@ class GeneratorEngine:
             masks = masks.double()
         Kp = warps.shape[1]
         H0, W0 = self.image_size
-        if repack:
+        if self._need_repack(repack):
             self.pack_weights()
         hs, wsz = self._sizes(H, W)
         tag = "%d_%d_%d" % (N, H, W)
@@ -315,8 +322,9 @@ class GeneratorEngine:
         return out
 
     # ------------------------------------------------------------------ backward
-    def backward(self, grads, dout_nchw=None, dout_nhwc=None, repack=True):
+    def backward(self, grads, dout_nchw=None, dout_nhwc=None):
         """Accumulate parameter gradients into `grads` (dict: parameter -> fp32 tensor of the same shape).
+        Uses the weight packs of the preceding forward().
         dout_nchw [N,3,H,W] and/or dout_nhwc (Slice over [N,H,W,*]) are gradients w.r.t. out_gen."""
         sv = self.saved
         assert sv is not None, "forward() must run before backward()"
@@ -324,8 +332,6 @@ class GeneratorEngine:
         N, H, W, hs, wsz, tag = sv["N"], sv["H"], sv["W"], sv["hs"], sv["ws"], sv["tag"]
         cats, stats, st_idx, drops = sv["cats"], sv["stats"], sv["st_idx"], sv["drops"]
         H0, W0 = self.image_size
-        if repack:
-            self.pack_weights_backward()
         max_w = max(c.taps * c.cin_pad * c.cout_pad for c in self.all_convs)
         scratch = ws.get("wgrad_scratch", (max_w,))
         sums = ws.get("sums" + tag, tuple(stats.shape), torch.float64, zero=True)
@@ -435,15 +441,16 @@ class DiscriminatorEngine:
         self._ensure(device)
         return self.ws.get("din_%d_%d_%d" % (M, H, W), (M, H, W, ceil4(self.m.input_nc)))
 
-    def pack_weights(self, backward=False):
+    def pack_weights(self):
         for c in self.convs:
             c.pack_forward()
-            if backward:
-                c.pack_backward()
+        self.packed_version = getattr(self.m, "_ptk_weights_version", None)
 
-    def pack_weights_backward(self):
-        for c in self.convs:
-            c.pack_backward()
+    def _need_repack(self, repack):
+        if repack is None:
+            v = getattr(self.m, "_ptk_weights_version", None)
+            return v is None or v != getattr(self, "packed_version", -1) or self.convs[0].w_fwd is None
+        return bool(repack)
 
     def forward(self, din, repack=True, probs=False):
         """din = input_buffer() filled by the caller.  Returns logits [M, OH*OW] (pre-sigmoid), or the sigmoid
@@ -451,7 +458,7 @@ class DiscriminatorEngine:
         M, H, W, _ = din.shape
         self._ensure(din.device)
         ws = self.ws
-        if repack:
+        if self._need_repack(repack):
             self.pack_weights()
         tag = "%d_%d_%d" % (M, H, W)
         nl = len(self.convs)
@@ -484,15 +491,13 @@ class DiscriminatorEngine:
         self.saved = sv
         return x
 
-    def backward(self, dlogits4, grads=None, need_input_grad=False, repack=True):
+    def backward(self, dlogits4, grads=None, need_input_grad=False):
         """dlogits4: [M*J, 4] (gradient w.r.t. the logits in channel 0, zero padding in 1..3).
         grads: dict parameter -> gradient tensor (None => no weight gradients, G-step use).
         Returns the gradient w.r.t. the NHWC input buffer if need_input_grad."""
         sv = self.saved
         ws = self.ws
         M, tag = sv["M"], sv["tag"]
-        if repack:
-            self.pack_weights_backward()
         nl = len(self.convs)
         stats = sv["stats"]
         sums = ws.get("dsums" + tag, tuple(stats.shape), torch.float64, zero=True)

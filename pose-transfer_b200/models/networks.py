@@ -49,6 +49,11 @@ class Cropping2D(nn.Module):
         return input[:, :, self.crop_size:-self.crop_size, self.crop_size:-self.crop_size]
 
 
+def _bump_weights_version(module, incompatible_keys):
+    """load_state_dict post hook: the engines' GEMM-layout weight copies are stale."""
+    module._ptk_weights_version = getattr(module, "_ptk_weights_version", 0) + 1
+
+
 def _no_eager(name):
     raise RuntimeError("%s.forward: this module only owns parameters; the computation runs inside the fused "
                        "CUDA schedule of its parent network (no eager fallback)" % name)
@@ -173,6 +178,8 @@ class Deformable_Generator(nn.Module):
         self.decoder = decoder(nfilters_dec, nfilters_enc, self.num_skips)
         self.engine = GeneratorEngine(self)
         self._drop_queue = None
+        self._ptk_weights_version = 0
+        self.register_load_state_dict_post_hook(_bump_weights_version)
 
     def set_dropout_noise(self, drops):
         """Test hook: the next forward uses these three [N,512,1,1] noise tensors instead of drawing."""
@@ -262,6 +269,8 @@ class Discriminator(nn.Module):
         self.checkMode = checkMode
         self.net = self.build_net()
         self.engine = DiscriminatorEngine(self)
+        self._ptk_weights_version = 0
+        self.register_load_state_dict_post_hook(_bump_weights_version)
 
     def build_net(self):
         model = [nn.Conv2d(self.input_nc, 64, kernel_size=4, stride=2), Block(64, 128), Block(128, 256)]

@@ -33,7 +33,12 @@ class ParamArena:
         self.params = [p for p in module.parameters()]
         self.bind()
 
+    def bump(self):
+        """Weights changed: the engines' GEMM-layout copies are stale."""
+        self.module._ptk_weights_version = getattr(self.module, "_ptk_weights_version", 0) + 1
+
     def bind(self):
+        self.bump()
         dev = self.params[0].device
         total = 0
         self.offsets = []
@@ -87,6 +92,7 @@ class FlatAdam(torch.optim.Optimizer):
         a = self.arena
         K.adam_step(a.flat, a.grad, a.exp_avg, a.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"], self.steps,
                     self.grad_scale)
+        a.bump()
 
     def zero_grad(self, set_to_none=False):
         self.arena.zero_grad()
@@ -193,8 +199,8 @@ class DeformablePose_GAN(nn.Module):
         din = self.disc.engine.input_buffer(N, H, W, dev)
         self._fill_disc_input(din, input, None, P)
         out_gen = self.gen.engine.forward(input, warps, masks, drop=drop if drop is not None else self.gen._next_drop(),
-                                          d_input=Slice(din, 3 + P, 3))
-        logits = self.disc.engine.forward(din)
+                                          repack=None, d_input=Slice(din, 3 + P, 3))
+        logits = self.disc.engine.forward(din, repack=None)
         J = logits.shape[1]
         dlog4 = self.disc.engine.ws.get("dlog4_%d_%d" % (N, J), (N * J, 4))
         # ad_loss = sum_n -mean_j log(out+1e-7), * gan_penalty_weight / batch_size   (pose_gan.py:90-98,107)
@@ -240,8 +246,8 @@ class DeformablePose_GAN(nn.Module):
         self._fill_disc_input(din[:nr], real_inp, real_target, P)        # real rows first (pose_gan.py:136)
         self._fill_disc_input(din[nr:], input, None, P)
         self.gen.engine.forward(input, warps, masks, drop=drop if drop is not None else self.gen._next_drop(),
-                                d_input=Slice(din[nr:], 3 + P, 3))
-        logits = self.disc.engine.forward(din)
+                                repack=None, d_input=Slice(din[nr:], 3 + P, 3))
+        logits = self.disc.engine.forward(din, repack=None)
         J = logits.shape[1]
         dlog4 = self.disc.engine.ws.get("dlog4_%d_%d" % (M, J), (M * J, 4))
         # rows < opt['batch_size'] are "true", the rest "fake"; both * gan_w / self.batch_size (pose_gan.py:140-163)

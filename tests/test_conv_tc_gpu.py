@@ -110,3 +110,60 @@ def test_conv_tc_matches_simt_full_size():
         outs.append(y)
     torch.cuda.synchronize()
     assert rel_l2(outs[1], outs[0]) < TF32_TOL
+
+
+def _network_layer_geometries():
+    """(name, transposed, pad, Cin, Cout, N, H, W) of every k4/s2 layer of G and D at 64x64 (N=2), the deep (small
+    spatial extent) layers at 256x256 (N=8) and the odd-extent PatchGAN layers."""
+    out = []
+    enc64 = (64, 128, 256, 512, 512, 512)
+    dec64 = (512, 512, 512, 256, 128, 3)
+    hs = [64, 32, 16, 8, 4, 2]
+    for i in range(1, 6):
+        out.append(("enc64_%d" % i, False, 1, enc64[i - 1], enc64[i], 2, hs[i - 1], hs[i - 1]))
+    for j in range(5):
+        i = 5 - j
+        cin = 2 * enc64[5] if j == 0 else 2 * enc64[i] + dec64[j - 1]
+        out.append(("dec64_%d" % j, True, 1, cin, dec64[j], 2, hs[i], hs[i]))
+    for i, (ci, co, h) in enumerate(((64, 128, 31), (128, 256, 15), (256, 512, 7))):
+        out.append(("disc64_%d" % (i + 1), False, 1, ci, co, 4, h, h))
+    for (ci, co, h) in ((512, 512, 16), (512, 512, 8)):
+        out.append(("enc256_%dto%d" % (h, h // 2), False, 1, ci, co, 8, h, h))
+    for (ci, co, h) in ((1024, 512, 4), (1536, 512, 8)):
+        out.append(("dec256_%d" % h, True, 1, ci, co, 8, h, h))
+    for i, (ci, co, h) in enumerate(((64, 128, 127), (128, 256, 63), (256, 512, 31))):
+        out.append(("disc256_%d" % (i + 1), False, 1, ci, co, 4, h, h))
+    return out
+
+
+@pytest.mark.parametrize("geo", _network_layer_geometries(), ids=[g[0] for g in _network_layer_geometries()])
+def test_conv_tc_vs_simt_on_network_geometries(geo):
+    """Every op the engines may route to the tensor cores, on the exact layer geometries of the networks:
+    tcgen05 result vs the fp32 CUDA-core kernels on the same device (no CPU reference needed)."""
+    import pose_transfer_b200  # noqa: F401
+    from pose_transfer_b200 import kernels as K
+    from pose_transfer_b200.engine import ConvLayer
+    name, tr, p, Cin, Cout, N, H, W = geo
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    wshape = (Cin, Cout, 4, 4) if tr else (Cout, Cin, 4, 4)
+    w = ((torch.rand(wshape, generator=g) * 2 - 1) / (Cin * 4) ** 0.5).cuda()
+    x = torch.randn(N, H, W, Cin, generator=g).cuda()
+    res = {}
+    for impl in (K.IMPL_SIMT, K.IMPL_AUTO):
+        layer = ConvLayer(torch.nn.Parameter(w), None, tr, 4, 2, p)
+        layer.impl = impl
+        layer.pack_forward()
+        OH, OW = layer.out_hw(H, W)
+        y = torch.zeros(N, OH, OW, Cout, device="cuda")
+        stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+        layer.forward(K.Slice(x), N, H, W, K.Slice(y), K.ACT_NONE, stats)
+        dy = torch.randn(N, OH, OW, Cout, generator=torch.Generator().manual_seed(7)).cuda()
+        dx = torch.zeros(N, H, W, Cin, device="cuda")
+        layer.dgrad(K.Slice(dy), N, H, W, K.Slice(dx))
+        gw = torch.zeros(wshape, device="cuda")
+        scratch = torch.full((layer.taps * layer.cin_pad * layer.cout_pad,), 3.0, device="cuda")
+        layer.wgrad(K.Slice(x), K.Slice(dy), N, H, W, scratch, gw)
+        torch.cuda.synchronize()
+        res[impl] = (y, stats, dx, gw)
+    for what, a, b in zip(("fprop", "stats", "dgrad", "wgrad"), res[K.IMPL_AUTO], res[K.IMPL_SIMT]):
+        assert rel_l2(a, b) < TF32_TOL, describe(a.float().cpu(), b.float().cpu(), "%s %s" % (name, what))

