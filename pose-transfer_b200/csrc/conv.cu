@@ -27,8 +27,8 @@ extern "C" int ptk_conv_forward(const ptk_conv_geom* g, const float* x, const fl
     PTK_REQUIRE(conv_tc_supported(*g), "conv_forward: geometry not supported by the tcgen05 path");
     use_tc = true;
   } else if (g->impl == PTK_IMPL_AUTO) {
-    use_tc = w_k != nullptr && y != nullptr && y_nchw == nullptr && bias == nullptr && act == PTK_ACT_NONE &&
-             conv_tc_supported(*g);
+    use_tc = w_k != nullptr && y != nullptr && y_nchw == nullptr &&
+             (act == PTK_ACT_NONE || act == PTK_ACT_LEAKY || act == PTK_ACT_RELU) && conv_tc_supported(*g);
   }
   if (use_tc) {
     PTK_REQUIRE(w_k != nullptr && y != nullptr && y_nchw == nullptr, "conv_forward(tc): needs w_k and an NHWC destination");

@@ -128,7 +128,7 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(192)
 conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcGeom g, float* __restrict__ y,
-               double* __restrict__ stats) {
+               double* __restrict__ stats, const float* __restrict__ bias, int act) {
   constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BLOCK_N * 128;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -214,11 +214,20 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
       float v[32];
       tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), v);
       if (valid) {
+        if (bias != nullptr) {
+          const float* bp = bias + blockIdx.y * BLOCK_N + c * 32;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] += __ldg(bp + q);
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) { s1 += v[q]; s2 = fmaf(v[q], v[q], s2); }
+        if (act != PTK_ACT_NONE) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = apply_act(v[q], act);
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-#pragma unroll
-        for (int q = 0; q < 32; ++q) { s1 += v[q]; s2 = fmaf(v[q], v[q], s2); }
       }
     }
     if (stats != nullptr) {
@@ -287,7 +296,7 @@ bool conv_tc_supported(const ptk_conv_geom& c) {
 
 int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, const float* bias, int act, float* y,
                     double* stats, cudaStream_t st) {
-  PTK_REQUIRE(bias == nullptr && act == PTK_ACT_NONE, "conv_forward(tc): bias / activation epilogues are not implemented");
+  PTK_REQUIRE(act == PTK_ACT_NONE || act == PTK_ACT_LEAKY || act == PTK_ACT_RELU, "conv_forward(tc): unsupported activation epilogue");
   PTK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(w_k) & 15) == 0, "conv_forward(tc): pointers must be 16-byte aligned");
   TcGeom g;
@@ -368,13 +377,13 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     const size_t smem = STAGES * (128 * 128 + 128 * 128) + 16 * STAGES + 16 + 1024;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<128, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    conv_tc_kernel<128, STAGES><<<grid, 192, smem, st>>>(maps, g, y, stats);
+    conv_tc_kernel<128, STAGES><<<grid, 192, smem, st>>>(maps, g, y, stats, bias, act);
   } else {
     constexpr int STAGES = 4;
     const size_t smem = STAGES * (128 * 128 + 64 * 128) + 16 * STAGES + 16 + 1024;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<64, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    conv_tc_kernel<64, STAGES><<<grid, 192, smem, st>>>(maps, g, y, stats);
+    conv_tc_kernel<64, STAGES><<<grid, 192, smem, st>>>(maps, g, y, stats, bias, act);
   }
   PTK_LAUNCH_CHECK("conv_tc_kernel");
   return 0;
@@ -389,6 +398,7 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
 // (4-pixel groups 512 B apart = SBO, next 32 channels = next box = LBO).  Split-K over pixel tiles across CTAs.
 struct WgTcGeom {
   int N, GH, GW;                 // small grid
+  int ntaps;
   int BW, BH, BI, tiles_x, tiles_y, tiles_i, ntiles;
   int Ca, Cb_pad;                // dw[t][Ca][Cb_pad]
   int splits;
@@ -496,6 +506,7 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
     for (int c = 0; c < BLOCK_N / 32; ++c) {
       float v[32];
       tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), v);
+      if (a >= g.Ca) continue;       // rows beyond Ca were TMA zero-fill (Ca = 64 layers use half of the M = 128 tile)
       if (g.splits == 1) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -515,9 +526,9 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
 }
 
 bool conv_wgrad_tc_supported(const ptk_conv_geom& c) {
-  if (c.k != 4 || c.stride != 2) return false;
+  if (!((c.k == 4 && c.stride == 2) || (c.k == 3 && c.stride == 1 && !c.transposed))) return false;
   const int Ca = c.transposed ? c.Cin : c.Cout, Cb = c.transposed ? c.Cout : c.Cin;
-  if (Ca % 128 != 0 || Cb % 64 != 0) return false;
+  if (Ca % 64 != 0 || Cb % 32 != 0) return false;
   if (c.ldx % 4 != 0 || c.ldy % 4 != 0) return false;
   const int GH = c.transposed ? c.H : c.OH, GW = c.transposed ? c.W : c.OW;
   if (GH < 2 || GW < 2) return false;
@@ -543,11 +554,16 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
   g.BI = 32 / (g.BW * g.BH);
   g.tiles_x = (g.GW + g.BW - 1) / g.BW; g.tiles_y = (g.GH + g.BH - 1) / g.BH; g.tiles_i = (c.N + g.BI - 1) / g.BI;
   g.ntiles = g.tiles_x * g.tiles_y * g.tiles_i;
-  for (int kh = 0; kh < 4; ++kh)
-    for (int kw = 0; kw < 4; ++kw) {
-      const int t = kh * 4 + kw, qy = kh - c.pad, qx = kw - c.pad;
-      g.map[t] = (unsigned char)((((qy % 2) + 2) % 2) * 2 + (((qx % 2) + 2) % 2));
-      g.cy[t] = (signed char)floordiv2(qy); g.cx[t] = (signed char)floordiv2(qx);
+  g.ntaps = c.k * c.k;
+  for (int kh = 0; kh < c.k; ++kh)
+    for (int kw = 0; kw < c.k; ++kw) {
+      const int t = kh * c.k + kw, qy = kh - c.pad, qx = kw - c.pad;
+      if (c.stride == 2) {
+        g.map[t] = (unsigned char)((((qy % 2) + 2) % 2) * 2 + (((qx % 2) + 2) % 2));
+        g.cy[t] = (signed char)floordiv2(qy); g.cx[t] = (signed char)floordiv2(qx);
+      } else {
+        g.map[t] = 0; g.cy[t] = (signed char)qy; g.cx[t] = (signed char)qx;
+      }
     }
   const uint32_t box[4] = {32u, (uint32_t)g.BW, (uint32_t)g.BH, (uint32_t)g.BI};
   {
@@ -556,16 +572,24 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     int rc = encode(&maps.s, S, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
-  for (int pyy = 0; pyy < 2; ++pyy)
-    for (int pxx = 0; pxx < 2; ++pxx) {
-      const uint64_t Hp = (uint64_t)(BHt - pyy + 1) / 2, Wp = (uint64_t)(BWt - pxx + 1) / 2;
-      const uint64_t dims[4] = {(uint64_t)Cb, Wp, Hp, (uint64_t)c.N};
-      const uint64_t str[3] = {(uint64_t)2 * ldb * 4, (uint64_t)2 * BWt * ldb * 4, (uint64_t)BHt * BWt * ldb * 4};
-      int rc = encode(&maps.b[pyy * 2 + pxx], Bg + ((int64_t)pyy * BWt + pxx) * ldb, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-      if (rc) return rc;
-    }
-  const int BN = (Cb % 128 == 0) ? 128 : 64;
-  const int base_ctas = (g.Ca / 128) * (Cb / BN) * 16;
+  if (c.stride == 2) {
+    for (int pyy = 0; pyy < 2; ++pyy)
+      for (int pxx = 0; pxx < 2; ++pxx) {
+        const uint64_t Hp = (uint64_t)(BHt - pyy + 1) / 2, Wp = (uint64_t)(BWt - pxx + 1) / 2;
+        const uint64_t dims[4] = {(uint64_t)Cb, Wp, Hp, (uint64_t)c.N};
+        const uint64_t str[3] = {(uint64_t)2 * ldb * 4, (uint64_t)2 * BWt * ldb * 4, (uint64_t)BHt * BWt * ldb * 4};
+        int rc = encode(&maps.b[pyy * 2 + pxx], Bg + ((int64_t)pyy * BWt + pxx) * ldb, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+      }
+  } else {
+    const uint64_t dims[4] = {(uint64_t)Cb, (uint64_t)BWt, (uint64_t)BHt, (uint64_t)c.N};
+    const uint64_t str[3] = {(uint64_t)ldb * 4, (uint64_t)BWt * ldb * 4, (uint64_t)BHt * BWt * ldb * 4};
+    int rc = encode(&maps.b[0], Bg, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
+  const int BN = (Cb % 128 == 0) ? 128 : (Cb % 64 == 0 ? 64 : 32);
+  const int atiles = (g.Ca + 127) / 128;
+  const int base_ctas = atiles * (Cb / BN) * g.ntaps;
   int splits = (num_sms() * 4 + base_ctas - 1) / base_ctas;
   if (splits > g.ntiles) splits = g.ntiles;
   if (splits < 1) splits = 1;
@@ -573,12 +597,17 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
   while (splits > 1 && (g.ntiles + splits - 1) / splits * (splits - 1) >= g.ntiles) --splits;
   g.splits = splits;
   if (splits > 1) {
-    int rc = ptk_fill(dw, (int64_t)16 * g.Ca * Cb, 0.f, st);
+    int rc = ptk_fill(dw, (int64_t)g.ntaps * g.Ca * Cb, 0.f, st);
     if (rc) return rc;
   }
-  dim3 grid((unsigned)((g.Ca / 128) * (Cb / BN)), 16u, (unsigned)splits);
+  dim3 grid((unsigned)(atiles * (Cb / BN)), (unsigned)g.ntaps, (unsigned)splits);
   constexpr int STAGES = 3;
-  if (BN == 128) {
+  if (BN == 32) {
+    const size_t smem = STAGES * (128 * 128 + 32 * 128) + 16 * STAGES + 16 + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<32, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    wgrad_tc_kernel<32, STAGES><<<grid, 192, smem, st>>>(maps, g, dw);
+  } else if (BN == 128) {
     const size_t smem = STAGES * (128 * 128 + 128 * 128) + 16 * STAGES + 16 + 1024;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<128, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }

@@ -18,6 +18,14 @@ def ceil4(x):
     return (x + 3) // 4 * 4
 
 
+def pad_in_channels(c):
+    """Input-channel padding of a conv: multiples of 32 (one 128-byte TMA/swizzle row of fp32) so that the stems
+    (21 / 18 / 42 channels) run on the tensor cores; tiny counts (the 3-channel gradients) only to a multiple of 4."""
+    if c % 32 == 0 or c < 16:
+        return ceil4(c)
+    return (c + 31) // 32 * 32
+
+
 class ConvLayer:
     """A Conv2d / ConvTranspose2d bound to its parameters.  Keeps GEMM-layout copies of the weight."""
 
@@ -28,7 +36,7 @@ class ConvLayer:
             self.cin, self.cout = weight.shape[0], weight.shape[1]
         else:
             self.cout, self.cin = weight.shape[0], weight.shape[1]
-        self.cin_pad, self.cout_pad = ceil4(self.cin), ceil4(self.cout)
+        self.cin_pad, self.cout_pad = pad_in_channels(self.cin), ceil4(self.cout)
         self.taps = k * k
         self.w_fwd = None    # [taps][cin_pad][cout_pad]
         self.w_bwd = None    # [taps][cout_pad][cin_pad]  (weights of the dgrad gather-conv)
@@ -263,7 +271,7 @@ class GeneratorEngine:
 
         for name, c_src0, cin in (("app", 0, 3 + P), ("pose", 3 + P, P)):
             convs, norms = self.enc_conv[name], self.enc_norm[name]
-            xin = ws.get("xin_%s_%s" % (name, tag), (N, H, W, ceil4(cin)))
+            xin = ws.get("xin_%s_%s" % (name, tag), (N, H, W, convs[0].cin_pad))
             K.nchw_to_nhwc(inp, c_src0, cin, Slice(xin, 0, cin))
             sv["xin"][name] = xin
             for i in range(L):
@@ -439,7 +447,7 @@ class DiscriminatorEngine:
     def input_buffer(self, M, H, W, device):
         """NHWC input buffer [M,H,W,ceil4(input_nc)] (zero padded channels) the caller fills by slices."""
         self._ensure(device)
-        return self.ws.get("din_%d_%d_%d" % (M, H, W), (M, H, W, ceil4(self.m.input_nc)))
+        return self.ws.get("din_%d_%d_%d" % (M, H, W), (M, H, W, self.convs[0].cin_pad))
 
     def pack_weights(self):
         for c in self.convs:

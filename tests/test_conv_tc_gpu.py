@@ -167,3 +167,52 @@ def test_conv_tc_vs_simt_on_network_geometries(geo):
         res[impl] = (y, stats, dx, gw)
     for what, a, b in zip(("fprop", "stats", "dgrad", "wgrad"), res[K.IMPL_AUTO], res[K.IMPL_SIMT]):
         assert rel_l2(a, b) < TF32_TOL, describe(a.float().cpu(), b.float().cpu(), "%s %s" % (name, what))
+
+
+STEM_CASES = [
+    # name, k, s, p, Cin, Cout, N, H, W, act
+    ("stem_k3_21to64", 3, 1, 1, 21, 64, 2, 20, 36, 0),
+    ("stem_k3_18to64_wide", 3, 1, 1, 18, 64, 2, 8, 256, 0),
+    ("dstem_k4_p0_42to64_leaky", 4, 2, 0, 42, 64, 3, 34, 62, 1),
+]
+
+
+@pytest.mark.parametrize("case", STEM_CASES, ids=[c[0] for c in STEM_CASES])
+def test_conv_tc_stems_with_bias_and_padding(case):
+    """The small-Cin stems (models/networks.py:186,341) on the tensor cores: input channels zero-padded to 32/64,
+    bias (+LeakyReLU for the PatchGAN stem) in the epilogue, wgrad with a half-filled M tile (Cout = 64)."""
+    import pose_transfer_b200  # noqa: F401
+    from pose_transfer_b200 import kernels as K
+    from pose_transfer_b200.engine import ConvLayer
+    name, k, s, p, Cin, Cout, N, H, W, act = case
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    w = (torch.rand(Cout, Cin, k, k, generator=g) * 2 - 1) / (Cin * k * k) ** 0.5
+    b = torch.rand(Cout, generator=g) - 0.5
+    x = torch.randn(N, Cin, H, W, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    z = F.conv2d(xr, wr, br, stride=s, padding=p)
+    yref = F.leaky_relu(z, 0.2) if act == 1 else z
+    dz = torch.randn(z.shape, generator=g)
+    z.backward(dz)
+    layer = ConvLayer(torch.nn.Parameter(w.cuda()), torch.nn.Parameter(b.cuda()), False, k, s, p)
+    layer.impl = K.IMPL_TC
+    layer.pack_forward()
+    assert layer.cin_pad % 32 == 0
+    xin = torch.zeros(N, H, W, layer.cin_pad, device="cuda")
+    xin[..., :Cin] = nhwc(x).cuda()
+    OH, OW = layer.out_hw(H, W)
+    y = torch.zeros(N, OH, OW, Cout, device="cuda")
+    layer.forward(K.Slice(xin), N, H, W, K.Slice(y), act, None)
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(y).cpu(), yref.detach()) < TF32_TOL, describe(nchw(y).cpu(), yref.detach(), "fprop")
+    dzd = nhwc(dz).cuda()
+    gw = torch.zeros(Cout, Cin, k, k, device="cuda")
+    scratch = torch.full((layer.taps * layer.cin_pad * layer.cout_pad,), 3.0, device="cuda")
+    layer.wgrad(K.Slice(xin), K.Slice(dzd), N, H, W, scratch, gw)
+    torch.cuda.synchronize()
+    assert rel_l2(gw, wr.grad) < TF32_TOL, describe(gw.cpu(), wr.grad, "wgrad")
+    if layer.cin_pad % 64 == 0:   # only the PatchGAN stem's input gradient is ever needed (gen_update), Cin_pad = 64
+        dx = torch.zeros(N, H, W, layer.cin_pad, device="cuda")
+        layer.dgrad(K.Slice(dzd), N, H, W, K.Slice(dx), dx_channels=layer.cin_pad)
+        torch.cuda.synchronize()
+        assert rel_l2(nchw(dx[..., :Cin]).cpu(), xr.grad) < TF32_TOL, describe(nchw(dx[..., :Cin]).cpu(), xr.grad, "dgrad")
