@@ -237,10 +237,22 @@ def run_ours(args):
     # per-kernel-family device times (CUDA events on the launching stream) over a few more steps
     prof_steps = min(args.steps, 3)
     barrier()
+    K.PROFILE_DETAIL = bool(args.layers)
     K.profile_start()
     for _ in range(prof_steps):
         step_resident()
     prof = K.profile_stop()
+    if args.layers and rank == 0:
+        rows = []
+        for k, (n, t) in prof.items():
+            if "|" in k:
+                kind, geo, flop = k.split("|")
+                rows.append((t / n, kind, geo, float(flop), n // prof_steps))
+        rows.sort(reverse=True)
+        with open(args.layers, "w") as f:
+            for t, kind, geo, flop, n in rows:
+                f.write("%-13s %-40s x%d  %8.3f ms  %7.1f TFLOP/s\n" % (kind, geo, n, t, flop / t / 1e9))
+        prof = {k: v for k, v in prof.items() if "|" not in k}
     hbm_peak, tf_peak, peak_src = measured_peaks()
     wl, wms = prof.get("warp_forward", (0, 0.0))
     # 2 generator forwards per step (dis_update + gen_update), 4 warped levels each
@@ -292,6 +304,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE configs[1]: 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", default="", help="write a per-conv-geometry timing table (CUDA events) to this file")
     ap.add_argument("--ncu-step", action="store_true", help="profiling aid: warm up, then run ONE step inside "
                     "cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off); prints no result line")
     args = ap.parse_args()

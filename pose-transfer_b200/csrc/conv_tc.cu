@@ -28,6 +28,7 @@ struct TcGeom {
   int N, OH, OW, ldy, so;
   int BW, BH, BI, tiles_x, tiles_y, tiles_i;
   int kchunks;
+  int splits;      // split-K factor (k-blocks of a tile are divided over `splits` CTAs that accumulate atomically)
   TcPhase ph[4];
 };
 
@@ -138,13 +139,17 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   const uint32_t tmem_slot = bar_tmem + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const TcPhase ph = g.ph[blockIdx.z];
+  const TcPhase ph = g.ph[blockIdx.z / g.splits];
+  const int split = blockIdx.z % g.splits;
   int t = blockIdx.x;
   const int tx = t % g.tiles_x; t /= g.tiles_x;
   const int ty = t % g.tiles_y;
   const int ti = t / g.tiles_y;
   const int gx0 = tx * g.BW, gy0 = ty * g.BH, n0 = ti * g.BI;
-  const int KB = ph.ntaps * g.kchunks;
+  const int KB_all = ph.ntaps * g.kchunks;
+  const int kb_per = (KB_all + g.splits - 1) / g.splits;
+  const int kb0 = split * kb_per;
+  const int KB = (kb0 + kb_per < KB_all ? kb0 + kb_per : KB_all) - kb0;   // k-blocks of this CTA (may be <= 0)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -167,8 +172,8 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
         const int s = kb % STAGES;
         const uint32_t par = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(bar_empty + 8 * s, par ^ 1u);
-        const int tap = kb / g.kchunks;
-        const int c0 = (kb - tap * g.kchunks) * 32;
+        const int tap = (kb0 + kb) / g.kchunks;
+        const int c0 = ((kb0 + kb) - tap * g.kchunks) * 32;
         mbar_expect_tx(bar_full + 8 * s, A_BYTES + B_BYTES);
         tma_load_4d(sA + s * A_BYTES, &maps.a[ph.map[tap]], bar_full + 8 * s, c0, gx0 + ph.cx[tap], gy0 + ph.cy[tap], n0);
         tma_load_3d(sB + s * B_BYTES, &maps.b, bar_full + 8 * s, c0, blockIdx.y * BLOCK_N, ph.wt[tap]);
@@ -189,10 +194,10 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
           tc_mma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         tc_commit(bar_empty + 8 * s);   // frees the smem stage once these MMAs have read it
       }
-      tc_commit(bar_tmem);              // accumulator complete
+      if (KB > 0) tc_commit(bar_tmem);  // accumulator complete
     }
     __syncwarp();
-  } else {
+  } else if (KB > 0) {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int lg = warp & 3;            // TMEM lane group this warp may access
     const int row = lg * 32 + lane;
@@ -213,7 +218,10 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
     for (int c = 0; c < BLOCK_N / 32; ++c) {
       float v[32];
       tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), v);
-      if (valid) {
+      if (valid && g.splits > 1) {        // split-K partial sums: accumulate into the zero-filled output
+#pragma unroll
+        for (int q = 0; q < 32; ++q) atomicAdd(dst + c * 32 + q, v[q]);
+      } else if (valid) {
         if (bias != nullptr) {
           const float* bp = bias + blockIdx.y * BLOCK_N + c * 32;
 #pragma unroll
@@ -230,7 +238,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
           *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     }
-    if (stats != nullptr) {
+    if (stats != nullptr && g.splits == 1) {
       if (g.BW * g.BH >= 32) {          // the warp's 32 rows belong to one image
         const float a = warp_sum(s1), b = warp_sum(s2);
         const int nw = n0 + (lg * 32) / (g.BW * g.BH);
@@ -371,7 +379,24 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     int rc = encode(&maps.b, w_k, 3, dims, str, boxB);
     if (rc) return rc;
   }
-  dim3 grid((unsigned)(g.tiles_x * g.tiles_y * g.tiles_i), (unsigned)(c.Cout / BN), (unsigned)nphases);
+  // Small-M layers (the 4x4 .. 16x16 levels at batch 8) have only a handful of output tiles but up to 16 taps x 48
+  // K-chunks each: split the K loop across CTAs so that the weight stream is spread over all SMs.
+  const int ctas = g.tiles_x * g.tiles_y * g.tiles_i * (c.Cout / BN) * nphases;
+  int min_kb = 1 << 30;
+  for (int i = 0; i < nphases; ++i) { const int kb = g.ph[i].ntaps * g.kchunks; if (kb < min_kb) min_kb = kb; }
+  int splits = 1;
+  if (ctas * 2 <= num_sms() && c.ldy == c.Cout && bias == nullptr && act == PTK_ACT_NONE) {
+    splits = (2 * num_sms() + ctas - 1) / ctas;
+    if (splits > min_kb / 4) splits = min_kb / 4;
+    if (splits < 1) splits = 1;
+    while (splits > 1 && (min_kb + splits - 1) / splits * (splits - 1) >= min_kb) --splits;
+  }
+  g.splits = splits;
+  if (splits > 1) {
+    int rc = ptk_fill(y, (int64_t)c.N * c.OH * c.OW * c.Cout, 0.f, st);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)(g.tiles_x * g.tiles_y * g.tiles_i), (unsigned)(c.Cout / BN), (unsigned)(nphases * splits));
   if (BN == 128) {
     constexpr int STAGES = 3;
     const size_t smem = STAGES * (128 * 128 + 128 * 128) + 16 * STAGES + 16 + 1024;
@@ -386,6 +411,8 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     conv_tc_kernel<64, STAGES><<<grid, 192, smem, st>>>(maps, g, y, stats, bias, act);
   }
   PTK_LAUNCH_CHECK("conv_tc_kernel");
+  if (splits > 1 && stats != nullptr)   // partial sums cannot feed the fused statistics: one extra pass over a tiny tensor
+    return ptk_gn_stats(y, c.ldy, c.N, (int64_t)c.OH * c.OW, c.Cout, stats, st);
   return 0;
 }
 

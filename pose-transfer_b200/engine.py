@@ -19,10 +19,9 @@ def ceil4(x):
 
 
 def pad_in_channels(c):
-    """Input-channel padding of a conv: multiples of 32 (one 128-byte TMA/swizzle row of fp32) so that the stems
-    (21 / 18 / 42 channels) run on the tensor cores; tiny counts (the 3-channel gradients) only to a multiple of 4."""
-    if c % 32 == 0 or c < 16:
-        return ceil4(c)
+    """Channel padding of a tensor that feeds a conv (activations, or output gradients feeding a dgrad): multiples
+    of 32 = one 128-byte TMA / swizzle row of fp32, so that the stems (21 / 18 / 42 channels) and the dgrads of the
+    narrow heads (3 / 1 channels) run on the tensor cores."""
     return (c + 31) // 32 * 32
 
 
@@ -37,16 +36,19 @@ class ConvLayer:
         else:
             self.cout, self.cin = weight.shape[0], weight.shape[1]
         self.cin_pad, self.cout_pad = pad_in_channels(self.cin), ceil4(self.cout)
+        self.dy_pad = pad_in_channels(self.cout)   # channel count of the gradient buffer that feeds this layer's dgrad
         self.taps = k * k
         self.w_fwd = None    # [taps][cin_pad][cout_pad]
-        self.w_bwd = None    # [taps][cout_pad][cin_pad]  (weights of the dgrad gather-conv)
+        self.w_bwd = None    # [taps][dy_pad][cin_pad]  (weights of the dgrad gather-conv)
+        self.w_dgrad_k = None  # [taps][cin_pad][dy_pad]: K-major tensor-core operand of the dgrad (== w_fwd unless narrow)
         self.impl = {"auto": K.IMPL_AUTO, "simt": K.IMPL_SIMT, "tc": K.IMPL_AUTO}[os.environ.get("PTK_CONV_IMPL", "auto")]
 
     def _alloc(self):
         if self.w_fwd is None or self.w_fwd.device != self.weight.device:
             dev = self.weight.device
             self.w_fwd = torch.empty(self.taps * self.cin_pad * self.cout_pad, device=dev)
-            self.w_bwd = torch.empty(self.taps * self.cin_pad * self.cout_pad, device=dev)
+            self.w_bwd = torch.empty(self.taps * self.cin_pad * self.dy_pad, device=dev)
+            self.w_dgrad_k = self.w_fwd if self.dy_pad == self.cout_pad else torch.empty(self.taps * self.cin_pad * self.dy_pad, device=dev)
 
     def pack_forward(self):
         """Both GEMM layouts are refreshed: w_fwd = [tap][cin][cout] is the CUDA-core fprop operand AND the K-major
@@ -63,9 +65,13 @@ class ConvLayer:
         self._alloc()
         w = self.weight.detach()
         if self.transposed:
-            K.pack_weight(w, self.w_bwd, self.cin, self.cout, self.taps, self.cin_pad, self.cout_pad, 1)
+            K.pack_weight(w, self.w_bwd, self.cin, self.cout, self.taps, self.cin_pad, self.dy_pad, 1)
+            if self.w_dgrad_k is not self.w_fwd:
+                K.pack_weight(w, self.w_dgrad_k, self.cin, self.cout, self.taps, self.cin_pad, self.dy_pad, 0)
         else:
-            K.pack_weight(w, self.w_bwd, self.cout, self.cin, self.taps, self.cout_pad, self.cin_pad, 0)
+            K.pack_weight(w, self.w_bwd, self.cout, self.cin, self.taps, self.dy_pad, self.cin_pad, 0)
+            if self.w_dgrad_k is not self.w_fwd:
+                K.pack_weight(w, self.w_dgrad_k, self.cout, self.cin, self.taps, self.dy_pad, self.cin_pad, 1)
 
     def out_hw(self, H, W):
         if self.transposed:
@@ -81,14 +87,14 @@ class ConvLayer:
         return OH, OW
 
     def dgrad(self, dy, N, H, W, dx, dx_channels=None):
-        """dy: Slice over the OUTPUT grid (cout_pad readable channels); dx: Slice over the input grid (H, W)."""
+        """dy: Slice over the OUTPUT grid (dy_pad readable channels); dx: Slice over the input grid (H, W)."""
         OH, OW = self.out_hw(H, W)
         cout_dx = self.cin if dx_channels is None else dx_channels
-        g = K.conv_geom(N, OH, OW, self.cout_pad, dy.ld, H, W, cout_dx, dx.ld, self.k, self.stride, self.pad,
+        g = K.conv_geom(N, OH, OW, self.dy_pad, dy.ld, H, W, cout_dx, dx.ld, self.k, self.stride, self.pad,
                         not self.transposed, self.impl)
-        # the dgrad weights are [taps][cout_pad][cin_pad]; the kernel's inner extent is ceil4(Cout')
+        # the dgrad weights are [taps][dy_pad][cin_pad]; the kernel's inner extent is ceil4(Cout')
         assert ceil4(cout_dx) == self.cin_pad
-        K.conv_forward(g, dy, self.w_bwd, self.w_fwd, None, ACT_NONE, dx, None, None)
+        K.conv_forward(g, dy, self.w_bwd, self.w_dgrad_k, None, ACT_NONE, dx, None, None)
 
     def wgrad(self, x, dy, N, H, W, scratch, grad_w):
         """grad_w (torch layout, fp32 view into the gradient arena) += dW."""
@@ -345,11 +351,13 @@ class GeneratorEngine:
         sums = ws.get("sums" + tag, tuple(stats.shape), torch.float64, zero=True)
 
         # final conv: tanh' then wgrad / bias grad / dgrad
-        dzf = ws.get("dzf" + tag, (N, H, W, 4))
-        K.tanh_bwd_combine(dout_nchw, dout_nhwc, sv["out"], dzf, 4, N, 3, H, W)
         fc = self.final_conv
-        fc.wgrad(Slice(cats[L - 1]), Slice(dzf), N, H, W, scratch, grads[fc.weight])
-        K.bias_grad(dzf, 4, N * H * W, 3, grads[fc.bias])
+        dzf = ws.get("dzf" + tag, (N, H, W, fc.dy_pad))      # channels 3.. stay zero (padding for the dgrad GEMM)
+        K.tanh_bwd_combine(dout_nchw, dout_nhwc, sv["out"], dzf, fc.dy_pad, N, 3, H, W)
+        dz4 = ws.get("dzf4" + tag, (N, H, W, 4))             # compact copy: one 16-byte load per pixel in the wgrad
+        K.tanh_bwd_combine(dout_nchw, dout_nhwc, sv["out"], dz4, 4, N, 3, H, W)
+        fc.wgrad(Slice(cats[L - 1]), Slice(dz4), N, H, W, scratch, grads[fc.weight])
+        K.bias_grad(dz4, 4, N * H * W, 3, grads[fc.bias])
         dcat = ws.get("dcat%d_%s" % (L - 1, tag), tuple(cats[L - 1].shape))
         fc.dgrad(Slice(dzf), N, H, W, Slice(dcat))
         dcats = {L - 1: dcat}
@@ -499,8 +507,12 @@ class DiscriminatorEngine:
         self.saved = sv
         return x
 
+    def dlogits_buffer(self, M, J):
+        """Zero-padded gradient buffer [M*J, dy_pad] for the logits (channel 0 carries the gradient)."""
+        return self.ws.get("dlog_%d_%d" % (M, J), (M * J, self.convs[-1].dy_pad))
+
     def backward(self, dlogits4, grads=None, need_input_grad=False):
-        """dlogits4: [M*J, 4] (gradient w.r.t. the logits in channel 0, zero padding in 1..3).
+        """dlogits4: dlogits_buffer() filled by the caller (gradient w.r.t. the logits in channel 0, zeros elsewhere).
         grads: dict parameter -> gradient tensor (None => no weight gradients, G-step use).
         Returns the gradient w.r.t. the NHWC input buffer if need_input_grad."""
         sv = self.saved

@@ -57,6 +57,16 @@ def profile_stop():
     return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (prof or {}).items()}
 
 
+PROFILE_DETAIL = False   # also key conv launches by geometry (bench.py --layers)
+
+
+def _conv_label(name, g):
+    pix = g.H * g.W if g.transposed else g.OH * g.OW
+    flop = 2.0 * g.N * pix * g.Cin * g.Cout * g.k * g.k
+    return "%s|N%d %dx%d c%d->%d k%ds%dp%d %s|%.4g" % (name, g.N, g.H, g.W, g.Cin, g.Cout, g.k, g.stride, g.pad,
+                                                   "T" if g.transposed else "C", flop)
+
+
 def _timed(name):
     def deco(fn):
         def wrapper(*a, **kw):
@@ -67,6 +77,8 @@ def _timed(name):
             r = fn(*a, **kw)
             e1.record()
             PROFILE.setdefault(name, []).append((e0, e1))
+            if PROFILE_DETAIL and name in ("conv_forward", "conv_wgrad"):
+                PROFILE.setdefault(_conv_label(name, a[0]), []).append((e0, e1))
             return r
         wrapper.__name__ = fn.__name__
         wrapper.__doc__ = fn.__doc__

@@ -245,7 +245,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         M, J = probs.shape
         # sigmoid' (tiny [M,J] tensor; part of the autograd glue, not of the step's hot path)
         dlog = (dprobs * probs * (1 - probs)).reshape(M * J, 1)
-        dlog4 = torch.zeros(M * J, 4, device=probs.device)
+        dlog4 = disc.engine.dlogits_buffer(M, J)
         dlog4[:, :1] = dlog
         grads = {p: torch.zeros_like(p) for p in ctx.params}
         need_x = ctx.needs_input_grad[1]

@@ -202,9 +202,9 @@ class DeformablePose_GAN(nn.Module):
                                           repack=None, d_input=Slice(din, 3 + P, 3))
         logits = self.disc.engine.forward(din, repack=None)
         J = logits.shape[1]
-        dlog4 = self.disc.engine.ws.get("dlog4_%d_%d" % (N, J), (N * J, 4))
+        dlog4 = self.disc.engine.dlogits_buffer(N, J)
         # ad_loss = sum_n -mean_j log(out+1e-7), * gan_penalty_weight / batch_size   (pose_gan.py:90-98,107)
-        K.adv_loss(logits, N, J, N, opt['gan_penalty_weight'] / self.batch_size, loss[0:2], dlog4, 4)
+        K.adv_loss(logits, N, J, N, opt['gan_penalty_weight'] / self.batch_size, loss[0:2], dlog4, dlog4.shape[1])
         din_grad = self.disc.engine.backward(dlog4, grads=None, need_input_grad=True)
 
         dpred = self.gen.engine.ws.get("dpred_%d_%d_%d" % (N, H, W), (N, 3, H, W))
@@ -249,9 +249,9 @@ class DeformablePose_GAN(nn.Module):
                                 repack=None, d_input=Slice(din[nr:], 3 + P, 3))
         logits = self.disc.engine.forward(din, repack=None)
         J = logits.shape[1]
-        dlog4 = self.disc.engine.ws.get("dlog4_%d_%d" % (M, J), (M * J, 4))
+        dlog4 = self.disc.engine.dlogits_buffer(M, J)
         # rows < opt['batch_size'] are "true", the rest "fake"; both * gan_w / self.batch_size (pose_gan.py:140-163)
-        K.adv_loss(logits, M, J, opt['batch_size'], opt['gan_penalty_weight'] / self.batch_size, loss[0:2], dlog4, 4)
+        K.adv_loss(logits, M, J, opt['batch_size'], opt['gan_penalty_weight'] / self.batch_size, loss[0:2], dlog4, dlog4.shape[1])
         self.disc.engine.backward(dlog4, grads=self.disc_arena.grads, need_input_grad=False)
         self._allreduce(self.disc_arena)
         self.disc_opt.step()

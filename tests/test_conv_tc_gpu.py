@@ -216,3 +216,29 @@ def test_conv_tc_stems_with_bias_and_padding(case):
         layer.dgrad(K.Slice(dzd), N, H, W, K.Slice(dx), dx_channels=layer.cin_pad)
         torch.cuda.synchronize()
         assert rel_l2(nchw(dx[..., :Cin]).cpu(), xr.grad) < TF32_TOL, describe(nchw(dx[..., :Cin]).cpu(), xr.grad, "dgrad")
+
+
+@pytest.mark.parametrize("name,k,s,p,Cin,Cout,N,H,W", [("final_dgrad", 3, 1, 1, 256, 3, 2, 24, 40),
+                                                         ("dhead_dgrad", 4, 2, 1, 512, 1, 4, 15, 15)])
+def test_conv_tc_dgrad_of_narrow_heads(name, k, s, p, Cin, Cout, N, H, W):
+    """dgrad of the 3-channel generator head and the 1-channel PatchGAN head on the tensor cores: the gradient
+    buffer is zero-padded to 32 channels (one K chunk)."""
+    import pose_transfer_b200  # noqa: F401
+    from pose_transfer_b200 import kernels as K
+    from pose_transfer_b200.engine import ConvLayer
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    w = (torch.rand(Cout, Cin, k, k, generator=g) * 2 - 1) / (Cin * k * k) ** 0.5
+    x = torch.randn(N, Cin, H, W, generator=g, requires_grad=True)
+    z = F.conv2d(x, w, None, stride=s, padding=p)
+    dz = torch.randn(z.shape, generator=g)
+    z.backward(dz)
+    layer = ConvLayer(torch.nn.Parameter(w.cuda()), None, False, k, s, p)
+    layer.impl = K.IMPL_TC
+    layer.pack_forward()
+    OH, OW = layer.out_hw(H, W)
+    dzd = torch.zeros(N, OH, OW, layer.dy_pad, device="cuda")
+    dzd[..., :Cout] = nhwc(dz).cuda()
+    dx = torch.zeros(N, H, W, Cin, device="cuda")
+    layer.dgrad(K.Slice(dzd), N, H, W, K.Slice(dx))
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(dx).cpu(), x.grad) < TF32_TOL, describe(nchw(dx).cpu(), x.grad, "dgrad")

@@ -83,7 +83,7 @@ def test_conv_simt_fprop_dgrad_wgrad(K, case):
     layer.impl = K.IMPL_SIMT
     layer.pack_forward()
     layer.pack_backward()
-    cin_pad, cout_pad = layer.cin_pad, layer.cout_pad
+    cin_pad, cout_pad = layer.cin_pad, layer.dy_pad
     xin = torch.zeros(N, H, W, cin_pad + 4, device="cuda")   # wider ld: exercise channel-slice addressing
     xin[..., :Cin] = nhwc(x).cuda()
     OH, OW = layer.out_hw(H, W)
