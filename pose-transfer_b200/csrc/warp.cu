@@ -164,6 +164,237 @@ warp_backward_kernel(const float* __restrict__ dy, int lddy, const float* __rest
   }
 }
 
+
+// ---------------------------------------------------------------- cooperative kernels (C >= 64)
+// A group of G = min(32, C/4) lanes owns one output pixel (a warp handles 32/G pixels at a time).  The per-part
+// geometry (mask value, bilinear footprint) is computed ONCE per pixel by lane k of the group and broadcast with
+// shuffles, so the per-element instruction stream is just the gather itself; parts whose mask is zero at the pixel
+// (or whose footprint is outside the image) are skipped -- they all contribute the same candidate "0, no gradient".
+struct PartGeom { float m; int x0, y0; float w00, w01, w10, w11; };
+
+__device__ __forceinline__ PartGeom shfl_geom(const PartGeom& g, int src) {
+  PartGeom r;
+  r.m = __shfl_sync(0xffffffffu, g.m, src);
+  r.x0 = __shfl_sync(0xffffffffu, g.x0, src);
+  r.y0 = __shfl_sync(0xffffffffu, g.y0, src);
+  r.w00 = __shfl_sync(0xffffffffu, g.w00, src);
+  r.w01 = __shfl_sync(0xffffffffu, g.w01, src);
+  r.w10 = __shfl_sync(0xffffffffu, g.w10, src);
+  r.w11 = __shfl_sync(0xffffffffu, g.w11, src);
+  return r;
+}
+
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
+  a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+}
+
+// Packed per-(pixel, part) geometry that travels through the shuffles: 4 registers.
+struct PackedGeom { float m, fx, fy; int xy; };   // xy = (y0 + 2) << 16 | (x0 + 2)   (x0, y0 in [-2, 32765])
+
+__device__ __forceinline__ PackedGeom shfl_packed(const PackedGeom& g, int src) {
+  PackedGeom r;
+  r.m = __shfl_sync(0xffffffffu, g.m, src);
+  r.fx = __shfl_sync(0xffffffffu, g.fx, src);
+  r.fy = __shfl_sync(0xffffffffu, g.fy, src);
+  r.xy = __shfl_sync(0xffffffffu, g.xy, src);
+  return r;
+}
+
+// Forward, G lanes per pixel, 8 channels (two float4) per lane and chunk: C = 64 -> G = 8 (4 pixels per warp),
+// C = 128 -> G = 16, C % 256 == 0 -> G = 32.  Lane gl of a group evaluates parts gl, gl + G, ... of its pixel.
+template <int G>
+__global__ void __launch_bounds__(256)
+warp_forward_coop_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ warps,
+                         const float* __restrict__ mask_lvl, float* __restrict__ y, int ldy, uint8_t* __restrict__ argk,
+                         int C, int h, int w, int K, int H0, int W0, int act) {
+  __shared__ Theta s_theta[kMaxParts];
+  const int n = blockIdx.y;
+  if (threadIdx.x < K) s_theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * K + threadIdx.x) * 8, h, w, H0, W0);
+  __syncthreads();
+  constexpr int PPW = 32 / G;                        // pixels per warp iteration
+  constexpr int SLOTS = (kMaxParts + G - 1) / G;     // parts evaluated per lane
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G, gbase = lane - gl, grp = lane / G;
+  const int HW = h * w;
+  const float inv_w = 1.f / (float)w, inv_h = 1.f / (float)h;
+  const float* xb = x + (int64_t)n * HW * ldx;
+  const float* mb = mask_lvl + (int64_t)n * HW * K;
+  float* yb = y + (int64_t)n * HW * ldy;
+  uint8_t* ab = argk + (int64_t)n * HW * C;
+  const int warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int iters = (HW + PPW - 1) / PPW;
+  const unsigned kmask = (1u << K) - 1u;
+  for (int it = warp_id; it < iters; it += nwarps) {
+    const int p = it * PPW + grp;
+    const bool pvalid = p < HW;
+    const int i = pvalid ? p / w : 0, j = pvalid ? p - i * w : 0;
+    PackedGeom mine[SLOTS];
+    unsigned my_active = 0;                          // bit s: slot s is an active part
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+      const int k = gl + sl * G;
+      mine[sl].m = 0.f; mine[sl].fx = 0.f; mine[sl].fy = 0.f; mine[sl].xy = 0;
+      if (pvalid && k < K) {
+        const float m = __ldg(mb + p * K + k);
+        if (m != 0.f) {
+          const Theta t = s_theta[k];
+          const float gx = (2.f * (float)j + 1.f) * inv_w - 1.f, gy = (2.f * (float)i + 1.f) * inv_h - 1.f;
+          const float px = ((t.a * gx + t.b * gy + t.tx + 1.f) * (float)w - 1.f) * 0.5f;
+          const float py = ((t.c * gx + t.d * gy + t.ty + 1.f) * (float)h - 1.f) * 0.5f;
+          const float fx0 = floorf(px), fy0 = floorf(py);
+          const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)w), y0 = (int)fminf(fmaxf(fy0, -2.f), (float)h);
+          if (x0 >= -1 && x0 < w && y0 >= -1 && y0 < h) {     // at least one neighbour inside the image
+            my_active |= 1u << sl;
+            mine[sl].m = m; mine[sl].fx = px - fx0; mine[sl].fy = py - fy0;
+            mine[sl].xy = ((y0 + 2) << 16) | (x0 + 2);
+          }
+        }
+      }
+    }
+    // active-part bit mask of every group (bit k), and their union over the warp
+    unsigned active = 0, uni = 0;
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+      const unsigned ball = __ballot_sync(0xffffffffu, (my_active >> sl) & 1u);
+      active |= ((ball >> gbase) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u))) << (sl * G);
+      unsigned u = ball;
+      if (G <= 16) u |= u >> 16;
+      if (G <= 8) u |= u >> 8;
+      u &= (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+      uni |= u << (sl * G);
+    }
+    active &= kmask; uni &= kmask;
+    const unsigned inactive = ~active & kmask;
+    const int kz = inactive ? __ffs(inactive) - 1 : 1 << 20;   // where the (single) "0, no gradient" candidate sits
+    for (int c0 = gl * 8; c0 < C; c0 += G * 8) {
+      float best[8];
+      unsigned char arg[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; arg[q] = 255; }
+      bool zero_done = false;
+      unsigned rem = uni;
+      while (rem) {
+        const int k = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const int sl = k / G;
+        PackedGeom g = shfl_packed(SLOTS == 1 ? mine[0] : (sl == 0 ? mine[0] : mine[SLOTS - 1]), gbase + (k - sl * G));
+        if (!((active >> k) & 1u)) continue;           // active only for another pixel of this warp
+        if (!zero_done && k > kz) {
+          zero_done = true;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) if (0.f > best[q]) { best[q] = 0.f; arg[q] = 255; }
+        }
+        const int x0 = (g.xy & 0xffff) - 2, y0 = (g.xy >> 16) - 2;
+        const bool xin0 = x0 >= 0, xin1 = x0 + 1 < w, yin0 = y0 >= 0, yin1 = y0 + 1 < h;
+        const float w00 = (yin0 && xin0) ? (1.f - g.fy) * (1.f - g.fx) * g.m : 0.f;
+        const float w01 = (yin0 && xin1) ? (1.f - g.fy) * g.fx * g.m : 0.f;
+        const float w10 = (yin1 && xin0) ? g.fy * (1.f - g.fx) * g.m : 0.f;
+        const float w11 = (yin1 && xin1) ? g.fy * g.fx * g.m : 0.f;
+        const float* r0 = xb + (y0 * w + x0) * ldx + c0;
+        const float* r1 = r0 + w * ldx;
+        float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), cb = ca;
+        if (yin0 && xin0) { fma4(ca, w00, __ldg(reinterpret_cast<const float4*>(r0))); fma4(cb, w00, __ldg(reinterpret_cast<const float4*>(r0 + 4))); }
+        if (yin0 && xin1) { fma4(ca, w01, __ldg(reinterpret_cast<const float4*>(r0 + ldx))); fma4(cb, w01, __ldg(reinterpret_cast<const float4*>(r0 + ldx + 4))); }
+        if (yin1 && xin0) { fma4(ca, w10, __ldg(reinterpret_cast<const float4*>(r1))); fma4(cb, w10, __ldg(reinterpret_cast<const float4*>(r1 + 4))); }
+        if (yin1 && xin1) { fma4(ca, w11, __ldg(reinterpret_cast<const float4*>(r1 + ldx))); fma4(cb, w11, __ldg(reinterpret_cast<const float4*>(r1 + ldx + 4))); }
+        const float cand[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (cand[q] > best[q]) { best[q] = cand[q]; arg[q] = (unsigned char)k; }
+      }
+      if (!zero_done && inactive) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (0.f > best[q]) { best[q] = 0.f; arg[q] = 255; }
+      }
+      if (pvalid) {
+        float* dst = yb + p * ldy + c0;
+        *reinterpret_cast<float4*>(dst) = make_float4(apply_act(best[0], act), apply_act(best[1], act), apply_act(best[2], act), apply_act(best[3], act));
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(apply_act(best[4], act), apply_act(best[5], act), apply_act(best[6], act), apply_act(best[7], act));
+        uint2 a8;
+        a8.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | ((unsigned)arg[3] << 24);
+        a8.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | ((unsigned)arg[7] << 24);
+        *reinterpret_cast<uint2*>(ab + p * C + c0) = a8;
+      }
+    }
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+warp_backward_coop_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, int act,
+                          const float* __restrict__ warps, const float* __restrict__ mask_lvl,
+                          const uint8_t* __restrict__ argk, float* __restrict__ dx, int C, int h, int w, int K, int H0,
+                          int W0, int align_corners) {
+  __shared__ Theta s_theta[kMaxParts];
+  const int n = blockIdx.y;
+  if (threadIdx.x < K) s_theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * K + threadIdx.x) * 8, h, w, H0, W0);
+  __syncthreads();
+  constexpr int PPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G, gbase = lane - gl;
+  const int64_t HW = (int64_t)h * w;
+  const float* mb = mask_lvl + (int64_t)n * HW * K;
+  float* dxb = dx + (int64_t)n * HW * C;
+  const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t iters = (HW + PPW - 1) / PPW;
+  for (int64_t it = warp_id; it < iters; it += nwarps) {
+    const int64_t p = it * PPW + lane / G;
+    const bool pvalid = p < HW;
+    const int i = pvalid ? (int)(p / w) : 0, j = pvalid ? (int)(p - (int64_t)i * w) : 0;
+    PartGeom mine;
+    mine.m = 0.f; mine.x0 = 0; mine.y0 = 0; mine.w00 = mine.w01 = mine.w10 = mine.w11 = 0.f;
+    if (pvalid && gl < K) {
+      mine.m = __ldg(mb + p * K + gl);
+      if (mine.m != 0.f) {
+        const Footprint f = footprint(s_theta[gl], i, j, h, w, align_corners);
+        mine.x0 = f.x0; mine.y0 = f.y0; mine.w00 = f.w00; mine.w01 = f.w01; mine.w10 = f.w10; mine.w11 = f.w11;
+      }
+    }
+    for (int c0 = gl * 4; c0 < C; c0 += G * 4) {
+      uchar4 a4 = make_uchar4(255, 255, 255, 255);
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pvalid) {
+        a4 = *reinterpret_cast<const uchar4*>(argk + ((int64_t)n * HW + p) * C + c0);
+        g = __ldg(reinterpret_cast<const float4*>(dy + ((int64_t)n * HW + p) * lddy + c0));
+        if (act != PTK_ACT_NONE) {
+          const float4 yv = __ldg(reinterpret_cast<const float4*>(y + ((int64_t)n * HW + p) * ldy + c0));
+          g.x *= act_grad_from_output(yv.x, act); g.y *= act_grad_from_output(yv.y, act);
+          g.z *= act_grad_from_output(yv.z, act); g.w *= act_grad_from_output(yv.w, act);
+        }
+      }
+      const unsigned char as[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float gs[4] = {g.x, g.y, g.z, g.w};
+      const bool uniform = a4.x == a4.y && a4.y == a4.z && a4.z == a4.w;
+      // every lane takes part in the shuffles; lanes without a winner read part 0 and add nothing
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = as[q] == 255 ? 0 : as[q];
+        const PartGeom f = shfl_geom(mine, gbase + k);
+        if (as[q] == 255) continue;
+        if (uniform) {
+          if (q > 0) continue;
+          float* r0 = dxb + ((int64_t)f.y0 * w + f.x0) * C + c0;
+          float* r1 = r0 + (int64_t)w * C;
+          const float4 gm = make_float4(g.x * f.m, g.y * f.m, g.z * f.m, g.w * f.m);
+          if (f.w00 != 0.f) atomicAdd(reinterpret_cast<float4*>(r0), make_float4(gm.x * f.w00, gm.y * f.w00, gm.z * f.w00, gm.w * f.w00));
+          if (f.w01 != 0.f) atomicAdd(reinterpret_cast<float4*>(r0 + C), make_float4(gm.x * f.w01, gm.y * f.w01, gm.z * f.w01, gm.w * f.w01));
+          if (f.w10 != 0.f) atomicAdd(reinterpret_cast<float4*>(r1), make_float4(gm.x * f.w10, gm.y * f.w10, gm.z * f.w10, gm.w * f.w10));
+          if (f.w11 != 0.f) atomicAdd(reinterpret_cast<float4*>(r1 + C), make_float4(gm.x * f.w11, gm.y * f.w11, gm.z * f.w11, gm.w * f.w11));
+        } else if (gs[q] != 0.f) {
+          const float gm = gs[q] * f.m;
+          float* r0 = dxb + ((int64_t)f.y0 * w + f.x0) * C + c0 + q;
+          float* r1 = r0 + (int64_t)w * C;
+          if (f.w00 != 0.f) atomicAdd(r0, gm * f.w00);
+          if (f.w01 != 0.f) atomicAdd(r0 + C, gm * f.w01);
+          if (f.w10 != 0.f) atomicAdd(r1, gm * f.w10);
+          if (f.w11 != 0.f) atomicAdd(r1 + C, gm * f.w11);
+        }
+      }
+    }
+  }
+}
+
 // cv2.resize(INTER_LINEAR) == half-pixel bilinear; computed in double like the reference (masks are f64).
 __global__ void mask_pyramid_kernel(const double* __restrict__ masks, int K, int H0, int W0,
                                     float* __restrict__ out, int h, int w, int64_t total) {
@@ -219,8 +450,21 @@ extern "C" int ptk_warp_forward(const float* x, int ldx, const float* warps, con
   PTK_REQUIRE(N > 0 && N <= 65535 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "warp_forward: C/ld must be multiples of 4");
   PTK_REQUIRE(K > 0 && K <= kMaxParts, "warp_forward: K must be in [1,%d]", kMaxParts);
   PTK_REQUIRE(act == PTK_ACT_NONE || act == PTK_ACT_RELU || act == PTK_ACT_LEAKY, "warp_forward: bad act");
-  warp_forward_kernel<<<warp_grid((int64_t)h * w * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(
-      x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, K, H0, W0, align_corners, act);
+  // the cooperative kernel uses 32-bit element offsets inside one image and packs (x0, y0) in 16 bits each
+  const bool coop_ok = !align_corners && h < 32000 && w < 32000 && (int64_t)h * w * (ldx > ldy ? ldx : ldy) < (1ll << 31);
+  if (coop_ok && C == 64) {
+    warp_forward_coop_kernel<8><<<warp_grid((int64_t)h * w * 8, N), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, K, H0, W0, act);
+  } else if (coop_ok && C == 128) {
+    warp_forward_coop_kernel<16><<<warp_grid((int64_t)h * w * 16, N), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, K, H0, W0, act);
+  } else if (coop_ok && C % 256 == 0) {
+    warp_forward_coop_kernel<32><<<warp_grid((int64_t)h * w * 32, N), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, K, H0, W0, act);
+  } else {
+    warp_forward_kernel<<<warp_grid((int64_t)h * w * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, K, H0, W0, align_corners, act);
+  }
   PTK_LAUNCH_CHECK("warp_forward_kernel");
   return 0;
 }
@@ -231,8 +475,16 @@ extern "C" int ptk_warp_backward(const float* dy, int lddy, const float* y, int 
   PTK_REQUIRE(N > 0 && N <= 65535 && C > 0 && C % 4 == 0 && lddy % 4 == 0, "warp_backward: C/ld must be multiples of 4");
   PTK_REQUIRE(K > 0 && K <= kMaxParts, "warp_backward: K must be in [1,%d]", kMaxParts);
   PTK_REQUIRE(act == PTK_ACT_NONE || (y != nullptr && ldy % 4 == 0), "warp_backward: y required for act backward");
-  warp_backward_kernel<<<warp_grid((int64_t)h * w * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(
-      dy, lddy, y, ldy, act, warps, mask_lvl, argk, dx, C, h, w, K, H0, W0, align_corners);
+  if (C == 64) {
+    warp_backward_coop_kernel<16><<<warp_grid((int64_t)h * w * 16, N), 256, 0, (cudaStream_t)stream>>>(
+        dy, lddy, y, ldy, act, warps, mask_lvl, argk, dx, C, h, w, K, H0, W0, align_corners);
+  } else if (C % 128 == 0) {
+    warp_backward_coop_kernel<32><<<warp_grid((int64_t)h * w * 32, N), 256, 0, (cudaStream_t)stream>>>(
+        dy, lddy, y, ldy, act, warps, mask_lvl, argk, dx, C, h, w, K, H0, W0, align_corners);
+  } else {
+    warp_backward_kernel<<<warp_grid((int64_t)h * w * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(
+        dy, lddy, y, ldy, act, warps, mask_lvl, argk, dx, C, h, w, K, H0, W0, align_corners);
+  }
   PTK_LAUNCH_CHECK("warp_backward_kernel");
   return 0;
 }

@@ -214,7 +214,7 @@ def test_mask_pyramid_matches_half_pixel_bilinear(K):
 def test_warp_full_size_vs_oracle_and_relu_epilogue(K):
     from oracle import restate, synth
     b = synth.make_batch(2, 256, 256, 2, seed=11)
-    for C, h in ((64, 256), (512, 32)):
+    for C, h in ((64, 256), (128, 64), (512, 32)):
         x = torch.randn(2, C, h, h, generator=gen(C))
         gy = torch.randn(2, C, h, h, generator=gen(C + 1))
         xr = x.clone().requires_grad_(True)
