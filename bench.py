@@ -179,8 +179,8 @@ def run_ours(args):
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
     resident = [dict(b, warps=b["warps"].float()) for b in resident]
-    h2d_bytes = sum(b[k].numel() * b[k].element_size() for b in pinned for k in ("input", "warps", "masks"))
-    h2d_bytes += pinned[1]["target"].numel() * 4 + pinned[2]["target"].numel() * 4
+    h2d_bytes = sum(pinned[i][k].numel() * pinned[i][k].element_size() for i in (0, 2) for k in ("input", "target", "warps", "masks"))
+    h2d_bytes += sum(pinned[1][k].numel() * pinned[1][k].element_size() for k in ("input", "target"))
     d2h_bytes = 2 * 4 * 4   # two 4-float loss buffers per step
 
     def step_resident():
@@ -188,13 +188,42 @@ def run_ours(args):
         model.dis_update(b["input"], b["target"], {"warps": b["warps"], "masks": b["masks"]}, r["input"], r["target"], od)
         model.gen_update(b2["input"], b2["target"], {"warps": b2["warps"], "masks": b2["masks"]}, od)
 
+    # End-to-end step: what main.py does per iteration (main.py:81-86,105-107) -- host batch -> device -> update ->
+    # python floats -- with the loader-side copies issued on a side stream so that the H2D transfer of the NEXT
+    # call's batch overlaps the current update (pinned memory + non_blocking, as a DataLoader(pin_memory=True) would).
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def upload(batch, keys):
+        out = {}
+        with torch.cuda.stream(copy_stream):
+            for k in keys:
+                t = batch[k].to(dev, non_blocking=True)
+                out[k] = t.float() if k == "warps" else t
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return out, ev
+
+    def ready(pair):
+        d, ev = pair
+        torch.cuda.current_stream().wait_event(ev)
+        for t in d.values():
+            t.record_stream(torch.cuda.current_stream())
+        return d
+
+    pending = {}
+
     def step_e2e():
-        # what main.py does per iteration (main.py:81-86,105-107): host batch -> .cuda() -> update -> .item()
         b, r, b2 = pinned
-        cu = lambda t: t.to(dev, non_blocking=True)  # noqa: E731
-        model.dis_update(cu(b["input"]), cu(b["target"]), {"warps": cu(b["warps"]).float(), "masks": cu(b["masks"])},
-                         cu(r["input"]), cu(r["target"]), od)
-        model.gen_update(cu(b2["input"]), cu(b2["target"]), {"warps": cu(b2["warps"]).float(), "masks": cu(b2["masks"])}, od)
+        if not pending:
+            pending["b"] = upload(b, ("input", "target", "warps", "masks"))
+            pending["r"] = upload(r, ("input", "target"))
+        gb, gr = ready(pending.pop("b")), ready(pending.pop("r"))
+        pending["b2"] = upload(b2, ("input", "target", "warps", "masks"))      # overlaps dis_update
+        model.dis_update(gb["input"], gb["target"], {"warps": gb["warps"], "masks": gb["masks"]}, gr["input"], gr["target"], od)
+        g2 = ready(pending.pop("b2"))
+        pending["b"] = upload(b, ("input", "target", "warps", "masks"))        # next step's batches overlap gen_update
+        pending["r"] = upload(r, ("input", "target"))
+        model.gen_update(g2["input"], g2["target"], {"warps": g2["warps"], "masks": g2["masks"]}, od)
 
     def barrier():
         if world > 1:

@@ -50,6 +50,10 @@ int ptk_nhwc_to_nchw(const float* src, int ld_src, int c_src0, float* dst, int N
  * Padding entries are written as zero. */
 int ptk_pack_weight(const float* src, float* dst, int A, int B, int taps, int A_pad, int B_pad,
                     int transpose, void* stream);
+/* Both layouts in one pass: dst0[tap][a][b] with row count rows0 / row stride cols0, dst1[tap][b][a] with rows1 / cols1.
+ * Padding entries are NOT written (the destination buffers must have been zero-initialised once). */
+int ptk_pack_weight_dual(const float* src, float* dst0, float* dst1, int A, int B, int taps, int rows0, int cols0,
+                         int rows1, int cols1, void* stream);
 /* grad[a][b][tap] (+)= src[tap][a][b_pad]  (inverse of transpose==0 packing, drops padding) */
 int ptk_unpack_weight_grad(const float* src, float* grad, int A, int B, int taps, int B_pad,
                            int accumulate, void* stream);

@@ -23,6 +23,7 @@ SIGNATURES = {
     "ptk_nchw_to_nhwc": [vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "ptk_nhwc_to_nchw": [vp, i32, i32, vp, i32, i32, i32, i32, vp],
     "ptk_pack_weight": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "ptk_pack_weight_dual": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "ptk_unpack_weight_grad": [vp, vp, i32, i32, i32, i32, i32, vp],
     "ptk_fill": [vp, i64, f32, vp],
     "ptk_conv_tc_supported": [ctypes.POINTER(ConvGeom)],

@@ -60,6 +60,37 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, float* __restr
   }
 }
 
+// Both GEMM layouts of one weight tensor in one pass over the checkpoint layout src[A][B][taps]:
+//   dst0[t][a][b] (row stride cols0)  and  dst1[t][b][a] (row stride cols1).
+// A tile of 16 a x 32 b x taps is read with fully coalesced loads, transposed through shared memory and written in
+// 128-byte (dst0) / 64-byte (dst1) runs.  Padding rows/columns are never written (buffers are zero-initialised).
+__global__ void __launch_bounds__(256)
+pack_weight_dual_kernel(const float* __restrict__ src, float* __restrict__ dst0, float* __restrict__ dst1, int A, int B,
+                        int taps, int rows0, int cols0, int rows1, int cols1) {
+  constexpr int TA = 16, TB = 32;
+  __shared__ float tile[TA][TB][17];
+  const int a0 = blockIdx.y * TA, b0 = blockIdx.x * TB;
+  const int tid = threadIdx.x;
+  const int nb = min(TB, B - b0);
+  // load: for each a the (nb * taps) floats starting at src[(a*B + b0)*taps] are contiguous
+  for (int a = 0; a < TA; ++a) {
+    if (a0 + a >= A) break;
+    const float* row = src + ((int64_t)(a0 + a) * B + b0) * taps;
+    for (int i = tid; i < nb * taps; i += 256) tile[a][i / taps][i % taps] = __ldg(row + i);
+  }
+  __syncthreads();
+  // dst0[t][a][b]: consecutive threads -> consecutive b
+  for (int i = tid; i < taps * TA * TB; i += 256) {
+    const int b = i % TB, a = (i / TB) % TA, t = i / (TB * TA);
+    if (a0 + a < A && b < nb) dst0[((int64_t)t * rows0 + a0 + a) * cols0 + b0 + b] = tile[a][b][t];
+  }
+  // dst1[t][b][a]: consecutive threads -> consecutive a
+  for (int i = tid; i < taps * TA * TB; i += 256) {
+    const int a = i % TA, b = (i / TA) % TB, t = i / (TB * TA);
+    if (a0 + a < A && b < nb) dst1[((int64_t)t * rows1 + b0 + b) * cols1 + a0 + a] = tile[a][b][t];
+  }
+}
+
 __global__ void unpack_weight_grad_kernel(const float* __restrict__ src, float* __restrict__ grad, int A, int B,
                                           int taps, int B_pad, int accumulate) {
   const int64_t total = (int64_t)A * B * taps;
@@ -69,6 +100,30 @@ __global__ void unpack_weight_grad_kernel(const float* __restrict__ src, float* 
     const int64_t a = i / ((int64_t)taps * B);
     const float v = src[((int64_t)t * A + a) * B_pad + b];
     grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+
+// tiled inverse of pack_weight_dual's dst0: grad[a][b][t] (+)= src[t][a][b_pad]; coalesced on both sides
+__global__ void __launch_bounds__(256)
+unpack_weight_grad_tiled_kernel(const float* __restrict__ src, float* __restrict__ grad, int A, int B, int taps, int B_pad,
+                                int accumulate) {
+  constexpr int TA = 16, TB = 32;
+  __shared__ float tile[TA][TB][17];
+  const int a0 = blockIdx.y * TA, b0 = blockIdx.x * TB;
+  const int tid = threadIdx.x;
+  const int nb = min(TB, B - b0);
+  for (int i = tid; i < taps * TA * TB; i += 256) {
+    const int b = i % TB, a = (i / TB) % TA, t = i / (TB * TA);
+    if (a0 + a < A && b < nb) tile[a][b][t] = __ldg(src + ((int64_t)t * A + a0 + a) * B_pad + b0 + b);
+  }
+  __syncthreads();
+  for (int a = 0; a < TA; ++a) {
+    if (a0 + a >= A) break;
+    float* row = grad + ((int64_t)(a0 + a) * B + b0) * taps;
+    for (int i = tid; i < nb * taps; i += 256) {
+      const float v = tile[a][i / taps][i % taps];
+      row[i] = accumulate ? row[i] + v : v;
+    }
   }
 }
 
@@ -118,10 +173,25 @@ extern "C" int ptk_pack_weight(const float* src, float* dst, int A, int B, int t
   return 0;
 }
 
+extern "C" int ptk_pack_weight_dual(const float* src, float* dst0, float* dst1, int A, int B, int taps, int rows0,
+                                    int cols0, int rows1, int cols1, void* stream) {
+  PTK_REQUIRE(rows0 >= A && cols0 >= B && rows1 >= B && cols1 >= A && taps > 0 && taps <= 16, "pack_weight_dual: bad extents");
+  dim3 grid((B + 31) / 32, (A + 15) / 16);
+  PTK_REQUIRE(grid.y <= 65535, "pack_weight_dual: A too large");
+  pack_weight_dual_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst0, dst1, A, B, taps, rows0, cols0, rows1, cols1);
+  PTK_LAUNCH_CHECK("pack_weight_dual_kernel");
+  return 0;
+}
+
 extern "C" int ptk_unpack_weight_grad(const float* src, float* grad, int A, int B, int taps, int B_pad,
                                       int accumulate, void* stream) {
   const int64_t total = (int64_t)A * B * taps;
-  unpack_weight_grad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, grad, A, B, taps, B_pad, accumulate);
+  if (taps <= 16 && (A + 15) / 16 <= 65535) {
+    dim3 grid((B + 31) / 32, (A + 15) / 16);
+    unpack_weight_grad_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, grad, A, B, taps, B_pad, accumulate);
+  } else {
+    unpack_weight_grad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, grad, A, B, taps, B_pad, accumulate);
+  }
   PTK_LAUNCH_CHECK("unpack_weight_grad_kernel");
   return 0;
 }

@@ -22,23 +22,31 @@ __device__ __forceinline__ void block_reduce2_atomic(double a, double b, double*
   }
 }
 
-// grid (chunks, N); every thread strides over float4 groups of sample n.
+// grid (chunks, N); every thread strides over float4 groups of sample n, two independent loads in flight.
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ z, int ld, int64_t HW, int C, double* __restrict__ stats) {
   const int n = blockIdx.y;
   const int C4 = C >> 2;
-  const int64_t total4 = HW * C4;
+  const int total4 = (int)(HW * C4);          // < 2^31 float4 groups per sample (checked by the host)
   const float* base = z + (int64_t)n * HW * ld;
   float s = 0.f, q = 0.f;
   double ds = 0.0, dq = 0.0;
   int cnt = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / C4;
-    const int c = (int)(i - p * C4) << 2;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(base + p * ld + c));
-    s += (v.x + v.y) + (v.z + v.w);
-    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-    if (++cnt == 64) { ds += s; dq += q; s = 0.f; q = 0.f; cnt = 0; }
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += 2 * stride) {
+    const int i2 = i + stride;
+    const int p = i / C4;
+    const int c = (i - p * C4) << 2;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)p * ld + c));
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i2 < total4) {
+      const int p2 = i2 / C4;
+      const int c2 = (i2 - p2 * C4) << 2;
+      u = __ldg(reinterpret_cast<const float4*>(base + (int64_t)p2 * ld + c2));
+    }
+    s += ((v.x + v.y) + (v.z + v.w)) + ((u.x + u.y) + (u.z + u.w));
+    q += ((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w)) + ((u.x * u.x + u.y * u.y) + (u.z * u.z + u.w * u.w));
+    if (++cnt == 32) { ds += s; dq += q; s = 0.f; q = 0.f; cnt = 0; }
   }
   ds += s; dq += q;
   block_reduce2_atomic(ds, dq, stats + 2 * n);
@@ -82,14 +90,14 @@ gn_apply_kernel(const float* __restrict__ z, int ldz, const double* __restrict__
     shift = b - mean * scale;
   }
   const int C4 = C >> 2;
-  const int64_t total4 = HW * C4;
+  const int total4 = (int)(HW * C4);
   const float* zb = z + (int64_t)n * HW * ldz;
   float* o1 = out1 + (int64_t)n * HW * ld1;
   float* o2 = out2 ? out2 + (int64_t)n * HW * ld2 : nullptr;
   const float* dr = drop ? drop + (int64_t)n * C : nullptr;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
     const int64_t p = i / C4;
-    const int c = (int)(i - p * C4) << 2;
+    const int c = (i - (int)p * C4) << 2;
     float4 v = __ldg(reinterpret_cast<const float4*>(zb + p * ldz + c));
     v.x = fmaf(v.x, scale, shift); v.y = fmaf(v.y, scale, shift);
     v.z = fmaf(v.z, scale, shift); v.w = fmaf(v.w, scale, shift);
@@ -117,15 +125,15 @@ gn_bwd_reduce_kernel(const float* __restrict__ g1, int ldg1, const float* __rest
   const bool normed = sums != nullptr;
   if (normed) mean_rstd(stats, n, (double)HW * C, &mean, &rstd);
   const int C4 = C >> 2;
-  const int64_t total4 = HW * C4;
+  const int total4 = (int)(HW * C4);
   const int64_t pix0 = (int64_t)n * HW;
   const float* dr = drop ? drop + (int64_t)n * C : nullptr;
   float s1 = 0.f, s2 = 0.f;
   double d1 = 0.0, d2 = 0.0;
   int cnt = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
     const int64_t p = i / C4;
-    const int c = (int)(i - p * C4) << 2;
+    const int c = (i - (int)p * C4) << 2;
     const int64_t pp = pix0 + p;
     float4 g = __ldg(reinterpret_cast<const float4*>(g1 + pp * ldg1 + c));
     if (a1) {
@@ -172,12 +180,12 @@ gn_bwd_apply_kernel(float* __restrict__ dy, const float* __restrict__ z, int ldz
   const float m1 = (float)(sums[2 * n] / count), m2 = (float)(sums[2 * n + 1] / count);
   const float k = g * rstd;
   const int C4 = C >> 2;
-  const int64_t total4 = HW * C4;
+  const int total4 = (int)(HW * C4);
   float* dyb = dy + (int64_t)n * HW * C;
   const float* zb = z + (int64_t)n * HW * ldz;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
     const int64_t p = i / C4;
-    const int c = (int)(i - p * C4) << 2;
+    const int c = (i - (int)p * C4) << 2;
     float4 d = *reinterpret_cast<const float4*>(dyb + p * C + c);
     const float4 zv = __ldg(reinterpret_cast<const float4*>(zb + p * ldz + c));
     d.x = k * (d.x - m1 - (zv.x - mean) * rstd * m2);
@@ -208,7 +216,7 @@ static inline dim3 grid2(int64_t work, int N) {
 using namespace ptk;
 
 extern "C" int ptk_gn_stats(const float* z, int ld, int N, int64_t HW, int C, double* stats, void* stream) {
-  PTK_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0, "gn_stats: bad extents");
+  PTK_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0 && HW * C < (1ll << 32), "gn_stats: bad extents");
   if (C % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
     gn_stats_kernel<<<grid2(HW * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(z, ld, HW, C, stats);
   } else {
@@ -221,7 +229,7 @@ extern "C" int ptk_gn_stats(const float* z, int ld, int N, int64_t HW, int C, do
 extern "C" int ptk_gn_apply(const float* z, int ldz, const double* stats, const float* gamma, const float* beta,
                             const float* drop, int N, int64_t HW, int C, float* out1, int ld1, int act1,
                             float* out2, int ld2, int act2, void* stream) {
-  PTK_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0, "gn_apply: bad extents");
+  PTK_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0 && HW * C < (1ll << 32), "gn_apply: bad extents");
   PTK_REQUIRE(C % 4 == 0 && ldz % 4 == 0 && ld1 % 4 == 0 && (!out2 || ld2 % 4 == 0), "gn_apply: C and strides must be multiples of 4");
   PTK_REQUIRE((gamma == nullptr) == (beta == nullptr), "gn_apply: gamma and beta must both be given or both NULL");
   PTK_REQUIRE(!gamma || stats, "gn_apply: stats required");
@@ -235,7 +243,7 @@ extern "C" int ptk_gn_bwd_reduce(const float* g1, int ldg1, const float* a1, int
                                  int ldg2, const float* a2, int lda2, int act2, const float* drop, const float* z,
                                  int ldz, const double* stats, int N, int64_t HW, int C, float* dy, double* sums,
                                  void* stream) {
-  PTK_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0 && C % 4 == 0, "gn_bwd_reduce: bad extents (C %% 4 == 0 required)");
+  PTK_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0 && C % 4 == 0 && HW * C < (1ll << 32), "gn_bwd_reduce: bad extents (C %% 4 == 0 required)");
   PTK_REQUIRE(ldg1 % 4 == 0 && (!a1 || lda1 % 4 == 0) && (!g2 || ldg2 % 4 == 0) && (!a2 || lda2 % 4 == 0) && (!sums || ldz % 4 == 0),
               "gn_bwd_reduce: strides must be multiples of 4");
   PTK_REQUIRE(!sums || (z && stats), "gn_bwd_reduce: z and stats required with sums");
@@ -248,7 +256,7 @@ extern "C" int ptk_gn_bwd_reduce(const float* g1, int ldg1, const float* a1, int
 extern "C" int ptk_gn_bwd_apply(float* dy, const float* z, int ldz, const double* stats, const double* sums,
                                 const float* gamma, int N, int64_t HW, int C, float* dgamma, float* dbeta,
                                 void* stream) {
-  PTK_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0 && C % 4 == 0 && ldz % 4 == 0, "gn_bwd_apply: bad extents");
+  PTK_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0 && C % 4 == 0 && ldz % 4 == 0 && HW * C < (1ll << 32), "gn_bwd_apply: bad extents");
   gn_bwd_apply_kernel<<<grid2(HW * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(dy, z, ldz, stats, sums, gamma, N, HW, C,
                                                                                dgamma, dbeta);
   PTK_LAUNCH_CHECK("gn_bwd_apply_kernel");

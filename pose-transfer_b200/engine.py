@@ -46,32 +46,31 @@ class ConvLayer:
     def _alloc(self):
         if self.w_fwd is None or self.w_fwd.device != self.weight.device:
             dev = self.weight.device
-            self.w_fwd = torch.empty(self.taps * self.cin_pad * self.cout_pad, device=dev)
-            self.w_bwd = torch.empty(self.taps * self.cin_pad * self.dy_pad, device=dev)
-            self.w_dgrad_k = self.w_fwd if self.dy_pad == self.cout_pad else torch.empty(self.taps * self.cin_pad * self.dy_pad, device=dev)
+            # zero-initialised once: the pack kernels never write the channel-padding entries
+            self.w_fwd = torch.zeros(self.taps * self.cin_pad * self.cout_pad, device=dev)
+            self.w_bwd = torch.zeros(self.taps * self.cin_pad * self.dy_pad, device=dev)
+            self.w_dgrad_k = self.w_fwd if self.dy_pad == self.cout_pad else torch.zeros(self.taps * self.cin_pad * self.dy_pad, device=dev)
 
     def pack_forward(self):
-        """Both GEMM layouts are refreshed: w_fwd = [tap][cin][cout] is the CUDA-core fprop operand AND the K-major
-        tensor-core operand of the dgrad; w_bwd = [tap][cout][cin] is the reverse."""
+        """Both GEMM layouts are refreshed in one pass: w_fwd = [tap][cin][cout] is the CUDA-core fprop operand AND the
+        K-major tensor-core operand of the dgrad; w_bwd = [tap][cout][cin] is the reverse."""
         self._alloc()
         w = self.weight.detach()
-        if self.transposed:   # torch layout [Cin][Cout][k][k]
-            K.pack_weight(w, self.w_fwd, self.cin, self.cout, self.taps, self.cin_pad, self.cout_pad, 0)
-        else:                 # torch layout [Cout][Cin][k][k]
-            K.pack_weight(w, self.w_fwd, self.cout, self.cin, self.taps, self.cout_pad, self.cin_pad, 1)
-        self.pack_backward()
-
-    def pack_backward(self):
-        self._alloc()
-        w = self.weight.detach()
-        if self.transposed:
-            K.pack_weight(w, self.w_bwd, self.cin, self.cout, self.taps, self.cin_pad, self.dy_pad, 1)
+        if self.transposed:   # torch layout [A=Cin][B=Cout][k][k]: w_fwd = [t][a][b], w_bwd = [t][b][a]
+            K.pack_weight_dual(w, self.w_fwd, self.w_bwd, self.cin, self.cout, self.taps, self.cin_pad, self.cout_pad,
+                               self.dy_pad, self.cin_pad)
             if self.w_dgrad_k is not self.w_fwd:
                 K.pack_weight(w, self.w_dgrad_k, self.cin, self.cout, self.taps, self.cin_pad, self.dy_pad, 0)
-        else:
-            K.pack_weight(w, self.w_bwd, self.cout, self.cin, self.taps, self.dy_pad, self.cin_pad, 0)
+        else:                 # torch layout [A=Cout][B=Cin][k][k]: w_bwd = [t][a][b], w_fwd = [t][b][a]
+            K.pack_weight_dual(w, self.w_bwd, self.w_fwd, self.cout, self.cin, self.taps, self.dy_pad, self.cin_pad,
+                               self.cin_pad, self.cout_pad)
             if self.w_dgrad_k is not self.w_fwd:
                 K.pack_weight(w, self.w_dgrad_k, self.cout, self.cin, self.taps, self.dy_pad, self.cin_pad, 1)
+
+    def pack_backward(self):
+        """Kept for API symmetry: pack_forward() already refreshes every layout."""
+        if self.w_bwd is None:
+            self.pack_forward()
 
     def out_hw(self, H, W):
         if self.transposed:

@@ -111,6 +111,12 @@ def pack_weight(src, dst, A, B, taps, A_pad, B_pad, transpose):
 
 
 @_timed("pack")
+def pack_weight_dual(src, dst0, dst1, A, B, taps, rows0, cols0, rows1, cols1):
+    check(_lib.lib().ptk_pack_weight_dual(_p(src), _p(dst0), _p(dst1), A, B, taps, rows0, cols0, rows1, cols1, _stream()),
+          "ptk_pack_weight_dual")
+
+
+@_timed("pack")
 def unpack_weight_grad(src, grad, A, B, taps, B_pad, accumulate=True):
     check(_lib.lib().ptk_unpack_weight_grad(_p(src), _p(grad), A, B, taps, B_pad, int(accumulate), _stream()),
           "ptk_unpack_weight_grad")

@@ -62,6 +62,13 @@ def install(K):
             full = full.permute(0, 2, 1)
         dst[:full.numel()].copy_(full.reshape(-1))
 
+    def pack_weight_dual(src, dst0, dst1, A, B, taps, rows0, cols0, rows1, cols1):
+        w = src.reshape(A, B, taps).permute(2, 0, 1)
+        d0 = dst0[:taps * rows0 * cols0].view(taps, rows0, cols0)
+        d1 = dst1[:taps * rows1 * cols1].view(taps, rows1, cols1)
+        d0[:, :A, :B] = w
+        d1[:, :B, :A] = w.permute(0, 2, 1)
+
     def unpack_weight_grad(src, grad, A, B, taps, B_pad, accumulate=True):
         v = src[:taps * A * B_pad].reshape(taps, A, B_pad)[:, :, :B].permute(1, 2, 0).reshape(grad.shape)
         if accumulate:
@@ -235,7 +242,7 @@ def install(K):
         bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
         p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
 
-    table = dict(nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, pack_weight=pack_weight,
+    table = dict(nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, pack_weight=pack_weight, pack_weight_dual=pack_weight_dual,
                  unpack_weight_grad=unpack_weight_grad, fill=fill, conv_forward=conv_forward, conv_wgrad=conv_wgrad,
                  bias_grad=bias_grad, gn_stats=gn_stats, gn_apply=gn_apply, gn_bwd_reduce=gn_bwd_reduce,
                  gn_bwd_apply=gn_bwd_apply, mask_pyramid=mask_pyramid, warp_forward=warp_forward,
