@@ -73,6 +73,11 @@ constexpr int kFeat = 64;
 constexpr int kChunk = 16;
 constexpr float kPadValue = -10000.f;  // pose_gan.py:176
 
+// conv1_1 weights [64][3][3][3] and bias [64] live in constant memory for the duration of a launch so that every FFMA
+// of the feature extractor takes its weight as a constant operand (no shared-memory load per multiply-add).
+__constant__ float c_vgg_w[kFeat * 27];
+__constant__ float c_vgg_b[kFeat];
+
 // utils/pose_utils.py:324-331: the NCHW buffer is re-viewed as NHWC, so element with flat per-sample index
 // i is normalised with mean[i % 3], std[i % 3].
 __device__ __forceinline__ float vgg_pre(float v, int64_t flat) {
@@ -101,9 +106,8 @@ __device__ __forceinline__ void load_patch(const float* __restrict__ img, int n,
 }
 
 // relu(conv1_1) for 16 consecutive channels [c0, c0+16) at patch position (py, px) = centre; patch is [3][R][R].
-__device__ __forceinline__ void feat16(const float* __restrict__ patch, int R, int py, int px,
-                                       const float* __restrict__ s_w, const float* __restrict__ s_b, int c0,
-                                       float* __restrict__ out) {
+template <int C0>
+__device__ __forceinline__ void feat16(const float* __restrict__ patch, int R, int py, int px, float* __restrict__ out) {
   float in[27];
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci)
@@ -113,79 +117,91 @@ __device__ __forceinline__ void feat16(const float* __restrict__ patch, int R, i
       for (int kx = 0; kx < 3; ++kx) in[(ci * 3 + ky) * 3 + kx] = patch[(ci * R + py - 1 + ky) * R + px - 1 + kx];
 #pragma unroll
   for (int c = 0; c < kChunk; ++c) {
-    float a = s_b[c0 + c];
-    const float* wp = s_w + (c0 + c) * 27;
+    float a = c_vgg_b[C0 + c];
 #pragma unroll
-    for (int t = 0; t < 27; ++t) a = fmaf(in[t], wp[t], a);
+    for (int t = 0; t < 27; ++t) a = fmaf(in[t], c_vgg_w[(C0 + c) * 27 + t], a);
     out[c] = a > 0.f ? a : 0.f;
   }
 }
 
-__global__ void __launch_bounds__(256)
-nnloss_forward_kernel(const float* __restrict__ pred, const float* __restrict__ target,
-                      const float* __restrict__ vgg_w, const float* __restrict__ vgg_b, int H, int W, int area,
+struct NnCtx {
+  const float* s_pin;   // pred input patch   [3][RPI][RPI]
+  const float* s_gin;   // target input patch [3][RGI][RGI]
+  int RPI, RGI, P, H, W, ty0, tx0, area;
+};
+
+// One 16-channel chunk of the forward: GT features over the (16+2P)^2 halo region -> shared memory (all threads),
+// then the 16x16 pixel threads accumulate the area^2 shifted L1 distances.
+template <int C0>
+__device__ __forceinline__ void nn_fwd_chunk(const NnCtx& c, float4* __restrict__ s_gf, int RG, bool live, int ly, int lx,
+                                             float* __restrict__ d) {
+  for (int pos = threadIdx.x; pos < RG * RG; pos += blockDim.x) {
+    const int ry = pos / RG, rx = pos - ry * RG;
+    const int iy = c.ty0 - c.P + ry, ix = c.tx0 - c.P + rx;
+    float f[kChunk];
+    if (iy >= 0 && iy < c.H && ix >= 0 && ix < c.W) {
+      feat16<C0>(c.s_gin, c.RGI, ry + 1, rx + 1, f);
+    } else {
+#pragma unroll
+      for (int q = 0; q < kChunk; ++q) f[q] = kPadValue;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s_gf[q * RG * RG + pos] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+  }
+  __syncthreads();
+  if (live) {
+    float p[kChunk];
+    feat16<C0>(c.s_pin, c.RPI, ly + 1, lx + 1, p);
+#pragma unroll
+    for (int si = 0; si < kMaxArea; ++si) {
+      if (si >= c.area) break;
+#pragma unroll
+      for (int sj = 0; sj < kMaxArea; ++sj) {
+        if (sj >= c.area) break;
+        const int pos = (ly + si) * RG + lx + sj;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 g = s_gf[q * RG * RG + pos];
+          acc += fabsf(g.x - p[4 * q]) + fabsf(g.y - p[4 * q + 1]) + fabsf(g.z - p[4 * q + 2]) + fabsf(g.w - p[4 * q + 3]);
+        }
+        d[si * kMaxArea + sj] += acc;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+constexpr int kNnFwdThreads = 416;   // >= (16 + 4)^2 halo positions in one round; threads 0..255 own the tile pixels
+constexpr int kNnBwdThreads = 352;   // >= 18^2 positions
+
+__global__ void __launch_bounds__(kNnFwdThreads)
+nnloss_forward_kernel(const float* __restrict__ pred, const float* __restrict__ target, int H, int W, int area,
                       float scale_over_count, float* __restrict__ loss, uint8_t* __restrict__ argmin) {
   const int P = area / 2;
   const int RG = kTile + 2 * P;        // GT feature region
   const int RGI = RG + 2;              // GT input patch
   const int RPI = kTile + 2;           // pred input patch
   extern __shared__ float smem[];
-  float* s_w = smem;                   // 64*27
-  float* s_b = s_w + kFeat * 27;       // 64
-  float* s_pin = s_b + kFeat;          // 3*RPI*RPI
+  float* s_pin = smem;                   // 3*RPI*RPI
   float* s_gin = s_pin + 3 * RPI * RPI;  // 3*RGI*RGI
   float4* s_gf = reinterpret_cast<float4*>(s_gin + ((3 * RGI * RGI + 3) & ~3));  // [4][RG*RG] float4
   const int n = blockIdx.z;
   const int ty0 = blockIdx.y * kTile, tx0 = blockIdx.x * kTile;
-  for (int i = threadIdx.x; i < kFeat * 27; i += blockDim.x) s_w[i] = vgg_w[i];
-  for (int i = threadIdx.x; i < kFeat; i += blockDim.x) s_b[i] = vgg_b[i];
   load_patch(pred, n, H, W, ty0 - 1, tx0 - 1, RPI, s_pin);
   load_patch(target, n, H, W, ty0 - P - 1, tx0 - P - 1, RGI, s_gin);
   __syncthreads();
   const int ly = threadIdx.x / kTile, lx = threadIdx.x % kTile;
   const int gy = ty0 + ly, gx = tx0 + lx;
-  const bool live = gy < H && gx < W;
+  const bool live = threadIdx.x < kTile * kTile && gy < H && gx < W;
+  NnCtx c{s_pin, s_gin, RPI, RGI, P, H, W, ty0, tx0, area};
   float d[kMaxArea * kMaxArea];
 #pragma unroll
   for (int s = 0; s < kMaxArea * kMaxArea; ++s) d[s] = 0.f;
-  for (int c0 = 0; c0 < kFeat; c0 += kChunk) {
-    // GT features of this channel chunk over the halo region (value -10000 outside the image)
-    for (int pos = threadIdx.x; pos < RG * RG; pos += blockDim.x) {
-      const int ry = pos / RG, rx = pos - ry * RG;
-      const int iy = ty0 - P + ry, ix = tx0 - P + rx;
-      float f[kChunk];
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        feat16(s_gin, RGI, ry + 1, rx + 1, s_w, s_b, c0, f);
-      } else {
-#pragma unroll
-        for (int c = 0; c < kChunk; ++c) f[c] = kPadValue;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) s_gf[q * RG * RG + pos] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-    }
-    __syncthreads();
-    if (live) {
-      float p[kChunk];
-      feat16(s_pin, RPI, ly + 1, lx + 1, s_w, s_b, c0, p);
-#pragma unroll
-      for (int si = 0; si < kMaxArea; ++si) {
-        if (si >= area) break;
-#pragma unroll
-        for (int sj = 0; sj < kMaxArea; ++sj) {
-          if (sj >= area) break;
-          const int pos = (ly + si) * RG + lx + sj;
-          float acc = 0.f;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 g = s_gf[q * RG * RG + pos];
-            acc += fabsf(g.x - p[4 * q]) + fabsf(g.y - p[4 * q + 1]) + fabsf(g.z - p[4 * q + 2]) + fabsf(g.w - p[4 * q + 3]);
-          }
-          d[si * kMaxArea + sj] += acc;
-        }
-      }
-    }
-    __syncthreads();
-  }
+  nn_fwd_chunk<0>(c, s_gf, RG, live, ly, lx, d);
+  nn_fwd_chunk<16>(c, s_gf, RG, live, ly, lx, d);
+  nn_fwd_chunk<32>(c, s_gf, RG, live, ly, lx, d);
+  nn_fwd_chunk<48>(c, s_gf, RG, live, ly, lx, d);
   float best = 0.f;
   if (live) {
     best = INFINITY;
@@ -198,92 +214,102 @@ nnloss_forward_kernel(const float* __restrict__ pred, const float* __restrict__ 
     argmin[((int64_t)n * H + gy) * W + gx] = (uint8_t)arg;
   }
   best = warp_sum(best);
-  __shared__ float sh[8];
+  __shared__ float sh[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) sh[wid] = best;
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f;
-    for (int i = 0; i < 8; ++i) s += sh[i];
+    for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) s += sh[i];
     atomicAdd(loss, s * scale_over_count);
   }
 }
 
-__global__ void __launch_bounds__(256)
-nnloss_backward_kernel(const float* __restrict__ pred, const float* __restrict__ target,
-                       const float* __restrict__ vgg_w, const float* __restrict__ vgg_b,
-                       const uint8_t* __restrict__ argmin, int H, int W, int area, float scale_over_count,
-                       float* __restrict__ dpred) {
-  const int P = area / 2;
-  const int RQ = kTile + 2;            // positions q whose feature gradient reaches this tile
-  const int RPI = RQ + 2;              // pred input patch
-  const int RGI = RQ + 2 * P + 2;      // GT input patch
-  extern __shared__ float smem[];
-  float* s_w = smem;
-  float* s_b = s_w + kFeat * 27;
-  float* s_pin = s_b + kFeat;
-  float* s_gin = s_pin + 3 * RPI * RPI;
-  float* s_G = s_gin + 3 * RGI * RGI;  // [RQ*RQ][16]
-  const int n = blockIdx.z;
-  const int ty0 = blockIdx.y * kTile, tx0 = blockIdx.x * kTile;
-  for (int i = threadIdx.x; i < kFeat * 27; i += blockDim.x) s_w[i] = vgg_w[i];
-  for (int i = threadIdx.x; i < kFeat; i += blockDim.x) s_b[i] = vgg_b[i];
-  load_patch(pred, n, H, W, ty0 - 2, tx0 - 2, RPI, s_pin);
-  load_patch(target, n, H, W, ty0 - 2 - P, tx0 - 2 - P, RGI, s_gin);
-  __syncthreads();
-  const int ly = threadIdx.x / kTile, lx = threadIdx.x % kTile;
-  float acc[3] = {0.f, 0.f, 0.f};
-  for (int c0 = 0; c0 < kFeat; c0 += kChunk) {
-    for (int pos = threadIdx.x; pos < RQ * RQ; pos += blockDim.x) {
-      const int ry = pos / RQ, rx = pos - ry * RQ;
-      const int qy = ty0 - 1 + ry, qx = tx0 - 1 + rx;
-      float gq[kChunk];
+// One 16-channel chunk of the backward: feature gradients G[c](q) on the 18x18 positions around the tile -> shared
+// memory, then every tile pixel gathers d xp[ci](r) = sum_{ky,kx,c} G[c](r - (ky-1,kx-1)) * w[c][ci][ky][kx].
+template <int C0>
+__device__ __forceinline__ void nn_bwd_chunk(const NnCtx& c, const uint8_t* __restrict__ argmin, int n, float* __restrict__ s_G,
+                                             int RQ, float scale_over_count, bool pix, int ly, int lx, float* __restrict__ acc) {
+  for (int pos = threadIdx.x; pos < RQ * RQ; pos += blockDim.x) {
+    const int ry = pos / RQ, rx = pos - ry * RQ;
+    const int qy = c.ty0 - 1 + ry, qx = c.tx0 - 1 + rx;
+    float gq[kChunk];
 #pragma unroll
-      for (int c = 0; c < kChunk; ++c) gq[c] = 0.f;
-      if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
-        const int arg = argmin[((int64_t)n * H + qy) * W + qx];
-        const int si = arg / area, sj = arg - si * area;
-        float p[kChunk], t[kChunk];
-        feat16(s_pin, RPI, ry + 1, rx + 1, s_w, s_b, c0, p);
-        const int gyy = qy + si - P, gxx = qx + sj - P;
-        if (gyy >= 0 && gyy < H && gxx >= 0 && gxx < W) {
-          feat16(s_gin, RGI, ry + si + 1, rx + sj + 1, s_w, s_b, c0, t);
-        } else {
+    for (int q = 0; q < kChunk; ++q) gq[q] = 0.f;
+    if (qy >= 0 && qy < c.H && qx >= 0 && qx < c.W) {
+      const int arg = argmin[((int64_t)n * c.H + qy) * c.W + qx];
+      const int si = arg / c.area, sj = arg - si * c.area;
+      float p[kChunk], t[kChunk];
+      feat16<C0>(c.s_pin, c.RPI, ry + 1, rx + 1, p);
+      const int gyy = qy + si - c.P, gxx = qx + sj - c.P;
+      if (gyy >= 0 && gyy < c.H && gxx >= 0 && gxx < c.W) {
+        feat16<C0>(c.s_gin, c.RGI, ry + si + 1, rx + sj + 1, t);
+      } else {
 #pragma unroll
-          for (int c = 0; c < kChunk; ++c) t[c] = kPadValue;
-        }
-#pragma unroll
-        for (int c = 0; c < kChunk; ++c) {
-          // d|gt - p|/dp = -sign(gt - p); relu'(feat) = [p > 0]
-          const float diff = t[c] - p[c];
-          const float sg = diff > 0.f ? -1.f : (diff < 0.f ? 1.f : 0.f);
-          gq[c] = p[c] > 0.f ? sg * scale_over_count : 0.f;
-        }
+        for (int q = 0; q < kChunk; ++q) t[q] = kPadValue;
       }
 #pragma unroll
-      for (int c = 0; c < kChunk; ++c) s_G[pos * kChunk + c] = gq[c];
+      for (int q = 0; q < kChunk; ++q) {
+        // d|gt - p|/dp = -sign(gt - p); relu'(feat) = [p > 0]
+        const float diff = t[q] - p[q];
+        const float sg = diff > 0.f ? -1.f : (diff < 0.f ? 1.f : 0.f);
+        gq[q] = p[q] > 0.f ? sg * scale_over_count : 0.f;
+      }
     }
-    __syncthreads();
-    // d xp[ci](r) = sum_{ky,kx,c} G[c](r - (ky-1,kx-1)) * w[c][ci][ky][kx]
+#pragma unroll
+    for (int q = 0; q < kChunk; ++q) s_G[pos * kChunk + q] = gq[q];
+  }
+  __syncthreads();
+  if (pix) {
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int pos = (ly + 1 - (ky - 1)) * RQ + (lx + 1 - (kx - 1));
-        const float* gp = s_G + pos * kChunk;
+        const float4* gp = reinterpret_cast<const float4*>(s_G + pos * kChunk);
 #pragma unroll
-        for (int c = 0; c < kChunk; ++c) {
-          const float gv = gp[c];
-          const float* wp = s_w + (c0 + c) * 27 + ky * 3 + kx;
-          acc[0] = fmaf(gv, wp[0], acc[0]);
-          acc[1] = fmaf(gv, wp[9], acc[1]);
-          acc[2] = fmaf(gv, wp[18], acc[2]);
+        for (int q4 = 0; q4 < kChunk / 4; ++q4) {
+          const float4 gv = gp[q4];
+          const float g[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = C0 + q4 * 4 + j;
+            acc[0] = fmaf(g[j], c_vgg_w[ch * 27 + ky * 3 + kx], acc[0]);
+            acc[1] = fmaf(g[j], c_vgg_w[ch * 27 + 9 + ky * 3 + kx], acc[1]);
+            acc[2] = fmaf(g[j], c_vgg_w[ch * 27 + 18 + ky * 3 + kx], acc[2]);
+          }
         }
       }
-    __syncthreads();
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kNnBwdThreads)
+nnloss_backward_kernel(const float* __restrict__ pred, const float* __restrict__ target, const uint8_t* __restrict__ argmin,
+                       int H, int W, int area, float scale_over_count, float* __restrict__ dpred) {
+  const int P = area / 2;
+  const int RQ = kTile + 2;            // positions q whose feature gradient reaches this tile
+  const int RPI = RQ + 2;              // pred input patch
+  const int RGI = RQ + 2 * P + 2;      // GT input patch
+  extern __shared__ float smem[];
+  float* s_pin = smem;
+  float* s_gin = s_pin + 3 * RPI * RPI;
+  float* s_G = s_gin + ((3 * RGI * RGI + 3) & ~3);  // [RQ*RQ][16], 16-byte aligned rows
+  const int n = blockIdx.z;
+  const int ty0 = blockIdx.y * kTile, tx0 = blockIdx.x * kTile;
+  load_patch(pred, n, H, W, ty0 - 2, tx0 - 2, RPI, s_pin);
+  load_patch(target, n, H, W, ty0 - 2 - P, tx0 - 2 - P, RGI, s_gin);
+  __syncthreads();
+  const int ly = threadIdx.x / kTile, lx = threadIdx.x % kTile;
+  const bool pix = threadIdx.x < kTile * kTile;
+  NnCtx c{s_pin, s_gin, RPI, RGI, P, H, W, ty0, tx0, area};
+  float acc[3] = {0.f, 0.f, 0.f};
+  nn_bwd_chunk<0>(c, argmin, n, s_G, RQ, scale_over_count, pix, ly, lx, acc);
+  nn_bwd_chunk<16>(c, argmin, n, s_G, RQ, scale_over_count, pix, ly, lx, acc);
+  nn_bwd_chunk<32>(c, argmin, n, s_G, RQ, scale_over_count, pix, ly, lx, acc);
+  nn_bwd_chunk<48>(c, argmin, n, s_G, RQ, scale_over_count, pix, ly, lx, acc);
   const int gy = ty0 + ly, gx = tx0 + lx;
-  if (gy < H && gx < W) {
+  if (pix && gy < H && gx < W) {
     const int64_t HW = (int64_t)H * W;
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
@@ -293,6 +319,13 @@ nnloss_backward_kernel(const float* __restrict__ pred, const float* __restrict__
       dpred[(int64_t)n * 3 * HW + flat] = acc[ci] / sd;
     }
   }
+}
+
+static int upload_vgg(const float* vgg_w, const float* vgg_b, cudaStream_t st) {
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_vgg_w, vgg_w, sizeof(float) * kFeat * 27, 0, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_vgg_b, vgg_b, sizeof(float) * kFeat, 0, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return fail(3, "nnloss: cudaMemcpyToSymbolAsync: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 __global__ void tanh_bwd_combine_kernel(const float* __restrict__ g_nchw, const float* __restrict__ g_nhwc, int ldg,
@@ -340,11 +373,13 @@ extern "C" int ptk_nnloss_forward(const float* pred, const float* target, const 
   PTK_REQUIRE(area >= 1 && area <= kMaxArea && (area & 1), "nnloss: area must be odd and <= %d", kMaxArea);
   PTK_REQUIRE(N > 0 && N <= 65535, "nnloss: bad batch");
   const int P = area / 2, RG = kTile + 2 * P, RGI = RG + 2, RPI = kTile + 2;
-  const size_t smem = sizeof(float) * (size_t)(kFeat * 27 + kFeat + 3 * RPI * RPI + ((3 * RGI * RGI + 3) & ~3) + 4 * 4 * RG * RG) + 16;
+  const size_t smem = sizeof(float) * (size_t)(3 * RPI * RPI + ((3 * RGI * RGI + 3) & ~3) + 4 * 4 * RG * RG) + 16;
+  int rc = upload_vgg(vgg_w, vgg_b, (cudaStream_t)stream);
+  if (rc) return rc;
   cudaFuncSetAttribute(nnloss_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, N);
-  nnloss_forward_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pred, target, vgg_w, vgg_b, H, W, area,
-                                                                  scale / ((float)N * H * W), loss, argmin);
+  nnloss_forward_kernel<<<grid, kNnFwdThreads, smem, (cudaStream_t)stream>>>(pred, target, H, W, area,
+                                                                            scale / ((float)N * H * W), loss, argmin);
   PTK_LAUNCH_CHECK("nnloss_forward_kernel");
   return 0;
 }
@@ -355,11 +390,13 @@ extern "C" int ptk_nnloss_backward(const float* pred, const float* target, const
   PTK_REQUIRE(area >= 1 && area <= kMaxArea && (area & 1), "nnloss: area must be odd and <= %d", kMaxArea);
   PTK_REQUIRE(N > 0 && N <= 65535, "nnloss: bad batch");
   const int P = area / 2, RQ = kTile + 2, RPI = RQ + 2, RGI = RQ + 2 * P + 2;
-  const size_t smem = sizeof(float) * (size_t)(kFeat * 27 + kFeat + 3 * RPI * RPI + 3 * RGI * RGI + RQ * RQ * kChunk);
+  const size_t smem = sizeof(float) * (size_t)(3 * RPI * RPI + ((3 * RGI * RGI + 3) & ~3) + RQ * RQ * kChunk) + 16;
+  int rc = upload_vgg(vgg_w, vgg_b, (cudaStream_t)stream);
+  if (rc) return rc;
   cudaFuncSetAttribute(nnloss_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, N);
-  nnloss_backward_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pred, target, vgg_w, vgg_b, argmin, H, W, area,
-                                                                   scale / ((float)N * H * W), dpred);
+  nnloss_backward_kernel<<<grid, kNnBwdThreads, smem, (cudaStream_t)stream>>>(pred, target, argmin, H, W, area,
+                                                                             scale / ((float)N * H * W), dpred);
   PTK_LAUNCH_CHECK("nnloss_backward_kernel");
   return 0;
 }
