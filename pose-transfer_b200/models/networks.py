@@ -54,6 +54,12 @@ def _bump_weights_version(module, incompatible_keys):
     module._ptk_weights_version = getattr(module, "_ptk_weights_version", 0) + 1
 
 
+def _require_cuda(t, who):
+    """The product has no CPU path: fail loudly (the CPU test-suite swaps this guard out together with the kernels)."""
+    if not t.is_cuda:
+        raise RuntimeError("%s: CUDA tensors required (no CPU fallback)" % who)
+
+
 def _no_eager(name):
     raise RuntimeError("%s.forward: this module only owns parameters; the computation runs inside the fused "
                        "CUDA schedule of its parent network (no eager fallback)" % name)
@@ -190,8 +196,7 @@ class Deformable_Generator(nn.Module):
         return d
 
     def forward(self, input, warps, masks):
-        if not input.is_cuda:
-            raise RuntimeError("Deformable_Generator: CUDA tensors required (no CPU fallback)")
+        _require_cuda(input, "Deformable_Generator")
         params = tuple(self.parameters())
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _GeneratorFn.apply(self, input, warps, masks, *params)
@@ -291,8 +296,7 @@ class Discriminator(nn.Module):
         return self.engine.forward(din, probs=True)
 
     def forward(self, input):
-        if not input.is_cuda:
-            raise RuntimeError("Discriminator: CUDA tensors required (no CPU fallback)")
+        _require_cuda(input, "Discriminator")
         params = tuple(self.parameters())
         if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params)):
             return _DiscriminatorFn.apply(self, input, *params)

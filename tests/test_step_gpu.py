@@ -250,3 +250,50 @@ def test_full_size_step_properties():
     # every parameter moved by exactly one Adam step of size <= lr(1+eps) after the first update
     for p in model.gen.parameters():
         assert torch.isfinite(p).all()
+
+
+@pytest.mark.parametrize("H,P,Nstep", [(224, 16, 16), (512, 18, 4)], ids=["cfg3_h36m_224_p16_n16", "cfg5_512_p18_n4"])
+def test_other_baseline_configs(H, P, Nstep, monkeypatch):
+    """BASELINE.json configs[2] (h36m 224x224, 2x16 pose channels, NN loss 5x5, batch 16: 6-level U-Net, D output 6x6)
+    and configs[4] (512x512, batch 4/GPU: 7 levels, bottleneck 8x8, D output 15x15).  (a) generator + discriminator
+    forward in exact-fp32 mode vs the CPU oracle on a batch of 2; (b) one full training step at the configured
+    per-GPU batch in TF32 mode: finite losses, total == sum of parts, every weight moved by at most one Adam step."""
+    from oracle import restate, synth
+    from pose_transfer_b200.models import pose_gan
+    from pose_transfer_b200.utils import pose_utils
+    W = H
+    monkeypatch.setenv("PTK_CONV_IMPL", "simt")
+    G, D = build_networks(H, W, P, 5)
+    b = synth.make_batch(2, H, W, P, seed=5)
+    drop = synth.dropout_masks(2, 512, 3, seed=5)
+    G.set_dropout_noise(drop)
+    with torch.no_grad():
+        out = G(b["input"].cuda(), b["warps"].cuda(), b["masks"].cuda())
+        img, src, tgt = pose_utils.get_imgpose(b["input"].cuda(), True, P)
+        d_out = D(torch.cat([img, src, out, tgt], 1))
+        gsd = synth.fill_state_dict(synth.generator_shapes(P, (H, W)), 5)
+        dsd = synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), 6)
+        ref = restate.generator_forward(gsd, b["input"], b["warps"], b["masks"], (H, W), P, drop)
+        rimg, rsrc, rtgt = restate.get_imgpose(b["input"], True, P)
+        d_ref = restate.discriminator_forward(dsd, torch.cat([rimg, rsrc, ref, rtgt], 1))
+    assert tuple(d_out.shape) == tuple(d_ref.shape) == (2, {224: 36, 512: 225}[H])
+    assert max_abs(out, ref) <= 3e-4
+    assert max_abs(d_out, d_ref) <= 3e-5
+    del G, D
+    torch.cuda.empty_cache()
+
+    monkeypatch.setenv("PTK_CONV_IMPL", "auto")
+    opt = make_opt(H, W, P, Nstep)
+    model = pose_gan.DeformablePose_GAN(opt).cuda()
+    model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), 5))
+    model.disc.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), 6))
+    before = model.gen_arena.flat.clone()
+    bb, rr = synth.make_batch(Nstep, H, W, P, seed=7), synth.make_batch(Nstep, H, W, P, seed=8)
+    io = {"warps": bb["warps"].cuda(), "masks": bb["masks"].cuda()}
+    d1 = model.dis_update(bb["input"].cuda(), bb["target"].cuda(), io, rr["input"].cuda(), rr["target"].cuda(), vars(opt))
+    out, _, g1 = model.gen_update(bb["input"].cuda(), bb["target"].cuda(), io, vars(opt))
+    assert all(np.isfinite(d1)) and all(np.isfinite(g1))
+    assert abs(d1[0] - (d1[1] + d1[2])) < 1e-5 and abs(g1[0] - (g1[1] + g1[2])) < 1e-5
+    assert tuple(out.shape) == (Nstep, 3, H, W) and float(out.abs().max()) <= 1.0
+    step = (model.gen_arena.flat - before).abs().max()
+    assert 0 < float(step) <= 2e-4 * 1.001 + 1e-9      # first Adam step: |delta| <= lr
