@@ -90,8 +90,10 @@ def test_reference_main_py_runs_on_the_product(tmp_path, monkeypatch):
             del dl._BaseDataLoaderIter.next
         if REF in sys.path:
             sys.path.remove(REF)
+        # drop only the names the launcher injected (native extension modules such as cv2 cannot be re-imported
+        # once removed from sys.modules), then restore whatever was there before
         for k in list(sys.modules):
-            if k not in saved_modules:
+            if k not in saved_modules and k.split(".")[0] in ("models", "utils", "datasets", "matplotlib", "pylab", "opts"):
                 del sys.modules[k]
         sys.modules.update(saved_modules)
 
