@@ -126,11 +126,15 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BLOCK_N, int STAGES>
+// MH = number of 128-pixel halves of the CTA's M tile (1 or 2): with MH = 2 the same weight (B) stage feeds two
+// M = 128 MMAs, and BLOCK_N = 256 lets one activation (A) stage feed a twice-as-wide MMA -- both raise the MACs per
+// byte fetched from L2, which (not the tensor pipe) is what bounds fp32-operand tiles.  TMEM: MH * BLOCK_N columns.
+template <int BLOCK_N, int STAGES, int MH>
 __global__ void __launch_bounds__(192)
 conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcGeom g, float* __restrict__ y,
                double* __restrict__ stats, const float* __restrict__ bias, int act) {
-  constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BLOCK_N * 128;
+  constexpr uint32_t A_BYTES = MH * 128 * 128, B_BYTES = BLOCK_N * 128, TMEM_COLS = MH * BLOCK_N;
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base, sB = base + STAGES * A_BYTES, sBar = sB + STAGES * B_BYTES;
@@ -157,7 +161,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BLOCK_N) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -191,7 +195,10 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
         const uint64_t da = smem_desc_k_sw128(sA + s * A_BYTES), db = smem_desc_k_sw128(sB + s * B_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzle row
-          tc_mma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int hm = 0; hm < MH; ++hm)   // pixel rows [128 hm, 128 hm + 128) of the stage -> accumulator hm
+            tc_mma_tf32(tmem_base + (uint32_t)(hm * BLOCK_N), da + (uint64_t)(hm * (16384 >> 4)) + 2 * k, db + 2 * k, idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
         tc_commit(bar_empty + 8 * s);   // frees the smem stage once these MMAs have read it
       }
       if (KB > 0) tc_commit(bar_tmem);  // accumulator complete
@@ -200,52 +207,55 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   } else if (KB > 0) {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int lg = warp & 3;            // TMEM lane group this warp may access
-    const int row = lg * 32 + lane;
-    const int x = row % g.BW;
-    const int yy = (row / g.BW) % g.BH;
-    const int ii = row / (g.BW * g.BH);
-    const int gx = gx0 + x, gy = gy0 + yy, n = n0 + ii;
-    const bool valid = gx < ph.GW && gy < ph.GH && n < g.N;
-    float* dst = nullptr;
-    if (valid) {
-      const int oy = gy * g.so + ph.py, ox = gx * g.so + ph.px;
-      dst = y + (((int64_t)n * g.OH + oy) * g.OW + ox) * g.ldy + blockIdx.y * BLOCK_N;
-    }
     mbar_wait(bar_tmem, 0);
     tc_fence_after();
-    float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      float v[32];
-      tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), v);
-      if (valid && g.splits > 1) {        // split-K partial sums: accumulate into the zero-filled output
-#pragma unroll
-        for (int q = 0; q < 32; ++q) atomicAdd(dst + c * 32 + q, v[q]);
-      } else if (valid) {
-        if (bias != nullptr) {
-          const float* bp = bias + blockIdx.y * BLOCK_N + c * 32;
-#pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] += __ldg(bp + q);
-        }
-#pragma unroll
-        for (int q = 0; q < 32; ++q) { s1 += v[q]; s2 = fmaf(v[q], v[q], s2); }
-        if (act != PTK_ACT_NONE) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = apply_act(v[q], act);
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int hm = 0; hm < MH; ++hm) {
+      const int row = hm * 128 + lg * 32 + lane;
+      const int x = row % g.BW;
+      const int yy = (row / g.BW) % g.BH;
+      const int ii = row / (g.BW * g.BH);
+      const int gx = gx0 + x, gy = gy0 + yy, n = n0 + ii;
+      const bool valid = gx < ph.GW && gy < ph.GH && n < g.N;
+      float* dst = nullptr;
+      if (valid) {
+        const int oy = gy * g.so + ph.py, ox = gx * g.so + ph.px;
+        dst = y + (((int64_t)n * g.OH + oy) * g.OW + ox) * g.ldy + blockIdx.y * BLOCK_N;
       }
-    }
-    if (stats != nullptr && g.splits == 1) {
-      if (g.BW * g.BH >= 32) {          // the warp's 32 rows belong to one image
-        const float a = warp_sum(s1), b = warp_sum(s2);
-        const int nw = n0 + (lg * 32) / (g.BW * g.BH);
-        if (lane == 0 && nw < g.N) { atomicAdd(stats + 2 * nw, (double)a); atomicAdd(stats + 2 * nw + 1, (double)b); }
-      } else if (valid) {
-        atomicAdd(stats + 2 * n, (double)s1);
-        atomicAdd(stats + 2 * n + 1, (double)s2);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        float v[32];
+        tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(hm * BLOCK_N + c * 32), v);
+        if (valid && g.splits > 1) {        // split-K partial sums: accumulate into the zero-filled output
+#pragma unroll
+          for (int q = 0; q < 32; ++q) atomicAdd(dst + c * 32 + q, v[q]);
+        } else if (valid) {
+          if (bias != nullptr) {
+            const float* bp = bias + blockIdx.y * BLOCK_N + c * 32;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] += __ldg(bp + q);
+          }
+#pragma unroll
+          for (int q = 0; q < 32; ++q) { s1 += v[q]; s2 = fmaf(v[q], v[q], s2); }
+          if (act != PTK_ACT_NONE) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = apply_act(v[q], act);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+      if (stats != nullptr && g.splits == 1) {
+        if (g.BW * g.BH >= 32) {          // the warp's 32 rows belong to one image
+          const float a = warp_sum(s1), b = warp_sum(s2);
+          const int nw = n0 + (hm * 128 + lg * 32) / (g.BW * g.BH);
+          if (lane == 0 && nw < g.N) { atomicAdd(stats + 2 * nw, (double)a); atomicAdd(stats + 2 * nw + 1, (double)b); }
+        } else if (valid) {
+          atomicAdd(stats + 2 * n, (double)s1);
+          atomicAdd(stats + 2 * n + 1, (double)s2);
+        }
       }
     }
   }
@@ -253,7 +263,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -349,9 +359,43 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
       }
   }
   for (int i = 0; i < nphases; ++i) { maxGH = g.ph[i].GH > maxGH ? g.ph[i].GH : maxGH; maxGW = g.ph[i].GW > maxGW ? g.ph[i].GW : maxGW; }
-  g.BW = pow2_ge(maxGW < 128 ? maxGW : 128);
-  g.BH = pow2_ge(maxGH < 128 / g.BW ? maxGH : 128 / g.BW);
-  g.BI = 128 / (g.BW * g.BH);
+  int min_kb = 1 << 30;
+  for (int i = 0; i < nphases; ++i) { const int kb = g.ph[i].ntaps * g.kchunks; if (kb < min_kb) min_kb = kb; }
+
+  // ---- tile selection.  fp32 operands make every tile L2-bandwidth bound (bytes per MAC ~ 1/M + 1/N), so the largest
+  // tile that still fills the machine wins: (MH = 2, BN = 256) moves half the bytes per MAC of (1, 128).  Cost model:
+  // waves x per-tile time, with a relative efficiency per tile shape and a fixed prologue/epilogue charge for the
+  // one-CTA-per-SM shapes (nothing overlaps them).  PTK_TC_TILE="mh,bn" overrides (tests / experiments).
+  struct TileCfg { int mh, bn, stages, occ; float eff; };
+  static const TileCfg kCfgs[] = {{1, 64, 4, 2, 0.36f}, {1, 128, 3, 2, 0.50f}, {1, 256, 4, 1, 0.64f}, {2, 128, 4, 1, 0.64f}, {2, 256, 3, 1, 0.80f}};
+  int forced_mh = 0, forced_bn = 0;
+  if (const char* e = getenv("PTK_TC_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
+  const TileCfg* best = nullptr;
+  double best_cost = 0.0;
+  for (const TileCfg& t : kCfgs) {
+    if (c.Cout % t.bn != 0) continue;
+    if (t.bn == 64 && c.Cout % 128 == 0) continue;
+    const int M = 128 * t.mh;
+    const int bw = pow2_ge(maxGW < M ? maxGW : M);
+    const int bh = pow2_ge(maxGH < M / bw ? maxGH : M / bw);
+    const int bi = M / (bw * bh);
+    if (bi > 256) continue;
+    const int64_t ctas = (int64_t)((maxGW + bw - 1) / bw) * ((maxGH + bh - 1) / bh) * ((c.N + bi - 1) / bi) * (c.Cout / t.bn) * nphases;
+    const int64_t slots = (int64_t)num_sms() * t.occ;
+    // the big one-CTA-per-SM shapes only pay once they fill the machine (small layers want many CTAs + split-K), and
+    // must not pad the batch dimension beyond the next power of two
+    if (t.occ == 1 && !(forced_mh == t.mh && forced_bn == t.bn) && (ctas < slots || bi > pow2_ge(c.N))) continue;
+    const double tile_clk = (double)min_kb * t.mh * (t.bn / 128.0) * 256.0 / t.eff + (t.occ == 1 ? 6000.0 : 1500.0);
+    const double cost = (double)((ctas + slots - 1) / slots) * t.occ * tile_clk;
+    const bool forced = forced_mh == t.mh && forced_bn == t.bn;
+    if (forced) { best = &t; break; }
+    if (!best || cost < best_cost) { best = &t; best_cost = cost; }
+  }
+  PTK_REQUIRE(best != nullptr, "conv_forward(tc): no tile configuration for Cout=%d", c.Cout);
+  const int MH = best->mh, BN = best->bn, MT = 128 * MH;
+  g.BW = pow2_ge(maxGW < MT ? maxGW : MT);
+  g.BH = pow2_ge(maxGH < MT / g.BW ? maxGH : MT / g.BW);
+  g.BI = MT / (g.BW * g.BH);
   g.tiles_x = (maxGW + g.BW - 1) / g.BW; g.tiles_y = (maxGH + g.BH - 1) / g.BH; g.tiles_i = (c.N + g.BI - 1) / g.BI;
 
   // activation tensor maps
@@ -371,7 +415,6 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     int rc = encode(&maps.a[0], x, 4, dims, str, boxA);
     if (rc) return rc;
   }
-  const int BN = (c.Cout % 128 == 0) ? 128 : 64;
   {
     const uint64_t dims[3] = {(uint64_t)c.Cin, (uint64_t)c.Cout, (uint64_t)(k * k)};
     const uint64_t str[2] = {(uint64_t)c.Cin * 4, (uint64_t)c.Cin * c.Cout * 4};
@@ -382,8 +425,6 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   // Small-M layers (the 4x4 .. 16x16 levels at batch 8) have only a handful of output tiles but up to 16 taps x 48
   // K-chunks each: split the K loop across CTAs so that the weight stream is spread over all SMs.
   const int ctas = g.tiles_x * g.tiles_y * g.tiles_i * (c.Cout / BN) * nphases;
-  int min_kb = 1 << 30;
-  for (int i = 0; i < nphases; ++i) { const int kb = g.ph[i].ntaps * g.kchunks; if (kb < min_kb) min_kb = kb; }
   int splits = 1;
   if (ctas * 2 <= num_sms() && c.ldy == c.Cout && bias == nullptr && act == PTK_ACT_NONE) {
     splits = (2 * num_sms() + ctas - 1) / ctas;
@@ -397,19 +438,19 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     if (rc) return rc;
   }
   dim3 grid((unsigned)(g.tiles_x * g.tiles_y * g.tiles_i), (unsigned)(c.Cout / BN), (unsigned)(nphases * splits));
-  if (BN == 128) {
-    constexpr int STAGES = 3;
-    const size_t smem = STAGES * (128 * 128 + 128 * 128) + 16 * STAGES + 16 + 1024;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<128, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    conv_tc_kernel<128, STAGES><<<grid, 192, smem, st>>>(maps, g, y, stats, bias, act);
-  } else {
-    constexpr int STAGES = 4;
-    const size_t smem = STAGES * (128 * 128 + 64 * 128) + 16 * STAGES + 16 + 1024;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<64, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    conv_tc_kernel<64, STAGES><<<grid, 192, smem, st>>>(maps, g, y, stats, bias, act);
-  }
+#define PTK_TC_LAUNCH(BN_, ST_, MH_)                                                                                       \
+  do {                                                                                                                     \
+    const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 16 + 1024;                                 \
+    static bool attr = false;                                                                                              \
+    if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
+    conv_tc_kernel<BN_, ST_, MH_><<<grid, 192, smem, st>>>(maps, g, y, stats, bias, act);                                   \
+  } while (0)
+  if (MH == 1 && BN == 64) PTK_TC_LAUNCH(64, 4, 1);
+  else if (MH == 1 && BN == 128) PTK_TC_LAUNCH(128, 3, 1);
+  else if (MH == 1 && BN == 256) PTK_TC_LAUNCH(256, 4, 1);
+  else if (MH == 2 && BN == 128) PTK_TC_LAUNCH(128, 4, 2);
+  else PTK_TC_LAUNCH(256, 3, 2);
+#undef PTK_TC_LAUNCH
   PTK_LAUNCH_CHECK("conv_tc_kernel");
   if (splits > 1 && stats != nullptr)   // partial sums cannot feed the fused statistics: one extra pass over a tiny tensor
     return ptk_gn_stats(y, c.ldy, c.N, (int64_t)c.OH * c.OW, c.Cout, stats, st);
@@ -448,11 +489,15 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t addr, uint32
   return d;
 }
 
-template <int BLOCK_N, int STAGES>
+// MH = number of 128-channel halves of the A (Ca) tile: MH = 2 / BLOCK_N = 256 halve the L2 bytes per MAC (see
+// conv_tc_kernel).  TMEM: MH * BLOCK_N columns.
+template <int BLOCK_N, int STAGES, int MH>
 __global__ void __launch_bounds__(192)
 wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ WgTcGeom g, float* __restrict__ dw) {
   constexpr uint32_t KP = 32;                                    // pixels per stage
-  constexpr uint32_t A_BYTES = 128 * KP * 4, B_BYTES = BLOCK_N * KP * 4, BOX_BYTES = 32 * KP * 4;
+  constexpr uint32_t A_BYTES = MH * 128 * KP * 4, B_BYTES = BLOCK_N * KP * 4, BOX_BYTES = 32 * KP * 4;
+  constexpr uint32_t TMEM_COLS = MH * BLOCK_N < 32 ? 32 : MH * BLOCK_N;
+  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base, sB = base + STAGES * A_BYTES, sBar = sB + STAGES * B_BYTES;
@@ -473,7 +518,7 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BLOCK_N) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -497,8 +542,8 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
         const int gx0 = tx * g.BW, gy0 = ty * g.BH, n0 = ti * g.BI;
         mbar_expect_tx(bar_full + 8 * s, A_BYTES + B_BYTES);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          tma_load_4d(sA + s * A_BYTES + j * BOX_BYTES, &maps.s, bar_full + 8 * s, at * 128 + j * 32, gx0, gy0, n0);
+        for (int j = 0; j < 4 * MH; ++j)
+          tma_load_4d(sA + s * A_BYTES + j * BOX_BYTES, &maps.s, bar_full + 8 * s, at * (128 * MH) + j * 32, gx0, gy0, n0);
 #pragma unroll
         for (int j = 0; j < BLOCK_N / 32; ++j)
           tma_load_4d(sB + s * B_BYTES + j * BOX_BYTES, mb, bar_full + 8 * s, bt * BLOCK_N + j * 32, gx0 + cxt, gy0 + cyt, n0);
@@ -517,7 +562,10 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
         const uint64_t da = smem_desc_mn_sw128_32b(sA + s * A_BYTES, BOX_BYTES), db = smem_desc_mn_sw128_32b(sB + s * B_BYTES, BOX_BYTES);
 #pragma unroll
         for (int k = 0; k < (int)KP / 8; ++k)   // 8 pixels (one 1024-byte swizzle atom row-group) per MMA
-          tc_mma_tf32(tmem_base, da + (uint64_t)(k * (1024 >> 4)), db + (uint64_t)(k * (1024 >> 4)), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int hm = 0; hm < MH; ++hm)       // channels [128 hm, 128 hm + 128) of the A stage = boxes 4 hm .. 4 hm + 3
+            tc_mma_tf32(tmem_base + (uint32_t)(hm * BLOCK_N), da + (uint64_t)((hm * 4 * BOX_BYTES) >> 4) + (uint64_t)(k * (1024 >> 4)),
+                        db + (uint64_t)(k * (1024 >> 4)), idesc, (kb > 0 || k > 0) ? 1u : 0u);
         tc_commit(bar_empty + 8 * s);
       }
       tc_commit(bar_tmem);
@@ -525,22 +573,25 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
     __syncwarp();
   } else if (KB > 0) {
     const int lg = warp & 3;
-    const int a = at * 128 + lg * 32 + lane;
-    float* dst = dw + ((int64_t)tap * g.Ca + a) * g.Cb_pad + bt * BLOCK_N;
     mbar_wait(bar_tmem, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      float v[32];
-      tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), v);
-      if (a >= g.Ca) continue;       // rows beyond Ca were TMA zero-fill (Ca = 64 layers use half of the M = 128 tile)
-      if (g.splits == 1) {
+    for (int hm = 0; hm < MH; ++hm) {
+      const int a = at * (128 * MH) + hm * 128 + lg * 32 + lane;
+      float* dst = dw + ((int64_t)tap * g.Ca + a) * g.Cb_pad + bt * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        float v[32];
+        tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(hm * BLOCK_N + c * 32), v);
+        if (a >= g.Ca) continue;       // rows beyond Ca were TMA zero-fill (Ca = 64 layers use half of the M = 128 tile)
+        if (g.splits == 1) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      } else {
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) atomicAdd(dst + c * 32 + q, v[q]);
+          for (int q = 0; q < 32; ++q) atomicAdd(dst + c * 32 + q, v[q]);
+        }
       }
     }
   }
@@ -548,7 +599,7 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -614,37 +665,61 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     int rc = encode(&maps.b[0], Bg, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
-  const int BN = (Cb % 128 == 0) ? 128 : (Cb % 64 == 0 ? 64 : 32);
-  const int atiles = (g.Ca + 127) / 128;
-  const int base_ctas = atiles * (Cb / BN) * g.ntaps;
-  int splits = (num_sms() * 4 + base_ctas - 1) / base_ctas;
-  if (splits > g.ntiles) splits = g.ntiles;
-  if (splits < 1) splits = 1;
-  // every split must own at least one pixel tile
-  while (splits > 1 && (g.ntiles + splits - 1) / splits * (splits - 1) >= g.ntiles) --splits;
+  // ---- tile + split-K selection (same reasoning as conv_forward_tc): candidates (MH, BN); for each, the split count
+  // that minimises waves x (k-iterations x stage time + fixed prologue/epilogue).
+  struct WgCfg { int mh, bn, occ; float eff; };
+  static const WgCfg kCfgs[] = {{1, 32, 2, 0.30f}, {1, 64, 2, 0.36f}, {1, 128, 2, 0.50f}, {2, 128, 1, 0.64f}, {1, 256, 1, 0.64f}, {2, 256, 1, 0.80f}};
+  int forced_mh = 0, forced_bn = 0;
+  if (const char* e = getenv("PTK_WG_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
+  const int bn_small = (Cb % 128 == 0) ? 128 : (Cb % 64 == 0 ? 64 : 32);
+  const WgCfg* best = nullptr;
+  int best_splits = 1;
+  double best_cost = 0.0;
+  for (const WgCfg& t : kCfgs) {
+    if (Cb % t.bn != 0) continue;
+    if (t.bn < bn_small) continue;
+    if (t.mh == 2 && g.Ca % 256 != 0) continue;
+    const bool forced = forced_mh == t.mh && forced_bn == t.bn;
+    const int64_t base_ctas = (int64_t)((g.Ca + 128 * t.mh - 1) / (128 * t.mh)) * (Cb / t.bn) * g.ntaps;
+    const int64_t slots = (int64_t)num_sms() * t.occ;
+    const double stage_clk = t.mh * (t.bn / 128.0) * 256.0 / t.eff;
+    int cfg_splits = 1;
+    double cfg_cost = 0.0;
+    for (int sp = 1; sp <= g.ntiles && sp <= 512; ++sp) {
+      if (sp > 1 && (g.ntiles + sp - 1) / sp * (sp - 1) >= g.ntiles) continue;   // every split must own a pixel tile
+      const int64_t ctas = base_ctas * sp;
+      const double tile_clk = (double)((g.ntiles + sp - 1) / sp) * stage_clk + (t.occ == 1 ? 6000.0 : 1500.0) +
+                              (sp > 1 ? 8.0 * t.mh * t.bn : 0.0);                 // atomic epilogue
+      const double cost = (double)((ctas + slots - 1) / slots) * t.occ * tile_clk;
+      if (sp == 1 || cost < cfg_cost) { cfg_cost = cost; cfg_splits = sp; }
+    }
+    if (forced) { best = &t; best_splits = cfg_splits; break; }
+    if (!best || cfg_cost < best_cost) { best = &t; best_cost = cfg_cost; best_splits = cfg_splits; }
+  }
+  PTK_REQUIRE(best != nullptr, "conv_wgrad(tc): no tile configuration for Ca=%d Cb=%d", g.Ca, Cb);
+  const int BN = best->bn, MH = best->mh;
+  const int atiles = (g.Ca + 128 * MH - 1) / (128 * MH);
+  const int splits = best_splits;
   g.splits = splits;
   if (splits > 1) {
     int rc = ptk_fill(dw, (int64_t)g.ntaps * g.Ca * Cb, 0.f, st);
     if (rc) return rc;
   }
   dim3 grid((unsigned)(atiles * (Cb / BN)), (unsigned)g.ntaps, (unsigned)splits);
-  constexpr int STAGES = 3;
-  if (BN == 32) {
-    const size_t smem = STAGES * (128 * 128 + 32 * 128) + 16 * STAGES + 16 + 1024;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<32, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    wgrad_tc_kernel<32, STAGES><<<grid, 192, smem, st>>>(maps, g, dw);
-  } else if (BN == 128) {
-    const size_t smem = STAGES * (128 * 128 + 128 * 128) + 16 * STAGES + 16 + 1024;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<128, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    wgrad_tc_kernel<128, STAGES><<<grid, 192, smem, st>>>(maps, g, dw);
-  } else {
-    const size_t smem = STAGES * (128 * 128 + 64 * 128) + 16 * STAGES + 16 + 1024;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<64, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    wgrad_tc_kernel<64, STAGES><<<grid, 192, smem, st>>>(maps, g, dw);
-  }
+#define PTK_WG_LAUNCH(BN_, ST_, MH_)                                                                                       \
+  do {                                                                                                                     \
+    const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 16 + 1024;                                 \
+    static bool attr = false;                                                                                              \
+    if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<BN_, ST_, MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
+    wgrad_tc_kernel<BN_, ST_, MH_><<<grid, 192, smem, st>>>(maps, g, dw);                                                   \
+  } while (0)
+  if (MH == 1 && BN == 32) PTK_WG_LAUNCH(32, 3, 1);
+  else if (MH == 1 && BN == 64) PTK_WG_LAUNCH(64, 3, 1);
+  else if (MH == 1 && BN == 128) PTK_WG_LAUNCH(128, 3, 1);
+  else if (MH == 1 && BN == 256) PTK_WG_LAUNCH(256, 4, 1);
+  else if (MH == 2 && BN == 128) PTK_WG_LAUNCH(128, 4, 2);
+  else PTK_WG_LAUNCH(256, 3, 2);
+#undef PTK_WG_LAUNCH
   PTK_LAUNCH_CHECK("wgrad_tc_kernel");
   return 0;
 }

@@ -267,7 +267,11 @@ warp_forward_coop_kernel(const float* __restrict__ x, int ldx, const float* __re
     active &= kmask; uni &= kmask;
     const unsigned inactive = ~active & kmask;
     const int kz = inactive ? __ffs(inactive) - 1 : 1 << 20;   // where the (single) "0, no gradient" candidate sits
-    for (int c0 = gl * 8; c0 < C; c0 += G * 8) {
+    // Each lane owns two float4 per chunk of G*8 channels: channels [cb + 4 gl, +4) and [cb + 4 G + 4 gl, +4), so that
+    // every 128-bit load / store instruction of a group covers one CONTIGUOUS run of 16*G bytes (whole L1 lines and
+    // full sectors per request instead of the half-used sectors of an "8 consecutive channels per lane" mapping).
+    for (int cb = 0; cb < C; cb += G * 8) {
+      const int c0 = cb + gl * 4, c1 = c0 + G * 4;
       float best[8];
       unsigned char arg[8];
 #pragma unroll
@@ -291,14 +295,14 @@ warp_forward_coop_kernel(const float* __restrict__ x, int ldx, const float* __re
         const float w01 = (yin0 && xin1) ? (1.f - g.fy) * g.fx * g.m : 0.f;
         const float w10 = (yin1 && xin0) ? g.fy * (1.f - g.fx) * g.m : 0.f;
         const float w11 = (yin1 && xin1) ? g.fy * g.fx * g.m : 0.f;
-        const float* r0 = xb + (y0 * w + x0) * ldx + c0;
+        const float* r0 = xb + (y0 * w + x0) * ldx;
         const float* r1 = r0 + w * ldx;
-        float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), cb = ca;
-        if (yin0 && xin0) { fma4(ca, w00, __ldg(reinterpret_cast<const float4*>(r0))); fma4(cb, w00, __ldg(reinterpret_cast<const float4*>(r0 + 4))); }
-        if (yin0 && xin1) { fma4(ca, w01, __ldg(reinterpret_cast<const float4*>(r0 + ldx))); fma4(cb, w01, __ldg(reinterpret_cast<const float4*>(r0 + ldx + 4))); }
-        if (yin1 && xin0) { fma4(ca, w10, __ldg(reinterpret_cast<const float4*>(r1))); fma4(cb, w10, __ldg(reinterpret_cast<const float4*>(r1 + 4))); }
-        if (yin1 && xin1) { fma4(ca, w11, __ldg(reinterpret_cast<const float4*>(r1 + ldx))); fma4(cb, w11, __ldg(reinterpret_cast<const float4*>(r1 + ldx + 4))); }
-        const float cand[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), cc = ca;
+        if (yin0 && xin0) { fma4(ca, w00, __ldg(reinterpret_cast<const float4*>(r0 + c0))); fma4(cc, w00, __ldg(reinterpret_cast<const float4*>(r0 + c1))); }
+        if (yin0 && xin1) { fma4(ca, w01, __ldg(reinterpret_cast<const float4*>(r0 + ldx + c0))); fma4(cc, w01, __ldg(reinterpret_cast<const float4*>(r0 + ldx + c1))); }
+        if (yin1 && xin0) { fma4(ca, w10, __ldg(reinterpret_cast<const float4*>(r1 + c0))); fma4(cc, w10, __ldg(reinterpret_cast<const float4*>(r1 + c1))); }
+        if (yin1 && xin1) { fma4(ca, w11, __ldg(reinterpret_cast<const float4*>(r1 + ldx + c0))); fma4(cc, w11, __ldg(reinterpret_cast<const float4*>(r1 + ldx + c1))); }
+        const float cand[8] = {ca.x, ca.y, ca.z, ca.w, cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
         for (int q = 0; q < 8; ++q) if (cand[q] > best[q]) { best[q] = cand[q]; arg[q] = (unsigned char)k; }
       }
@@ -307,13 +311,11 @@ warp_forward_coop_kernel(const float* __restrict__ x, int ldx, const float* __re
         for (int q = 0; q < 8; ++q) if (0.f > best[q]) { best[q] = 0.f; arg[q] = 255; }
       }
       if (pvalid) {
-        float* dst = yb + p * ldy + c0;
-        *reinterpret_cast<float4*>(dst) = make_float4(apply_act(best[0], act), apply_act(best[1], act), apply_act(best[2], act), apply_act(best[3], act));
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(apply_act(best[4], act), apply_act(best[5], act), apply_act(best[6], act), apply_act(best[7], act));
-        uint2 a8;
-        a8.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | ((unsigned)arg[3] << 24);
-        a8.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | ((unsigned)arg[7] << 24);
-        *reinterpret_cast<uint2*>(ab + p * C + c0) = a8;
+        float* dst = yb + p * ldy;
+        *reinterpret_cast<float4*>(dst + c0) = make_float4(apply_act(best[0], act), apply_act(best[1], act), apply_act(best[2], act), apply_act(best[3], act));
+        *reinterpret_cast<float4*>(dst + c1) = make_float4(apply_act(best[4], act), apply_act(best[5], act), apply_act(best[6], act), apply_act(best[7], act));
+        *reinterpret_cast<uint32_t*>(ab + p * C + c0) = arg[0] | (arg[1] << 8) | (arg[2] << 16) | ((unsigned)arg[3] << 24);
+        *reinterpret_cast<uint32_t*>(ab + p * C + c1) = arg[4] | (arg[5] << 8) | (arg[6] << 16) | ((unsigned)arg[7] << 24);
       }
     }
   }

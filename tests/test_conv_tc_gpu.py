@@ -242,3 +242,61 @@ def test_conv_tc_dgrad_of_narrow_heads(name, k, s, p, Cin, Cout, N, H, W):
     layer.dgrad(K.Slice(dzd), N, H, W, K.Slice(dx))
     torch.cuda.synchronize()
     assert rel_l2(nchw(dx).cpu(), x.grad) < TF32_TOL, describe(nchw(dx).cpu(), x.grad, "dgrad")
+
+
+TILE_CFGS = ["1,128", "1,256", "2,128", "2,256"]
+TILE_GEOS = [
+    # name, transposed, Cin, Cout, N, H, W  (k4 s2 p1): ragged tiles in x / y / batch, phases, multi N-tiles
+    ("down_64to256_ragged", False, 64, 256, 3, 22, 38),
+    ("up_128to512_ragged", True, 128, 512, 3, 9, 21),
+    ("down_128to256_tiny", False, 128, 256, 2, 8, 8),
+    ("down_256to256_ragged", False, 256, 256, 3, 12, 20),
+    ("up_256to256_ragged", True, 256, 256, 2, 7, 11),
+]
+
+
+@pytest.mark.parametrize("tile", TILE_CFGS)
+@pytest.mark.parametrize("geo", TILE_GEOS, ids=[g[0] for g in TILE_GEOS])
+def test_conv_tc_tile_shapes(geo, tile, monkeypatch):
+    """Every (M-halves, BLOCK_N) tile shape of conv_tc_kernel, forced through PTK_TC_TILE, against torch CPU fp32:
+    fprop + fused statistics + dgrad on geometries whose tiles are ragged in x, y and batch."""
+    import pose_transfer_b200  # noqa: F401
+    from pose_transfer_b200 import kernels as K
+    from pose_transfer_b200.engine import ConvLayer
+    name, tr, Cin, Cout, N, H, W = geo
+    monkeypatch.setenv("PTK_TC_TILE", tile)
+    monkeypatch.setenv("PTK_WG_TILE", tile)
+    g = torch.Generator().manual_seed(sum(map(ord, name + tile)))
+    wshape = (Cin, Cout, 4, 4) if tr else (Cout, Cin, 4, 4)
+    w = (torch.rand(wshape, generator=g) * 2 - 1) / (Cin * 16 / (4 if tr else 1)) ** 0.5
+    x = torch.randn(N, Cin, H, W, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    z = F.conv_transpose2d(xr, wr, None, stride=2, padding=1) if tr else F.conv2d(xr, wr, None, stride=2, padding=1)
+    dz = torch.randn(z.shape, generator=g)
+    z.backward(dz)
+    zd = z.detach()
+    layer = ConvLayer(torch.nn.Parameter(w.cuda()), None, tr, 4, 2, 1)
+    layer.impl = K.IMPL_TC
+    layer.pack_forward()
+    xin = nhwc(x).cuda()
+    OH, OW = layer.out_hw(H, W)
+    y = torch.full((N, OH, OW, Cout + 32), 7.0, device="cuda")
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    layer.forward(K.Slice(xin), N, H, W, K.Slice(y, 32, Cout), K.ACT_NONE, stats)
+    torch.cuda.synchronize()
+    got = nchw(y[..., 32:]).cpu()
+    assert rel_l2(got, zd) < TF32_TOL, describe(got, zd, "fprop " + tile)
+    assert float((y[..., :32] - 7.0).abs().max()) == 0, "wrote outside its channel slice"
+    ref_sq = (zd.double() ** 2).reshape(N, -1).sum(1)
+    assert rel_l2(stats[:, 1].cpu(), ref_sq) < 2e-3
+    dx = torch.zeros(N, H, W, Cin, device="cuda")
+    layer.dgrad(K.Slice(nhwc(dz).cuda()), N, H, W, K.Slice(dx))
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(dx).cpu(), xr.grad) < TF32_TOL, describe(nchw(dx).cpu(), xr.grad, "dgrad " + tile)
+    # wgrad with the same forced (channel-halves, BLOCK_N) shape where the channel counts allow it
+    gw = torch.zeros(wshape, device="cuda")
+    scratch = torch.full((layer.taps * layer.cin_pad * layer.cout_pad,), 3.0, device="cuda")
+    layer.wgrad(K.Slice(xin), K.Slice(nhwc(dz).cuda()), N, H, W, scratch, gw)
+    torch.cuda.synchronize()
+    assert rel_l2(gw.cpu(), wr.grad) < TF32_TOL, describe(gw.cpu(), wr.grad, "wgrad " + tile)
