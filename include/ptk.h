@@ -57,6 +57,9 @@ int ptk_pack_weight_dual(const float* src, float* dst0, float* dst1, int A, int 
 /* grad[a][b][tap] (+)= src[tap][a][b_pad]  (inverse of transpose==0 packing, drops padding) */
 int ptk_unpack_weight_grad(const float* src, float* grad, int A, int B, int taps, int B_pad,
                            int accumulate, void* stream);
+/* grad[a][b][tap] (+)= sum_{q < nparts} src[q * part_stride + (tap*A + a)*B_pad + b] */
+int ptk_unpack_weight_grad_parts(const float* src, int nparts, int64_t part_stride, float* grad, int A, int B,
+                                 int taps, int B_pad, int accumulate, void* stream);
 int ptk_fill(float* dst, int64_t n, float value, void* stream);
 
 /* ---------------------------------------------------------------- convolutions
@@ -93,6 +96,11 @@ int ptk_conv_forward(const ptk_conv_geom* g, const float* x, const float* w_t, c
  * zero-fills it itself when it needs split-K accumulation).  tcgen05 TF32 path for k4 s2 layers with wide channels,
  * fp32 CUDA-core path otherwise. */
 int ptk_conv_wgrad(const ptk_conv_geom* g, const float* x, const float* dy, float* dw, void* stream);
+/* Same gradient, split-K without atomics: dw has room for dw_capacity floats (>= one gradient = k*k*Cin*Cout); the
+ * kernel may write *nparts partial gradients (each k*k*Cin*Cout floats, back to back) that the caller sums with
+ * ptk_unpack_weight_grad_parts -- a fixed summation order, i.e. a deterministic weight gradient. */
+int ptk_conv_wgrad_parts(const ptk_conv_geom* g, const float* x, const float* dy, float* dw, int64_t dw_capacity,
+                         int* nparts, void* stream);
 /* dbias[c] += sum_pixels dy[pixel][c] */
 int ptk_bias_grad(const float* dy, int ld, int64_t pixels, int C, float* dbias, void* stream);
 

@@ -9,7 +9,8 @@ bool conv_tc_supported(const ptk_conv_geom& c);
 int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, const float* bias, int act, float* y,
                     double* stats, cudaStream_t st);
 bool conv_wgrad_tc_supported(const ptk_conv_geom& c);
-int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float* dw, cudaStream_t st);
+int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float* dw, int64_t dw_capacity, int* nparts,
+                  cudaStream_t st);
 }  // namespace ptk
 
 using namespace ptk;
@@ -48,8 +49,23 @@ extern "C" int ptk_conv_forward(const ptk_conv_geom* g, const float* x, const fl
 extern "C" int ptk_conv_wgrad(const ptk_conv_geom* g, const float* x, const float* dy, float* dw, void* stream) {
   PTK_REQUIRE(g && x && dy && dw, "conv_wgrad: null argument");
   if (g->impl == PTK_IMPL_TC) PTK_REQUIRE(conv_wgrad_tc_supported(*g), "conv_wgrad: geometry not supported by the tcgen05 path");
-  if (g->impl != PTK_IMPL_SIMT && conv_wgrad_tc_supported(*g)) return conv_wgrad_tc(*g, x, dy, dw, (cudaStream_t)stream);
+  if (g->impl != PTK_IMPL_SIMT && conv_wgrad_tc_supported(*g)) return conv_wgrad_tc(*g, x, dy, dw, 0, nullptr, (cudaStream_t)stream);
   int rc = ptk_fill(dw, (int64_t)g->k * g->k * (g->transposed ? (int64_t)g->Cin * g->Cout : (int64_t)g->Cout * g->Cin), 0.f, stream);
+  if (rc) return rc;
+  return conv_wgrad_simt(*g, x, dy, dw, (cudaStream_t)stream);
+}
+
+extern "C" int ptk_conv_wgrad_parts(const ptk_conv_geom* g, const float* x, const float* dy, float* dw, int64_t dw_capacity,
+                                    int* nparts, void* stream) {
+  PTK_REQUIRE(g && x && dy && dw && nparts, "conv_wgrad_parts: null argument");
+  const int64_t part = (int64_t)g->k * g->k * (int64_t)g->Cin * g->Cout;
+  PTK_REQUIRE(dw_capacity >= part, "conv_wgrad_parts: dw_capacity (%lld) smaller than one gradient (%lld floats)",
+              (long long)dw_capacity, (long long)part);
+  if (g->impl == PTK_IMPL_TC) PTK_REQUIRE(conv_wgrad_tc_supported(*g), "conv_wgrad: geometry not supported by the tcgen05 path");
+  if (g->impl != PTK_IMPL_SIMT && conv_wgrad_tc_supported(*g))
+    return conv_wgrad_tc(*g, x, dy, dw, dw_capacity, nparts, (cudaStream_t)stream);
+  *nparts = 1;
+  int rc = ptk_fill(dw, part, 0.f, stream);
   if (rc) return rc;
   return conv_wgrad_simt(*g, x, dy, dw, (cudaStream_t)stream);
 }

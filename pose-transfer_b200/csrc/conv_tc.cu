@@ -470,6 +470,8 @@ struct WgTcGeom {
   int BW, BH, BI, tiles_x, tiles_y, tiles_i, ntiles;
   int Ca, Cb_pad;                // dw[t][Ca][Cb_pad]
   int splits;
+  long long part_stride;         // > 0: split z writes its own partial buffer dw + z * part_stride (plain stores, summed
+                                 // by ptk_unpack_weight_grad_parts => deterministic); 0: splits accumulate atomically
   signed char cy[16], cx[16];
   unsigned char map[16];
 };
@@ -578,13 +580,13 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
 #pragma unroll 1
     for (int hm = 0; hm < MH; ++hm) {
       const int a = at * (128 * MH) + hm * 128 + lg * 32 + lane;
-      float* dst = dw + ((int64_t)tap * g.Ca + a) * g.Cb_pad + bt * BLOCK_N;
+      float* dst = dw + (int64_t)split * g.part_stride + ((int64_t)tap * g.Ca + a) * g.Cb_pad + bt * BLOCK_N;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         float v[32];
         tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(hm * BLOCK_N + c * 32), v);
         if (a >= g.Ca) continue;       // rows beyond Ca were TMA zero-fill (Ca = 64 layers use half of the M = 128 tile)
-        if (g.splits == 1) {
+        if (g.splits == 1 || g.part_stride > 0) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -613,9 +615,12 @@ bool conv_wgrad_tc_supported(const ptk_conv_geom& c) {
   return true;
 }
 
-// dw must hold taps*Ca*Cb floats; it is fully overwritten when the launch uses a single split, otherwise the caller's
-// zero-fill is accumulated into (the function reports which via *overwrote).
-int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float* dw, cudaStream_t st) {
+// Legacy mode (nparts == nullptr): dw holds taps*Ca*Cb floats and receives the complete gradient (split-K partials are
+// accumulated atomically into a zero fill issued here).  Partial mode (nparts != nullptr): dw has room for
+// dw_capacity floats; every split writes its own buffer of taps*Ca*Cb floats with plain stores and *nparts reports
+// how many there are -- the caller sums them (ptk_unpack_weight_grad_parts), which makes the result deterministic.
+int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float* dw, int64_t dw_capacity, int* nparts,
+                  cudaStream_t st) {
   WgTcGeom g;
   memset(&g, 0, sizeof(g));
   WgTmapSet maps;
@@ -685,12 +690,15 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     const double stage_clk = t.mh * (t.bn / 128.0) * 256.0 / t.eff;
     int cfg_splits = 1;
     double cfg_cost = 0.0;
+    const int64_t part_floats = (int64_t)g.ntaps * g.Ca * Cb;
     for (int sp = 1; sp <= g.ntiles && sp <= 512; ++sp) {
       if (sp > 1 && (g.ntiles + sp - 1) / sp * (sp - 1) >= g.ntiles) continue;   // every split must own a pixel tile
+      if (nparts != nullptr && sp > 1 && part_floats * sp > dw_capacity) break;
       const int64_t ctas = base_ctas * sp;
-      const double tile_clk = (double)((g.ntiles + sp - 1) / sp) * stage_clk + (t.occ == 1 ? 6000.0 : 1500.0) +
-                              (sp > 1 ? 8.0 * t.mh * t.bn : 0.0);                 // atomic epilogue
-      const double cost = (double)((ctas + slots - 1) / slots) * t.occ * tile_clk;
+      const double tile_clk = (double)((g.ntiles + sp - 1) / sp) * stage_clk + (t.occ == 1 ? 6000.0 : 1500.0);
+      // cost of combining the splits: L2 atomics (~100 floats / clk chip-wide) or one more streamed read per part
+      const double combine = sp > 1 ? (double)part_floats * sp / (nparts != nullptr ? 800.0 : 100.0) : 0.0;
+      const double cost = (double)((ctas + slots - 1) / slots) * t.occ * tile_clk + combine;
       if (sp == 1 || cost < cfg_cost) { cfg_cost = cost; cfg_splits = sp; }
     }
     if (forced) { best = &t; best_splits = cfg_splits; break; }
@@ -701,7 +709,9 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
   const int atiles = (g.Ca + 128 * MH - 1) / (128 * MH);
   const int splits = best_splits;
   g.splits = splits;
-  if (splits > 1) {
+  g.part_stride = nparts != nullptr ? (long long)g.ntaps * g.Ca * Cb : 0;
+  if (nparts != nullptr) *nparts = splits;
+  if (splits > 1 && nparts == nullptr) {
     int rc = ptk_fill(dw, (int64_t)g.ntaps * g.Ca * Cb, 0.f, st);
     if (rc) return rc;
   }

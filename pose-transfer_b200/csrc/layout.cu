@@ -104,9 +104,11 @@ __global__ void unpack_weight_grad_kernel(const float* __restrict__ src, float* 
 }
 
 // tiled inverse of pack_weight_dual's dst0: grad[a][b][t] (+)= src[t][a][b_pad]; coalesced on both sides
+// (nparts partial buffers part_stride floats apart are summed in a fixed order: the split-K reduction of the tensor-core
+// wgrad, deterministic)
 __global__ void __launch_bounds__(256)
-unpack_weight_grad_tiled_kernel(const float* __restrict__ src, float* __restrict__ grad, int A, int B, int taps, int B_pad,
-                                int accumulate) {
+unpack_weight_grad_tiled_kernel(const float* __restrict__ src, int nparts, int64_t part_stride, float* __restrict__ grad,
+                                int A, int B, int taps, int B_pad, int accumulate) {
   constexpr int TA = 16, TB = 32;
   __shared__ float tile[TA][TB][17];
   const int a0 = blockIdx.y * TA, b0 = blockIdx.x * TB;
@@ -114,7 +116,12 @@ unpack_weight_grad_tiled_kernel(const float* __restrict__ src, float* __restrict
   const int nb = min(TB, B - b0);
   for (int i = tid; i < taps * TA * TB; i += 256) {
     const int b = i % TB, a = (i / TB) % TA, t = i / (TB * TA);
-    if (a0 + a < A && b < nb) tile[a][b][t] = __ldg(src + ((int64_t)t * A + a0 + a) * B_pad + b0 + b);
+    if (a0 + a < A && b < nb) {
+      const float* sp = src + ((int64_t)t * A + a0 + a) * B_pad + b0 + b;
+      float v = __ldg(sp);
+      for (int q = 1; q < nparts; ++q) v += __ldg(sp + q * part_stride);
+      tile[a][b][t] = v;
+    }
   }
   __syncthreads();
   for (int a = 0; a < TA; ++a) {
@@ -183,12 +190,21 @@ extern "C" int ptk_pack_weight_dual(const float* src, float* dst0, float* dst1, 
   return 0;
 }
 
+extern "C" int ptk_unpack_weight_grad_parts(const float* src, int nparts, int64_t part_stride, float* grad, int A, int B,
+                                            int taps, int B_pad, int accumulate, void* stream) {
+  PTK_REQUIRE(nparts >= 1 && taps > 0 && taps <= 16 && (A + 15) / 16 <= 65535, "unpack_weight_grad_parts: bad extents");
+  dim3 grid((B + 31) / 32, (A + 15) / 16);
+  unpack_weight_grad_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, nparts, part_stride, grad, A, B, taps, B_pad, accumulate);
+  PTK_LAUNCH_CHECK("unpack_weight_grad_tiled_kernel");
+  return 0;
+}
+
 extern "C" int ptk_unpack_weight_grad(const float* src, float* grad, int A, int B, int taps, int B_pad,
                                       int accumulate, void* stream) {
   const int64_t total = (int64_t)A * B * taps;
   if (taps <= 16 && (A + 15) / 16 <= 65535) {
     dim3 grid((B + 31) / 32, (A + 15) / 16);
-    unpack_weight_grad_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, grad, A, B, taps, B_pad, accumulate);
+    unpack_weight_grad_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, 1, 0, grad, A, B, taps, B_pad, accumulate);
   } else {
     unpack_weight_grad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, grad, A, B, taps, B_pad, accumulate);
   }

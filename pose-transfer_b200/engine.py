@@ -107,10 +107,10 @@ class ConvLayer:
             A, B, B_pad = self.cout, self.cin, self.cin_pad
             a_rows = self.cout if self.cout <= 4 else self.cout_pad
         n = self.taps * a_rows * B_pad
-        dw = scratch[:n]
-        K.conv_wgrad(g, x, dy, dw)
         if a_rows == A:
-            K.unpack_weight_grad(dw, grad_w, A, B, self.taps, B_pad, True)
+            # split-K partial gradients land back to back in the scratch and are summed (fixed order) by the unpack
+            nparts = K.conv_wgrad_parts(g, x, dy, scratch)
+            K.unpack_weight_grad_parts(scratch, nparts, n, grad_w, A, B, self.taps, B_pad, True)
         else:  # padded row count (never hit for this network: every wide channel count is a multiple of 4)
             raise RuntimeError("wgrad: padded A rows unsupported")
 
@@ -346,7 +346,7 @@ class GeneratorEngine:
         cats, stats, st_idx, drops = sv["cats"], sv["stats"], sv["st_idx"], sv["drops"]
         H0, W0 = self.image_size
         max_w = max(c.taps * c.cin_pad * c.cout_pad for c in self.all_convs)
-        scratch = ws.get("wgrad_scratch", (max_w,))
+        scratch = ws.get("wgrad_scratch", (max(4 * max_w, 1 << 24),))   # room for split-K partial gradients
         sums = ws.get("sums" + tag, tuple(stats.shape), torch.float64, zero=True)
 
         # final conv: tanh' then wgrad / bias grad / dgrad
@@ -521,7 +521,7 @@ class DiscriminatorEngine:
         stats = sv["stats"]
         sums = ws.get("dsums" + tag, tuple(stats.shape), torch.float64, zero=True)
         max_w = max(c.taps * c.cin_pad * c.cout_pad for c in self.convs)
-        scratch = ws.get("wgrad_scratch", (max_w,)) if grads is not None else None
+        scratch = ws.get("wgrad_scratch", (max(4 * max_w, 1 << 24),)) if grads is not None else None
         dummy = ws.get("dummy_gb", (2,))
         dy = dlogits4
         din_grad = None

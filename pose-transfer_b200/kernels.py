@@ -145,6 +145,21 @@ def conv_wgrad(g, x, dy, dw):
     check(_lib.lib().ptk_conv_wgrad(g, _p(x), _p(dy), _p(dw), _stream()), "ptk_conv_wgrad")
 
 
+@_timed("conv_wgrad")
+def conv_wgrad_parts(g, x, dy, dw):
+    """Split-K weight gradient without atomics: returns the number of partial gradients written back to back into dw."""
+    import ctypes
+    n = ctypes.c_int(0)
+    check(_lib.lib().ptk_conv_wgrad_parts(g, _p(x), _p(dy), _p(dw), dw.numel(), ctypes.byref(n), _stream()), "ptk_conv_wgrad_parts")
+    return n.value
+
+
+@_timed("pack")
+def unpack_weight_grad_parts(src, nparts, part_stride, grad, A, B, taps, B_pad, accumulate=True):
+    check(_lib.lib().ptk_unpack_weight_grad_parts(_p(src), nparts, part_stride, _p(grad), A, B, taps, B_pad, int(accumulate),
+                                                  _stream()), "ptk_unpack_weight_grad_parts")
+
+
 def bias_grad(dy, ld, pixels, C, dbias):
     check(_lib.lib().ptk_bias_grad(_p(dy), ld, pixels, C, _p(dbias), _stream()), "ptk_bias_grad")
 

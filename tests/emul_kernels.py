@@ -76,6 +76,11 @@ def install(K):
         else:
             grad.copy_(v)
 
+    def unpack_weight_grad_parts(src, nparts, part_stride, grad, A, B, taps, B_pad, accumulate=True):
+        n = taps * A * B_pad
+        total = sum(src[q * part_stride:q * part_stride + n] for q in range(nparts))
+        unpack_weight_grad(total, grad, A, B, taps, B_pad, accumulate)
+
     def fill(dst, value=0.0):
         dst.fill_(value)
 
@@ -119,6 +124,16 @@ def install(K):
             gw, = torch.autograd.grad(z, w, dys)
             res = gw.permute(2, 3, 0, 1).reshape(k * k, g.Cout, g.Cin)       # [tap][Cout][Cin]
         dw[:res.numel()].copy_(res.reshape(-1))   # scratch is overwritten (include/ptk.h)
+
+    def conv_wgrad_parts(g, x, dy, dw):
+        """Emulates a 2-way split: two partial buffers whose sum is the gradient (exercises the reduction)."""
+        n = g.k * g.k * g.Cin * g.Cout
+        conv_wgrad(g, x, dy, dw)
+        if dw.numel() < 2 * n:
+            return 1
+        dw[n:2 * n].copy_(dw[:n] * 0.25)
+        dw[:n].mul_(0.75)
+        return 2
 
     def bias_grad(dy, ld, pixels, C, dbias):
         dbias.add_(dy.reshape(-1, ld)[:pixels, :C].sum(0))
@@ -243,7 +258,8 @@ def install(K):
         p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
 
     table = dict(nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, pack_weight=pack_weight, pack_weight_dual=pack_weight_dual,
-                 unpack_weight_grad=unpack_weight_grad, fill=fill, conv_forward=conv_forward, conv_wgrad=conv_wgrad,
+                 unpack_weight_grad=unpack_weight_grad, unpack_weight_grad_parts=unpack_weight_grad_parts, fill=fill,
+                 conv_forward=conv_forward, conv_wgrad=conv_wgrad, conv_wgrad_parts=conv_wgrad_parts,
                  bias_grad=bias_grad, gn_stats=gn_stats, gn_apply=gn_apply, gn_bwd_reduce=gn_bwd_reduce,
                  gn_bwd_apply=gn_bwd_apply, mask_pyramid=mask_pyramid, warp_forward=warp_forward,
                  warp_backward=warp_backward, adv_loss=adv_loss, l1_loss=l1_loss, nnloss_forward=nnloss_forward,

@@ -296,7 +296,11 @@ def test_conv_tc_tile_shapes(geo, tile, monkeypatch):
     assert rel_l2(nchw(dx).cpu(), xr.grad) < TF32_TOL, describe(nchw(dx).cpu(), xr.grad, "dgrad " + tile)
     # wgrad with the same forced (channel-halves, BLOCK_N) shape where the channel counts allow it
     gw = torch.zeros(wshape, device="cuda")
-    scratch = torch.full((layer.taps * layer.cin_pad * layer.cout_pad,), 3.0, device="cuda")
+    scratch = torch.full((6 * layer.taps * layer.cin_pad * layer.cout_pad,), 3.0, device="cuda")   # room for split-K parts
     layer.wgrad(K.Slice(xin), K.Slice(nhwc(dz).cuda()), N, H, W, scratch, gw)
     torch.cuda.synchronize()
     assert rel_l2(gw.cpu(), wr.grad) < TF32_TOL, describe(gw.cpu(), wr.grad, "wgrad " + tile)
+    gw2 = torch.zeros(wshape, device="cuda")                                                        # deterministic reduction
+    layer.wgrad(K.Slice(xin), K.Slice(nhwc(dz).cuda()), N, H, W, scratch, gw2)
+    torch.cuda.synchronize()
+    assert torch.equal(gw, gw2), "split-K weight gradient is not bit-reproducible"
