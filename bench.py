@@ -165,7 +165,9 @@ def run_ours(args):
 
     N = args.batch
     opt = make_opt(N)
-    model = pose_gan.DeformablePose_GAN(opt).cuda()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # the constructor prints like the reference's; keep stdout = the JSON line
+        model = pose_gan.DeformablePose_GAN(opt).cuda()
     model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), 0))
     model.disc.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), 1))
     vw, vb = synth.vgg_conv1_1(0)

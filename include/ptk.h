@@ -60,6 +60,12 @@ int ptk_unpack_weight_grad(const float* src, float* grad, int A, int B, int taps
 /* grad[a][b][tap] (+)= sum_{q < nparts} src[q * part_stride + (tap*A + a)*B_pad + b] */
 int ptk_unpack_weight_grad_parts(const float* src, int nparts, int64_t part_stride, float* grad, int A, int B,
                                  int taps, int B_pad, int accumulate, void* stream);
+/* dst[tap][b][a] = src[tap][a][b]; A and Bp multiples of 32.  With the weights kept in GEMM layout ([tap][A][B_pad] =
+ * the K-major tensor-core operand of one direction = the layout the weight gradient is produced in) this is the only
+ * repacking left per optimiser step. */
+int ptk_transpose_weight(const float* src, float* dst, int taps, int A, int Bp, void* stream);
+/* dst[i] (+)= sum_{q < nparts} src[q * part_stride + i]  (fixed summation order; n, part_stride multiples of 4) */
+int ptk_sum_parts(const float* src, int nparts, int64_t part_stride, float* dst, int64_t n, int accumulate, void* stream);
 int ptk_fill(float* dst, int64_t n, float value, void* stream);
 
 /* ---------------------------------------------------------------- convolutions
@@ -101,6 +107,9 @@ int ptk_conv_wgrad(const ptk_conv_geom* g, const float* x, const float* dy, floa
  * ptk_unpack_weight_grad_parts -- a fixed summation order, i.e. a deterministic weight gradient. */
 int ptk_conv_wgrad_parts(const ptk_conv_geom* g, const float* x, const float* dy, float* dw, int64_t dw_capacity,
                          int* nparts, void* stream);
+/* How many partial gradients ptk_conv_wgrad_parts would write for this geometry and scratch capacity (a pure function of
+ * its arguments; with dw_capacity == one gradient the answer is always 1, i.e. the kernel writes the final result). */
+int ptk_conv_wgrad_plan(const ptk_conv_geom* g, int64_t dw_capacity, int* nparts);
 /* dbias[c] += sum_pixels dy[pixel][c] */
 int ptk_bias_grad(const float* dy, int ld, int64_t pixels, int C, float* dbias, void* stream);
 

@@ -10,7 +10,7 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
                     double* stats, cudaStream_t st);
 bool conv_wgrad_tc_supported(const ptk_conv_geom& c);
 int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float* dw, int64_t dw_capacity, int* nparts,
-                  cudaStream_t st);
+                  cudaStream_t st, bool plan_only = false);
 }  // namespace ptk
 
 using namespace ptk;
@@ -68,4 +68,12 @@ extern "C" int ptk_conv_wgrad_parts(const ptk_conv_geom* g, const float* x, cons
   int rc = ptk_fill(dw, part, 0.f, stream);
   if (rc) return rc;
   return conv_wgrad_simt(*g, x, dy, dw, (cudaStream_t)stream);
+}
+
+extern "C" int ptk_conv_wgrad_plan(const ptk_conv_geom* g, int64_t dw_capacity, int* nparts) {
+  PTK_REQUIRE(g && nparts, "conv_wgrad_plan: null argument");
+  *nparts = 1;
+  if (g->impl != PTK_IMPL_SIMT && conv_wgrad_tc_supported(*g))
+    return conv_wgrad_tc(*g, nullptr, nullptr, nullptr, dw_capacity, nparts, nullptr, true);
+  return 0;
 }

@@ -620,7 +620,7 @@ bool conv_wgrad_tc_supported(const ptk_conv_geom& c) {
 // dw_capacity floats; every split writes its own buffer of taps*Ca*Cb floats with plain stores and *nparts reports
 // how many there are -- the caller sums them (ptk_unpack_weight_grad_parts), which makes the result deterministic.
 int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float* dw, int64_t dw_capacity, int* nparts,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool plan_only) {
   WgTcGeom g;
   memset(&g, 0, sizeof(g));
   WgTmapSet maps;
@@ -629,8 +629,8 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
   int lda, ldb, BHt, BWt, Cb;
   if (!c.transposed) { S = dy; lda = c.ldy; g.Ca = c.Cout; g.GH = c.OH; g.GW = c.OW; Bg = x; ldb = c.ldx; Cb = c.Cin; BHt = c.H; BWt = c.W; }
   else { S = x; lda = c.ldx; g.Ca = c.Cin; g.GH = c.H; g.GW = c.W; Bg = dy; ldb = c.ldy; Cb = c.Cout; BHt = c.OH; BWt = c.OW; }
-  PTK_REQUIRE((reinterpret_cast<uintptr_t>(S) & 15) == 0 && (reinterpret_cast<uintptr_t>(Bg) & 15) == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0,
-              "conv_wgrad(tc): pointers must be 16-byte aligned");
+  PTK_REQUIRE(plan_only || ((reinterpret_cast<uintptr_t>(S) & 15) == 0 && (reinterpret_cast<uintptr_t>(Bg) & 15) == 0 &&
+                            (reinterpret_cast<uintptr_t>(dw) & 15) == 0), "conv_wgrad(tc): pointers must be 16-byte aligned");
   g.N = c.N; g.Cb_pad = Cb;
   g.BW = pow2_ge(g.GW < 32 ? g.GW : 32);
   g.BH = pow2_ge(g.GH < 32 / g.BW ? g.GH : 32 / g.BW);
@@ -649,13 +649,14 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
       }
     }
   const uint32_t box[4] = {32u, (uint32_t)g.BW, (uint32_t)g.BH, (uint32_t)g.BI};
-  {
+  if (!plan_only) {
     const uint64_t dims[4] = {(uint64_t)g.Ca, (uint64_t)g.GW, (uint64_t)g.GH, (uint64_t)c.N};
     const uint64_t str[3] = {(uint64_t)lda * 4, (uint64_t)g.GW * lda * 4, (uint64_t)g.GH * g.GW * lda * 4};
     int rc = encode(&maps.s, S, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
-  if (c.stride == 2) {
+  if (plan_only) {
+  } else if (c.stride == 2) {
     for (int pyy = 0; pyy < 2; ++pyy)
       for (int pxx = 0; pxx < 2; ++pxx) {
         const uint64_t Hp = (uint64_t)(BHt - pyy + 1) / 2, Wp = (uint64_t)(BWt - pxx + 1) / 2;
@@ -711,6 +712,7 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
   g.splits = splits;
   g.part_stride = nparts != nullptr ? (long long)g.ntaps * g.Ca * Cb : 0;
   if (nparts != nullptr) *nparts = splits;
+  if (plan_only) return 0;
   if (splits > 1 && nparts == nullptr) {
     int rc = ptk_fill(dw, (int64_t)g.ntaps * g.Ca * Cb, 0.f, st);
     if (rc) return rc;

@@ -134,6 +134,36 @@ unpack_weight_grad_tiled_kernel(const float* __restrict__ src, int nparts, int64
   }
 }
 
+// src [taps][A][Bp] -> dst [taps][Bp][A]; A and Bp are multiples of 32 (GEMM-layout master weights: the other operand
+// layout is a plain per-tap matrix transpose).  32 x 32 tiles through shared memory, both sides fully coalesced.
+__global__ void __launch_bounds__(256)
+transpose_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int A, int Bp) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z, b0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* s = src + (int64_t)t * A * Bp;
+  float* d = dst + (int64_t)t * A * Bp;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tile[ty + 8 * i][tx] = __ldg(s + (int64_t)(a0 + ty + 8 * i) * Bp + b0 + tx);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d[(int64_t)(b0 + ty + 8 * i) * A + a0 + tx] = tile[tx][ty + 8 * i];
+}
+
+// dst[i] (+)= sum_q src[q * stride + i]   (fixed order: the deterministic split-K reduction)
+__global__ void __launch_bounds__(256)
+sum_parts_kernel(const float4* __restrict__ src, int nparts, int64_t stride4, float4* __restrict__ dst, int64_t n4, int accumulate) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(src + i);
+    for (int q = 1; q < nparts; ++q) {
+      const float4 u = __ldg(src + q * stride4 + i);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    if (accumulate) { const float4 o = dst[i]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+    dst[i] = v;
+  }
+}
+
 __global__ void fill_kernel(float* __restrict__ dst, int64_t n, float v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = v;
@@ -209,6 +239,25 @@ extern "C" int ptk_unpack_weight_grad(const float* src, float* grad, int A, int 
     unpack_weight_grad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, grad, A, B, taps, B_pad, accumulate);
   }
   PTK_LAUNCH_CHECK("unpack_weight_grad_kernel");
+  return 0;
+}
+
+extern "C" int ptk_transpose_weight(const float* src, float* dst, int taps, int A, int Bp, void* stream) {
+  PTK_REQUIRE(src && dst && taps > 0 && A > 0 && Bp > 0 && A % 32 == 0 && Bp % 32 == 0 && A / 32 <= 65535 && taps <= 65535,
+              "transpose_weight: A and Bp must be multiples of 32");
+  dim3 grid(Bp / 32, A / 32, taps);
+  transpose_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, A, Bp);
+  PTK_LAUNCH_CHECK("transpose_weight_kernel");
+  return 0;
+}
+
+extern "C" int ptk_sum_parts(const float* src, int nparts, int64_t part_stride, float* dst, int64_t n, int accumulate,
+                             void* stream) {
+  PTK_REQUIRE(src && dst && nparts >= 1 && n > 0 && n % 4 == 0 && part_stride % 4 == 0, "sum_parts: n and part_stride must be multiples of 4");
+  PTK_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "sum_parts: pointers must be 16-byte aligned");
+  sum_parts_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), nparts, part_stride / 4,
+                                                                         reinterpret_cast<float4*>(dst), n / 4, accumulate);
+  PTK_LAUNCH_CHECK("sum_parts_kernel");
   return 0;
 }
 

@@ -321,6 +321,155 @@ warp_forward_coop_kernel(const float* __restrict__ x, int ldx, const float* __re
   }
 }
 
+// ---------------------------------------------------------------- tiled forward (K == KP parts, C >= 64)
+// One CTA owns a strip of XW = 8 * (32 / G) pixels x TH rows of one image and walks it row by row, so that the two
+// source rows a bilinear footprint touches stay in this SM's L1 from one row to the next (the row-major grid-stride
+// order of the kernel above re-fetched every source row from L2: 37 % L1 hit rate, 2.8x the input bytes over the
+// crossbar).  The strip's mask values are staged once in shared memory together with a per-pixel bit set of the
+// parts whose mask is non-zero; the row loop then iterates over set bits only and reads mask value and transform
+// from shared memory, which leaves the gather as the only global load on the dependent chain.  Every lane of a
+// pixel's group evaluates the (cheap) footprint itself: no shuffles, no ballots.
+// max over parts with torch.max's first-maximum rule: parts whose mask is zero (or whose footprint lies outside the
+// image) all contribute the same candidate "0, no gradient" (argk = 255); the first of them is merged into the bit
+// loop as a pseudo part at its own index kz, so real candidates before / after it keep their tie-breaking order.
+template <int ACT>
+__device__ __forceinline__ float warp_act(float v) {
+  if (ACT == PTK_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == PTK_ACT_LEAKY) return v > 0.f ? v : 0.2f * v;
+  return v;
+}
+
+// G lanes per pixel, NV float4 (4 NV channels) per lane and channel chunk: lane gl owns channels
+// [cb + 4 G q + 4 gl, +4) for q < NV, so every 128-bit request of a group is one contiguous run of 16 G bytes.
+// ACT == ReLU (the only way the network uses this layer: the warped skip is stored post-ReLU and the backward masks the
+// gradient with y > 0) folds the "0, no gradient" candidates into the initial value max(., 0) -- no pseudo part.
+template <int G, int NV, int KP, int ACT>
+__global__ void __launch_bounds__(256, (NV > 2 ? 2 : 4))
+warp_forward_tile_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ warps,
+                         const float* __restrict__ mask_lvl, float* __restrict__ y, int ldy, uint8_t* __restrict__ argk,
+                         int C, int h, int w, int H0, int W0, int TH, int strips_x) {
+  static_assert(KP % 2 == 0 && KP <= kMaxParts, "mask rows are staged as float2");
+  constexpr int PPW = 32 / G, XW = 8 * PPW, NC = 4 * NV;
+  constexpr bool kRelu = ACT == PTK_ACT_RELU;
+  extern __shared__ float s_dyn[];                       // [TH * XW][KP] mask values, then [TH * XW] part bit sets
+  __shared__ Theta s_theta[KP];
+  float* s_m = s_dyn;
+  unsigned* s_bits = reinterpret_cast<unsigned*>(s_dyn + TH * XW * KP);
+  const int n = blockIdx.y;
+  const int sx = blockIdx.x % strips_x, sy = blockIdx.x / strips_x;
+  const int x_begin = sx * XW, y_begin = sy * TH;
+  const int rows = min(TH, h - y_begin), cols = min(XW, w - x_begin);
+  const int tid = threadIdx.x;
+  const int HW = h * w;
+  if (tid < KP) s_theta[tid] = normalized_theta(warps + ((int64_t)n * KP + tid) * 8, h, w, H0, W0);
+  // stage: one thread per pixel of the strip (KP floats = KP/2 float2, 8-byte aligned because KP is even)
+  const float* mb = mask_lvl + (int64_t)n * HW * KP;
+  for (int t = tid; t < rows * XW; t += 256) {
+    const int r = t / XW, cx = t - r * XW;
+    unsigned bits = 0u;
+    if (cx < cols) {
+      const float2* src = reinterpret_cast<const float2*>(mb + ((y_begin + r) * w + x_begin + cx) * KP);
+      float2 v[KP / 2];
+#pragma unroll
+      for (int q = 0; q < KP / 2; ++q) v[q] = __ldg(src + q);
+#pragma unroll
+      for (int q = 0; q < KP / 2; ++q) {
+        *reinterpret_cast<float2*>(s_m + t * KP + 2 * q) = v[q];
+        bits |= ((v[q].x != 0.f ? 1u : 0u) | (v[q].y != 0.f ? 2u : 0u)) << (2 * q);
+      }
+    }
+    s_bits[t] = bits;
+  }
+  __syncthreads();
+
+  const int lane = tid & 31, wi = tid >> 5;
+  const int gl = lane % G, grp = lane / G;
+  const int lx = wi * PPW + grp;                           // pixel column inside the strip
+  const int j = x_begin + lx;
+  if (j >= w) return;
+  const float fw = (float)w, fh = (float)h;
+  const float gx = (2.f * (float)j + 1.f) / fw - 1.f;
+  const float* xb = x + (int64_t)n * HW * ldx + gl * 4;
+  float* yrow = y + ((int64_t)n * HW + (int64_t)y_begin * w + j) * ldy + gl * 4;
+  uint8_t* arow = argk + ((int64_t)n * HW + (int64_t)y_begin * w + j) * C + gl * 4;
+  const int ystep = w * ldy, astep = w * C;
+  constexpr unsigned kmask = (1u << KP) - 1u;
+  for (int r = 0; r < rows; ++r, yrow += ystep, arow += astep) {
+    const int lp = r * XW + lx;
+    const unsigned bits = s_bits[lp];
+    const float gy = (2.f * (float)(y_begin + r) + 1.f) / fh - 1.f;
+    const unsigned inactive = ~bits & kmask;
+    const int kz = (!kRelu && inactive) ? __ffs(inactive) - 1 : -1;
+    // ReLU: real parts only.  Otherwise: real parts + the first zero candidate as a pseudo part at its own index.
+    const unsigned todo = kRelu ? bits : (bits | (inactive & (0u - inactive)));
+    const float* mrow = s_m + lp * KP;
+    for (int cb = 0; cb < C; cb += G * NC) {
+      float best[NC];
+      int arg[NC];
+#pragma unroll
+      for (int q = 0; q < NC; ++q) { best[q] = kRelu ? 0.f : -INFINITY; arg[q] = 255; }
+      unsigned rem = todo;
+      while (rem) {
+        const int k = __ffs(rem) - 1;
+        rem &= rem - 1;
+        float4 acc[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int tag = 255;
+        if (kRelu || k != kz) {
+          const Theta t = s_theta[k];
+          const float m = mrow[k];
+          const float px = ((t.a * gx + t.b * gy + t.tx + 1.f) * fw - 1.f) * 0.5f;
+          const float py = ((t.c * gx + t.d * gy + t.ty + 1.f) * fh - 1.f) * 0.5f;
+          const float fx0 = floorf(px), fy0 = floorf(py);
+          const int x0 = (int)fminf(fmaxf(fx0, -2.f), fw), y0 = (int)fminf(fmaxf(fy0, -2.f), fh);
+          if (x0 >= -1 && x0 < w && y0 >= -1 && y0 < h) {        // otherwise: footprint outside = "0, no gradient"
+            tag = k;
+            const float fx = px - fx0, fy = py - fy0;
+            // Out-of-image taps: weight 0 at a clamped (valid) address, so that all 4 NV loads are unconditional and
+            // issue back to back (one memory round trip per part instead of one per tap).
+            const bool xin0 = x0 >= 0, xin1 = x0 + 1 < w, yin0 = y0 >= 0, yin1 = y0 + 1 < h;
+            const float wy0 = yin0 ? (1.f - fy) * m : 0.f, wy1 = yin1 ? fy * m : 0.f;
+            const float wx0 = xin0 ? 1.f - fx : 0.f, wx1 = xin1 ? fx : 0.f;
+            const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+            const int xa = max(x0, 0), xc = min(x0 + 1, w - 1), ya = max(y0, 0), yc = min(y0 + 1, h - 1);
+            const float* p00 = xb + (ya * w + xa) * ldx + cb;
+            const float* p01 = xb + (ya * w + xc) * ldx + cb;
+            const float* p10 = xb + (yc * w + xa) * ldx + cb;
+            const float* p11 = xb + (yc * w + xc) * ldx + cb;
+            float4 v00[NV], v01[NV], v10[NV], v11[NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+              v00[q] = __ldg(reinterpret_cast<const float4*>(p00 + q * G * 4));
+              v01[q] = __ldg(reinterpret_cast<const float4*>(p01 + q * G * 4));
+              v10[q] = __ldg(reinterpret_cast<const float4*>(p10 + q * G * 4));
+              v11[q] = __ldg(reinterpret_cast<const float4*>(p11 + q * G * 4));
+            }
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+              fma4(acc[q], w00, v00[q]); fma4(acc[q], w01, v01[q]); fma4(acc[q], w10, v10[q]); fma4(acc[q], w11, v11[q]);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          if (acc[q].x > best[4 * q + 0]) { best[4 * q + 0] = acc[q].x; arg[4 * q + 0] = tag; }
+          if (acc[q].y > best[4 * q + 1]) { best[4 * q + 1] = acc[q].y; arg[4 * q + 1] = tag; }
+          if (acc[q].z > best[4 * q + 2]) { best[4 * q + 2] = acc[q].z; arg[4 * q + 2] = tag; }
+          if (acc[q].w > best[4 * q + 3]) { best[4 * q + 3] = acc[q].w; arg[4 * q + 3] = tag; }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        *reinterpret_cast<float4*>(yrow + cb + q * G * 4) = make_float4(warp_act<ACT>(best[4 * q]), warp_act<ACT>(best[4 * q + 1]),
+                                                                        warp_act<ACT>(best[4 * q + 2]), warp_act<ACT>(best[4 * q + 3]));
+        *reinterpret_cast<uint32_t*>(arow + cb + q * G * 4) = (unsigned)arg[4 * q] | ((unsigned)arg[4 * q + 1] << 8) |
+                                                              ((unsigned)arg[4 * q + 2] << 16) | ((unsigned)arg[4 * q + 3] << 24);
+      }
+    }
+  }
+}
+
 template <int G>
 __global__ void __launch_bounds__(256)
 warp_backward_coop_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, int act,
@@ -454,7 +603,43 @@ extern "C" int ptk_warp_forward(const float* x, int ldx, const float* warps, con
   PTK_REQUIRE(act == PTK_ACT_NONE || act == PTK_ACT_RELU || act == PTK_ACT_LEAKY, "warp_forward: bad act");
   // the cooperative kernel uses 32-bit element offsets inside one image and packs (x0, y0) in 16 bits each
   const bool coop_ok = !align_corners && h < 32000 && w < 32000 && (int64_t)h * w * (ldx > ldy ? ldx : ldy) < (1ll << 31);
-  if (coop_ok && C == 64) {
+  if (coop_ok && K == 10 && (C == 64 || C == 128 || C == 256 || C % 512 == 0)) {
+    // NV float4 per lane and chunk (PTK_WARP_NV = 2 | 4, default 4): G = C / (4 NV) lanes per pixel, at most 32
+    static int nv_env = -1;
+    if (nv_env < 0) { const char* e = getenv("PTK_WARP_NV"); nv_env = (e && atoi(e) == 2) ? 2 : 4; }
+    const int NV = nv_env;
+    const int G = C / (4 * NV) >= 32 ? 32 : C / (4 * NV);
+    const int XW = 8 * (32 / G);
+    const int strips_x = (w + XW - 1) / XW;
+    // rows per strip: 3..8, chosen for the fullest last wave
+    const int occ = NV == 4 ? 2 : 4;
+    int TH = 8;
+    double best_eff = -1.0;
+    for (int th = 8; th >= 3; --th) {
+      if (th > h) continue;
+      const int64_t blocks = (int64_t)strips_x * ((h + th - 1) / th) * N, slots = (int64_t)num_sms() * occ;
+      const double eff = (double)blocks / (double)((blocks + slots - 1) / slots * slots) * (th / (th + 1.0));
+      if (eff > best_eff) { best_eff = eff; TH = th; }
+    }
+    if (TH > h) TH = h;
+    const int strips_y = (h + TH - 1) / TH;
+    const size_t smem = (size_t)TH * XW * (10 + 1) * sizeof(float);
+    dim3 grid((unsigned)(strips_x * strips_y), (unsigned)N);
+#define PTK_WARP_TILE(G_, NV_, A_) warp_forward_tile_kernel<G_, NV_, 10, A_><<<grid, 256, smem, (cudaStream_t)stream>>>(x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, H0, W0, TH, strips_x)
+#define PTK_WARP_TILE_G(G_, NV_) do { if (act == PTK_ACT_RELU) PTK_WARP_TILE(G_, NV_, PTK_ACT_RELU); else if (act == PTK_ACT_LEAKY) PTK_WARP_TILE(G_, NV_, PTK_ACT_LEAKY); else PTK_WARP_TILE(G_, NV_, PTK_ACT_NONE); } while (0)
+    if (NV == 4) {
+      if (G == 4) PTK_WARP_TILE_G(4, 4);
+      else if (G == 8) PTK_WARP_TILE_G(8, 4);
+      else if (G == 16) PTK_WARP_TILE_G(16, 4);
+      else PTK_WARP_TILE_G(32, 4);
+    } else {
+      if (G == 8) PTK_WARP_TILE_G(8, 2);
+      else if (G == 16) PTK_WARP_TILE_G(16, 2);
+      else PTK_WARP_TILE_G(32, 2);
+    }
+#undef PTK_WARP_TILE_G
+#undef PTK_WARP_TILE
+  } else if (coop_ok && C == 64) {
     warp_forward_coop_kernel<8><<<warp_grid((int64_t)h * w * 8, N), 256, 0, (cudaStream_t)stream>>>(
         x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, K, H0, W0, act);
   } else if (coop_ok && C == 128) {

@@ -41,7 +41,24 @@ class ConvLayer:
         self.w_fwd = None    # [taps][cin_pad][cout_pad]
         self.w_bwd = None    # [taps][dy_pad][cin_pad]  (weights of the dgrad gather-conv)
         self.w_dgrad_k = None  # [taps][cin_pad][dy_pad]: K-major tensor-core operand of the dgrad (== w_fwd unless narrow)
+        self._derived = None   # GEMM-layout master weights: the transposed copy
+        self._plans = {}       # wgrad geometry -> number of split-K partial gradients
         self.impl = {"auto": K.IMPL_AUTO, "simt": K.IMPL_SIMT, "tc": K.IMPL_AUTO}[os.environ.get("PTK_CONV_IMPL", "auto")]
+
+    def _master(self):
+        """(flat weight [tap][A][B_pad], flat grad, A, B_pad, taps) if the parameter lives in the arena in GEMM layout
+        (models/pose_gan.ParamArena) and that layout matches this layer's operand paddings, else None."""
+        m = getattr(self.weight, "_ptk_master", None)
+        if m is None:
+            return None
+        flat, grad, A, Bp, taps = m
+        if flat.device != self.weight.device or self.weight.data_ptr() != flat.data_ptr():
+            return None
+        if self.transposed:      # [tap][Cin][Cout_pad] == w_fwd ; derived w_bwd = [tap][dy_pad][cin_pad]
+            ok = A == self.cin_pad and Bp == self.cout_pad and Bp == self.dy_pad
+        else:                    # [tap][Cout][Cin_pad] == w_bwd ; derived w_fwd = [tap][cin_pad][cout_pad]
+            ok = A == self.dy_pad and A == self.cout_pad and Bp == self.cin_pad
+        return m if ok and taps == self.taps else None
 
     def _alloc(self):
         if self.w_fwd is None or self.w_fwd.device != self.weight.device:
@@ -54,6 +71,21 @@ class ConvLayer:
     def pack_forward(self):
         """Both GEMM layouts are refreshed in one pass: w_fwd = [tap][cin][cout] is the CUDA-core fprop operand AND the
         K-major tensor-core operand of the dgrad; w_bwd = [tap][cout][cin] is the reverse."""
+        m = self._master()
+        if m is not None:
+            # the arena storage IS one of the two layouts; the other one is its per-tap transpose
+            flat, _, A, Bp, taps = m
+            if self._derived is None or self._derived.device != flat.device:
+                self._derived = torch.empty(taps * A * Bp, device=flat.device)
+            K.transpose_weight(flat, self._derived, taps, A, Bp)
+            if self.transposed:
+                self.w_fwd, self.w_bwd = flat, self._derived
+            else:
+                self.w_bwd, self.w_fwd = flat, self._derived
+            self.w_dgrad_k = self.w_fwd
+            return
+        if self._derived is not None:     # parameter storage moved out of the arena: back to private copies
+            self._derived, self.w_fwd = None, None
         self._alloc()
         w = self.weight.detach()
         if self.transposed:   # torch layout [A=Cin][B=Cout][k][k]: w_fwd = [t][a][b], w_bwd = [t][b][a]
@@ -107,7 +139,21 @@ class ConvLayer:
             A, B, B_pad = self.cout, self.cin, self.cin_pad
             a_rows = self.cout if self.cout <= 4 else self.cout_pad
         n = self.taps * a_rows * B_pad
-        if a_rows == A:
+        m = self._master()
+        if m is not None and m[1].numel() == n:
+            # GEMM-layout arena: the kernel's output layout IS the gradient's storage layout
+            gflat = m[1]
+            key = (N, H, W, x.ld, dy.ld, scratch.numel())
+            nparts = self._plans.get(key)
+            if nparts is None:
+                nparts = self._plans[key] = K.conv_wgrad_plan(g, scratch.numel())
+            if nparts == 1:
+                got = K.conv_wgrad_parts(g, x, dy, gflat)           # capacity == one gradient => written in place
+                assert got == 1
+            else:
+                got = K.conv_wgrad_parts(g, x, dy, scratch)
+                K.sum_parts(scratch, got, n, gflat, n, False)
+        elif a_rows == A:
             # split-K partial gradients land back to back in the scratch and are summed (fixed order) by the unpack
             nparts = K.conv_wgrad_parts(g, x, dy, scratch)
             K.unpack_weight_grad_parts(scratch, nparts, n, grad_w, A, B, self.taps, B_pad, True)

@@ -154,6 +154,25 @@ def conv_wgrad_parts(g, x, dy, dw):
     return n.value
 
 
+def conv_wgrad_plan(g, capacity):
+    """Number of split-K partial gradients conv_wgrad_parts will write into a scratch of `capacity` floats."""
+    import ctypes
+    n = ctypes.c_int(0)
+    check(_lib.lib().ptk_conv_wgrad_plan(g, int(capacity), ctypes.byref(n)), "ptk_conv_wgrad_plan")
+    return n.value
+
+
+@_timed("pack")
+def transpose_weight(src, dst, taps, A, Bp):
+    """dst[tap][b][a] = src[tap][a][b] (A, Bp multiples of 32)."""
+    check(_lib.lib().ptk_transpose_weight(_p(src), _p(dst), taps, A, Bp, _stream()), "ptk_transpose_weight")
+
+
+@_timed("pack")
+def sum_parts(src, nparts, part_stride, dst, n, accumulate=False):
+    check(_lib.lib().ptk_sum_parts(_p(src), nparts, part_stride, _p(dst), n, int(accumulate), _stream()), "ptk_sum_parts")
+
+
 @_timed("pack")
 def unpack_weight_grad_parts(src, nparts, part_stride, grad, A, B, taps, B_pad, accumulate=True):
     check(_lib.lib().ptk_unpack_weight_grad_parts(_p(src), nparts, part_stride, _p(grad), A, B, taps, B_pad, int(accumulate),

@@ -37,15 +37,30 @@ class ParamArena:
         """Weights changed: the engines' GEMM-layout copies are stale."""
         self.module._ptk_weights_version = getattr(self.module, "_ptk_weights_version", 0) + 1
 
+    @staticmethod
+    def _gemm_master(p):
+        """Conv / ConvTranspose weights [A][B][kh][kw] with A % 32 == 0 live in the arena in GEMM layout
+        [tap][A][B_pad] (B_pad = B rounded up to 32): that is at once the K-major tensor-core operand of one
+        direction and the layout the weight gradient is produced in, so the optimiser step needs no unpack and
+        only ONE derived layout (a per-tap transpose).  The nn.Parameter is a strided VIEW of that storage with the
+        checkpoint shape, so state_dict()/load_state_dict() keep the reference's ABI."""
+        return p.dim() == 4 and p.shape[0] % 32 == 0 and p.shape[2] * p.shape[3] <= 16
+
     def bind(self):
         self.bump()
         dev = self.params[0].device
         total = 0
-        self.offsets = []
+        self.offsets, self.lengths = [], []
         for p in self.params:
             total = (total + 3) // 4 * 4          # keep every tensor 16-byte aligned
             self.offsets.append(total)
-            total += p.numel()
+            if self._gemm_master(p):
+                A, B, kh, kw = p.shape
+                n = kh * kw * A * ((B + 31) // 32 * 32)
+            else:
+                n = p.numel()
+            self.lengths.append(n)
+            total += n
         self.total = (total + 3) // 4 * 4
         self.flat = torch.zeros(self.total, device=dev)
         self.grad = torch.zeros(self.total, device=dev)
@@ -53,11 +68,20 @@ class ParamArena:
         self.exp_avg_sq = torch.zeros(self.total, device=dev)
         self.grads = {}
         with torch.no_grad():
-            for p, off in zip(self.params, self.offsets):
-                view = self.flat[off:off + p.numel()].view(p.shape)
+            for p, off, n in zip(self.params, self.offsets, self.lengths):
+                if self._gemm_master(p):
+                    A, B, kh, kw = p.shape
+                    Bp = n // (kh * kw * A)
+                    strides = (Bp, 1, kw * A * Bp, A * Bp)
+                    view = self.flat[off:off + n].as_strided(tuple(p.shape), strides)
+                    g = self.grad[off:off + n].as_strided(tuple(p.shape), strides)
+                    p._ptk_master = (self.flat[off:off + n], self.grad[off:off + n], A, Bp, kh * kw)
+                else:
+                    view = self.flat[off:off + n].view(p.shape)
+                    g = self.grad[off:off + n].view(p.shape)
+                    p._ptk_master = None
                 view.copy_(p.data)
                 p.data = view
-                g = self.grad[off:off + p.numel()].view(p.shape)
                 p.grad = g
                 self.grads[p] = g
 

@@ -81,6 +81,19 @@ def install(K):
         total = sum(src[q * part_stride:q * part_stride + n] for q in range(nparts))
         unpack_weight_grad(total, grad, A, B, taps, B_pad, accumulate)
 
+    def transpose_weight(src, dst, taps, A, Bp):
+        dst[:taps * A * Bp].copy_(src[:taps * A * Bp].reshape(taps, A, Bp).permute(0, 2, 1).reshape(-1))
+
+    def sum_parts(src, nparts, part_stride, dst, n, accumulate=False):
+        total = sum(src[q * part_stride:q * part_stride + n] for q in range(nparts))
+        if accumulate:
+            dst[:n].add_(total)
+        else:
+            dst[:n].copy_(total)
+
+    def conv_wgrad_plan(g, capacity):
+        return 2 if capacity >= 2 * g.k * g.k * g.Cin * g.Cout else 1
+
     def fill(dst, value=0.0):
         dst.fill_(value)
 
@@ -259,6 +272,7 @@ def install(K):
 
     table = dict(nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, pack_weight=pack_weight, pack_weight_dual=pack_weight_dual,
                  unpack_weight_grad=unpack_weight_grad, unpack_weight_grad_parts=unpack_weight_grad_parts, fill=fill,
+                 transpose_weight=transpose_weight, sum_parts=sum_parts, conv_wgrad_plan=conv_wgrad_plan,
                  conv_forward=conv_forward, conv_wgrad=conv_wgrad, conv_wgrad_parts=conv_wgrad_parts,
                  bias_grad=bias_grad, gn_stats=gn_stats, gn_apply=gn_apply, gn_bwd_reduce=gn_bwd_reduce,
                  gn_bwd_apply=gn_bwd_apply, mask_pyramid=mask_pyramid, warp_forward=warp_forward,
