@@ -350,6 +350,7 @@ warp_forward_tile_kernel(const float* __restrict__ x, int ldx, const float* __re
                          int C, int h, int w, int H0, int W0, int TH, int strips_x) {
   static_assert(KP % 2 == 0 && KP <= kMaxParts, "mask rows are staged as float2");
   constexpr int PPW = 32 / G, XW = 8 * PPW, NC = 4 * NV;
+  constexpr int PD = 0;                                  // L1 prefetch distance in rows (measured: no gain on B200)
   constexpr bool kRelu = ACT == PTK_ACT_RELU;
   extern __shared__ float s_dyn[];                       // [TH * XW][KP] mask values, then [TH * XW] part bit sets
   __shared__ Theta s_theta[KP];
@@ -398,6 +399,32 @@ warp_forward_tile_kernel(const float* __restrict__ x, int ldx, const float* __re
     const int lp = r * XW + lx;
     const unsigned bits = s_bits[lp];
     const float gy = (2.f * (float)(y_begin + r) + 1.f) / fh - 1.f;
+    if (PD > 0 && r + PD < rows) {
+      // L1 prefetch of the first part's footprint PD rows ahead: holds no registers, so the gather of row r + PD finds
+      // its lines on chip and the row loop stops being bound by one DRAM round trip per row.
+      const unsigned pb = s_bits[lp + PD * XW];
+      if (pb) {
+        const int k = __ffs(pb) - 1;
+        const Theta t = s_theta[k];
+        const float gy2 = (2.f * (float)(y_begin + r + PD) + 1.f) / fh - 1.f;
+        const float px = ((t.a * gx + t.b * gy2 + t.tx + 1.f) * fw - 1.f) * 0.5f;
+        const float py = ((t.c * gx + t.d * gy2 + t.ty + 1.f) * fh - 1.f) * 0.5f;
+        const int x0 = (int)fminf(fmaxf(floorf(px), -2.f), fw), y0 = (int)fminf(fmaxf(floorf(py), -2.f), fh);
+        if (x0 >= -1 && x0 < w && y0 >= -1 && y0 < h) {
+          const int xa = max(x0, 0), xc = min(x0 + 1, w - 1), yc = min(y0 + 1, h - 1);
+          // the upper footprint row was (for near-identity transforms) the lower row of an earlier output row
+          const float* p10 = xb + (yc * w + xa) * ldx;
+          const float* p11 = xb + (yc * w + xc) * ldx;
+          for (int cb = 0; cb < C; cb += G * NC) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(p10 + cb + q * G * 4));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(p11 + cb + q * G * 4));
+            }
+          }
+        }
+      }
+    }
     const unsigned inactive = ~bits & kmask;
     const int kz = (!kRelu && inactive) ? __ffs(inactive) - 1 : -1;
     // ReLU: real parts only.  Otherwise: real parts + the first zero candidate as a pseudo part at its own index.
