@@ -156,6 +156,11 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device -- there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # Everything below until the result line may write to fd 1 from native code (NCCL prints its version banner to
+    # stdout): park stdout on stderr so that the JSON line is the only thing on stdout.
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import pose_transfer_b200  # noqa: F401
@@ -315,6 +320,9 @@ def run_ours(args):
                               "frac": conv_tflops / (tf_peak / 2), "peak_source": peak_src + " bf16 sustained / 2 (tf32)",
                               "algorithmic_gflop_per_img": CONV_GFLOP_PER_IMG, "conv_ms_per_step": conv_ms},
             "kernel_ms_per_step": {k: v[1] / prof_steps for k, v in sorted(prof.items())}}
+    sys.stdout.flush()
+    os.dup2(saved_stdout_fd, 1)
+    os.close(saved_stdout_fd)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             torch.cuda.synchronize()

@@ -372,6 +372,8 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   if (const char* e = getenv("PTK_TC_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
   const TileCfg* best = nullptr;
   double best_cost = 0.0;
+  int best_splits = 1;
+  const bool can_split = c.ldy == c.Cout && bias == nullptr && act == PTK_ACT_NONE;
   for (const TileCfg& t : kCfgs) {
     if (c.Cout % t.bn != 0) continue;
     if (t.bn == 64 && c.Cout % 128 == 0) continue;
@@ -380,16 +382,25 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     const int bh = pow2_ge(maxGH < M / bw ? maxGH : M / bw);
     const int bi = M / (bw * bh);
     if (bi > 256) continue;
+    const bool forced = forced_mh == t.mh && forced_bn == t.bn;
+    if (t.mh > 1 && !forced && bi > pow2_ge(c.N)) continue;        // do not pad the batch beyond the next power of two
     const int64_t ctas = (int64_t)((maxGW + bw - 1) / bw) * ((maxGH + bh - 1) / bh) * ((c.N + bi - 1) / bi) * (c.Cout / t.bn) * nphases;
     const int64_t slots = (int64_t)num_sms() * t.occ;
-    // the big one-CTA-per-SM shapes only pay once they fill the machine (small layers want many CTAs + split-K), and
-    // must not pad the batch dimension beyond the next power of two
-    if (t.occ == 1 && !(forced_mh == t.mh && forced_bn == t.bn) && (ctas < slots || bi > pow2_ge(c.N))) continue;
-    const double tile_clk = (double)min_kb * t.mh * (t.bn / 128.0) * 256.0 / t.eff + (t.occ == 1 ? 6000.0 : 1500.0);
-    const double cost = (double)((ctas + slots - 1) / slots) * t.occ * tile_clk;
-    const bool forced = forced_mh == t.mh && forced_bn == t.bn;
-    if (forced) { best = &t; break; }
-    if (!best || cost < best_cost) { best = &t; best_cost = cost; }
+    // Layers with fewer tiles than CTA slots split the K loop so that every slot of ONE wave is busy (traffic per MAC
+    // is set by the tile shape, not by the split; the partial sums are combined with atomics).
+    int sp = 1;
+    if (can_split && ctas * 2 <= slots) {
+      sp = (int)(slots / ctas);
+      if (sp > min_kb / 4) sp = min_kb / 4;
+      if (sp < 1) sp = 1;
+      while (sp > 1 && (min_kb + sp - 1) / sp * (sp - 1) >= min_kb) --sp;
+    }
+    if (t.occ == 1 && !forced && ctas * sp < slots / 2) continue;   // big one-CTA-per-SM shapes must fill the machine
+    const double tile_clk = (double)((min_kb + sp - 1) / sp) * t.mh * (t.bn / 128.0) * 256.0 / t.eff + (t.occ == 1 ? 6000.0 : 1500.0);
+    const double combine = sp > 1 ? (double)c.N * c.OH * c.OW * c.Cout * sp / 100.0 : 0.0;
+    const double cost = (double)((ctas * sp + slots - 1) / slots) * t.occ * tile_clk + combine;
+    if (forced) { best = &t; best_splits = sp; break; }
+    if (!best || cost < best_cost) { best = &t; best_cost = cost; best_splits = sp; }
   }
   PTK_REQUIRE(best != nullptr, "conv_forward(tc): no tile configuration for Cout=%d", c.Cout);
   const int MH = best->mh, BN = best->bn, MT = 128 * MH;
@@ -422,16 +433,7 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     int rc = encode(&maps.b, w_k, 3, dims, str, boxB);
     if (rc) return rc;
   }
-  // Small-M layers (the 4x4 .. 16x16 levels at batch 8) have only a handful of output tiles but up to 16 taps x 48
-  // K-chunks each: split the K loop across CTAs so that the weight stream is spread over all SMs.
-  const int ctas = g.tiles_x * g.tiles_y * g.tiles_i * (c.Cout / BN) * nphases;
-  int splits = 1;
-  if (ctas * 2 <= num_sms() && c.ldy == c.Cout && bias == nullptr && act == PTK_ACT_NONE) {
-    splits = (2 * num_sms() + ctas - 1) / ctas;
-    if (splits > min_kb / 4) splits = min_kb / 4;
-    if (splits < 1) splits = 1;
-    while (splits > 1 && (min_kb + splits - 1) / splits * (splits - 1) >= min_kb) --splits;
-  }
+  const int splits = best_splits;
   g.splits = splits;
   if (splits > 1) {
     int rc = ptk_fill(y, (int64_t)c.N * c.OH * c.OW * c.Cout, 0.f, st);
