@@ -111,6 +111,19 @@ int ptk_conv_wgrad_parts(const ptk_conv_geom* g, const float* x, const float* dy
  * its arguments; with dw_capacity == one gradient the answer is always 1, i.e. the kernel writes the final result). */
 int ptk_conv_wgrad_plan(const ptk_conv_geom* g, int64_t dw_capacity, int* nparts);
 /* dbias[c] += sum_pixels dy[pixel][c] */
+/* ---- narrow 3x3 output head (ReLU -> Conv2d(C -> Co<=3, k3, p1) -> Tanh, models/networks.py:227-232) as three 1x1 GEMMs
+ * on a 32-column "tap x channel" tensor, so that the C-channel operand is read / written once per pass (csrc/head.cu).
+ * wk [32][Cin] / wd [Cin][32]: the two GEMM layouts of the torch weight [Co][Cin][3][3]. */
+int ptk_head_pack_weights(const float* w, int Co, int Cin, float* wk, float* wd, void* stream);
+/* y = act(bias + sum_tap z[p + off(tap)][tap*Co + co]); z [N,H,W,32]; y written NCHW and/or into an NHWC slice (ldy) */
+int ptk_head_shift_add(const float* z, const float* bias, int N, int Co, int H, int W, int act, float* y_nchw,
+                       float* y_nhwc, int ldy, void* stream);
+/* dzs[q][tap*Co + co] = dz[q - off(tap)][co]; dz [N,H,W,ldz], dzs [N,H,W,32] (columns >= 9*Co zero) */
+int ptk_head_shift_gather(const float* dz, int ldz, int N, int Co, int H, int W, float* dzs, void* stream);
+/* grad[co][c][tap] (+)= sum_{q<nparts} dwT[q*part_stride + c*32 + tap*Co + co]   (torch layout [Co][Cin][3][3]) */
+int ptk_head_wgrad_scatter(const float* dwT, int nparts, int64_t part_stride, int Co, int Cin, float* grad,
+                           int accumulate, void* stream);
+
 int ptk_bias_grad(const float* dy, int ld, int64_t pixels, int C, float* dbias, void* stream);
 
 /* ---------------------------------------------------------------- norm (models/networks.py:159,164-172) */

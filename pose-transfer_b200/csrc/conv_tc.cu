@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(192)
 conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcGeom g, float* __restrict__ y,
                double* __restrict__ stats, const float* __restrict__ bias, int act) {
   constexpr uint32_t A_BYTES = MH * 128 * 128, B_BYTES = BLOCK_N * 128, TMEM_COLS = MH * BLOCK_N;
-  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+  static_assert(TMEM_COLS == 32 || TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base, sB = base + STAGES * A_BYTES, sBar = sB + STAGES * B_BYTES;
@@ -304,9 +304,9 @@ static int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 static int floordiv2(int q) { return q >= 0 ? q / 2 : -((-q + 1) / 2); }
 
 bool conv_tc_supported(const ptk_conv_geom& c) {
-  if (c.Cin % 32 != 0 || c.Cout % 64 != 0) return false;
+  if (c.Cin % 32 != 0 || c.Cout % 32 != 0) return false;
   if (c.ldx % 4 != 0 || c.ldy % 4 != 0) return false;
-  if (!((c.k == 4 && c.stride == 2) || (c.k == 3 && c.stride == 1))) return false;
+  if (!((c.k == 4 && c.stride == 2) || (c.k == 3 && c.stride == 1) || (c.k == 1 && c.stride == 1 && c.pad == 0 && !c.transposed))) return false;
   if (c.H < 4 || c.W < 4 || c.OH < 4 || c.OW < 4) return false;
   if (c.N < 1 || c.N > 4096) return false;
   return true;
@@ -367,7 +367,8 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   // waves x per-tile time, with a relative efficiency per tile shape and a fixed prologue/epilogue charge for the
   // one-CTA-per-SM shapes (nothing overlaps them).  PTK_TC_TILE="mh,bn" overrides (tests / experiments).
   struct TileCfg { int mh, bn, stages, occ; float eff; };
-  static const TileCfg kCfgs[] = {{1, 64, 4, 2, 0.36f}, {1, 128, 3, 2, 0.50f}, {1, 256, 4, 1, 0.64f}, {2, 128, 4, 1, 0.64f}, {2, 256, 3, 1, 0.80f}};
+  static const TileCfg kCfgs[] = {{1, 32, 4, 2, 0.20f}, {2, 32, 3, 2, 0.25f}, {1, 64, 4, 2, 0.36f}, {1, 128, 3, 2, 0.50f},
+                                  {1, 256, 4, 1, 0.64f}, {2, 128, 4, 1, 0.64f}, {2, 256, 3, 1, 0.80f}};
   int forced_mh = 0, forced_bn = 0;
   if (const char* e = getenv("PTK_TC_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
   const TileCfg* best = nullptr;
@@ -377,6 +378,7 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   for (const TileCfg& t : kCfgs) {
     if (c.Cout % t.bn != 0) continue;
     if (t.bn == 64 && c.Cout % 128 == 0) continue;
+    if (t.bn == 32 && c.Cout % 64 == 0) continue;
     const int M = 128 * t.mh;
     const int bw = pow2_ge(maxGW < M ? maxGW : M);
     const int bh = pow2_ge(maxGH < M / bw ? maxGH : M / bw);
@@ -447,7 +449,9 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
     conv_tc_kernel<BN_, ST_, MH_><<<grid, 192, smem, st>>>(maps, g, y, stats, bias, act);                                   \
   } while (0)
-  if (MH == 1 && BN == 64) PTK_TC_LAUNCH(64, 4, 1);
+  if (MH == 1 && BN == 32) PTK_TC_LAUNCH(32, 4, 1);
+  else if (MH == 2 && BN == 32) PTK_TC_LAUNCH(32, 3, 2);
+  else if (MH == 1 && BN == 64) PTK_TC_LAUNCH(64, 4, 1);
   else if (MH == 1 && BN == 128) PTK_TC_LAUNCH(128, 3, 1);
   else if (MH == 1 && BN == 256) PTK_TC_LAUNCH(256, 4, 1);
   else if (MH == 2 && BN == 128) PTK_TC_LAUNCH(128, 4, 2);
@@ -608,7 +612,7 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
 }
 
 bool conv_wgrad_tc_supported(const ptk_conv_geom& c) {
-  if (!((c.k == 4 && c.stride == 2) || (c.k == 3 && c.stride == 1 && !c.transposed))) return false;
+  if (!((c.k == 4 && c.stride == 2) || (c.k == 3 && c.stride == 1 && !c.transposed) || (c.k == 1 && c.stride == 1 && c.pad == 0))) return false;
   const int Ca = c.transposed ? c.Cin : c.Cout, Cb = c.transposed ? c.Cout : c.Cin;
   if (Ca % 64 != 0 || Cb % 32 != 0) return false;
   if (c.ldx % 4 != 0 || c.ldy % 4 != 0) return false;
@@ -676,7 +680,7 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
   // ---- tile + split-K selection (same reasoning as conv_forward_tc): candidates (MH, BN); for each, the split count
   // that minimises waves x (k-iterations x stage time + fixed prologue/epilogue).
   struct WgCfg { int mh, bn, occ; float eff; };
-  static const WgCfg kCfgs[] = {{1, 32, 2, 0.30f}, {1, 64, 2, 0.36f}, {1, 128, 2, 0.50f}, {2, 128, 1, 0.64f}, {1, 256, 1, 0.64f}, {2, 256, 1, 0.80f}};
+  static const WgCfg kCfgs[] = {{1, 32, 2, 0.30f}, {2, 32, 2, 0.33f}, {1, 64, 2, 0.36f}, {1, 128, 2, 0.50f}, {2, 128, 1, 0.64f}, {1, 256, 1, 0.64f}, {2, 256, 1, 0.80f}};
   int forced_mh = 0, forced_bn = 0;
   if (const char* e = getenv("PTK_WG_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
   const int bn_small = (Cb % 128 == 0) ? 128 : (Cb % 64 == 0 ? 64 : 32);
@@ -728,6 +732,7 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     wgrad_tc_kernel<BN_, ST_, MH_><<<grid, 192, smem, st>>>(maps, g, dw);                                                   \
   } while (0)
   if (MH == 1 && BN == 32) PTK_WG_LAUNCH(32, 3, 1);
+  else if (MH == 2 && BN == 32) PTK_WG_LAUNCH(32, 3, 2);
   else if (MH == 1 && BN == 64) PTK_WG_LAUNCH(64, 3, 1);
   else if (MH == 1 && BN == 128) PTK_WG_LAUNCH(128, 3, 1);
   else if (MH == 1 && BN == 256) PTK_WG_LAUNCH(256, 4, 1);

@@ -232,9 +232,24 @@ class GeneratorEngine:
         if self.ws is None or self.ws.device != device:
             self.ws = _Workspace(device)
 
+    def _fast_head(self):
+        """The narrow output head (Conv2d(C -> 3, k3, p1) + tanh) runs as 1x1 tensor-core GEMMs over a 32-column
+        'tap x channel' tensor (csrc/head.cu) unless the exact-fp32 CUDA-core mode is selected."""
+        fc = self.final_conv
+        return fc.impl != K.IMPL_SIMT and fc.cout <= 3 and fc.k == 3 and fc.cin % 32 == 0
+
     def pack_weights(self, backward=False):
         for c in self.all_convs:
+            if c is self.final_conv and self._fast_head():
+                continue
             c.pack_forward()
+        if self._fast_head():
+            fc = self.final_conv
+            dev = fc.weight.device
+            if getattr(self, "head_wk", None) is None or self.head_wk.device != dev:
+                self.head_wk = torch.zeros(32 * fc.cin, device=dev)     # [32][Cin]: forward B operand
+                self.head_wd = torch.zeros(fc.cin * 32, device=dev)     # [Cin][32]: dgrad B operand
+            K.head_pack_weights(fc.weight.detach().contiguous(), self.head_wk, self.head_wd)
         self.packed_version = getattr(self.m, "_ptk_weights_version", None)
 
     def pack_weights_backward(self):
@@ -375,7 +390,14 @@ class GeneratorEngine:
             zd.append(z)
         sv["zd"] = zd
         out = torch.empty(N, 3, H, W, device=inp.device)
-        self.final_conv.forward(Slice(cats[L - 1]), N, H, W, d_input, ACT_TANH, None, out)
+        fc = self.final_conv
+        if self._fast_head():
+            z27 = ws.get("head_z" + tag, (N, H, W, 32))
+            g1 = K.conv_geom(N, H, W, fc.cin, cats[L - 1].shape[-1], H, W, 32, 32, 1, 1, 0, False, K.IMPL_TC)
+            K.conv_forward(g1, Slice(cats[L - 1]), None, self.head_wk, None, ACT_NONE, Slice(z27), None, None)
+            K.head_shift_add(z27, fc.bias.detach(), fc.cout, ACT_TANH, out, d_input)
+        else:
+            fc.forward(Slice(cats[L - 1]), N, H, W, d_input, ACT_TANH, None, out)
         sv["out"] = out
         self.saved = sv
         return out
@@ -397,14 +419,26 @@ class GeneratorEngine:
 
         # final conv: tanh' then wgrad / bias grad / dgrad
         fc = self.final_conv
-        dzf = ws.get("dzf" + tag, (N, H, W, fc.dy_pad))      # channels 3.. stay zero (padding for the dgrad GEMM)
-        K.tanh_bwd_combine(dout_nchw, dout_nhwc, sv["out"], dzf, fc.dy_pad, N, 3, H, W)
-        dz4 = ws.get("dzf4" + tag, (N, H, W, 4))             # compact copy: one 16-byte load per pixel in the wgrad
+        dz4 = ws.get("dzf4" + tag, (N, H, W, 4))             # compact gradient w.r.t. the pre-tanh output (3 channels + pad)
         K.tanh_bwd_combine(dout_nchw, dout_nhwc, sv["out"], dz4, 4, N, 3, H, W)
-        fc.wgrad(Slice(cats[L - 1]), Slice(dz4), N, H, W, scratch, grads[fc.weight])
-        K.bias_grad(dz4, 4, N * H * W, 3, grads[fc.bias])
         dcat = ws.get("dcat%d_%s" % (L - 1, tag), tuple(cats[L - 1].shape))
-        fc.dgrad(Slice(dzf), N, H, W, Slice(dcat))
+        if self._fast_head():
+            dzs = ws.get("head_dzs" + tag, (N, H, W, 32))
+            K.head_shift_gather(dz4, fc.cout, dzs)
+            ldc = cats[L - 1].shape[-1]
+            # dW^T[c][tap*3+co] = sum_pixels x[q][c] dzs[q][.]: a 1x1 "transposed" weight-gradient GEMM (S = x, B = dzs)
+            gw = K.conv_geom(N, H, W, fc.cin, ldc, H, W, 32, 32, 1, 1, 0, True, K.IMPL_TC)
+            nparts = K.conv_wgrad_parts(gw, Slice(cats[L - 1]), Slice(dzs), scratch)
+            K.head_wgrad_scatter(scratch, nparts, fc.cin * 32, fc.cout, fc.cin, grads[fc.weight], True)
+            K.bias_grad(dz4, 4, N * H * W, 3, grads[fc.bias])
+            gd = K.conv_geom(N, H, W, 32, 32, H, W, fc.cin, ldc, 1, 1, 0, False, K.IMPL_TC)
+            K.conv_forward(gd, Slice(dzs), None, self.head_wd, None, ACT_NONE, Slice(dcat), None, None)
+        else:
+            dzf = ws.get("dzf" + tag, (N, H, W, fc.dy_pad))      # channels 3.. stay zero (padding for the dgrad GEMM)
+            K.tanh_bwd_combine(dout_nchw, dout_nhwc, sv["out"], dzf, fc.dy_pad, N, 3, H, W)
+            fc.wgrad(Slice(cats[L - 1]), Slice(dz4), N, H, W, scratch, grads[fc.weight])
+            K.bias_grad(dz4, 4, N * H * W, 3, grads[fc.bias])
+            fc.dgrad(Slice(dzf), N, H, W, Slice(dcat))
         dcats = {L - 1: dcat}
 
         # decoder blocks, last to first

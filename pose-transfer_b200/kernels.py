@@ -179,6 +179,32 @@ def unpack_weight_grad_parts(src, nparts, part_stride, grad, A, B, taps, B_pad, 
                                                   _stream()), "ptk_unpack_weight_grad_parts")
 
 
+@_timed("pack")
+def head_pack_weights(w, wk, wd):
+    Co, Cin = w.shape[0], w.shape[1]
+    check(_lib.lib().ptk_head_pack_weights(_p(w), Co, Cin, _p(wk), _p(wd), _stream()), "ptk_head_pack_weights")
+
+
+@_timed("head")
+def head_shift_add(z, bias, Co, act, y_nchw, y_nhwc=None):
+    N, H, W, _ = z.shape
+    o2 = _as_slice(y_nhwc) if y_nhwc is not None else None
+    check(_lib.lib().ptk_head_shift_add(_p(z), _p(bias), N, Co, H, W, act, _p(y_nchw), o2.ptr if o2 else None,
+                                        o2.ld if o2 else 0, _stream()), "ptk_head_shift_add")
+
+
+@_timed("head")
+def head_shift_gather(dz, Co, dzs):
+    N, H, W, ldz = dz.shape
+    check(_lib.lib().ptk_head_shift_gather(_p(dz), ldz, N, Co, H, W, _p(dzs), _stream()), "ptk_head_shift_gather")
+
+
+@_timed("head")
+def head_wgrad_scatter(dwT, nparts, part_stride, Co, Cin, grad, accumulate=True):
+    check(_lib.lib().ptk_head_wgrad_scatter(_p(dwT), nparts, part_stride, Co, Cin, _p(grad), int(accumulate), _stream()),
+          "ptk_head_wgrad_scatter")
+
+
 def bias_grad(dy, ld, pixels, C, dbias):
     check(_lib.lib().ptk_bias_grad(_p(dy), ld, pixels, C, _p(dbias), _stream()), "ptk_bias_grad")
 

@@ -97,15 +97,61 @@ def install(K):
     def fill(dst, value=0.0):
         dst.fill_(value)
 
-    def _weights(g, w_t):
+    def _weights(g, w_t, w_k=None):
         cout_pad = (g.Cout + 3) // 4 * 4
         k = g.k
+        if w_t is None:     # only the K-major tensor-core operand [tap][Cout][Cin] was supplied
+            return w_k[:k * k * g.Cout * g.Cin].reshape(k, k, g.Cout, g.Cin).permute(0, 1, 3, 2)
         w = w_t[:k * k * g.Cin * cout_pad].reshape(k, k, g.Cin, cout_pad)[..., :g.Cout]
         return w   # [kh][kw][ci][co]
 
+    def head_pack_weights(w, wk, wd):
+        Co, Cin = w.shape[0], w.shape[1]
+        full = torch.zeros(32, Cin)
+        full[:9 * Co] = w.reshape(Co, Cin, 9).permute(2, 0, 1).reshape(9 * Co, Cin)     # row j = tap*Co + co
+        wk[:32 * Cin].copy_(full.reshape(-1))
+        wd[:32 * Cin].copy_(full.t().reshape(-1))
+
+    def _shift(t, dy, dx):
+        """out[n, y, x] = t[n, y + dy, x + dx] with zero fill; t [N,H,W,C]."""
+        N, H, W, C = t.shape
+        out = torch.zeros_like(t)
+        ys, ye = max(0, -dy), min(H, H - dy)
+        xs_, xe = max(0, -dx), min(W, W - dx)
+        if ys < ye and xs_ < xe:
+            out[:, ys:ye, xs_:xe] = t[:, ys + dy:ye + dy, xs_ + dx:xe + dx]
+        return out
+
+    def head_shift_add(z, bias, Co, act, y_nchw, y_nhwc=None):
+        acc = 0
+        for kh in range(3):
+            for kw in range(3):
+                t = kh * 3 + kw
+                acc = acc + _shift(z[..., t * Co:(t + 1) * Co], kh - 1, kw - 1)
+        v = _act(acc + (bias if bias is not None else 0), act)
+        if y_nchw is not None:
+            y_nchw.copy_(nchw(v))
+        if y_nhwc is not None:
+            view(y_nhwc, Co).copy_(v)
+
+    def head_shift_gather(dz, Co, dzs):
+        dzs.zero_()
+        for kh in range(3):
+            for kw in range(3):
+                t = kh * 3 + kw
+                dzs[..., t * Co:(t + 1) * Co] = _shift(dz[..., :Co], -(kh - 1), -(kw - 1))
+
+    def head_wgrad_scatter(dwT, nparts, part_stride, Co, Cin, grad, accumulate=True):
+        tot = sum(dwT[q * part_stride:q * part_stride + Cin * 32] for q in range(nparts)).reshape(Cin, 32)[:, :9 * Co]
+        v = tot.reshape(Cin, 9, Co).permute(2, 0, 1).reshape(grad.shape)
+        if accumulate:
+            grad.add_(v)
+        else:
+            grad.copy_(v)
+
     def conv_forward(g, x, w_t, w_k, bias, act, y, y_nchw=None, stats=None):
         xs = nchw(view(x, g.Cin)).reshape(g.N, g.Cin, g.H, g.W)
-        w = _weights(g, w_t)
+        w = _weights(g, w_t, w_k)
         if g.transposed:
             # a strided conv's input extent is not determined by its output extent: dgrad needs output_padding
             op = (g.OH - ((g.H - 1) * g.stride - 2 * g.pad + g.k), g.OW - ((g.W - 1) * g.stride - 2 * g.pad + g.k))
@@ -273,6 +319,8 @@ def install(K):
     table = dict(nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, pack_weight=pack_weight, pack_weight_dual=pack_weight_dual,
                  unpack_weight_grad=unpack_weight_grad, unpack_weight_grad_parts=unpack_weight_grad_parts, fill=fill,
                  transpose_weight=transpose_weight, sum_parts=sum_parts, conv_wgrad_plan=conv_wgrad_plan,
+                 head_pack_weights=head_pack_weights, head_shift_add=head_shift_add, head_shift_gather=head_shift_gather,
+                 head_wgrad_scatter=head_wgrad_scatter,
                  conv_forward=conv_forward, conv_wgrad=conv_wgrad, conv_wgrad_parts=conv_wgrad_parts,
                  bias_grad=bias_grad, gn_stats=gn_stats, gn_apply=gn_apply, gn_bwd_reduce=gn_bwd_reduce,
                  gn_bwd_apply=gn_bwd_apply, mask_pyramid=mask_pyramid, warp_forward=warp_forward,

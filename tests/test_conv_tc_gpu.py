@@ -304,3 +304,52 @@ def test_conv_tc_tile_shapes(geo, tile, monkeypatch):
     layer.wgrad(K.Slice(xin), K.Slice(nhwc(dz).cuda()), N, H, W, scratch, gw2)
     torch.cuda.synchronize()
     assert torch.equal(gw, gw2), "split-K weight gradient is not bit-reproducible"
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 20, 36), (3, 256, 17, 9)], ids=["c64_20x36", "c256_17x9"])
+def test_head_as_1x1_gemms(shape):
+    """csrc/head.cu: Conv2d(C -> 3, k3, p1) + tanh re-expressed as 1x1 tensor-core GEMMs over a 32-column
+    'tap x channel' tensor -- forward, weight gradient and input gradient against torch CPU fp32 autograd."""
+    import pose_transfer_b200  # noqa: F401
+    from pose_transfer_b200 import kernels as K
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(N * 1000 + C)
+    w = (torch.rand(3, C, 3, 3, generator=g) * 2 - 1) / (9 * C) ** 0.5
+    b = torch.rand(3, generator=g) - 0.5
+    x = torch.randn(N, C, H, W, generator=g)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    y = torch.tanh(F.conv2d(xr, wr, b, padding=1))
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+
+    wk = torch.zeros(32 * C, device="cuda")
+    wd = torch.zeros(C * 32, device="cuda")
+    K.head_pack_weights(w.cuda(), wk, wd)
+    xin = torch.zeros(N, H, W, C + 32, device="cuda")           # channel slice of a wider buffer
+    xin[..., 32:] = nhwc(x).cuda()
+    z27 = torch.empty(N, H, W, 32, device="cuda")
+    g1 = K.conv_geom(N, H, W, C, C + 32, H, W, 32, 32, 1, 1, 0, False, K.IMPL_TC)
+    K.conv_forward(g1, K.Slice(xin, 32, C), None, wk, None, K.ACT_NONE, K.Slice(z27), None, None)
+    out = torch.empty(N, 3, H, W, device="cuda")
+    out_nhwc = torch.full((N, H, W, 8), 7.0, device="cuda")
+    K.head_shift_add(z27, b.cuda(), 3, K.ACT_TANH, out, K.Slice(out_nhwc, 2, 3))
+    torch.cuda.synchronize()
+    assert float((out.cpu() - y.detach()).abs().max()) < 2e-3
+    assert torch.equal(nchw(out_nhwc[..., 2:5]), out) and float((out_nhwc[..., :2] - 7).abs().max()) == 0
+
+    dz4 = torch.zeros(N, H, W, 4, device="cuda")
+    dz4[..., :3] = nhwc(gy * (1 - y.detach() ** 2)).cuda()
+    dzs = torch.empty(N, H, W, 32, device="cuda")
+    K.head_shift_gather(dz4, 3, dzs)
+    scratch = torch.empty(64 * C * 32, device="cuda")
+    gw = K.conv_geom(N, H, W, C, C + 32, H, W, 32, 32, 1, 1, 0, True, K.IMPL_TC)
+    nparts = K.conv_wgrad_parts(gw, K.Slice(xin, 32, C), K.Slice(dzs), scratch)
+    grad = torch.zeros(3, C, 3, 3, device="cuda")
+    K.head_wgrad_scatter(scratch, nparts, C * 32, 3, C, grad, True)
+    dx = torch.full((N, H, W, C + 32), 5.0, device="cuda")
+    gd = K.conv_geom(N, H, W, 32, 32, H, W, C, C + 32, 1, 1, 0, False, K.IMPL_TC)
+    K.conv_forward(gd, K.Slice(dzs), None, wd, None, K.ACT_NONE, K.Slice(dx, 32, C), None, None)
+    torch.cuda.synchronize()
+    assert rel_l2(grad.cpu(), wr.grad) < TF32_TOL, describe(grad.cpu(), wr.grad, "head wgrad")
+    assert rel_l2(nchw(dx[..., 32:]).cpu(), xr.grad) < TF32_TOL, describe(nchw(dx[..., 32:]).cpu(), xr.grad, "head dgrad")
+    assert float((dx[..., :32] - 5).abs().max()) == 0
