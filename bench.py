@@ -31,6 +31,9 @@ PER_GPU_BATCH = 8
 # SURVEY 8d work model (256^2, P=18): necessary conv FLOPs per image per iteration and warp bytes per image
 CONV_GFLOP_PER_IMG = 582.3
 WARP_FWD_BYTES_PER_IMG = 66.40e6
+# dram__bytes_read.sum + dram__bytes_write.sum of the 4 warp_forward launches of one generator forward at batch 8, from
+# the committed `ncu --set full` capture (profiles/r1b_ncu_summary.txt): 255.6 + 97.7 + 32.2 + 14.5 MB
+WARP_FWD_TRAFFIC_BATCH8 = 400.0e6
 
 
 def make_opt(N, content="block1_conv2", area=5, l1_w=0.01):
@@ -312,8 +315,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "warp_forward_kernel (4 levels)", "achieved": warp_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": warp_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "warp_forward_tile_kernel (one launch set = the 4 warped skip levels of one generator forward)", "achieved": warp_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": warp_gbs / hbm_peak,
+                         "traffic": WARP_FWD_TRAFFIC_BATCH8 if N == 8 else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch_set": warp_bytes_per_launch_set,
                          "ms_per_launch_set": wms / warp_sets if warp_sets else None},
             "conv_roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": tf_peak / 2, "unit": "TFLOP/s",

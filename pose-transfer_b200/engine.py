@@ -403,10 +403,12 @@ class GeneratorEngine:
         return out
 
     # ------------------------------------------------------------------ backward
-    def backward(self, grads, dout_nchw=None, dout_nhwc=None):
+    def backward(self, grads, dout_nchw=None, dout_nhwc=None, on_stage=None):
         """Accumulate parameter gradients into `grads` (dict: parameter -> fp32 tensor of the same shape).
         Uses the weight packs of the preceding forward().
-        dout_nchw [N,3,H,W] and/or dout_nhwc (Slice over [N,H,W,*]) are gradients w.r.t. out_gen."""
+        dout_nchw [N,3,H,W] and/or dout_nhwc (Slice over [N,H,W,*]) are gradients w.r.t. out_gen.
+        on_stage(name) is called once every gradient of a sub-network ("decoder", "app", "pose") has been enqueued
+        (the data-parallel trainer starts that bucket's all-reduce there)."""
         sv = self.saved
         assert sv is not None, "forward() must run before backward()"
         ws, L = self.ws, self.L
@@ -459,6 +461,8 @@ class GeneratorEngine:
             cv.dgrad(Slice(dy), N, hs[i], wsz[i], Slice(dc))
             dcats[j] = dc
 
+        if on_stage is not None:
+            on_stage("decoder")
         # encoders, deepest level first
         for name in ("app", "pose"):
             convs, norms = self.enc_conv[name], self.enc_norm[name]
@@ -501,6 +505,8 @@ class GeneratorEngine:
                     dact = ws.get("dact_%s%d_%s" % (name, i - 1, tag), (N, hs[i - 1], wsz[i - 1], self.enc[i - 1]))
                     cv.dgrad(Slice(dy), N, hs[i - 1], wsz[i - 1], Slice(dact))
                     dact_next = dact
+            if on_stage is not None:
+                on_stage(name)
 
 
 class DiscriminatorEngine:

@@ -99,6 +99,16 @@ class ParamArena:
     def zero_grad(self):
         K.fill(self.grad, 0.0)
 
+    def segment(self, submodule):
+        """Flat gradient view covering every parameter of `submodule` (parameters() enumerates sub-module by
+        sub-module, so the range is contiguous)."""
+        ids = {id(p) for p in submodule.parameters()}
+        idx = [i for i, p in enumerate(self.params) if id(p) in ids]
+        assert idx and idx == list(range(idx[0], idx[-1] + 1)), "sub-module parameters are not contiguous in the arena"
+        lo = self.offsets[idx[0]]
+        hi = self.offsets[idx[-1]] + self.lengths[idx[-1]]
+        return self.grad[lo:hi]
+
 
 class FlatAdam(torch.optim.Optimizer):
     """torch.optim.Adam(lr, betas=(0.5, 0.999)) semantics (pose_gan.py:49-51) on a ParamArena."""
@@ -243,8 +253,19 @@ class DeformablePose_GAN(nn.Module):
         else:
             K.l1_loss(out_gen, target, opt['l1_penalty_weight'], loss[2:3], dpred)
 
-        self.gen.engine.backward(self.gen_arena.grads, dout_nchw=dpred, dout_nhwc=Slice(din_grad, 3 + P, 3))
-        self._allreduce(self.gen_arena)
+        # Data parallel: the gradient all-reduce of a sub-network is issued (asynchronously, on NCCL's own stream) as soon
+        # as its backward is enqueued, so the 205 MB decoder bucket travels under the encoders' backward passes.
+        pending = []
+
+        def stage_done(stage):
+            if self.world > 1:
+                sub = {"decoder": self.gen.decoder, "app": self.gen.encoder_app, "pose": self.gen.encoder_pose}[stage]
+                pending.append(torch.distributed.all_reduce(self.gen_arena.segment(sub), async_op=True))
+
+        self.gen.engine.backward(self.gen_arena.grads, dout_nchw=dpred, dout_nhwc=Slice(din_grad, 3 + P, 3),
+                                 on_stage=stage_done)
+        for work in pending:
+            work.wait()
         self.gen_opt.step()
         host = loss.tolist()                                             # single device->host sync
         self.gen_ad_loss, self.gen_ll_loss = host[0], host[2]
