@@ -462,6 +462,9 @@ class GeneratorEngine:
             fc.dgrad(Slice(dzf), N, H, W, Slice(dcat))
         dcats = {L - 1: dcat}
 
+        side = self._side_stream(dcat.device)
+        main = torch.cuda.current_stream() if side is not None else None
+        scratch_side = ws.get("wgrad_scratch_side", (max(4 * max_w, 1 << 24),)) if side is not None else scratch
         # decoder blocks, last to first
         for j in range(L - 2, -1, -1):
             i, dprev, width = self._cat_layout(j)
@@ -475,19 +478,22 @@ class GeneratorEngine:
             K.gn_bwd_apply(dy, sv["zd"][j], stats[si], sums[si], nl.weight.detach(), N, oh * ow, co, grads[nl.weight],
                            grads[nl.bias])
             cv = self.dec_conv[j]
-            cv.wgrad(Slice(cats[j]), Slice(dy), N, hs[i], wsz[i], scratch, grads[cv.weight])
+            # weight gradient and input gradient of a layer both only read dy: the weight gradients go to the side stream
+            if side is not None:
+                side.wait_stream(main)
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                cv.wgrad(Slice(cats[j]), Slice(dy), N, hs[i], wsz[i], scratch_side, grads[cv.weight])
             dc = ws.get("dcat%d_%s" % (j, tag), tuple(cats[j].shape))
             cv.dgrad(Slice(dy), N, hs[i], wsz[i], Slice(dc))
             dcats[j] = dc
 
-        if on_stage is not None:
-            on_stage("decoder")
-        # encoders, deepest level first
-        side = self._side_stream(dcats[L - 1].device)
-        main = torch.cuda.current_stream() if side is not None else None
-        scratch_side = ws.get("wgrad_scratch_side", (max(4 * max_w, 1 << 24),)) if side is not None else scratch
         if side is not None:
             side.wait_stream(main)
+        if on_stage is not None:
+            # the decoder's weight gradients are on the side stream: issue the bucket's all-reduce behind them
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                on_stage("decoder")
+        # encoders, deepest level first
         for name in ("app", "pose"):
           on_side = side is not None and name == "pose"
           scratch_e = scratch_side if on_side else scratch
@@ -642,6 +648,12 @@ class DiscriminatorEngine:
         dummy = ws.get("dummy_gb", (2,))
         dy = dlogits4
         din_grad = None
+        side = None
+        if grads is not None and dlogits4.is_cuda and os.environ.get("PTK_STREAMS", "1") != "0":
+            side = getattr(self, "_side", None)
+            if side is None or side.device != dlogits4.device:
+                side = self._side = torch.cuda.Stream(device=dlogits4.device)
+        main = torch.cuda.current_stream() if side is not None else None
         for i in range(nl - 1, -1, -1):
             cv = self.convs[i]
             h, w = sv["hw"][i]
@@ -649,9 +661,13 @@ class DiscriminatorEngine:
             x = sv["din"] if i == 0 else sv["act"][i - 1]
             dy_s = Slice(dy.view(M, oh, ow, -1))
             if grads is not None:
-                cv.wgrad(Slice(x), dy_s, M, h, w, scratch, grads[cv.weight])
-                if cv.bias is not None:
-                    K.bias_grad(dy, dy_s.ld, M * oh * ow, cv.cout, grads[cv.bias])
+                # weight / bias gradients only read dy: side stream, concurrent with the input-gradient chain
+                if side is not None:
+                    side.wait_stream(main)
+                with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                    cv.wgrad(Slice(x), dy_s, M, h, w, scratch, grads[cv.weight])
+                    if cv.bias is not None:
+                        K.bias_grad(dy, dy_s.ld, M * oh * ow, cv.cout, grads[cv.bias])
             if i == 0:
                 if need_input_grad:
                     din_grad = ws.get("din_grad" + tag, tuple(sv["din"].shape))
@@ -673,4 +689,6 @@ class DiscriminatorEngine:
                 K.gn_bwd_reduce(Slice(dact), Slice(sv["act"][i - 1]), ACT_LEAKY, None, None, ACT_NONE, None, None, None, M,
                                 h * w, pc.cout, dprev, None)
             dy = dprev
+        if side is not None:
+            main.wait_stream(side)
         return din_grad

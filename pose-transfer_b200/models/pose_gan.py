@@ -12,6 +12,7 @@ Data parallelism (absent from the reference): if ``torch.distributed`` is initia
 summed over ranks with NCCL on the flat gradient arena and the 1/world scale is folded into Adam;
 ``opt.batch_size`` is the PER-RANK batch.
 """
+import contextlib
 import os
 
 import torch
@@ -234,24 +235,33 @@ class DeformablePose_GAN(nn.Module):
         self._fill_disc_input(din, input, None, P)
         out_gen = self.gen.engine.forward(input, warps, masks, drop=drop if drop is not None else self.gen._next_drop(),
                                           repack=None, d_input=Slice(din, 3 + P, 3))
+        # The content loss (VGG conv1_1 + 5x5 NN loss, FFMA-bound) and the adversarial branch (D forward + input
+        # gradient, tensor-core / memory bound) only share out_gen: they run concurrently on two streams.
+        dpred = self.gen.engine.ws.get("dpred_%d_%d_%d" % (N, H, W), (N, 3, H, W))
+        side = self.gen.engine._side_stream(dev)
+        main = torch.cuda.current_stream() if side is not None else None
+        if side is not None:
+            side.wait_stream(main)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            if self.content_loss_layer != 'none':
+                if pose_utils.get_layer_ind(self.content_loss_layer) != 1:
+                    raise NotImplementedError("only content_loss_layer='block1_conv2' is on the B200 hot path")
+                vw, vb = self._vgg_params(dev)
+                area = self.nn_loss_area_size
+                argmin = self.gen.engine.ws.get("nn_argmin_%d_%d_%d" % (N, H, W), (N, H, W), torch.uint8)
+                K.nnloss_forward(out_gen, target, vw, vb, area, opt['l1_penalty_weight'], loss[2:3], argmin)
+                K.nnloss_backward(out_gen, target, vw, vb, argmin, area, opt['l1_penalty_weight'], dpred)
+            else:
+                K.l1_loss(out_gen, target, opt['l1_penalty_weight'], loss[2:3], dpred)
+
         logits = self.disc.engine.forward(din, repack=None)
         J = logits.shape[1]
         dlog4 = self.disc.engine.dlogits_buffer(N, J)
         # ad_loss = sum_n -mean_j log(out+1e-7), * gan_penalty_weight / batch_size   (pose_gan.py:90-98,107)
         K.adv_loss(logits, N, J, N, opt['gan_penalty_weight'] / self.batch_size, loss[0:2], dlog4, dlog4.shape[1])
         din_grad = self.disc.engine.backward(dlog4, grads=None, need_input_grad=True)
-
-        dpred = self.gen.engine.ws.get("dpred_%d_%d_%d" % (N, H, W), (N, 3, H, W))
-        if self.content_loss_layer != 'none':
-            if pose_utils.get_layer_ind(self.content_loss_layer) != 1:
-                raise NotImplementedError("only content_loss_layer='block1_conv2' is on the B200 hot path")
-            vw, vb = self._vgg_params(dev)
-            area = self.nn_loss_area_size
-            argmin = self.gen.engine.ws.get("nn_argmin_%d_%d_%d" % (N, H, W), (N, H, W), torch.uint8)
-            K.nnloss_forward(out_gen, target, vw, vb, area, opt['l1_penalty_weight'], loss[2:3], argmin)
-            K.nnloss_backward(out_gen, target, vw, vb, argmin, area, opt['l1_penalty_weight'], dpred)
-        else:
-            K.l1_loss(out_gen, target, opt['l1_penalty_weight'], loss[2:3], dpred)
+        if side is not None:
+            main.wait_stream(side)
 
         # Data parallel: the gradient all-reduce of a sub-network is issued (asynchronously, on NCCL's own stream) as soon
         # as its backward is enqueued, so the 205 MB decoder bucket travels under the encoders' backward passes.
