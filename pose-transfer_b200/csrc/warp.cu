@@ -347,10 +347,9 @@ template <int G, int NV, int KP, int ACT>
 __global__ void __launch_bounds__(256, (NV > 2 ? 2 : 4))
 warp_forward_tile_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ warps,
                          const float* __restrict__ mask_lvl, float* __restrict__ y, int ldy, uint8_t* __restrict__ argk,
-                         int C, int h, int w, int H0, int W0, int TH, int strips_x) {
+                         int C, int h, int w, int H0, int W0, int TH, int strips_x, int PD) {
   static_assert(KP % 2 == 0 && KP <= kMaxParts, "mask rows are staged as float2");
-  constexpr int PPW = 32 / G, XW = 8 * PPW, NC = 4 * NV;
-  constexpr int PD = 0;                                  // L1 prefetch distance in rows (measured: no gain on B200)
+  constexpr int PPW = 32 / G, XW = 8 * PPW, NC = 4 * NV;   // PD: L1 prefetch distance in rows (0 = off)
   constexpr bool kRelu = ACT == PTK_ACT_RELU;
   extern __shared__ float s_dyn[];                       // [TH * XW][KP] mask values, then [TH * XW] part bit sets
   __shared__ Theta s_theta[KP];
@@ -399,10 +398,11 @@ warp_forward_tile_kernel(const float* __restrict__ x, int ldx, const float* __re
     const int lp = r * XW + lx;
     const unsigned bits = s_bits[lp];
     const float gy = (2.f * (float)(y_begin + r) + 1.f) / fh - 1.f;
-    if (PD > 0 && r + PD < rows) {
+    if (PD > 0 && y_begin + r + PD < h) {
       // L1 prefetch of the first part's footprint PD rows ahead: holds no registers, so the gather of row r + PD finds
-      // its lines on chip and the row loop stops being bound by one DRAM round trip per row.
-      const unsigned pb = s_bits[lp + PD * XW];
+      // its lines on chip and the row loop stops being bound by one DRAM round trip per row.  Rows past the end of the
+      // strip (another CTA's) are prefetched with this row's part set as a guess: that warms L2 for the neighbour.
+      const unsigned pb = r + PD < rows ? s_bits[lp + PD * XW] : bits;
       if (pb) {
         const int k = __ffs(pb) - 1;
         const Theta t = s_theta[k];
@@ -632,6 +632,8 @@ extern "C" int ptk_warp_forward(const float* x, int ldx, const float* warps, con
   const bool coop_ok = !align_corners && h < 32000 && w < 32000 && (int64_t)h * w * (ldx > ldy ? ldx : ldy) < (1ll << 31);
   if (coop_ok && K == 10 && (C == 64 || C == 128 || C == 256 || C % 512 == 0)) {
     // NV float4 per lane and chunk (PTK_WARP_NV = 2 | 4, default 4): G = C / (4 NV) lanes per pixel, at most 32
+    static int pd_env = -1;
+    if (pd_env < 0) { const char* e = getenv("PTK_WARP_PD"); pd_env = e ? atoi(e) : 0; if (pd_env < 0 || pd_env > 8) pd_env = 0; }
     static int nv_env = -1;
     if (nv_env < 0) { const char* e = getenv("PTK_WARP_NV"); nv_env = (e && atoi(e) == 2) ? 2 : 4; }
     const int NV = nv_env;
@@ -652,7 +654,7 @@ extern "C" int ptk_warp_forward(const float* x, int ldx, const float* warps, con
     const int strips_y = (h + TH - 1) / TH;
     const size_t smem = (size_t)TH * XW * (10 + 1) * sizeof(float);
     dim3 grid((unsigned)(strips_x * strips_y), (unsigned)N);
-#define PTK_WARP_TILE(G_, NV_, A_) warp_forward_tile_kernel<G_, NV_, 10, A_><<<grid, 256, smem, (cudaStream_t)stream>>>(x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, H0, W0, TH, strips_x)
+#define PTK_WARP_TILE(G_, NV_, A_) warp_forward_tile_kernel<G_, NV_, 10, A_><<<grid, 256, smem, (cudaStream_t)stream>>>(x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, H0, W0, TH, strips_x, pd_env)
 #define PTK_WARP_TILE_G(G_, NV_) do { if (act == PTK_ACT_RELU) PTK_WARP_TILE(G_, NV_, PTK_ACT_RELU); else if (act == PTK_ACT_LEAKY) PTK_WARP_TILE(G_, NV_, PTK_ACT_LEAKY); else PTK_WARP_TILE(G_, NV_, PTK_ACT_NONE); } while (0)
     if (NV == 4) {
       if (G == 4) PTK_WARP_TILE_G(4, 4);

@@ -15,6 +15,11 @@ from . import kernels as K
 from .kernels import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, Slice
 
 
+# Stream-level concurrency of independent branches (pose encoder, weight gradients, content loss).  bench.py switches it
+# off for its per-kernel timing pass so that each kernel's CUDA-event duration is exclusive.
+STREAMS = True
+
+
 def ceil4(x):
     return (x + 3) // 4 * 4
 
@@ -228,8 +233,8 @@ class GeneratorEngine:
         self.layers_built = True
 
     def _side_stream(self, device):
-        """Second CUDA stream for the pose encoder (PTK_STREAMS=0 disables)."""
-        if device.type != "cuda" or os.environ.get("PTK_STREAMS", "1") == "0":
+        """Second CUDA stream for the pose encoder (PTK_STREAMS=0 or engine.STREAMS = False disables)."""
+        if device.type != "cuda" or not STREAMS or os.environ.get("PTK_STREAMS", "1") == "0":
             return None
         st = getattr(self, "_side", None)
         if st is None or st.device != device:
@@ -649,7 +654,7 @@ class DiscriminatorEngine:
         dy = dlogits4
         din_grad = None
         side = None
-        if grads is not None and dlogits4.is_cuda and os.environ.get("PTK_STREAMS", "1") != "0":
+        if grads is not None and dlogits4.is_cuda and STREAMS and os.environ.get("PTK_STREAMS", "1") != "0":
             side = getattr(self, "_side", None)
             if side is None or side.device != dlogits4.device:
                 side = self._side = torch.cuda.Stream(device=dlogits4.device)
