@@ -497,6 +497,211 @@ warp_forward_tile_kernel(const float* __restrict__ x, int ldx, const float* __re
   }
 }
 
+// ---------------------------------------------------------------- tiled forward with an asynchronous row pipeline
+// EXPERIMENT (PTK_WARP_PF=1, off by default): measured 10 % SLOWER than warp_forward_tile_kernel on B200 -- ncu shows
+// the extra LDGSTS + LDS traffic pushing the L1/TEX pipe to 80 % busy, so the kernel trades a latency bound for an L1
+// bound.  Kept as the documented negative result (profiles/README.md).
+// Same strip walk as warp_forward_tile_kernel (ReLU epilogue only), but the gather of the FIRST active part of row r + 1
+// (the body part, present at every pixel) is issued with cp.async into a lane-private shared-memory slot while row r is
+// still being reduced and stored: the copies hold no registers, so every warp keeps two rows of loads in flight and the
+// row loop is no longer bound by one DRAM round trip per row.  Further parts of a pixel (sparse) use direct loads.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int G, int NV, int KP>
+__global__ void __launch_bounds__(256, 2)
+warp_forward_pf_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ warps,
+                       const float* __restrict__ mask_lvl, float* __restrict__ y, int ldy, uint8_t* __restrict__ argk,
+                       int C, int h, int w, int H0, int W0, int TH, int strips_x) {
+  static_assert(KP % 2 == 0 && KP <= kMaxParts, "mask rows are staged as float2");
+  constexpr int PPW = 32 / G, XW = 8 * PPW, NC = 4 * NV;
+  extern __shared__ __align__(16) float s_dyn[];           // [4 NV][256] float4 gather slots, [TH*XW][KP] masks, [TH*XW] bit sets
+  __shared__ Theta s_theta[KP];
+  float4* s_slot = reinterpret_cast<float4*>(s_dyn);
+  float* s_m = s_dyn + 4 * NV * 256 * 4;
+  unsigned* s_bits = reinterpret_cast<unsigned*>(s_m + TH * XW * KP);
+  const int n = blockIdx.y;
+  const int sx = blockIdx.x % strips_x, sy = blockIdx.x / strips_x;
+  const int x_begin = sx * XW, y_begin = sy * TH;
+  const int rows = min(TH, h - y_begin), cols = min(XW, w - x_begin);
+  const int tid = threadIdx.x;
+  const int HW = h * w;
+  if (tid < KP) s_theta[tid] = normalized_theta(warps + ((int64_t)n * KP + tid) * 8, h, w, H0, W0);
+  const float* mb = mask_lvl + (int64_t)n * HW * KP;
+  for (int t = tid; t < rows * XW; t += 256) {
+    const int r = t / XW, cx = t - r * XW;
+    unsigned bits = 0u;
+    if (cx < cols) {
+      const float2* src = reinterpret_cast<const float2*>(mb + ((y_begin + r) * w + x_begin + cx) * KP);
+      float2 v[KP / 2];
+#pragma unroll
+      for (int q = 0; q < KP / 2; ++q) v[q] = __ldg(src + q);
+#pragma unroll
+      for (int q = 0; q < KP / 2; ++q) {
+        *reinterpret_cast<float2*>(s_m + t * KP + 2 * q) = v[q];
+        bits |= ((v[q].x != 0.f ? 1u : 0u) | (v[q].y != 0.f ? 2u : 0u)) << (2 * q);
+      }
+    }
+    s_bits[t] = bits;
+  }
+  __syncthreads();
+
+  const int lane = tid & 31, wi = tid >> 5;
+  const int gl = lane % G, grp = lane / G;
+  const int lx = wi * PPW + grp;
+  const int j = x_begin + lx;
+  if (j >= w) return;
+  const float fw = (float)w, fh = (float)h;
+  const float gx = (2.f * (float)j + 1.f) / fw - 1.f;
+  const float* xb = x + (int64_t)n * HW * ldx + gl * 4;
+  float* yrow = y + ((int64_t)n * HW + (int64_t)y_begin * w + j) * ldy + gl * 4;
+  uint8_t* arow = argk + ((int64_t)n * HW + (int64_t)y_begin * w + j) * C + gl * 4;
+  const int ystep = w * ldy, astep = w * C;
+  const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(s_slot + tid);      // slot s of this lane: + s * 256 float4
+
+  // footprint of part k at row (y_begin + r): returns false if it lies outside the image
+  struct Geo { int x0, y0; float fx, fy; };
+  auto footprint_of = [&](int k, int r, Geo& g) -> bool {
+    const Theta t = s_theta[k];
+    const float gy = (2.f * (float)(y_begin + r) + 1.f) / fh - 1.f;
+    const float px = ((t.a * gx + t.b * gy + t.tx + 1.f) * fw - 1.f) * 0.5f;
+    const float py = ((t.c * gx + t.d * gy + t.ty + 1.f) * fh - 1.f) * 0.5f;
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    g.x0 = (int)fminf(fmaxf(fx0, -2.f), fw); g.y0 = (int)fminf(fmaxf(fy0, -2.f), fh);
+    g.fx = px - fx0; g.fy = py - fy0;
+    return g.x0 >= -1 && g.x0 < w && g.y0 >= -1 && g.y0 < h;
+  };
+  // issue the asynchronous gather of the first active part of row r (channel chunk 0); returns its index or -1
+  auto prefetch_row = [&](int r, Geo& g) -> int {
+    const unsigned b = s_bits[r * XW + lx];
+    if (!b) return -1;
+    const int k = __ffs(b) - 1;
+    if (!footprint_of(k, r, g)) return -1;
+    const int xa = max(g.x0, 0), xc = min(g.x0 + 1, w - 1), ya = max(g.y0, 0), yc = min(g.y0 + 1, h - 1);
+    const float* p00 = xb + (ya * w + xa) * ldx;
+    const float* p01 = xb + (ya * w + xc) * ldx;
+    const float* p10 = xb + (yc * w + xa) * ldx;
+    const float* p11 = xb + (yc * w + xc) * ldx;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      cp_async16(slot0 + (uint32_t)((0 * NV + q) * 256 * 16), p00 + q * G * 4);
+      cp_async16(slot0 + (uint32_t)((1 * NV + q) * 256 * 16), p01 + q * G * 4);
+      cp_async16(slot0 + (uint32_t)((2 * NV + q) * 256 * 16), p10 + q * G * 4);
+      cp_async16(slot0 + (uint32_t)((3 * NV + q) * 256 * 16), p11 + q * G * 4);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    return k;
+  };
+
+  Geo gcur;
+  int pk = prefetch_row(0, gcur);
+  for (int r = 0; r < rows; ++r, yrow += ystep, arow += astep) {
+    const int lp = r * XW + lx;
+    const unsigned bits = s_bits[lp];
+    const float* mrow = s_m + lp * KP;
+    float best[NC];
+    int arg[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) { best[q] = 0.f; arg[q] = 255; }      // ReLU: max(., 0), "no gradient"
+    unsigned rem = bits;
+    Geo gnext;
+    int pk_next = -1;
+    if (pk >= 0) {
+      // ---- first part: operands arrive through the lane-private shared-memory slots
+      rem &= rem - 1;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      float4 acc[NV];
+      {
+        const float m = mrow[pk];
+        const bool xin0 = gcur.x0 >= 0, xin1 = gcur.x0 + 1 < w, yin0 = gcur.y0 >= 0, yin1 = gcur.y0 + 1 < h;
+        const float wy0 = yin0 ? (1.f - gcur.fy) * m : 0.f, wy1 = yin1 ? gcur.fy * m : 0.f;
+        const float wx0 = xin0 ? 1.f - gcur.fx : 0.f, wx1 = xin1 ? gcur.fx : 0.f;
+        const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          fma4(acc[q], w00, s_slot[(0 * NV + q) * 256 + tid]);
+          fma4(acc[q], w01, s_slot[(1 * NV + q) * 256 + tid]);
+          fma4(acc[q], w10, s_slot[(2 * NV + q) * 256 + tid]);
+          fma4(acc[q], w11, s_slot[(3 * NV + q) * 256 + tid]);
+        }
+      }
+      // the slots are consumed (the FMAs above depend on every shared-memory read): refill them for the next row
+      if (r + 1 < rows) pk_next = prefetch_row(r + 1, gnext);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        if (acc[q].x > best[4 * q + 0]) { best[4 * q + 0] = acc[q].x; arg[4 * q + 0] = pk; }
+        if (acc[q].y > best[4 * q + 1]) { best[4 * q + 1] = acc[q].y; arg[4 * q + 1] = pk; }
+        if (acc[q].z > best[4 * q + 2]) { best[4 * q + 2] = acc[q].z; arg[4 * q + 2] = pk; }
+        if (acc[q].w > best[4 * q + 3]) { best[4 * q + 3] = acc[q].w; arg[4 * q + 3] = pk; }
+      }
+    } else if (r + 1 < rows) {
+      pk_next = prefetch_row(r + 1, gnext);
+    }
+    // ---- remaining parts (and every part of further channel chunks): direct loads
+    for (int cb = 0; cb < C; cb += G * NC) {
+      if (cb > 0) {
+        // store the finished chunk, restart the reduction for the next one with ALL parts
+        const int co = cb - G * NC;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          *reinterpret_cast<float4*>(yrow + co + q * G * 4) = make_float4(best[4 * q], best[4 * q + 1], best[4 * q + 2], best[4 * q + 3]);
+          *reinterpret_cast<uint32_t*>(arow + co + q * G * 4) = (unsigned)arg[4 * q] | ((unsigned)arg[4 * q + 1] << 8) |
+                                                                ((unsigned)arg[4 * q + 2] << 16) | ((unsigned)arg[4 * q + 3] << 24);
+        }
+#pragma unroll
+        for (int q = 0; q < NC; ++q) { best[q] = 0.f; arg[q] = 255; }
+        rem = bits;
+      }
+      while (rem) {
+        const int k = __ffs(rem) - 1;
+        rem &= rem - 1;
+        Geo g;
+        if (!footprint_of(k, r, g)) continue;
+        const float m = mrow[k];
+        const bool xin0 = g.x0 >= 0, xin1 = g.x0 + 1 < w, yin0 = g.y0 >= 0, yin1 = g.y0 + 1 < h;
+        const float wy0 = yin0 ? (1.f - g.fy) * m : 0.f, wy1 = yin1 ? g.fy * m : 0.f;
+        const float wx0 = xin0 ? 1.f - g.fx : 0.f, wx1 = xin1 ? g.fx : 0.f;
+        const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+        const int xa = max(g.x0, 0), xc = min(g.x0 + 1, w - 1), ya = max(g.y0, 0), yc = min(g.y0 + 1, h - 1);
+        const float* p00 = xb + (ya * w + xa) * ldx + cb;
+        const float* p01 = xb + (ya * w + xc) * ldx + cb;
+        const float* p10 = xb + (yc * w + xa) * ldx + cb;
+        const float* p11 = xb + (yc * w + xc) * ldx + cb;
+        float4 v00[NV], v01[NV], v10[NV], v11[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          v00[q] = __ldg(reinterpret_cast<const float4*>(p00 + q * G * 4));
+          v01[q] = __ldg(reinterpret_cast<const float4*>(p01 + q * G * 4));
+          v10[q] = __ldg(reinterpret_cast<const float4*>(p10 + q * G * 4));
+          v11[q] = __ldg(reinterpret_cast<const float4*>(p11 + q * G * 4));
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          fma4(a, w00, v00[q]); fma4(a, w01, v01[q]); fma4(a, w10, v10[q]); fma4(a, w11, v11[q]);
+          if (a.x > best[4 * q + 0]) { best[4 * q + 0] = a.x; arg[4 * q + 0] = k; }
+          if (a.y > best[4 * q + 1]) { best[4 * q + 1] = a.y; arg[4 * q + 1] = k; }
+          if (a.z > best[4 * q + 2]) { best[4 * q + 2] = a.z; arg[4 * q + 2] = k; }
+          if (a.w > best[4 * q + 3]) { best[4 * q + 3] = a.w; arg[4 * q + 3] = k; }
+        }
+      }
+    }
+    {
+      const int co = ((C - 1) / (G * NC)) * (G * NC);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        *reinterpret_cast<float4*>(yrow + co + q * G * 4) = make_float4(best[4 * q], best[4 * q + 1], best[4 * q + 2], best[4 * q + 3]);
+        *reinterpret_cast<uint32_t*>(arow + co + q * G * 4) = (unsigned)arg[4 * q] | ((unsigned)arg[4 * q + 1] << 8) |
+                                                              ((unsigned)arg[4 * q + 2] << 16) | ((unsigned)arg[4 * q + 3] << 24);
+      }
+    }
+    pk = pk_next;
+    gcur = gnext;
+  }
+}
+
 template <int G>
 __global__ void __launch_bounds__(256)
 warp_backward_coop_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, int act,
@@ -656,7 +861,22 @@ extern "C" int ptk_warp_forward(const float* x, int ldx, const float* warps, con
     dim3 grid((unsigned)(strips_x * strips_y), (unsigned)N);
 #define PTK_WARP_TILE(G_, NV_, A_) warp_forward_tile_kernel<G_, NV_, 10, A_><<<grid, 256, smem, (cudaStream_t)stream>>>(x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, H0, W0, TH, strips_x, pd_env)
 #define PTK_WARP_TILE_G(G_, NV_) do { if (act == PTK_ACT_RELU) PTK_WARP_TILE(G_, NV_, PTK_ACT_RELU); else if (act == PTK_ACT_LEAKY) PTK_WARP_TILE(G_, NV_, PTK_ACT_LEAKY); else PTK_WARP_TILE(G_, NV_, PTK_ACT_NONE); } while (0)
-    if (NV == 4) {
+    static int pf_env = -1;
+    if (pf_env < 0) { const char* e = getenv("PTK_WARP_PF"); pf_env = (e && atoi(e) == 1) ? 1 : 0; }   // measured slower: opt-in
+    if (NV == 4 && act == PTK_ACT_RELU && pf_env) {
+      const size_t smem_pf = smem + (size_t)4 * 4 * 256 * 16;
+#define PTK_WARP_PF(G_)                                                                                                   \
+  do {                                                                                                                    \
+    static bool attr = false;                                                                                             \
+    if (!attr) { cudaFuncSetAttribute(warp_forward_pf_kernel<G_, 4, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+    warp_forward_pf_kernel<G_, 4, 10><<<grid, 256, smem_pf, (cudaStream_t)stream>>>(x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, H0, W0, TH, strips_x); \
+  } while (0)
+      if (G == 4) PTK_WARP_PF(4);
+      else if (G == 8) PTK_WARP_PF(8);
+      else if (G == 16) PTK_WARP_PF(16);
+      else PTK_WARP_PF(32);
+#undef PTK_WARP_PF
+    } else if (NV == 4) {
       if (G == 4) PTK_WARP_TILE_G(4, 4);
       else if (G == 8) PTK_WARP_TILE_G(8, 4);
       else if (G == 16) PTK_WARP_TILE_G(16, 4);
