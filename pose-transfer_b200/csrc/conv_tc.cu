@@ -279,7 +279,7 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   // waves x per-tile time, with a relative efficiency per tile shape and a fixed prologue/epilogue charge for the
   // one-CTA-per-SM shapes (nothing overlaps them).  PTK_TC_TILE="mh,bn" overrides (tests / experiments).
   struct TileCfg { int mh, bn, stages, occ; float eff; };
-  static const TileCfg kCfgs[] = {{1, 32, 4, 2, 0.20f}, {2, 32, 3, 2, 0.25f}, {1, 64, 4, 2, 0.36f}, {1, 128, 3, 2, 0.50f},
+  static const TileCfg kCfgs[] = {{1, 32, 4, 2, 0.20f}, {2, 32, 3, 2, 0.25f}, {1, 64, 4, 2, 0.36f}, {2, 64, 4, 1, 0.43f}, {1, 128, 3, 2, 0.50f},
                                   {1, 256, 4, 1, 0.64f}, {2, 128, 4, 1, 0.64f}, {2, 256, 3, 1, 0.80f}};
   int forced_mh = 0, forced_bn = 0;
   if (const char* e = getenv("PTK_TC_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
@@ -364,6 +364,7 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   if (MH == 1 && BN == 32) PTK_TC_LAUNCH(32, 4, 1);
   else if (MH == 2 && BN == 32) PTK_TC_LAUNCH(32, 3, 2);
   else if (MH == 1 && BN == 64) PTK_TC_LAUNCH(64, 4, 1);
+  else if (MH == 2 && BN == 64) PTK_TC_LAUNCH(64, 4, 2);
   else if (MH == 1 && BN == 128) PTK_TC_LAUNCH(128, 3, 1);
   else if (MH == 1 && BN == 256) PTK_TC_LAUNCH(256, 4, 1);
   else if (MH == 2 && BN == 128) PTK_TC_LAUNCH(128, 4, 2);

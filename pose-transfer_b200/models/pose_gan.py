@@ -100,14 +100,18 @@ class ParamArena:
     def zero_grad(self):
         K.fill(self.grad, 0.0)
 
-    def segment(self, submodule):
-        """Flat gradient view covering every parameter of `submodule` (parameters() enumerates sub-module by
-        sub-module, so the range is contiguous)."""
+    def segment_range(self, submodule):
+        """[lo, hi) of the flat arenas covering every parameter of `submodule` (parameters() enumerates sub-module by
+        sub-module, so the range is contiguous; 16-byte aligned at both ends)."""
         ids = {id(p) for p in submodule.parameters()}
         idx = [i for i, p in enumerate(self.params) if id(p) in ids]
         assert idx and idx == list(range(idx[0], idx[-1] + 1)), "sub-module parameters are not contiguous in the arena"
         lo = self.offsets[idx[0]]
-        hi = self.offsets[idx[-1]] + self.lengths[idx[-1]]
+        hi = self.offsets[idx[-1] + 1] if idx[-1] + 1 < len(self.offsets) else self.total
+        return lo, hi
+
+    def segment(self, submodule):
+        lo, hi = self.segment_range(submodule)
         return self.grad[lo:hi]
 
 
@@ -122,12 +126,23 @@ class FlatAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
-        g = self.param_groups[0]
+        self.begin_step()
+        self.step_range(0, self.arena.total)
+        self.end_step()
+
+    # The same update issued range by range (a sub-network's bucket as soon as its gradients are final):
+    def begin_step(self):
         self.steps += 1
+
+    @torch.no_grad()
+    def step_range(self, lo, hi):
+        g = self.param_groups[0]
         a = self.arena
-        K.adam_step(a.flat, a.grad, a.exp_avg, a.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"], self.steps,
-                    self.grad_scale)
-        a.bump()
+        K.adam_step(a.flat[lo:hi], a.grad[lo:hi], a.exp_avg[lo:hi], a.exp_avg_sq[lo:hi], g["lr"], g["betas"][0], g["betas"][1],
+                    g["eps"], self.steps, self.grad_scale)
+
+    def end_step(self):
+        self.arena.bump()
 
     def zero_grad(self, set_to_none=False):
         self.arena.zero_grad()
@@ -201,6 +216,16 @@ class DeformablePose_GAN(nn.Module):
                              conv.bias.detach().to(device, torch.float32).contiguous())
         return self._vgg_dev
 
+    def _opt_stream(self, dev):
+        """Stream for the per-bucket all-reduce + Adam (None on CPU / with PTK_STREAMS=0)."""
+        from .. import engine as _engine
+        if dev.type != "cuda" or not _engine.STREAMS or os.environ.get("PTK_STREAMS", "1") == "0":
+            return None
+        st = getattr(self, "_ost", None)
+        if st is None or st.device != dev:
+            st = self._ost = torch.cuda.Stream(device=dev)
+        return st
+
     def _allreduce(self, arena):
         if self.world > 1:
             torch.distributed.all_reduce(arena.grad)
@@ -265,18 +290,30 @@ class DeformablePose_GAN(nn.Module):
 
         # Data parallel: the gradient all-reduce of a sub-network is issued (asynchronously, on NCCL's own stream) as soon
         # as its backward is enqueued, so the 205 MB decoder bucket travels under the encoders' backward passes.
-        pending = []
+        # ... and that bucket's Adam update follows it on the same "optimiser stream", so on one GPU the 2.3 GB of optimiser
+        # traffic also hides under the rest of the backward pass.
+        ost = self._opt_stream(dev)
+        self.gen_opt.begin_step()
+        covered = []
 
         def stage_done(stage):
-            if self.world > 1:
-                sub = {"decoder": self.gen.decoder, "app": self.gen.encoder_app, "pose": self.gen.encoder_pose}[stage]
-                pending.append(torch.distributed.all_reduce(self.gen_arena.segment(sub), async_op=True))
+            sub = {"decoder": self.gen.decoder, "app": self.gen.encoder_app, "pose": self.gen.encoder_pose}[stage]
+            lo, hi = self.gen_arena.segment_range(sub)
+            covered.append((lo, hi))
+            if ost is not None:
+                ost.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(ost) if ost is not None else contextlib.nullcontext()):
+                if self.world > 1:
+                    torch.distributed.all_reduce(self.gen_arena.grad[lo:hi])
+                self.gen_opt.step_range(lo, hi)
 
         self.gen.engine.backward(self.gen_arena.grads, dout_nchw=dpred, dout_nhwc=Slice(din_grad, 3 + P, 3),
                                  on_stage=stage_done)
-        for work in pending:
-            work.wait()
-        self.gen_opt.step()
+        assert sorted(covered)[0][0] == 0 and sorted(covered)[-1][1] == self.gen_arena.total and \
+            all(a[1] == b[0] for a, b in zip(sorted(covered), sorted(covered)[1:])), "optimiser buckets do not tile the arena"
+        if ost is not None:
+            torch.cuda.current_stream().wait_stream(ost)
+        self.gen_opt.end_step()
         host = loss.tolist()                                             # single device->host sync
         self.gen_ad_loss, self.gen_ll_loss = host[0], host[2]
         self.gen_total_loss = float(torch.tensor(host[0]) + torch.tensor(host[2]))

@@ -244,7 +244,7 @@ def test_conv_tc_dgrad_of_narrow_heads(name, k, s, p, Cin, Cout, N, H, W):
     assert rel_l2(nchw(dx).cpu(), x.grad) < TF32_TOL, describe(nchw(dx).cpu(), x.grad, "dgrad")
 
 
-TILE_CFGS = ["1,128", "1,256", "2,128", "2,256"]
+TILE_CFGS = ["1,128", "1,256", "2,64", "2,128", "2,256"]
 TILE_GEOS = [
     # name, transposed, Cin, Cout, N, H, W  (k4 s2 p1): ragged tiles in x / y / batch, phases, multi N-tiles
     ("down_64to256_ragged", False, 64, 256, 3, 22, 38),
