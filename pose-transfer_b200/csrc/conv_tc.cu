@@ -411,23 +411,28 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t addr, uint32
 }
 
 // MH = number of 128-channel halves of the A (Ca) tile: MH = 2 / BLOCK_N = 256 halve the L2 bytes per MAC (see
-// conv_tc_kernel).  TMEM: MH * BLOCK_N columns.
-template <int BLOCK_N, int STAGES, int MH>
+// conv_tc_kernel).  TPC = taps per CTA (MH == 1 only): narrow layers (Ca <= 128, Cb <= 64: stems, encoder level 1, the
+// PatchGAN stem) let one staged gradient tile S feed TPC taps' worth of MMAs, each tap with its own shifted activation
+// tile and its own TMEM accumulator -- 2-3.5x fewer L2 bytes per MAC than one tap per CTA.  TMEM: TPC * MH * BLOCK_N cols.
+template <int BLOCK_N, int STAGES, int MH, int TPC>
 __global__ void __launch_bounds__(192)
 wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ WgTcGeom g, float* __restrict__ dw) {
+  static_assert(TPC == 1 || MH == 1, "taps-per-CTA > 1 needs a single 128-channel A half");
   constexpr uint32_t KP = 32;                                    // pixels per stage
   constexpr uint32_t A_BYTES = MH * 128 * KP * 4, B_BYTES = BLOCK_N * KP * 4, BOX_BYTES = 32 * KP * 4;
-  constexpr uint32_t TMEM_COLS = MH * BLOCK_N < 32 ? 32 : MH * BLOCK_N;
-  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
+  constexpr uint32_t NEED_COLS = TPC * MH * BLOCK_N;
+  constexpr uint32_t TMEM_COLS = NEED_COLS <= 32 ? 32 : NEED_COLS <= 64 ? 64 : NEED_COLS <= 128 ? 128 : NEED_COLS <= 256 ? 256 : 512;
+  static_assert(NEED_COLS <= 512, "accumulators exceed TMEM");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base, sB = base + STAGES * A_BYTES, sBar = sB + STAGES * B_BYTES;
+  const uint32_t sA = base, sB = base + STAGES * A_BYTES, sBar = sB + STAGES * TPC * B_BYTES;
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_tmem = sBar + 16 * STAGES;
   const uint32_t tmem_slot = bar_tmem + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int btiles = g.Cb_pad / BLOCK_N;
   const int at = blockIdx.x / btiles, bt = blockIdx.x - at * btiles;
-  const int tap = blockIdx.y, split = blockIdx.z;
+  const int tap0 = blockIdx.y * TPC, split = blockIdx.z;
+  const int ntap = (g.ntaps - tap0 < TPC) ? g.ntaps - tap0 : TPC;        // taps of this CTA
   const int per = (g.ntiles + g.splits - 1) / g.splits;
   const int t_begin = split * per;
   const int t_end = t_begin + per < g.ntiles ? t_begin + per : g.ntiles;
@@ -450,8 +455,6 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      const int cyt = g.cy[tap], cxt = g.cx[tap];
-      const CUtensorMap* mb = &maps.b[g.map[tap]];
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
         const uint32_t par = (uint32_t)(kb / STAGES) & 1u;
@@ -461,13 +464,19 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
         const int ty = t % g.tiles_y;
         const int ti = t / g.tiles_y;
         const int gx0 = tx * g.BW, gy0 = ty * g.BH, n0 = ti * g.BI;
-        mbar_expect_tx(bar_full + 8 * s, A_BYTES + B_BYTES);
+        mbar_expect_tx(bar_full + 8 * s, A_BYTES + (uint32_t)ntap * B_BYTES);
 #pragma unroll
         for (int j = 0; j < 4 * MH; ++j)
           tma_load_4d(sA + s * A_BYTES + j * BOX_BYTES, &maps.s, bar_full + 8 * s, at * (128 * MH) + j * 32, gx0, gy0, n0);
+#pragma unroll 1
+        for (int q = 0; q < ntap; ++q) {
+          const int tap = tap0 + q;
+          const CUtensorMap* mb = &maps.b[g.map[tap]];
 #pragma unroll
-        for (int j = 0; j < BLOCK_N / 32; ++j)
-          tma_load_4d(sB + s * B_BYTES + j * BOX_BYTES, mb, bar_full + 8 * s, bt * BLOCK_N + j * 32, gx0 + cxt, gy0 + cyt, n0);
+          for (int j = 0; j < BLOCK_N / 32; ++j)
+            tma_load_4d(sB + (s * TPC + q) * B_BYTES + j * BOX_BYTES, mb, bar_full + 8 * s, bt * BLOCK_N + j * 32, gx0 + g.cx[tap],
+                        gy0 + g.cy[tap], n0);
+        }
       }
     }
     __syncwarp();
@@ -480,13 +489,17 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
         const uint32_t par = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(bar_full + 8 * s, par);
         tc_fence_after();
-        const uint64_t da = smem_desc_mn_sw128_32b(sA + s * A_BYTES, BOX_BYTES), db = smem_desc_mn_sw128_32b(sB + s * B_BYTES, BOX_BYTES);
+        const uint64_t da = smem_desc_mn_sw128_32b(sA + s * A_BYTES, BOX_BYTES);
+#pragma unroll 1
+        for (int q = 0; q < ntap; ++q) {
+          const uint64_t db = smem_desc_mn_sw128_32b(sB + (s * TPC + q) * B_BYTES, BOX_BYTES);
 #pragma unroll
-        for (int k = 0; k < (int)KP / 8; ++k)   // 8 pixels (one 1024-byte swizzle atom row-group) per MMA
+          for (int k = 0; k < (int)KP / 8; ++k)   // 8 pixels (one 1024-byte swizzle atom row-group) per MMA
 #pragma unroll
-          for (int hm = 0; hm < MH; ++hm)       // channels [128 hm, 128 hm + 128) of the A stage = boxes 4 hm .. 4 hm + 3
-            tc_mma_tf32(tmem_base + (uint32_t)(hm * BLOCK_N), da + (uint64_t)((hm * 4 * BOX_BYTES) >> 4) + (uint64_t)(k * (1024 >> 4)),
-                        db + (uint64_t)(k * (1024 >> 4)), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int hm = 0; hm < MH; ++hm)       // channels [128 hm, 128 hm + 128) of the A stage = boxes 4 hm .. 4 hm + 3
+              tc_mma_tf32(tmem_base + (uint32_t)((q * MH + hm) * BLOCK_N), da + (uint64_t)((hm * 4 * BOX_BYTES) >> 4) + (uint64_t)(k * (1024 >> 4)),
+                          db + (uint64_t)(k * (1024 >> 4)), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
         tc_commit(bar_empty + 8 * s);
       }
       tc_commit(bar_tmem);
@@ -497,21 +510,24 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
     mbar_wait(bar_tmem, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int hm = 0; hm < MH; ++hm) {
-      const int a = at * (128 * MH) + hm * 128 + lg * 32 + lane;
-      float* dst = dw + (int64_t)split * g.part_stride + ((int64_t)tap * g.Ca + a) * g.Cb_pad + bt * BLOCK_N;
+    for (int q = 0; q < ntap; ++q) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        float v[32];
-        tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(hm * BLOCK_N + c * 32), v);
-        if (a >= g.Ca) continue;       // rows beyond Ca were TMA zero-fill (Ca = 64 layers use half of the M = 128 tile)
-        if (g.splits == 1 || g.part_stride > 0) {
+      for (int hm = 0; hm < MH; ++hm) {
+        const int a = at * (128 * MH) + hm * 128 + lg * 32 + lane;
+        float* dst = dw + (int64_t)split * g.part_stride + ((int64_t)(tap0 + q) * g.Ca + a) * g.Cb_pad + bt * BLOCK_N;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          float v[32];
+          tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((q * MH + hm) * BLOCK_N + c * 32), v);
+          if (a >= g.Ca) continue;       // rows beyond Ca were TMA zero-fill (Ca = 64 layers use half of the M = 128 tile)
+          if (g.splits == 1 || g.part_stride > 0) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
+            for (int q4 = 0; q4 < 8; ++q4)
+              *reinterpret_cast<float4*>(dst + c * 32 + q4 * 4) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+          } else {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) atomicAdd(dst + c * 32 + q, v[q]);
+            for (int q1 = 0; q1 < 32; ++q1) atomicAdd(dst + c * 32 + q1, v[q1]);
+          }
         }
       }
     }
@@ -592,8 +608,12 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
   }
   // ---- tile + split-K selection (same reasoning as conv_forward_tc): candidates (MH, BN); for each, the split count
   // that minimises waves x (k-iterations x stage time + fixed prologue/epilogue).
-  struct WgCfg { int mh, bn, occ; float eff; };
-  static const WgCfg kCfgs[] = {{1, 32, 2, 0.30f}, {2, 32, 2, 0.33f}, {1, 64, 2, 0.36f}, {1, 128, 2, 0.50f}, {2, 128, 1, 0.64f}, {1, 256, 1, 0.64f}, {2, 256, 1, 0.80f}};
+  struct WgCfg { int mh, bn, occ; float eff; int tpc; };
+  static const WgCfg kCfgs[] = {{1, 32, 2, 0.30f, 1}, {2, 32, 2, 0.33f, 1}, {1, 64, 2, 0.36f, 1}, {1, 128, 2, 0.50f, 1},
+                                {2, 128, 1, 0.64f, 1}, {1, 256, 1, 0.64f, 1}, {2, 256, 1, 0.80f, 1},
+                                {1, 32, 1, 0.60f, 9}, {1, 64, 1, 0.60f, 4}};     // several taps per CTA (narrow layers)
+  static int tpc_env = -1;
+  if (tpc_env < 0) { const char* e = getenv("PTK_WG_TPC"); tpc_env = (e && atoi(e) == 0) ? 0 : 1; }
   int forced_mh = 0, forced_bn = 0;
   if (const char* e = getenv("PTK_WG_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
   const int bn_small = (Cb % 128 == 0) ? 128 : (Cb % 64 == 0 ? 64 : 32);
@@ -604,10 +624,11 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     if (Cb % t.bn != 0) continue;
     if (t.bn < bn_small) continue;
     if (t.mh == 2 && g.Ca % 256 != 0) continue;
-    const bool forced = forced_mh == t.mh && forced_bn == t.bn;
-    const int64_t base_ctas = (int64_t)((g.Ca + 128 * t.mh - 1) / (128 * t.mh)) * (Cb / t.bn) * g.ntaps;
+    if (t.tpc > 1 && (!tpc_env || g.Ca > 128 || Cb != t.bn || g.ntaps < t.tpc)) continue;
+    const bool forced = forced_mh == t.mh && forced_bn == t.bn && t.tpc == 1;
+    const int64_t base_ctas = (int64_t)((g.Ca + 128 * t.mh - 1) / (128 * t.mh)) * (Cb / t.bn) * ((g.ntaps + t.tpc - 1) / t.tpc);
     const int64_t slots = (int64_t)num_sms() * t.occ;
-    const double stage_clk = t.mh * (t.bn / 128.0) * 256.0 / t.eff;
+    const double stage_clk = t.tpc * t.mh * (t.bn / 128.0) * 256.0 / t.eff;
     int cfg_splits = 1;
     double cfg_cost = 0.0;
     const int64_t part_floats = (int64_t)g.ntaps * g.Ca * Cb;
@@ -625,7 +646,7 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     if (!best || cfg_cost < best_cost) { best = &t; best_cost = cfg_cost; best_splits = cfg_splits; }
   }
   PTK_REQUIRE(best != nullptr, "conv_wgrad(tc): no tile configuration for Ca=%d Cb=%d", g.Ca, Cb);
-  const int BN = best->bn, MH = best->mh;
+  const int BN = best->bn, MH = best->mh, TPC = best->tpc;
   const int atiles = (g.Ca + 128 * MH - 1) / (128 * MH);
   const int splits = best_splits;
   g.splits = splits;
@@ -636,21 +657,23 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     int rc = ptk_fill(dw, (int64_t)g.ntaps * g.Ca * Cb, 0.f, st);
     if (rc) return rc;
   }
-  dim3 grid((unsigned)(atiles * (Cb / BN)), (unsigned)g.ntaps, (unsigned)splits);
-#define PTK_WG_LAUNCH(BN_, ST_, MH_)                                                                                       \
+  dim3 grid((unsigned)(atiles * (Cb / BN)), (unsigned)((g.ntaps + TPC - 1) / TPC), (unsigned)splits);
+#define PTK_WG_LAUNCH(BN_, ST_, MH_, TPC_)                                                                                 \
   do {                                                                                                                     \
-    const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 16 + 1024;                                 \
+    const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + TPC_ * BN_ * 128) + 16 * ST_ + 16 + 1024;                          \
     static bool attr = false;                                                                                              \
-    if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<BN_, ST_, MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
-    wgrad_tc_kernel<BN_, ST_, MH_><<<grid, 192, smem, st>>>(maps, g, dw);                                                   \
+    if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<BN_, ST_, MH_, TPC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
+    wgrad_tc_kernel<BN_, ST_, MH_, TPC_><<<grid, 192, smem, st>>>(maps, g, dw);                                             \
   } while (0)
-  if (MH == 1 && BN == 32) PTK_WG_LAUNCH(32, 3, 1);
-  else if (MH == 2 && BN == 32) PTK_WG_LAUNCH(32, 3, 2);
-  else if (MH == 1 && BN == 64) PTK_WG_LAUNCH(64, 3, 1);
-  else if (MH == 1 && BN == 128) PTK_WG_LAUNCH(128, 3, 1);
-  else if (MH == 1 && BN == 256) PTK_WG_LAUNCH(256, 4, 1);
-  else if (MH == 2 && BN == 128) PTK_WG_LAUNCH(128, 4, 2);
-  else PTK_WG_LAUNCH(256, 3, 2);
+  if (TPC == 9) PTK_WG_LAUNCH(32, 3, 1, 9);
+  else if (TPC == 4) PTK_WG_LAUNCH(64, 4, 1, 4);
+  else if (MH == 1 && BN == 32) PTK_WG_LAUNCH(32, 3, 1, 1);
+  else if (MH == 2 && BN == 32) PTK_WG_LAUNCH(32, 3, 2, 1);
+  else if (MH == 1 && BN == 64) PTK_WG_LAUNCH(64, 3, 1, 1);
+  else if (MH == 1 && BN == 128) PTK_WG_LAUNCH(128, 3, 1, 1);
+  else if (MH == 1 && BN == 256) PTK_WG_LAUNCH(256, 4, 1, 1);
+  else if (MH == 2 && BN == 128) PTK_WG_LAUNCH(128, 4, 2, 1);
+  else PTK_WG_LAUNCH(256, 3, 2, 1);
 #undef PTK_WG_LAUNCH
   PTK_LAUNCH_CHECK("wgrad_tc_kernel");
   return 0;

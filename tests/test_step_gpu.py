@@ -148,8 +148,11 @@ def _run_steps(tag, content, area, l1_w, steps, seed, impl):
         gnames = sorted(k for k, _ in model.gen.named_parameters())
         gpar = dict(model.gen.named_parameters())
         assert_summary_close(np.stack([summarize(gpar[k].grad) for k in gnames]), g["g_grad_%d" % s], what="g_grad step %d" % s, **loose)
-        assert_summary_close(np.stack([summarize(gpar[k]) for k in gnames]), g["g_param_%d" % s], what="g_param", **ptol)
-        assert_summary_close(np.stack([summarize(dpar[k]) for k in dnames]), g["d_param_%d" % s], what="d_param", **ptol)
+        # TF32 mode: the run-to-run order of fp32 atomics (split-K, warp backward) can flip the sign of a ~0 gradient element,
+        # which Adam turns into a 2*lr difference of that element (lr = 2e-4)
+        slack = 5e-4 if impl == "auto" else 0.0
+        assert_summary_close(np.stack([summarize(gpar[k]) for k in gnames]), g["g_param_%d" % s], what="g_param", abs_slack=slack, **ptol)
+        assert_summary_close(np.stack([summarize(dpar[k]) for k in dnames]), g["d_param_%d" % s], what="d_param", abs_slack=slack, **ptol)
 
 
 def test_train_step_nn_loss_matches_reference_golden(impl):
