@@ -5,24 +5,26 @@
 
 namespace ptk {
 
-// src NCHW plane-major -> dst NHWC slice.  Tile: 32 pixels x 32 channels through shared memory.
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C_src, int c_src0, float* __restrict__ dst,
+// src NCHW plane-major -> dst NHWC slice.  A CTA moves 256 consecutive pixels x up to 32 channels: 1 KB coalesced reads
+// per plane into shared memory, then one pixel-major pass whose consecutive threads write consecutive channels.
+constexpr int kNhwcPix = 256, kNhwcCh = 32;
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ src, int C_src, int c_src0, float* __restrict__ dst,
                                     int ld_dst, int c_dst0, int C, int64_t HW, int act) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[kNhwcCh][kNhwcPix + 1];
   const int n = blockIdx.z;
-  const int64_t p0 = (int64_t)blockIdx.x * 32;
-  const int c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i;
-    const int64_t p = p0 + tx;
-    tile[i][tx] = (c < C && p < HW) ? src[((int64_t)n * C_src + c_src0 + c) * HW + p] : 0.f;
-  }
+  const int64_t p0 = (int64_t)blockIdx.x * kNhwcPix;
+  const int c0 = blockIdx.y * kNhwcCh;
+  const int nc = min(kNhwcCh, C - c0);
+  const int np = (int)min((int64_t)kNhwcPix, HW - p0);
+  const float* sb = src + ((int64_t)n * C_src + c_src0 + c0) * HW + p0;
+  for (int c = 0; c < nc; ++c)
+    if ((int)threadIdx.x < np) tile[c][threadIdx.x] = __ldg(sb + (int64_t)c * HW + threadIdx.x);
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int64_t p = p0 + i;
-    const int c = c0 + tx;
-    if (c < C && p < HW) dst[((int64_t)n * HW + p) * ld_dst + c_dst0 + c] = apply_act(tile[tx][i], act);
+  float* db = dst + ((int64_t)n * HW + p0) * ld_dst + c_dst0 + c0;
+  for (int e = threadIdx.x; e < np * nc; e += 256) {
+    const int p = e / nc, c = e - p * nc;
+    db[(int64_t)p * ld_dst + c] = apply_act(tile[c][p], act);
   }
 }
 
@@ -185,8 +187,8 @@ extern "C" int ptk_nchw_to_nhwc(const float* src, int C_src, int c_src0, float* 
                                 int N, int C, int H, int W, int act, void* stream) {
   PTK_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && N <= 65535, "nchw_to_nhwc: bad extents");
   const int64_t HW = (int64_t)H * W;
-  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, C_src, c_src0, dst, ld_dst, c_dst0, C, HW, act);
+  dim3 grid((unsigned)((HW + kNhwcPix - 1) / kNhwcPix), (C + kNhwcCh - 1) / kNhwcCh, N);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, C_src, c_src0, dst, ld_dst, c_dst0, C, HW, act);
   PTK_LAUNCH_CHECK("nchw_to_nhwc_kernel");
   return 0;
 }

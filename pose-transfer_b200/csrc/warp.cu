@@ -779,15 +779,19 @@ warp_backward_coop_kernel(const float* __restrict__ dy, int lddy, const float* _
 }
 
 // cv2.resize(INTER_LINEAR) == half-pixel bilinear; computed in double like the reference (masks are f64).
-__global__ void mask_pyramid_kernel(const double* __restrict__ masks, int K, int H0, int W0,
-                                    float* __restrict__ out, int h, int w, int64_t total) {
+// A CTA produces 256 consecutive output pixels of one image for all K parts: the source planes are read part by part
+// (coalesced along x), the [pixel][part] rows are transposed through shared memory and written as one contiguous run.
+constexpr int kPyrPix = 256;
+__global__ void __launch_bounds__(256)
+mask_pyramid_kernel(const double* __restrict__ masks, int K, int H0, int W0, float* __restrict__ out, int h, int w) {
+  extern __shared__ float s_row[];                 // [kPyrPix][K + 1]
+  const int n = blockIdx.y;
+  const int hw = h * w;
+  const int p0 = blockIdx.x * kPyrPix;
+  const int p = p0 + threadIdx.x;
   const double sy = (double)H0 / h, sx = (double)W0 / w;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    // idx = ((n*K + k)*h + i)*w + j  (read-coalesced); written to [n][i][j][k]
-    const int j = (int)(idx % w);
-    const int i = (int)((idx / w) % h);
-    const int k = (int)((idx / ((int64_t)w * h)) % K);
-    const int64_t n = idx / ((int64_t)w * h * K);
+  if (p < hw) {
+    const int i = p / w, j = p - i * w;
     double fy = (i + 0.5) * sy - 0.5, fx = (j + 0.5) * sx - 0.5;
     if (fy < 0) fy = 0;
     if (fx < 0) fx = 0;
@@ -796,10 +800,22 @@ __global__ void mask_pyramid_kernel(const double* __restrict__ masks, int K, int
     if (x0 > W0 - 1) x0 = W0 - 1;
     const int y1 = y0 + 1 < H0 ? y0 + 1 : H0 - 1, x1 = x0 + 1 < W0 ? x0 + 1 : W0 - 1;
     const double ly = fy - y0, lx = fx - x0;
-    const double* src = masks + (n * K + k) * (int64_t)H0 * W0;
-    const double v = (1 - ly) * ((1 - lx) * src[(int64_t)y0 * W0 + x0] + lx * src[(int64_t)y0 * W0 + x1]) +
-                     ly * ((1 - lx) * src[(int64_t)y1 * W0 + x0] + lx * src[(int64_t)y1 * W0 + x1]);
-    out[((n * h + i) * (int64_t)w + j) * K + k] = (float)v;
+    const bool exact = ly == 0.0 && lx == 0.0;      // same-size level: a plain conversion
+    for (int k = 0; k < K; ++k) {
+      const double* src = masks + ((int64_t)n * K + k) * (int64_t)H0 * W0;
+      double v;
+      if (exact) v = src[(int64_t)y0 * W0 + x0];
+      else v = (1 - ly) * ((1 - lx) * src[(int64_t)y0 * W0 + x0] + lx * src[(int64_t)y0 * W0 + x1]) +
+               ly * ((1 - lx) * src[(int64_t)y1 * W0 + x0] + lx * src[(int64_t)y1 * W0 + x1]);
+      s_row[threadIdx.x * (K + 1) + k] = (float)v;
+    }
+  }
+  __syncthreads();
+  const int npix = min(kPyrPix, hw - p0);
+  float* dst = out + ((int64_t)n * hw + p0) * K;
+  for (int e = threadIdx.x; e < npix * K; e += 256) {
+    const int pp = e / K, k = e - pp * K;
+    dst[e] = s_row[pp * (K + 1) + k];
   }
 }
 
@@ -818,11 +834,9 @@ static inline dim3 warp_grid(int64_t work, int N) {
 
 extern "C" int ptk_mask_pyramid(const double* masks, int N, int K, int H0, int W0, float* out, int h, int w,
                                 void* stream) {
-  PTK_REQUIRE(N > 0 && K > 0 && h > 0 && w > 0, "mask_pyramid: bad extents");
-  const int64_t total = (int64_t)N * K * h * w;
-  int64_t b = (total + 255) / 256;
-  if (b > (int64_t)num_sms() * 16) b = (int64_t)num_sms() * 16;
-  mask_pyramid_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(masks, K, H0, W0, out, h, w, total);
+  PTK_REQUIRE(N > 0 && N <= 65535 && K > 0 && K <= 64 && h > 0 && w > 0, "mask_pyramid: bad extents");
+  dim3 grid((unsigned)(((int64_t)h * w + kPyrPix - 1) / kPyrPix), (unsigned)N);
+  mask_pyramid_kernel<<<grid, 256, kPyrPix * (K + 1) * sizeof(float), (cudaStream_t)stream>>>(masks, K, H0, W0, out, h, w);
   PTK_LAUNCH_CHECK("mask_pyramid_kernel");
   return 0;
 }
