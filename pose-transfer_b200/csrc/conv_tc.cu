@@ -277,9 +277,10 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   // ---- tile selection.  fp32 operands make every tile L2-bandwidth bound (bytes per MAC ~ 1/M + 1/N), so the largest
   // tile that still fills the machine wins: (MH = 2, BN = 256) moves half the bytes per MAC of (1, 128).  Cost model:
   // waves x per-tile time, with a relative efficiency per tile shape and a fixed prologue/epilogue charge for the
-  // one-CTA-per-SM shapes (nothing overlaps them).  PTK_TC_TILE="mh,bn" overrides (tests / experiments).
+  // one-CTA-per-SM shapes (nothing overlaps them).  PTK_TC_TILE="mh,bn" overrides (tests / experiments).  (2, 64) is kept
+  // for the sweep test but rated below (1, 64): measured slower on every Cout = 64 layer of the network.
   struct TileCfg { int mh, bn, stages, occ; float eff; };
-  static const TileCfg kCfgs[] = {{1, 32, 4, 2, 0.20f}, {2, 32, 3, 2, 0.25f}, {1, 64, 4, 2, 0.36f}, {2, 64, 4, 1, 0.43f}, {1, 128, 3, 2, 0.50f},
+  static const TileCfg kCfgs[] = {{1, 32, 4, 2, 0.20f}, {2, 32, 3, 2, 0.25f}, {1, 64, 4, 2, 0.36f}, {2, 64, 4, 1, 0.30f}, {1, 128, 3, 2, 0.50f},
                                   {1, 256, 4, 1, 0.64f}, {2, 128, 4, 1, 0.64f}, {2, 256, 3, 1, 0.80f}};
   int forced_mh = 0, forced_bn = 0;
   if (const char* e = getenv("PTK_TC_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
