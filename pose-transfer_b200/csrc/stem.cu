@@ -53,7 +53,7 @@ stem_conv_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(bar_full, 128); mbar_init(bar_full + 8, 128);
+    mbar_init(bar_full, 4); mbar_init(bar_full + 8, 4);       // one arrival per builder warp
     mbar_init(bar_empty, 1); mbar_init(bar_empty + 8, 1);
     mbar_init(bar_tmem, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -76,20 +76,43 @@ stem_conv_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // The halo of the NEXT tile is fetched into registers right after the current one is published, so its global-memory
+  // latency hides under the build / MMA / epilogue of the current tile.
+  constexpr int kHaloVec = kHaloH * kHaloW * (kStemCpad / 4);      // 1080 float4
+  constexpr int kHaloPer = (kHaloVec + 191) / 192;                  // 6 per thread
+  float4 hreg[kHaloPer];
+  auto fetch_halo = [&](int tile) {
+    const int n = tile / tiles_per_img, tt = tile - n * tiles_per_img;
+    const int ty0 = (tt / tiles_x) * kTileH, tx0 = (tt % tiles_x) * kTileW;
+    const float* xb = x + (int64_t)n * H * W * ldx;
+#pragma unroll
+    for (int q = 0; q < kHaloPer; ++q) {
+      const int i = tid + q * 192;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < kHaloVec) {
+        const int p = i / (kStemCpad / 4), f = i - p * (kStemCpad / 4);
+        const int yy = ty0 - 1 + p / kHaloW, xx = tx0 - 1 + p % kHaloW;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(reinterpret_cast<const float4*>(xb + ((int64_t)yy * W + xx) * ldx + f * 4));
+      }
+      hreg[q] = v;
+    }
+  };
+  if ((int)blockIdx.x < total_tiles) fetch_halo(blockIdx.x);
   int it = 0;                                                   // tiles done by this CTA (ring / barrier phases continue)
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
     const int n = tile / tiles_per_img, tt = tile - n * tiles_per_img;
     const int ty0 = (tt / tiles_x) * kTileH, tx0 = (tt % tiles_x) * kTileW;
-    // ---- stage the halo (zero outside the image); the previous tile's builders are past their last read
-    const float* xb = x + (int64_t)n * H * W * ldx;
-    for (int i = tid; i < kHaloH * kHaloW * (kStemCpad / 4); i += 192) {
-      const int p = i / (kStemCpad / 4), f = i - p * (kStemCpad / 4);
-      const int yy = ty0 - 1 + p / kHaloW, xx = tx0 - 1 + p % kHaloW;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(reinterpret_cast<const float4*>(xb + ((int64_t)yy * W + xx) * ldx + f * 4));
-      *reinterpret_cast<float4*>(halo + p * kHaloStride + f * 4) = v;
+    // ---- publish the halo (the previous tile's builders are past their last read: end-of-tile barrier)
+#pragma unroll
+    for (int q = 0; q < kHaloPer; ++q) {
+      const int i = tid + q * 192;
+      if (i < kHaloVec) {
+        const int p = i / (kStemCpad / 4), f = i - p * (kStemCpad / 4);
+        *reinterpret_cast<float4*>(halo + p * kHaloStride + f * 4) = hreg[q];
+      }
     }
     __syncthreads();
+    if (tile + (int)gridDim.x < total_tiles) fetch_halo(tile + gridDim.x);
     const int c0 = it * kStemChunks;                            // global chunk counter of this tile's first chunk
 
     if (warp == 1) {
@@ -129,8 +152,9 @@ stem_conv_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
           }
           *reinterpret_cast<float4*>(dst + ((i ^ (b & 7)) << 4)) = v;
         }
-        fence_proxy_async();
-        mbar_arrive(bar_full + 8 * s);
+        fence_proxy_async();               // every lane orders its own generic-proxy writes before the async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);
       }
       // ---- epilogue (the next tile's first MMA is ordered behind these TMEM reads through the full barrier)
       const int lg = warp & 3;                    // TMEM lane group of this warp

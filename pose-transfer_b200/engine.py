@@ -124,11 +124,10 @@ class ConvLayer:
         return (H + 2 * self.pad - self.k) // self.stride + 1, (W + 2 * self.pad - self.k) // self.stride + 1
 
     def _is_stem(self):
-        """Conv2d(Cin <= 24 -> 64, k3, s1, p1): the encoder stems can run on csrc/stem.cu (im2col assembled in shared
-        memory).  Opt-in (PTK_STEM=1): correct (tests/test_conv_tc_gpu.py::test_stem_conv_smem_im2col) but, with its
-        two-slot operand ring, still slower than the generic implicit-GEMM kernel (0.18 vs 0.154 ms at 256x256, N=8)."""
+        """Conv2d(Cin <= 24 -> 64, k3, s1, p1): the encoder stems run on csrc/stem.cu (im2col assembled in shared memory;
+        0.139 ms vs 0.153 ms for the generic implicit-GEMM kernel at 256x256, N=8).  PTK_STEM=0 falls back."""
         return (self.impl != K.IMPL_SIMT and not self.transposed and self.k == 3 and self.stride == 1 and self.pad == 1 and
-                self.cout == 64 and self.cin <= 24 and os.environ.get("PTK_STEM", "0") == "1")
+                self.cout == 64 and self.cin <= 24 and os.environ.get("PTK_STEM", "1") != "0")
 
     def forward(self, x, N, H, W, y, act=ACT_NONE, stats=None, y_nchw=None):
         """x: Slice with cin_pad readable channels; y: Slice (cout channels) or None."""
