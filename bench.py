@@ -134,11 +134,19 @@ def run_reference(args):
         return
     N = 2
     model, batches = make_cpu_reference(N)
-    for _ in range(args.warmup):
+    # Bounded run: one CPU iteration takes seconds, so warm-up + timed iterations are capped to ~4 minutes of wall time
+    # (at least one of each); the line reports how many timed iterations actually ran.
+    budget_s = 240.0
+    t_first = cpu_reference_iteration(model, batches, N)
+    fit = max(int(budget_s / max(t_first, 1e-3)), 2)
+    warm = max(min(args.warmup, fit // 4) - 1, 0)
+    for _ in range(warm):
         cpu_reference_iteration(model, batches, N)
-    times = [cpu_reference_iteration(model, batches, N) for _ in range(args.steps)]
+    steps = max(min(args.steps, fit - 1 - warm), 1)
+    times = [cpu_reference_iteration(model, batches, N) for _ in range(steps)]
     total = sum(times)
-    v = N * args.steps / total
+    v = N * steps / total
+    args.steps = steps
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": "training images/sec at 256x256 warp_skip=mask", "value": v, "unit": "img/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
