@@ -342,10 +342,13 @@ class GeneratorEngine:
                 st_idx[key] = len(st_idx)
             return stats[st_idx[key]]
 
-        # dropout noise (Dropout2d(0.5), models/networks.py:161; active in every forward of the reference)
+        # dropout noise (Dropout2d(0.5), models/networks.py:161; active in every forward of the reference, which never
+        # calls .eval() -- a caller that does gets nn.Dropout2d's eval behaviour: identity)
         drops = []
         for j in range(min(3, L - 1)):
-            if drop is None:
+            if drop is None and not self.m.training:
+                d = torch.ones(N, self.dec[j], 1, 1, device=inp.device)
+            elif drop is None:
                 d = torch.empty(N, self.dec[j], 1, 1, device=inp.device).bernoulli_(0.5).div_(0.5)
             else:
                 d = drop[j].to(inp.device, torch.float32)

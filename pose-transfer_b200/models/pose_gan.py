@@ -160,7 +160,17 @@ class DeformablePose_GAN(nn.Module):
         self.pose_dim = opt.pose_dim
         self.image_size = tuple(opt.image_size)
         if opt.gen_type == 'stacked':
-            raise NotImplementedError("gen_type='stacked' is outside the B200 hot path (SURVEY 8f-3)")
+            # the stacked generator is a composition of the same Deformable_Generator; its forward (what
+            # test.py runs: model.gen(input, interpol_pose, interpol_warps, interpol_masks)) is on the B200 path, its
+            # training branches (pose_gan.py:72-77,120-125) are not (gen_update / dis_update raise).
+            self.gen = Stacked_Generator(input_nc, opt.num_stacks, opt.image_size, opt.pose_dim, nfilters_encoder,
+                                         nfilters_decoder, opt.warp_skip, use_input_pose=opt.use_input_pose)
+            pretrained_gen_path = '../exp/' + 'full_' + opt.dataset + '/models/gen_090.pkl'   # pose_gan.py:31-32
+            try:
+                self.gen.generator.load_state_dict(torch.load(pretrained_gen_path))
+                print("Loaded generator from pretrained model ")
+            except (FileNotFoundError, OSError):
+                print("No pretrained generator at %s -- keeping default initialisation" % pretrained_gen_path)
         elif opt.gen_type == 'baseline':
             self.gen = Deformable_Generator(input_nc, self.pose_dim, opt.image_size, nfilters_encoder, nfilters_decoder,
                                             opt.warp_skip, use_input_pose=opt.use_input_pose)

@@ -137,3 +137,42 @@ def test_trainer_schedule_nn_loss():
 
 def test_trainer_schedule_l1():
     _steps("64x64_p18_l1", "none", 1, 100.0, 1, 3)
+
+
+def test_stacked_generator_forward_matches_reference(monkeypatch):
+    """SURVEY 8f-3 (forward only, what test.py runs): DeformablePose_GAN(gen_type='stacked').gen(input, interpol_pose,
+    interpol_warps, interpol_masks) against the reference Stacked_Generator with the same weights, both in eval mode
+    (Dropout2d = identity).  Kernels are the torch emulation; the host composition under test is the product's."""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not mounted")
+    from pose_transfer_b200.models import pose_gan, networks
+    ns = ref_import.load()
+    H = W = 64
+    P, N, S = 18, 2, 3
+    opt = argparse.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=S,
+                             gen_type="stacked", warp_skip="mask", dataset="fasion", learning_rate=2e-4,
+                             content_loss_layer="none", nn_loss_area_size=1, gan_penalty_weight=1.0, l1_penalty_weight=100.0)
+    gsd = synth.fill_state_dict(synth.generator_shapes(P, (H, W)), 3)
+    enc, dec = (64, 128, 256, 512, 512, 512), (512, 512, 512, 256, 128, 3)
+    ref = ns.networks.Stacked_Generator(3 + 2 * P, S, (H, W), P, enc, dec, "mask")
+    ref.generator.load_state_dict(gsd)
+    ref.eval()
+    bs = [synth.make_batch(N, H, W, P, seed=20 + i) for i in range(S)]
+    inp = bs[0]["input"]
+    interpol_pose = torch.cat([b["input"][:, 3 + P:] for b in bs], 1)                  # [N, S*P, H, W]
+    interpol_warps = torch.stack([b["warps"] for b in bs], 1)                           # [N, S, 10, 8]
+    interpol_masks = torch.stack([b["masks"] for b in bs], 1)                           # [N, S, 10, H, W]
+    with torch.no_grad():
+        want = ref(inp, interpol_pose, interpol_warps.clone(), interpol_masks.clone())
+    monkeypatch.setattr(networks, "_require_cuda", lambda t, who: None)
+    with _CpuGAN(), emul_kernels.install(K), torch.no_grad():
+        model = pose_gan.DeformablePose_GAN(opt)
+        model.gen.generator.load_state_dict(gsd)
+        model.eval()
+        got = model.gen(inp, interpol_pose, interpol_warps, interpol_masks)
+        with pytest.raises(NotImplementedError):
+            model.gen_update(inp, bs[0]["target"], {}, vars(opt))
+    assert len(got) == len(want) == S
+    for a, b in zip(got, want):
+        assert max_abs(a, b) <= 2e-4
