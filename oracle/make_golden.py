@@ -141,6 +141,68 @@ def gen_step(ns, H, W, P, N, seed, tag, content="block1_conv2", area=5, l1_w=0.0
     np.savez_compressed(os.path.join(GOLDEN_DIR, "step_%s.npz" % tag), **rec)
 
 
+def gen_step_baseline(H, W, P, N, seed, tag, l1_w=100.0):
+    """BASELINE configs[0]: src_baseline Pose_GAN (single-encoder Generator, L1 + adversarial), one iteration.  Weights:
+    the reference's own xavier initialisation under torch.manual_seed(seed); they are stored so the product starts from
+    the same point without the reference tree."""
+    import argparse as ap
+    import contextlib
+    import io
+    nsb = ref_import.load_baseline()
+    opt = ap.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=4, checkMode=0,
+                       gen_type="baseline", dataset="fasion128", learning_rate=2e-4, gan_penalty_weight=1.0,
+                       l1_penalty_weight=l1_w)
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = nsb.pose_gan.Pose_GAN(opt)
+    # deterministic weights that travel: seeded fills instead of the xavier draw
+    g = torch.Generator().manual_seed(seed + 100)
+    with torch.no_grad():
+        for net in (model.gen, model.disc):
+            for k, p in sorted(net.named_parameters()):
+                if p.dim() == 4:
+                    fan = p.shape[1] * p.shape[2] * p.shape[3]
+                    p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * (3.0 / fan) ** 0.5)
+                elif p.numel() == 1:
+                    p.fill_(1.0 if k.endswith("weight") else 0.0)
+                else:
+                    p.copy_((torch.rand(p.shape, generator=g) - 0.5) * 0.1)
+    od = vars(opt)
+    rec = {"seed": np.int64(seed)}
+    b = synth.make_batch(N, H, W, P, seed=seed)
+    r = synth.make_batch(N, H, W, P, seed=seed + 1)
+    b2 = synth.make_batch(N, H, W, P, seed=seed + 2)
+    with _DropPatch(synth.dropout_masks(N, 512, 3, seed=seed)):
+        dl = model.dis_update(b["input"], b["target"], None, r["input"], r["target"], od)
+    rec["d_loss"] = np.array(dl)
+    rec["d_grad"] = np.stack([summarize(p.grad) for _, p in sorted(model.disc.named_parameters())])
+    with _DropPatch(synth.dropout_masks(N, 512, 3, seed=seed + 2)):
+        out, _, gl = model.gen_update(b2["input"], b2["target"], None, od)
+    rec["g_loss"] = np.array(gl)
+    rec["out_gen"] = out.detach().numpy()
+    rec["g_grad"] = np.stack([summarize(p.grad) for _, p in sorted(model.gen.named_parameters())])
+    rec["g_param"] = np.stack([summarize(p) for _, p in sorted(model.gen.named_parameters())])
+    rec["d_param"] = np.stack([summarize(p) for _, p in sorted(model.disc.named_parameters())])
+    print("baseline step", tag, dl, gl)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "step_%s.npz" % tag), **rec)
+
+
+def baseline_initial_weights(model_gen, model_disc, seed):
+    """The seeded fills of gen_step_baseline, applied to any pair of modules with the same parameter names (shared with
+    the tests so the product starts from the fixture's weights)."""
+    g = torch.Generator().manual_seed(seed + 100)
+    with torch.no_grad():
+        for net in (model_gen, model_disc):
+            for k, p in sorted(net.named_parameters()):
+                if p.dim() == 4:
+                    fan = p.shape[1] * p.shape[2] * p.shape[3]
+                    p.copy_(((torch.rand(p.shape, generator=g) * 2 - 1) * (3.0 / fan) ** 0.5).to(p.device))
+                elif p.numel() == 1:
+                    p.fill_(1.0 if k.endswith("weight") else 0.0)
+                else:
+                    p.copy_(((torch.rand(p.shape, generator=g) - 0.5) * 0.1).to(p.device))
+
+
 def main():
     apx = argparse.ArgumentParser()
     apx.add_argument("--only", default="")
@@ -156,6 +218,8 @@ def main():
     if a.only in ("", "step"):
         gen_step(ns, 64, 64, 18, 2, 0, "64x64_p18_nn5")
         gen_step(ns, 64, 64, 18, 2, 3, "64x64_p18_l1", content="none", area=1, l1_w=100.0, steps=1)
+    if a.only in ("", "baseline"):
+        gen_step_baseline(128, 64, 18, 4, 11, "baseline_128x64_p18")
     if a.only in ("", "params"):
         # known answers from the reference logs (gen_full_fasion:158,193 ; gen_full_h36m:136,171)
         for (H, P, ng, nd) in ((256, 18, 82080611, 2803782), (224, 16, 61106781, 2799686)):

@@ -33,14 +33,32 @@ def _stub(name, **attrs):
 
 
 _loaded = None
+_loaded_by_root = {}
+BASELINE_ROOT = os.path.join(os.path.dirname(REFERENCE_ROOT), "src_baseline")
 
 
-def load():
+def load_baseline():
+    """The src_baseline tree (Generator / Pose_GAN), imported the same way under private module names."""
+    return load(BASELINE_ROOT)
+
+
+def load(root=None):
     """Returns a namespace with the reference modules: networks, pose_gan, pose_transform, pose_utils."""
     global _loaded
+    if root is not None and root != REFERENCE_ROOT:
+        if root not in _loaded_by_root:
+            _loaded_by_root[root] = _load_tree(root, "_ptk_reference_" + os.path.basename(root) + ".")
+        return _loaded_by_root[root]
     if _loaded is not None:
         return _loaded
     if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    _loaded = _load_tree(REFERENCE_ROOT, "_ptk_reference.")
+    return _loaded
+
+
+def _load_tree(REFERENCE_ROOT, private_prefix):
+    if not os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "networks.py")):
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
     saved = {k: sys.modules.get(k) for k in ("models", "utils", "models.networks", "models.pose_gan",
                                              "utils.pose_transform", "utils.pose_utils")}
@@ -78,10 +96,9 @@ def load():
               "utils.pose_utils"):
         mod = sys.modules.pop(k, None)
         if mod is not None:
-            sys.modules["_ptk_reference." + k] = mod
+            sys.modules[private_prefix + k] = mod
         if saved[k] is not None:
             sys.modules[k] = saved[k]
-    _loaded = ns
     return ns
 
 

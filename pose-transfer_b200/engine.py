@@ -214,11 +214,20 @@ class GeneratorEngine:
 
     def __init__(self, module):
         self.m = module
-        self.P = module.pose_dim
+        # Encoder branches: (name, sub-module, first input channel, input channels, warped skips).  The deformable
+        # generator has an appearance branch (warped) and a pose branch; the src_baseline Generator
+        # (src_baseline/models/networks.py:238-254) is the same U-Net with ONE un-warped encoder over the whole input.
+        if hasattr(module, "encoder_app"):
+            P = module.pose_dim
+            self.specs = [("app", module.encoder_app, 0, 3 + P, True), ("pose", module.encoder_pose, 3 + P, P, False)]
+        else:
+            self.specs = [("enc", module.encoder, 0, module.input_nc, False)]
+        self.in_channels = sum(sp[3] for sp in self.specs)
+        self.stage_modules = dict([("decoder", module.decoder)] + [(sp[0], sp[1]) for sp in self.specs])
         self.enc = list(module.nfilters_enc)
         self.dec = list(module.nfilters_dec)
         self.L = len(self.enc)
-        self.image_size = tuple(module.image_size)
+        self.image_size = tuple(module.image_size) if getattr(module, "image_size", None) is not None else None
         self.ws = None
         self.layers_built = False
         self.saved = None
@@ -228,7 +237,7 @@ class GeneratorEngine:
         m = self.m
         self.enc_conv = {}
         self.enc_norm = {}
-        for name, e in (("app", m.encoder_app), ("pose", m.encoder_pose)):
+        for name, e, _, _, _ in self.specs:
             convs, norms = [], []
             for i, mod in enumerate(e.net):
                 if i == 0:
@@ -246,7 +255,7 @@ class GeneratorEngine:
             self.dec_norm.append(NormLayer(blk.net[3].weight, blk.net[3].bias))
         fin = m.decoder.net[self.L]
         self.final_conv = ConvLayer(fin.weight, fin.bias, False, 3, 1, 1)
-        self.all_convs = self.enc_conv["app"] + self.enc_conv["pose"] + self.dec_conv + [self.final_conv]
+        self.all_convs = sum((self.enc_conv[sp[0]] for sp in self.specs), []) + self.dec_conv + [self.final_conv]
         self.layers_built = True
 
     def _side_stream(self, device):
@@ -305,10 +314,10 @@ class GeneratorEngine:
         return hs, wsz
 
     def _cat_layout(self, j):
-        """Channel layout of decoder level j's input: (dec_prev, enc_i) with i = L-1-j."""
+        """Channel layout of decoder level j's input: (dec_prev, one slot of enc_i channels per encoder branch), i = L-1-j."""
         i = self.L - 1 - j
         dprev = 0 if j == 0 else self.dec[j - 1]
-        return i, dprev, dprev + 2 * self.enc[i]
+        return i, dprev, dprev + len(self.specs) * self.enc[i]
 
     # ------------------------------------------------------------------ forward
     def forward(self, inp, warps, masks, drop=None, repack=True, d_input=None):
@@ -318,22 +327,26 @@ class GeneratorEngine:
         assert inp.dtype == torch.float32 and inp.dim() == 4   # device is enforced by the kernel wrappers
         N, Ct, H, W = inp.shape
         assert N >= 2, "the reference's .squeeze() (models/networks.py:169) makes N=1 unsupported"
-        P, L = self.P, self.L
-        assert Ct == 3 + 2 * P
+        L = self.L
+        assert Ct == self.in_channels
         self._ensure(inp.device)
         ws = self.ws
         inp = inp.contiguous()
-        warps = warps.contiguous().float()
-        masks = masks.contiguous()
-        if masks.dtype != torch.float64:
-            masks = masks.double()
-        Kp = warps.shape[1]
-        H0, W0 = self.image_size
+        any_warp = any(sp[4] for sp in self.specs)
+        if any_warp:
+            warps = warps.contiguous().float()
+            masks = masks.contiguous()
+            if masks.dtype != torch.float64:
+                masks = masks.double()
+            Kp = warps.shape[1]
+            H0, W0 = self.image_size
+        else:
+            Kp, H0, W0 = 0, H, W
         if self._need_repack(repack):
             self.pack_weights()
         hs, wsz = self._sizes(H, W)
         tag = "%d_%d_%d" % (N, H, W)
-        n_norm = 2 * (L - 2) + (L - 1)
+        n_norm = len(self.specs) * (L - 2) + (L - 1)
         stats = ws.get("stats" + tag, (n_norm, N, 2), torch.float64, zero=True)
         st_idx = {}
 
@@ -362,7 +375,7 @@ class GeneratorEngine:
 
         # mask pyramid for the 4 warped levels
         mlv = []
-        for i in range(min(4, L)):
+        for i in range(min(4, L) if any_warp else 0):
             mk = ws.get("mask%d_%s" % (i, tag), (N, hs[i], wsz[i], Kp))
             K.mask_pyramid(masks, mk)
             mlv.append(mk)
@@ -376,8 +389,8 @@ class GeneratorEngine:
         main = torch.cuda.current_stream() if side is not None else None
         if side is not None:
             side.wait_stream(main)
-        for name, c_src0, cin in (("app", 0, 3 + P), ("pose", 3 + P, P)):
-          with (torch.cuda.stream(side) if (side is not None and name == "pose") else contextlib.nullcontext()):
+        for e_idx, (name, _, c_src0, cin, warped_branch) in enumerate(self.specs):
+          with (torch.cuda.stream(side) if (side is not None and e_idx == 1) else contextlib.nullcontext()):
               convs, norms = self.enc_conv[name], self.enc_norm[name]
               xin = ws.get("xin_%s_%s" % (name, tag), (N, H, W, convs[0].cin_pad))
               K.nchw_to_nhwc(inp, c_src0, cin, Slice(xin, 0, cin))
@@ -386,7 +399,7 @@ class GeneratorEngine:
                   j = L - 1 - i
                   _, dprev, _ = self._cat_layout(j)
                   c = self.enc[i]
-                  cat_slice = Slice(cats[j], dprev + (0 if name == "app" else c), c)
+                  cat_slice = Slice(cats[j], dprev + e_idx * c, c)
                   z = ws.get("z_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
                   src = Slice(xin) if i == 0 else Slice(sv["act"][(name, i - 1)])
                   norm = norms[i]
@@ -396,7 +409,7 @@ class GeneratorEngine:
                   HW = hs[i] * wsz[i]
                   gam = norm.weight.detach() if norm is not None else None
                   bet = norm.bias.detach() if norm is not None else None
-                  warped = name == "app" and i < 4
+                  warped = warped_branch and i < 4
                   if i < L - 1:
                       act = ws.get("act_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
                       sv["act"][(name, i)] = act
@@ -458,7 +471,7 @@ class GeneratorEngine:
         ws, L = self.ws, self.L
         N, H, W, hs, wsz, tag = sv["N"], sv["H"], sv["W"], sv["hs"], sv["ws"], sv["tag"]
         cats, stats, st_idx, drops = sv["cats"], sv["stats"], sv["st_idx"], sv["drops"]
-        H0, W0 = self.image_size
+        H0, W0 = self.image_size if self.image_size is not None else (H, W)
         max_w = max(c.taps * c.cin_pad * c.cout_pad for c in self.all_convs)
         scratch = ws.get("wgrad_scratch", (max(4 * max_w, 1 << 24),))   # room for split-K partial gradients
         sums = ws.get("sums" + tag, tuple(stats.shape), torch.float64, zero=True)
@@ -519,8 +532,8 @@ class GeneratorEngine:
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                 on_stage("decoder")
         # encoders, deepest level first
-        for name in ("app", "pose"):
-          on_side = side is not None and name == "pose"
+        for e_idx, (name, _, _, _, warped_branch) in enumerate(self.specs):
+          on_side = side is not None and e_idx == 1
           scratch_e = scratch_side if on_side else scratch
           with (torch.cuda.stream(side) if on_side else contextlib.nullcontext()):
               convs, norms = self.enc_conv[name], self.enc_norm[name]
@@ -530,8 +543,8 @@ class GeneratorEngine:
                   _, dprev, _ = self._cat_layout(j)
                   c = self.enc[i]
                   HW = hs[i] * wsz[i]
-                  off = dprev + (0 if name == "app" else c)
-                  warped = name == "app" and i < 4
+                  off = dprev + e_idx * c
+                  warped = warped_branch and i < 4
                   if warped:
                       dwarp = ws.get("dwarp%d_%s" % (i, tag), (N, hs[i], wsz[i], c))
                       K.fill(dwarp, 0.0)
@@ -563,12 +576,12 @@ class GeneratorEngine:
                       dact = ws.get("dact_%s%d_%s" % (name, i - 1, tag), (N, hs[i - 1], wsz[i - 1], self.enc[i - 1]))
                       cv.dgrad(Slice(dy), N, hs[i - 1], wsz[i - 1], Slice(dact))
                       dact_next = dact
-          if name == "app" and on_stage is not None:
-              on_stage("app")
+          if e_idx == 0 and on_stage is not None:
+              on_stage(name)
         if side is not None:
             main.wait_stream(side)
-        if on_stage is not None:
-            on_stage("pose")
+        if on_stage is not None and len(self.specs) > 1:
+            on_stage(self.specs[1][0])
 
 
 class DiscriminatorEngine:

@@ -203,6 +203,41 @@ class Deformable_Generator(nn.Module):
         return self.engine.forward(input, warps, masks, drop=self._next_drop())
 
 
+class Generator(nn.Module):
+    """Drop-in for src_baseline/models/networks.py:238-254: the same U-Net with ONE encoder over the whole
+    input and no warp (num_skips = 1), on the same kernels / engine.  state_dict keys: encoder.net.*, decoder.net.*."""
+
+    def __init__(self, input_nc, nfilters_enc, nfilters_dec, num_skips=1, warp_skip=False, use_input_pose=True):
+        super(Generator, self).__init__()
+        if num_skips != 1:
+            raise NotImplementedError("src_baseline Generator: only num_skips=1 (the reference's only use) is supported")
+        self.input_nc = input_nc
+        self.num_skips = num_skips
+        self.nfilters_dec = nfilters_dec
+        self.nfilters_enc = nfilters_enc
+        self.image_size = None
+        self.encoder = encoder(input_nc, nfilters_enc)
+        self.decoder = decoder(nfilters_dec, nfilters_enc, num_skips)
+        self.engine = GeneratorEngine(self)
+        self._drop_queue = None
+        self._ptk_weights_version = 0
+        self.register_load_state_dict_post_hook(_bump_weights_version)
+
+    def set_dropout_noise(self, drops):
+        self._drop_queue = drops
+
+    def _next_drop(self):
+        d, self._drop_queue = self._drop_queue, None
+        return d
+
+    def forward(self, input):
+        _require_cuda(input, "Generator")
+        params = tuple(self.parameters())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _GeneratorFn.apply(self, input, None, None, *params)
+        return self.engine.forward(input, None, None, drop=self._next_drop())
+
+
 class Stacked_Generator(nn.Module):
     """models/networks.py:290-327 -- pure composition of Deformable_Generator."""
 

@@ -22,7 +22,7 @@ from torchvision.models import vgg19
 from .. import kernels as K
 from ..kernels import Slice
 from ..utils import pose_utils
-from .networks import Deformable_Generator, Discriminator, Stacked_Generator  # noqa: F401
+from .networks import Deformable_Generator, Discriminator, Generator, Stacked_Generator, xavier_weights_init  # noqa: F401
 
 
 class ParamArena:
@@ -185,6 +185,10 @@ class DeformablePose_GAN(nn.Module):
         except (FileNotFoundError, OSError):
             print("No pretrained discriminator at %s -- keeping default initialisation" % pretrained_disc_path)
 
+        self._finish_init(opt)
+
+    def _finish_init(self, opt):
+        """Everything after the networks exist: rank discovery, content model, parameter arenas, optimisers."""
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
             self.rank = torch.distributed.get_rank()
@@ -256,9 +260,11 @@ class DeformablePose_GAN(nn.Module):
     def gen_update(self, input, target, other_inputs, opt, drop=None):
         if opt['gen_type'] != 'baseline':
             raise NotImplementedError("gen_type='stacked' is outside the B200 hot path")
+        return self._gen_step(input, target, other_inputs['warps'], other_inputs['masks'], opt, drop)
+
+    def _gen_step(self, input, target, warps, masks, opt, drop=None):
         P = opt['pose_dim']
         input, target = self._prep(input), self._prep(target)
-        warps, masks = other_inputs['warps'], other_inputs['masks']
         N, _, H, W = input.shape
         dev = input.device
         self.gen_arena.check()
@@ -307,7 +313,7 @@ class DeformablePose_GAN(nn.Module):
         covered = []
 
         def stage_done(stage):
-            sub = {"decoder": self.gen.decoder, "app": self.gen.encoder_app, "pose": self.gen.encoder_pose}[stage]
+            sub = self.gen.engine.stage_modules[stage]
             lo, hi = self.gen_arena.segment_range(sub)
             covered.append((lo, hi))
             if ost is not None:
@@ -332,9 +338,11 @@ class DeformablePose_GAN(nn.Module):
     def dis_update(self, input, target, other_inputs, real_inp, real_target, opt, drop=None):
         if opt['gen_type'] != 'baseline':
             raise NotImplementedError("gen_type='stacked' is outside the B200 hot path")
+        return self._dis_step(input, target, other_inputs['warps'], other_inputs['masks'], real_inp, real_target, opt, drop)
+
+    def _dis_step(self, input, target, warps, masks, real_inp, real_target, opt, drop=None):
         P = opt['pose_dim']
         input, real_inp, real_target = self._prep(input), self._prep(real_inp), self._prep(real_target)
-        warps, masks = other_inputs['warps'], other_inputs['masks']
         N, _, H, W = input.shape
         dev = input.device
         self.gen_arena.check()
@@ -393,3 +401,49 @@ class DeformablePose_GAN(nn.Module):
 
     def normalize_image(self, x):
         return x[:, 0:3, :, :]
+
+
+class Pose_GAN(DeformablePose_GAN):
+    """Drop-in for src_baseline/models/pose_gan.py:10-170: single-encoder Generator, PatchGAN, adversarial +
+    L1 loss, xavier initialisation, Adam(2e-4, (0.5, 0.999)); update methods take `interpol_pose` where the deformable
+    trainer takes `other_inputs` (unused for gen_type='baseline').  Runs on the same engines / kernels."""
+
+    def __init__(self, opt):
+        nn.Module.__init__(self)
+        if getattr(opt, "checkMode", 0) != 0:
+            raise NotImplementedError("src_baseline --checkMode nets are outside the B200 path")
+        nfilters_decoder = (512, 512, 512, 256, 128, 3) if max(opt.image_size) < 256 else (512, 512, 512, 512, 256, 128, 3)
+        nfilters_encoder = (64, 128, 256, 512, 512, 512) if max(opt.image_size) < 256 else (64, 128, 256, 512, 512, 512, 512)
+        input_nc = 3 + 2 * opt.pose_dim if opt.use_input_pose else 3 + opt.pose_dim
+        if not opt.use_input_pose:
+            raise NotImplementedError("only use_input_pose=True is on the B200 path")
+        self.num_stacks = opt.num_stacks
+        self.batch_size = opt.batch_size
+        self.pose_dim = opt.pose_dim
+        self.image_size = tuple(opt.image_size)
+        if opt.gen_type != 'baseline':
+            raise NotImplementedError("src_baseline gen_type='stacked' is outside the B200 path")
+        self.gen = Generator(input_nc, nfilters_encoder, nfilters_decoder, use_input_pose=opt.use_input_pose)
+        self.disc = Discriminator(input_nc + 3, use_input_pose=opt.use_input_pose)
+        self.disc.apply(xavier_weights_init)            # src_baseline/models/pose_gan.py:51-52
+        self.gen.apply(xavier_weights_init)
+        base = argparse_like(opt, content_loss_layer='none', nn_loss_area_size=1)
+        self._finish_init(base)
+
+    def gen_update(self, input, target, interpol_pose, opt, drop=None):
+        if opt['gen_type'] != 'baseline':
+            raise NotImplementedError("src_baseline gen_type='stacked' is outside the B200 path")
+        return self._gen_step(input, target, None, None, opt, drop)
+
+    def dis_update(self, input, target, interpol_pose, real_inp, real_target, opt, drop=None):
+        if opt['gen_type'] != 'baseline':
+            raise NotImplementedError("src_baseline gen_type='stacked' is outside the B200 path")
+        return self._dis_step(input, target, None, None, real_inp, real_target, opt, drop)
+
+
+def argparse_like(opt, **overrides):
+    """A shallow copy of an options namespace with some attributes replaced."""
+    import argparse
+    d = dict(vars(opt))
+    d.update(overrides)
+    return argparse.Namespace(**d)

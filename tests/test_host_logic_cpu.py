@@ -176,3 +176,93 @@ def test_stacked_generator_forward_matches_reference(monkeypatch):
     assert len(got) == len(want) == S
     for a, b in zip(got, want):
         assert max_abs(a, b) <= 2e-4
+
+
+def test_src_baseline_pose_gan_step_matches_reference(monkeypatch):
+    """SURVEY 8f-4 / BASELINE configs[0] (src_baseline, fasion 128x64, batch 4, CPU): the product's Pose_GAN / Generator
+    against the LIVE reference src_baseline classes from identical weights, inputs and dropout noise -- generator
+    output, the six returned losses and the Adam-updated weights of one dis_update + gen_update.  Kernels are the
+    torch emulation; engine, trainer and arena logic are the product's."""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not mounted")
+    from pose_transfer_b200.models import pose_gan, networks
+    ns = ref_import.load_baseline()
+    H, W, P, N = 128, 64, 18, 4
+    opt = argparse.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=4, checkMode=0,
+                             gen_type="baseline", dataset="fasion128", learning_rate=2e-4, gan_penalty_weight=1.0,
+                             l1_penalty_weight=100.0)
+    import contextlib, io
+    with _CpuGAN():
+        with contextlib.redirect_stdout(io.StringIO()):
+            torch.manual_seed(5)
+            ref = ns.pose_gan.Pose_GAN(opt)
+        gsd = {k: v.clone() for k, v in ref.gen.state_dict().items()}
+        dsd = {k: v.clone() for k, v in ref.disc.state_dict().items()}
+        b = synth.make_batch(N, H, W, P, seed=7)
+        r = synth.make_batch(N, H, W, P, seed=8)
+        drop = synth.dropout_masks(N, 512, 3, seed=9)
+        od = vars(opt)
+
+        # reference step with the dropout noise pinned (Dropout2d modules -> fixed masks, in decoder order)
+        drops = [d.reshape(N, 512, 1, 1) for d in drop]
+        dmods = [m for m in ref.gen.modules() if isinstance(m, torch.nn.Dropout2d)]
+        assert len(dmods) == 3
+        state = {"i": 0}
+
+        def make_fwd(j):
+            return lambda x: x * drops[j]
+        for j, m in enumerate(dmods):
+            m.forward = make_fwd(j)
+        dl_ref = ref.dis_update(b["input"], b["target"], None, r["input"], r["target"], od)
+        out_ref, _, gl_ref = ref.gen_update(b["input"], b["target"], None, od)
+        out_ref = out_ref.detach()
+
+        monkeypatch.setattr(networks, "_require_cuda", lambda t, who: None)
+        with emul_kernels.install(K), contextlib.redirect_stdout(io.StringIO()):
+            model = pose_gan.Pose_GAN(opt)
+            model.gen.load_state_dict(gsd)
+            model.disc.load_state_dict(dsd)
+            dl = model.dis_update(b["input"], b["target"], None, r["input"], r["target"], od, drop=drop)
+            out, _, gl = model.gen_update(b["input"], b["target"], None, od, drop=drop)
+    np.testing.assert_allclose(dl, dl_ref, rtol=2e-4)
+    np.testing.assert_allclose(gl, gl_ref, rtol=2e-4)
+    assert max_abs(out, out_ref) <= 2e-4
+    # Adam-updated weights (+-lr per element on the first step: allow a few sign flips of ~0 gradients)
+    for name, sd_ref, mod in (("gen", ref.gen.state_dict(), model.gen), ("disc", ref.disc.state_dict(), model.disc)):
+        got = mod.state_dict()
+        assert set(got) == set(sd_ref)
+        for k in sd_ref:
+            d = (got[k].double() - sd_ref[k].double()).abs()
+            assert float(d.max()) <= 4.1e-4, (name, k, float(d.max()))
+            assert float((d > 1e-5).double().mean()) <= 2e-3, (name, k, float((d > 1e-5).double().mean()))
+
+
+def test_src_baseline_step_matches_golden_fixture(monkeypatch):
+    """The same BASELINE configs[0] record the GPU suite checks (tests/golden/step_baseline_128x64_p18.npz), here against
+    the product's host logic on emulated kernels -- runs without the reference tree."""
+    from oracle import make_golden
+    from pose_transfer_b200.models import pose_gan, networks
+    H, W, P, N = 128, 64, 18, 4
+    g = golden("step_baseline_128x64_p18")
+    seed = int(g["seed"])
+    opt = argparse.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=4, checkMode=0,
+                             gen_type="baseline", dataset="fasion128", learning_rate=2e-4, gan_penalty_weight=1.0,
+                             l1_penalty_weight=100.0)
+    monkeypatch.setattr(networks, "_require_cuda", lambda t, who: None)
+    with _CpuGAN(), emul_kernels.install(K):
+        model = pose_gan.Pose_GAN(opt)
+        make_golden.baseline_initial_weights(model.gen, model.disc, seed)
+        model.gen._ptk_weights_version += 1
+        model.disc._ptk_weights_version += 1
+        od = vars(opt)
+        b, r, b2 = (synth.make_batch(N, H, W, P, seed=seed + i) for i in range(3))
+        dl = model.dis_update(b["input"], b["target"], None, r["input"], r["target"], od, drop=synth.dropout_masks(N, 512, 3, seed=seed))
+        out, _, gl = model.gen_update(b2["input"], b2["target"], None, od, drop=synth.dropout_masks(N, 512, 3, seed=seed + 2))
+    np.testing.assert_allclose(dl, g["d_loss"], rtol=2e-4)
+    np.testing.assert_allclose(gl, g["g_loss"], rtol=2e-4)
+    assert max_abs(out, g["out_gen"]) <= 2e-4
+    gnames = sorted(k for k, _ in model.gen.named_parameters())
+    gpar = dict(model.gen.named_parameters())
+    assert_summary_close(np.stack([summarize(gpar[k]) for k in gnames]), g["g_param"], what="g_param", tol_norm=1e-4,
+                         tol_samp=2e-3, tol_scalar=2e-3, abs_slack=4.1e-4)

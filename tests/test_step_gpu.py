@@ -300,3 +300,46 @@ def test_other_baseline_configs(H, P, Nstep, monkeypatch):
     assert tuple(out.shape) == (Nstep, 3, H, W) and float(out.abs().max()) <= 1.0
     step = (model.gen_arena.flat - before).abs().max()
     assert 0 < float(step) <= 2e-4 * 1.001 + 1e-9      # first Adam step: |delta| <= lr
+
+
+def test_src_baseline_step_matches_reference_golden(impl):
+    """BASELINE configs[0] (src_baseline gen_type=baseline, 128x64, batch 4): the product's Pose_GAN / single-encoder
+    Generator on the CUDA kernels against the golden record of the unmodified src_baseline reference run on CPU
+    (oracle/make_golden.py::gen_step_baseline): losses, generator output, gradient and updated-parameter summaries of one
+    dis_update + gen_update from the same weights, inputs and dropout noise."""
+    from oracle import make_golden, synth
+    from pose_transfer_b200.models import pose_gan
+    H, W, P, N = 128, 64, 18, 4
+    g = golden("step_baseline_128x64_p18")
+    seed = int(g["seed"])
+    opt = argparse.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=4, checkMode=0,
+                             gen_type="baseline", dataset="fasion128", learning_rate=2e-4, gan_penalty_weight=1.0,
+                             l1_penalty_weight=100.0)
+    model = pose_gan.Pose_GAN(opt).cuda()
+    make_golden.baseline_initial_weights(model.gen, model.disc, seed)
+    model.gen._ptk_weights_version += 1
+    model.disc._ptk_weights_version += 1
+    od = vars(opt)
+    T = TOL[impl]
+    b = synth.make_batch(N, H, W, P, seed=seed)
+    r = synth.make_batch(N, H, W, P, seed=seed + 1)
+    b2 = synth.make_batch(N, H, W, P, seed=seed + 2)
+    dl = model.dis_update(b["input"].cuda(), b["target"].cuda(), None, r["input"].cuda(), r["target"].cuda(), od,
+                          drop=synth.dropout_masks(N, 512, 3, seed=seed))
+    np.testing.assert_allclose(dl, g["d_loss"], rtol=T["loss"])
+    dnames = sorted(k for k, _ in model.disc.named_parameters())
+    dpar = dict(model.disc.named_parameters())
+    # (the scalar norm gains start at gamma = 1, beta = 0 here: their gradients are ~1e-6 cancellation residues of O(1e-2)
+    #  terms, i.e. fp32 noise -- hence the absolute allowance)
+    gslack = 3e-5
+    assert_summary_close(np.stack([summarize(dpar[k].grad) for k in dnames]), g["d_grad"], what="d_grad", abs_slack=gslack, **T["grad"])
+    out, _, gl = model.gen_update(b2["input"].cuda(), b2["target"].cuda(), None, od,
+                                  drop=synth.dropout_masks(N, 512, 3, seed=seed + 2))
+    np.testing.assert_allclose(gl, g["g_loss"], rtol=T["loss"])
+    assert max_abs(out, g["out_gen"]) <= T["out"]
+    gnames = sorted(k for k, _ in model.gen.named_parameters())
+    gpar = dict(model.gen.named_parameters())
+    assert_summary_close(np.stack([summarize(gpar[k].grad) for k in gnames]), g["g_grad"], what="g_grad", abs_slack=gslack, **T["grad"])
+    slack = 5e-4      # Adam turns the sign of a ~0 gradient element into +-lr
+    assert_summary_close(np.stack([summarize(gpar[k]) for k in gnames]), g["g_param"], what="g_param", abs_slack=slack, **T["param"])
+    assert_summary_close(np.stack([summarize(dpar[k]) for k in dnames]), g["d_param"], what="d_param", abs_slack=slack, **T["param"])
