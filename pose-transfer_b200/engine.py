@@ -390,45 +390,45 @@ class GeneratorEngine:
         if side is not None:
             side.wait_stream(main)
         for e_idx, (name, _, c_src0, cin, warped_branch) in enumerate(self.specs):
-          with (torch.cuda.stream(side) if (side is not None and e_idx == 1) else contextlib.nullcontext()):
-              convs, norms = self.enc_conv[name], self.enc_norm[name]
-              xin = ws.get("xin_%s_%s" % (name, tag), (N, H, W, convs[0].cin_pad))
-              K.nchw_to_nhwc(inp, c_src0, cin, Slice(xin, 0, cin))
-              sv["xin"][name] = xin
-              for i in range(L):
-                  j = L - 1 - i
-                  _, dprev, _ = self._cat_layout(j)
-                  c = self.enc[i]
-                  cat_slice = Slice(cats[j], dprev + e_idx * c, c)
-                  z = ws.get("z_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
-                  src = Slice(xin) if i == 0 else Slice(sv["act"][(name, i - 1)])
-                  norm = norms[i]
-                  st = stat_for((name, i)) if norm is not None else None
-                  convs[i].forward(src, N, hs[i - 1] if i else H, wsz[i - 1] if i else W, Slice(z), ACT_NONE, st)
-                  sv["z"][(name, i)] = z
-                  HW = hs[i] * wsz[i]
-                  gam = norm.weight.detach() if norm is not None else None
-                  bet = norm.bias.detach() if norm is not None else None
-                  warped = warped_branch and i < 4
-                  if i < L - 1:
-                      act = ws.get("act_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
-                      sv["act"][(name, i)] = act
-                      if warped:
-                          if norm is not None:
-                              yraw = ws.get("yraw_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
-                              K.gn_apply(z, st, gam, bet, None, N, HW, c, act, ACT_LEAKY, yraw, ACT_NONE)
-                          else:
-                              yraw = z
-                              K.gn_apply(z, None, None, None, None, N, HW, c, act, ACT_LEAKY)
-                          sv["yraw"][i] = yraw
-                      else:
-                          K.gn_apply(z, st, gam, bet, None, N, HW, c, act, ACT_LEAKY, cat_slice, ACT_RELU)
-                  else:
-                      K.gn_apply(z, st, gam, bet, None, N, HW, c, cat_slice, ACT_RELU)
-                  if warped:
-                      argk = ws.get("argk%d_%s" % (i, tag), (N, hs[i], wsz[i], c), torch.uint8)
-                      K.warp_forward(sv["yraw"][i], warps, mlv[i], cat_slice, argk, N, c, hs[i], wsz[i], Kp, H0, W0, ACT_RELU)
-                      sv["argk"][i] = argk
+            with (torch.cuda.stream(side) if (side is not None and e_idx == 1) else contextlib.nullcontext()):
+                convs, norms = self.enc_conv[name], self.enc_norm[name]
+                xin = ws.get("xin_%s_%s" % (name, tag), (N, H, W, convs[0].cin_pad))
+                K.nchw_to_nhwc(inp, c_src0, cin, Slice(xin, 0, cin))
+                sv["xin"][name] = xin
+                for i in range(L):
+                    j = L - 1 - i
+                    _, dprev, _ = self._cat_layout(j)
+                    c = self.enc[i]
+                    cat_slice = Slice(cats[j], dprev + e_idx * c, c)
+                    z = ws.get("z_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
+                    src = Slice(xin) if i == 0 else Slice(sv["act"][(name, i - 1)])
+                    norm = norms[i]
+                    st = stat_for((name, i)) if norm is not None else None
+                    convs[i].forward(src, N, hs[i - 1] if i else H, wsz[i - 1] if i else W, Slice(z), ACT_NONE, st)
+                    sv["z"][(name, i)] = z
+                    HW = hs[i] * wsz[i]
+                    gam = norm.weight.detach() if norm is not None else None
+                    bet = norm.bias.detach() if norm is not None else None
+                    warped = warped_branch and i < 4
+                    if i < L - 1:
+                        act = ws.get("act_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
+                        sv["act"][(name, i)] = act
+                        if warped:
+                            if norm is not None:
+                                yraw = ws.get("yraw_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
+                                K.gn_apply(z, st, gam, bet, None, N, HW, c, act, ACT_LEAKY, yraw, ACT_NONE)
+                            else:
+                                yraw = z
+                                K.gn_apply(z, None, None, None, None, N, HW, c, act, ACT_LEAKY)
+                            sv["yraw"][i] = yraw
+                        else:
+                            K.gn_apply(z, st, gam, bet, None, N, HW, c, act, ACT_LEAKY, cat_slice, ACT_RELU)
+                    else:
+                        K.gn_apply(z, st, gam, bet, None, N, HW, c, cat_slice, ACT_RELU)
+                    if warped:
+                        argk = ws.get("argk%d_%s" % (i, tag), (N, hs[i], wsz[i], c), torch.uint8)
+                        K.warp_forward(sv["yraw"][i], warps, mlv[i], cat_slice, argk, N, c, hs[i], wsz[i], Kp, H0, W0, ACT_RELU)
+                        sv["argk"][i] = argk
         if side is not None:
             main.wait_stream(side)
 
@@ -533,51 +533,51 @@ class GeneratorEngine:
                 on_stage("decoder")
         # encoders, deepest level first
         for e_idx, (name, _, _, _, warped_branch) in enumerate(self.specs):
-          on_side = side is not None and e_idx == 1
-          scratch_e = scratch_side if on_side else scratch
-          with (torch.cuda.stream(side) if on_side else contextlib.nullcontext()):
-              convs, norms = self.enc_conv[name], self.enc_norm[name]
-              dact_next = None
-              for i in range(L - 1, -1, -1):
-                  j = L - 1 - i
-                  _, dprev, _ = self._cat_layout(j)
-                  c = self.enc[i]
-                  HW = hs[i] * wsz[i]
-                  off = dprev + e_idx * c
-                  warped = warped_branch and i < 4
-                  if warped:
-                      dwarp = ws.get("dwarp%d_%s" % (i, tag), (N, hs[i], wsz[i], c))
-                      K.fill(dwarp, 0.0)
-                      K.warp_backward(Slice(dcats[j], off, c), Slice(cats[j], off, c), ACT_RELU, sv["warps"], sv["mlv"][i],
-                                      sv["argk"][i], dwarp, N, c, hs[i], wsz[i], sv["K"], H0, W0)
-                      skip_g, skip_a, skip_act = Slice(dwarp), None, ACT_NONE
-                  else:
-                      skip_g, skip_a, skip_act = Slice(dcats[j], off, c), Slice(cats[j], off, c), ACT_RELU
-                  norm = norms[i]
-                  z = sv["z"][(name, i)]
-                  dy = ws.get("dye_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
-                  si = st_idx[(name, i)] if norm is not None else None
-                  st = stats[si] if norm is not None else None
-                  sm = sums[si] if norm is not None else None
-                  if dact_next is not None:
-                      K.gn_bwd_reduce(Slice(dact_next), Slice(sv["act"][(name, i)]), ACT_LEAKY, skip_g, skip_a, skip_act,
-                                      None, z if norm is not None else None, st, N, HW, c, dy, sm)
-                  else:
-                      K.gn_bwd_reduce(skip_g, skip_a, skip_act, None, None, ACT_NONE, None, z if norm is not None else None,
-                                      st, N, HW, c, dy, sm)
-                  if norm is not None:
-                      K.gn_bwd_apply(dy, z, st, sm, norm.weight.detach(), N, HW, c, grads[norm.weight], grads[norm.bias])
-                  cv = convs[i]
-                  if i == 0:
-                      cv.wgrad(Slice(sv["xin"][name]), Slice(dy), N, H, W, scratch_e, grads[cv.weight])
-                      K.bias_grad(dy, c, N * HW, c, grads[cv.bias])
-                  else:
-                      cv.wgrad(Slice(sv["act"][(name, i - 1)]), Slice(dy), N, hs[i - 1], wsz[i - 1], scratch_e, grads[cv.weight])
-                      dact = ws.get("dact_%s%d_%s" % (name, i - 1, tag), (N, hs[i - 1], wsz[i - 1], self.enc[i - 1]))
-                      cv.dgrad(Slice(dy), N, hs[i - 1], wsz[i - 1], Slice(dact))
-                      dact_next = dact
-          if e_idx == 0 and on_stage is not None:
-              on_stage(name)
+            on_side = side is not None and e_idx == 1
+            scratch_e = scratch_side if on_side else scratch
+            with (torch.cuda.stream(side) if on_side else contextlib.nullcontext()):
+                convs, norms = self.enc_conv[name], self.enc_norm[name]
+                dact_next = None
+                for i in range(L - 1, -1, -1):
+                    j = L - 1 - i
+                    _, dprev, _ = self._cat_layout(j)
+                    c = self.enc[i]
+                    HW = hs[i] * wsz[i]
+                    off = dprev + e_idx * c
+                    warped = warped_branch and i < 4
+                    if warped:
+                        dwarp = ws.get("dwarp%d_%s" % (i, tag), (N, hs[i], wsz[i], c))
+                        K.fill(dwarp, 0.0)
+                        K.warp_backward(Slice(dcats[j], off, c), Slice(cats[j], off, c), ACT_RELU, sv["warps"], sv["mlv"][i],
+                                        sv["argk"][i], dwarp, N, c, hs[i], wsz[i], sv["K"], H0, W0)
+                        skip_g, skip_a, skip_act = Slice(dwarp), None, ACT_NONE
+                    else:
+                        skip_g, skip_a, skip_act = Slice(dcats[j], off, c), Slice(cats[j], off, c), ACT_RELU
+                    norm = norms[i]
+                    z = sv["z"][(name, i)]
+                    dy = ws.get("dye_%s%d_%s" % (name, i, tag), (N, hs[i], wsz[i], c))
+                    si = st_idx[(name, i)] if norm is not None else None
+                    st = stats[si] if norm is not None else None
+                    sm = sums[si] if norm is not None else None
+                    if dact_next is not None:
+                        K.gn_bwd_reduce(Slice(dact_next), Slice(sv["act"][(name, i)]), ACT_LEAKY, skip_g, skip_a, skip_act,
+                                        None, z if norm is not None else None, st, N, HW, c, dy, sm)
+                    else:
+                        K.gn_bwd_reduce(skip_g, skip_a, skip_act, None, None, ACT_NONE, None, z if norm is not None else None,
+                                        st, N, HW, c, dy, sm)
+                    if norm is not None:
+                        K.gn_bwd_apply(dy, z, st, sm, norm.weight.detach(), N, HW, c, grads[norm.weight], grads[norm.bias])
+                    cv = convs[i]
+                    if i == 0:
+                        cv.wgrad(Slice(sv["xin"][name]), Slice(dy), N, H, W, scratch_e, grads[cv.weight])
+                        K.bias_grad(dy, c, N * HW, c, grads[cv.bias])
+                    else:
+                        cv.wgrad(Slice(sv["act"][(name, i - 1)]), Slice(dy), N, hs[i - 1], wsz[i - 1], scratch_e, grads[cv.weight])
+                        dact = ws.get("dact_%s%d_%s" % (name, i - 1, tag), (N, hs[i - 1], wsz[i - 1], self.enc[i - 1]))
+                        cv.dgrad(Slice(dy), N, hs[i - 1], wsz[i - 1], Slice(dact))
+                        dact_next = dact
+            if e_idx == 0 and on_stage is not None:
+                on_stage(name)
         if side is not None:
             main.wait_stream(side)
         if on_stage is not None and len(self.specs) > 1:
