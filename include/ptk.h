@@ -188,6 +188,13 @@ int ptk_nnloss_forward(const float* pred, const float* target, const float* vgg_
 int ptk_nnloss_backward(const float* pred, const float* target, const float* vgg_w, const float* vgg_b,
                         const uint8_t* argmin, int N, int H, int W, int area, float scale, float* dpred,
                         void* stream);
+/* nn_loss on MATERIALISED features (the public method DeformablePose_GAN.nn_loss, models/pose_gan.py:173-199):
+ * pred / gt NCHW [N,C,H,W]; loss[0] += scale * mean_{n,y,x} min_shift sum_c |gt_shift - pred| with -10000 padding;
+ * argmin[n,y,x] = winning shift.  Backward: dpred = scale * (-sign(gt_shift* - pred)) / (N*H*W) (overwrites). */
+int ptk_nnloss_features_forward(const float* pred, const float* gt, int N, int C, int H, int W, int area, float scale,
+                                float* loss, uint8_t* argmin, void* stream);
+int ptk_nnloss_features_backward(const float* pred, const float* gt, const uint8_t* argmin, int N, int C, int H, int W,
+                                 int area, float scale, float* dpred, void* stream);
 /* dz[n,y,x,c] (NHWC, ld) = (g_nchw[n,c,y,x] + g_nhwc[(n,y,x)*ldg + c]) * (1 - out[n,c,y,x]^2); either g may be NULL */
 int ptk_tanh_bwd_combine(const float* g_nchw, const float* g_nhwc, int ldg, const float* out_nchw,
                          float* dz, int ld, int N, int C, int H, int W, void* stream);

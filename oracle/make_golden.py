@@ -141,6 +141,75 @@ def gen_step(ns, H, W, P, N, seed, tag, content="block1_conv2", area=5, l1_w=0.0
     np.savez_compressed(os.path.join(GOLDEN_DIR, "step_%s.npz" % tag), **rec)
 
 
+BIG_SAMPLES = 16384     # elements of every gradient tensor kept by the benchmark-size step fixtures
+BIG_CASES = [
+    # tag, H, W, P, N, seed, out_gen pixel stride   (BASELINE.json configs[1], [2], [4] geometry at batch 2)
+    ("256x256_p18_n2", 256, 256, 18, 2, 21, 2),
+    ("224x224_p16_n2", 224, 224, 16, 2, 22, 2),
+    ("512x512_p18_n2", 512, 512, 18, 2, 23, 4),
+]
+
+
+def big_sample_idx(numel, count=BIG_SAMPLES):
+    """Fixed pseudo-random element subset of a tensor (all of it when it is small)."""
+    if numel <= count:
+        return np.arange(numel, dtype=np.int64)
+    return ((np.arange(count, dtype=np.int64) * 2654435761 + 12345) % numel).astype(np.int64)
+
+
+def big_summary(t):
+    """(norm, sampled values) of a tensor: enough to check direction (cosine on the sample) and magnitude."""
+    f = t.detach().reshape(-1).float().cpu()
+    idx = torch.from_numpy(big_sample_idx(f.numel()))
+    return np.float64(f.double().norm().item()), f[idx].numpy().astype(np.float32)
+
+
+def gen_step_big(ns, tag, H, W, P, N, seed, stride):
+    """One dis_update + gen_update of the UNMODIFIED reference at a benchmarked geometry (NN loss 5x5 on block1_conv2,
+    the bench.py objective).  Records losses, out_gen on a pixel lattice, and for every parameter the gradient norm plus
+    a fixed 16k-element sample of the gradient and of the Adam-updated parameter."""
+    import argparse as ap
+    import torchvision
+    opt = ap.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=4,
+                       gen_type="baseline", warp_skip="mask", dataset="fasion", learning_rate=2e-4,
+                       content_loss_layer="block1_conv2", nn_loss_area_size=5, gan_penalty_weight=1.0,
+                       l1_penalty_weight=0.01)
+    dsd = synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1)
+    vgg = torchvision.models.vgg19(weights=None)
+    vw, vb = synth.vgg_conv1_1(seed)
+    with torch.no_grad():
+        vgg.features[0].weight.copy_(vw)
+        vgg.features[0].bias.copy_(vb)
+    model = ref_import.make_reference_gan(opt, dsd, vgg)
+    model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed))
+    od = vars(opt)
+    b = synth.make_batch(N, H, W, P, seed=seed)
+    r = synth.make_batch(N, H, W, P, seed=seed + 1)
+    b2 = synth.make_batch(N, H, W, P, seed=seed + 2)
+    rec = {"seed": np.int64(seed), "stride": np.int64(stride)}
+    with _DropPatch(synth.dropout_masks(N, 512, 3, seed=seed)):
+        dl = model.dis_update(b["input"], b["target"], {"warps": b["warps"].clone(), "masks": b["masks"].clone()},
+                              r["input"], r["target"], od)
+    rec["d_loss"] = np.array(dl)
+    dn, ds = zip(*[big_summary(p.grad) for _, p in sorted(model.disc.named_parameters())])
+    rec["d_grad_norm"] = np.array(dn)
+    for i, v in enumerate(ds):
+        rec["d_grad_%02d" % i] = v
+    with _DropPatch(synth.dropout_masks(N, 512, 3, seed=seed + 2)):
+        out, _, gl = model.gen_update(b2["input"], b2["target"], {"warps": b2["warps"].clone(), "masks": b2["masks"].clone()}, od)
+    rec["g_loss"] = np.array(gl)
+    rec["out_gen"] = out.detach()[:, :, ::stride, ::stride].contiguous().numpy()
+    rec["out_gen_norm"] = np.float64(out.detach().double().norm().item())
+    gn, gs = zip(*[big_summary(p.grad) for _, p in sorted(model.gen.named_parameters())])
+    rec["g_grad_norm"] = np.array(gn)
+    for i, v in enumerate(gs):
+        rec["g_grad_%02d" % i] = v
+    rec["g_param"] = np.stack([summarize(p) for _, p in sorted(model.gen.named_parameters())])
+    rec["d_param"] = np.stack([summarize(p) for _, p in sorted(model.disc.named_parameters())])
+    print("big step", tag, dl, gl)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "step_%s.npz" % tag), **rec)
+
+
 def gen_step_baseline(H, W, P, N, seed, tag, l1_w=100.0):
     """BASELINE configs[0]: src_baseline Pose_GAN (single-encoder Generator, L1 + adversarial), one iteration.  Weights:
     the reference's own xavier initialisation under torch.manual_seed(seed); they are stored so the product starts from
@@ -218,6 +287,11 @@ def main():
     if a.only in ("", "step"):
         gen_step(ns, 64, 64, 18, 2, 0, "64x64_p18_nn5")
         gen_step(ns, 64, 64, 18, 2, 3, "64x64_p18_l1", content="none", area=1, l1_w=100.0, steps=1)
+    if a.only in ("", "big") or a.only.startswith("big:"):
+        for case in BIG_CASES:
+            if a.only.startswith("big:") and a.only[4:] != case[0]:
+                continue
+            gen_step_big(ns, *case)
     if a.only in ("", "baseline"):
         gen_step_baseline(128, 64, 18, 4, 11, "baseline_128x64_p18")
     if a.only in ("", "params"):

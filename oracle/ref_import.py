@@ -18,7 +18,10 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("PTK_REFERENCE_ROOT", "/root/reference/src_deformable")
+from . import fetch_ref
+
+# the mounted reference in the build container, else the verbatim copy that travels to the GPU box (oracle/fetch_ref.py)
+REFERENCE_ROOT = os.environ.get("PTK_REFERENCE_ROOT") or fetch_ref.root("src_deformable") or "/root/reference/src_deformable"
 
 
 def available() -> bool:
@@ -78,8 +81,7 @@ def _load_tree(REFERENCE_ROOT, private_prefix):
     if "pylab" not in sys.modules:
         _stub("pylab")
     if not torch.cuda.is_available():
-        torch.Tensor.cuda = lambda self, *a, **k: self
-        torch.nn.Module.cuda = lambda self, *a, **k: self
+        _patch_cuda_identity()
     for k in list(saved):
         sys.modules.pop(k, None)
     sys.path.insert(0, REFERENCE_ROOT)
@@ -100,6 +102,31 @@ def _load_tree(REFERENCE_ROOT, private_prefix):
         if saved[k] is not None:
             sys.modules[k] = saved[k]
     return ns
+
+
+_orig_cuda = None
+
+
+def _patch_cuda_identity():
+    global _orig_cuda
+    if _orig_cuda is None:
+        _orig_cuda = (torch.Tensor.cuda, torch.nn.Module.cuda)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+
+
+class cpu_only:
+    """Context manager: the reference hard-codes ``.cuda()``; inside this block those calls are the identity even on a
+    box that has a GPU, so the reference's step runs on the host cores (bench.py's cpu_baseline / reference arm)."""
+
+    def __enter__(self):
+        self.saved = (torch.Tensor.cuda, torch.nn.Module.cuda)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        return self
+
+    def __exit__(self, *a):
+        torch.Tensor.cuda, torch.nn.Module.cuda = self.saved
 
 
 def make_reference_gan(opt, disc_state, vgg):

@@ -52,6 +52,8 @@ SIGNATURES = {
     "ptk_l1_loss": [vp, vp, i64, f32, vp, vp, vp],
     "ptk_nnloss_forward": [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp],
     "ptk_nnloss_backward": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp],
+    "ptk_nnloss_features_forward": [vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp],
+    "ptk_nnloss_features_backward": [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp],
     "ptk_tanh_bwd_combine": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp],
     "ptk_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
 }

@@ -321,6 +321,76 @@ nnloss_backward_kernel(const float* __restrict__ pred, const float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------- NN loss on materialised features
+// DeformablePose_GAN.nn_loss(predicted, ground_truth, nh, nw) (models/pose_gan.py:173-199) as a public method: NCHW
+// feature tensors of any channel count.  One thread per pixel (coalesced along x), channels streamed.
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+nnloss_feat_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int C, int H, int W, int area,
+                   float scale_over_count, float* __restrict__ loss, uint8_t* __restrict__ argmin, float* __restrict__ dpred) {
+  const int n = blockIdx.y;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = p < HW;
+  const int y = live ? (int)(p / W) : 0, x = live ? (int)(p - (int64_t)y * W) : 0;
+  const int P = area / 2;
+  const float* pb = pred + (int64_t)n * C * HW + p;
+  const float* gb = gt + (int64_t)n * C * HW;
+  float best = 0.f;
+  if (live && !BWD) {
+    float d[kMaxArea * kMaxArea];
+#pragma unroll
+    for (int s = 0; s < kMaxArea * kMaxArea; ++s) d[s] = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float pv = __ldg(pb + c * HW);
+#pragma unroll
+      for (int si = 0; si < kMaxArea; ++si) {
+        if (si >= area) break;
+        const int yy = y + si - P;
+#pragma unroll
+        for (int sj = 0; sj < kMaxArea; ++sj) {
+          if (sj >= area) break;
+          const int xx = x + sj - P;
+          const float g = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(gb + c * HW + (int64_t)yy * W + xx) : kPadValue;
+          d[si * kMaxArea + sj] += fabsf(g - pv);
+        }
+      }
+    }
+    best = INFINITY;
+    int arg = 0;
+    for (int si = 0; si < area; ++si)
+      for (int sj = 0; sj < area; ++sj) {
+        const float v = d[si * kMaxArea + sj];
+        if (v < best) { best = v; arg = si * area + sj; }   // torch.min: first minimum (pose_gan.py:195)
+      }
+    argmin[(int64_t)n * HW + p] = (uint8_t)arg;
+  }
+  if (live && BWD) {
+    const int arg = argmin[(int64_t)n * HW + p];
+    const int si = arg / area, sj = arg - si * area;
+    const int yy = y + si - P, xx = x + sj - P;
+    const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    for (int c = 0; c < C; ++c) {
+      const float pv = __ldg(pb + c * HW);
+      const float g = in ? __ldg(gb + c * HW + (int64_t)yy * W + xx) : kPadValue;
+      const float diff = g - pv;
+      dpred[(int64_t)n * C * HW + c * HW + p] = diff > 0.f ? -scale_over_count : (diff < 0.f ? scale_over_count : 0.f);
+    }
+  }
+  if (!BWD) {
+    best = warp_sum(best);
+    __shared__ float sh[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sh[wid] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < 8; ++i) s += sh[i];
+      atomicAdd(loss, s * scale_over_count);
+    }
+  }
+}
+
 static int upload_vgg(const float* vgg_w, const float* vgg_b, cudaStream_t st) {
   cudaError_t e = cudaMemcpyToSymbolAsync(c_vgg_w, vgg_w, sizeof(float) * kFeat * 27, 0, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_vgg_b, vgg_b, sizeof(float) * kFeat, 0, cudaMemcpyDeviceToDevice, st);
@@ -398,6 +468,28 @@ extern "C" int ptk_nnloss_backward(const float* pred, const float* target, const
   nnloss_backward_kernel<<<grid, kNnBwdThreads, smem, (cudaStream_t)stream>>>(pred, target, argmin, H, W, area,
                                                                              scale / ((float)N * H * W), dpred);
   PTK_LAUNCH_CHECK("nnloss_backward_kernel");
+  return 0;
+}
+
+extern "C" int ptk_nnloss_features_forward(const float* pred, const float* gt, int N, int C, int H, int W, int area,
+                                           float scale, float* loss, uint8_t* argmin, void* stream) {
+  PTK_REQUIRE(area >= 1 && area <= kMaxArea && (area & 1), "nnloss_features: area must be odd and <= %d", kMaxArea);
+  PTK_REQUIRE(N > 0 && N <= 65535 && C > 0 && H > 0 && W > 0, "nnloss_features: bad extents");
+  dim3 grid((unsigned)(((int64_t)H * W + 255) / 256), (unsigned)N);
+  nnloss_feat_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(pred, gt, C, H, W, area, scale / ((float)N * H * W), loss,
+                                                                   argmin, nullptr);
+  PTK_LAUNCH_CHECK("nnloss_feat_kernel<fwd>");
+  return 0;
+}
+
+extern "C" int ptk_nnloss_features_backward(const float* pred, const float* gt, const uint8_t* argmin, int N, int C, int H,
+                                            int W, int area, float scale, float* dpred, void* stream) {
+  PTK_REQUIRE(area >= 1 && area <= kMaxArea && (area & 1), "nnloss_features: area must be odd and <= %d", kMaxArea);
+  PTK_REQUIRE(N > 0 && N <= 65535 && C > 0 && H > 0 && W > 0, "nnloss_features: bad extents");
+  dim3 grid((unsigned)(((int64_t)H * W + 255) / 256), (unsigned)N);
+  nnloss_feat_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(pred, gt, C, H, W, area, scale / ((float)N * H * W), nullptr,
+                                                                  const_cast<uint8_t*>(argmin), dpred);
+  PTK_LAUNCH_CHECK("nnloss_feat_kernel<bwd>");
   return 0;
 }
 

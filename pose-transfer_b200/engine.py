@@ -163,8 +163,10 @@ class ConvLayer:
             a_rows = self.cout if self.cout <= 4 else self.cout_pad
         n = self.taps * a_rows * B_pad
         m = self._master()
-        if m is not None and m[1].numel() == n:
-            # GEMM-layout arena: the kernel's output layout IS the gradient's storage layout
+        if m is not None and m[1].numel() == n and grad_w.data_ptr() == m[1].data_ptr():
+            # Trainer path: grad_w IS the arena gradient of this weight (GEMM layout = the kernel's output layout), which
+            # the trainer zero-filled at the start of the update, so the kernel writes it in place.  Any other grad_w
+            # (the autograd Functions of models/networks.py pass fresh tensors) takes the accumulate path below.
             gflat = m[1]
             key = (N, H, W, x.ld, dy.ld, scratch.numel())
             nparts = self._plans.get(key)
@@ -178,6 +180,7 @@ class ConvLayer:
                 K.sum_parts(scratch, got, n, gflat, n, False)
         elif a_rows == A:
             # split-K partial gradients land back to back in the scratch and are summed (fixed order) by the unpack
+            assert grad_w.is_contiguous(), "wgrad: grad_w must be a contiguous torch-layout tensor (or the arena gradient)"
             nparts = K.conv_wgrad_parts(g, x, dy, scratch)
             K.unpack_weight_grad_parts(scratch, nparts, n, grad_w, A, B, self.taps, B_pad, True)
         else:  # padded row count (never hit for this network: every wide channel count is a multiple of 4)

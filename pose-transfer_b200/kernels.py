@@ -303,6 +303,19 @@ def nnloss_backward(pred, target, vgg_w, vgg_b, argmin, area, scale, dpred):
                                          float(scale), _p(dpred), _stream()), "ptk_nnloss_backward")
 
 
+def nnloss_features_forward(pred, gt, area, scale, loss, argmin):
+    """nn_loss on materialised NCHW features (DeformablePose_GAN.nn_loss, pose_gan.py:173-199)."""
+    N, C, H, W = pred.shape
+    check(_lib.lib().ptk_nnloss_features_forward(_p(pred), _p(gt), N, C, H, W, area, float(scale), _p(loss), _p(argmin),
+                                                 _stream()), "ptk_nnloss_features_forward")
+
+
+def nnloss_features_backward(pred, gt, argmin, area, scale, dpred):
+    N, C, H, W = pred.shape
+    check(_lib.lib().ptk_nnloss_features_backward(_p(pred), _p(gt), _p(argmin), N, C, H, W, area, float(scale), _p(dpred),
+                                                  _stream()), "ptk_nnloss_features_backward")
+
+
 def tanh_bwd_combine(g_nchw, g_nhwc, out_nchw, dz, ld, N, C, H, W):
     g2 = _as_slice(g_nhwc) if g_nhwc is not None else None
     check(_lib.lib().ptk_tanh_bwd_combine(_p(g_nchw), g2.ptr if g2 else None, g2.ld if g2 else 0, _p(out_nchw), _p(dz), ld,

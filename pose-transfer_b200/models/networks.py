@@ -158,7 +158,8 @@ class _GeneratorFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         gen = ctx.gen
-        grads = {p: torch.zeros_like(p) for p in ctx.params}
+        # fresh contiguous tensors (zeros_like would inherit the GEMM-layout strides of arena-backed parameters)
+        grads = {p: torch.zeros(p.shape, device=p.device) for p in ctx.params}
         gen.engine.backward(grads, dout_nchw=dout.contiguous())
         return (None, None, None, None) + tuple(grads[p] if p.requires_grad else None for p in ctx.params)
 
@@ -287,7 +288,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         dlog = (dprobs * probs * (1 - probs)).reshape(M * J, 1)
         dlog4 = disc.engine.dlogits_buffer(M, J)
         dlog4[:, :1] = dlog
-        grads = {p: torch.zeros_like(p) for p in ctx.params}
+        grads = {p: torch.zeros(p.shape, device=p.device) for p in ctx.params}
         need_x = ctx.needs_input_grad[1]
         din_grad = disc.engine.backward(dlog4, grads, need_input_grad=need_x)
         dx = None

@@ -148,6 +148,30 @@ class FlatAdam(torch.optim.Optimizer):
         self.arena.zero_grad()
 
 
+class _NNLossFn(torch.autograd.Function):
+    """nn_loss on feature tensors through ptk_nnloss_features_* (gradient w.r.t. the prediction only is ever used)."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, area):
+        if not pred.is_cuda:
+            raise RuntimeError("nn_loss: CUDA tensors required (no CPU fallback)")
+        pred, gt = pred.detach().float().contiguous(), gt.detach().float().contiguous()
+        N, C, H, W = pred.shape
+        loss = torch.zeros(1, device=pred.device)
+        argmin = torch.empty(N, H, W, dtype=torch.uint8, device=pred.device)
+        K.nnloss_features_forward(pred, gt, area, 1.0, loss, argmin)
+        ctx.save_for_backward(pred, gt, argmin)
+        ctx.area = area
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        pred, gt, argmin = ctx.saved_tensors
+        dpred = torch.empty_like(pred)
+        K.nnloss_features_backward(pred, gt, argmin, ctx.area, 1.0, dpred)
+        return dpred * gout, None, None
+
+
 class DeformablePose_GAN(nn.Module):
     def __init__(self, opt):
         super(DeformablePose_GAN, self).__init__()
@@ -371,9 +395,12 @@ class DeformablePose_GAN(nn.Module):
         return [self.dis_total_loss, self.dis_true_loss, self.dis_fake_loss]
 
     def nn_loss(self, predicted, ground_truth, nh=3, nw=3):
-        """pose_gan.py:173-199 on feature tensors (API parity; the training step uses the fused kernels)."""
-        raise NotImplementedError("nn_loss on materialised features is fused into ptk_nnloss_* on the B200 path; "
-                                  "use DeformablePose_GAN.gen_update")
+        """pose_gan.py:173-199 on materialised feature tensors [N,C,H,W] (differentiable w.r.t. `predicted`).  The training
+        step itself uses ptk_nnloss_forward/backward, which fuse the VGG feature extractor into this loss."""
+        if nh != nw:
+            # the reference's ConstantPad2d((v_pad, v_pad, h_pad, h_pad)) mixes the axes: only square windows run there
+            raise RuntimeError("nn_loss: the reference only supports square windows (nh == nw)")
+        return _NNLossFn.apply(predicted, ground_truth, int(nh))
 
     # ------------------------------------------------------------------ checkpoints (pose_gan.py:201-220)
     def resume(self, save_dir):

@@ -1,0 +1,193 @@
+"""GPU parity at the BENCHMARKED geometries, TF32 tensor-core path (the arithmetic bench.py times).
+
+(a) against committed fixtures dumped from the unmodified reference on CPU fp32 (oracle/make_golden.py::gen_step_big):
+    256x256 P=18, 224x224 P=16, 512x512 P=18 at batch 2 -- losses, out_gen on a pixel lattice, and for EVERY parameter
+    tensor the gradient norm and the cosine against a fixed 16k-element sample of the reference gradient;
+(b) against the LIVE reference running on the same GPU in strict fp32 (cudnn.allow_tf32 = False) from baseline/_ref at
+    the bench configuration itself (256x256, batch 8): full-tensor gradient cosines, out_gen, losses.  Skipped where
+    baseline/_ref is absent (it is git-ignored; __graft_entry__.build() makes it in the build container).
+
+Stated tolerances (SURVEY 8c, TF32 operands = 10-bit mantissa, fp32 accumulate): losses <= 1e-2 rel, out_gen <= 1e-2 abs,
+gradient norm <= 5 % and cosine >= COS_MIN per tensor.  The scalar norm gains / biases (1-element tensors) are global sums
+of ~1e7 signed terms and only get a magnitude sanity bound under TF32; their tight check is the exact-fp32 mode at 64x64
+(tests/test_step_gpu.py).
+"""
+import argparse
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, max_abs
+
+pytestmark = pytest.mark.gpu
+
+COS_MIN = 0.999          # per-tensor gradient direction, tensors with >= 4096 elements
+COS_MIN_SMALL = 0.995    # biases / narrow tensors (64 .. 4095 elements)
+NORM_TOL = 5e-2
+LOSS_RTOL = 1e-2
+OUT_ATOL = 1e-2
+
+
+def make_opt(H, W, P, N):
+    return argparse.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=4,
+                              gen_type="baseline", warp_skip="mask", dataset="fasion", learning_rate=2e-4,
+                              content_loss_layer="block1_conv2", nn_loss_area_size=5, gan_penalty_weight=1.0,
+                              l1_penalty_weight=0.01)
+
+
+def build_model(H, W, P, N, seed):
+    from oracle import synth
+    from pose_transfer_b200.models import pose_gan
+    opt = make_opt(H, W, P, N)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = pose_gan.DeformablePose_GAN(opt).cuda()
+    model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed))
+    model.disc.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1))
+    vw, vb = synth.vgg_conv1_1(seed)
+    with torch.no_grad():
+        model.content_model.features[0].weight.copy_(vw)
+        model.content_model.features[0].bias.copy_(vb)
+    return model, opt
+
+
+def cosine(a, b):
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300))
+
+
+def check_grad(name, got_full, want_norm, want_sample, idx, report):
+    """got_full: our gradient (torch, any layout); want_*: reference norm and sample at flat (row-major) indices idx."""
+    g = got_full.detach().contiguous().reshape(-1).double().cpu().numpy()
+    n = g.size
+    if n == 1:
+        report.append((name, n, None, float(g[0]), float(want_sample[0])))
+        assert np.isfinite(g[0]) and abs(g[0]) <= 50.0 * abs(want_sample[0]) + 1.0, (name, g[0], want_sample[0])
+        return
+    cos = cosine(g[idx], want_sample)
+    nrm = float(np.linalg.norm(g))
+    report.append((name, n, cos, nrm, float(want_norm)))
+    if n >= 64:
+        assert cos >= (COS_MIN if n >= 4096 else COS_MIN_SMALL), "%s: gradient cosine %.5f" % (name, cos)
+    assert abs(nrm - want_norm) <= NORM_TOL * want_norm + 1e-12, "%s: gradient norm %g vs %g" % (name, nrm, want_norm)
+
+
+def print_report(title, report):
+    worst = min((r for r in report if r[2] is not None), key=lambda r: r[2])
+    print("\n%s: %d tensors, worst cosine %.6f (%s, %d elements)" % (title, len(report), worst[2], worst[0], worst[1]))
+    for name, n, cos, a, b in sorted(report, key=lambda r: (r[2] is None, r[2]))[:6]:
+        print("   %-40s n=%-9d cos=%s ours=%.5g ref=%.5g" % (name, n, "%.6f" % cos if cos is not None else "  --  ", a, b))
+
+
+@pytest.mark.parametrize("tag", ["256x256_p18_n2", "224x224_p16_n2", "512x512_p18_n2"])
+def test_tf32_step_matches_reference_fixture(tag, monkeypatch):
+    from oracle import synth
+    from oracle.make_golden import BIG_CASES, big_sample_idx
+    monkeypatch.setenv("PTK_CONV_IMPL", "auto")
+    case = [c for c in BIG_CASES if c[0] == tag][0]
+    _, H, W, P, N, seed, stride = case
+    g = golden("step_" + tag)
+    assert int(g["seed"]) == seed and int(g["stride"]) == stride
+    model, opt = build_model(H, W, P, N, seed)
+    od = vars(opt)
+    b, r, b2 = (synth.make_batch(N, H, W, P, seed=seed + i) for i in range(3))
+    dl = model.dis_update(b["input"].cuda(), b["target"].cuda(), {"warps": b["warps"].cuda(), "masks": b["masks"].cuda()},
+                          r["input"].cuda(), r["target"].cuda(), od, drop=synth.dropout_masks(N, 512, 3, seed=seed))
+    np.testing.assert_allclose(dl, g["d_loss"], rtol=LOSS_RTOL)
+    report = []
+    for i, (k, p) in enumerate(sorted(model.disc.named_parameters())):
+        check_grad("disc." + k, p.grad, g["d_grad_norm"][i], g["d_grad_%02d" % i], big_sample_idx(p.numel()), report)
+    out, _, gl = model.gen_update(b2["input"].cuda(), b2["target"].cuda(), {"warps": b2["warps"].cuda(), "masks": b2["masks"].cuda()},
+                                  od, drop=synth.dropout_masks(N, 512, 3, seed=seed + 2))
+    np.testing.assert_allclose(gl, g["g_loss"], rtol=LOSS_RTOL)
+    err = max_abs(out[:, :, ::stride, ::stride], g["out_gen"])
+    print("\n%s: losses D %s G %s  max|out_gen - ref| on the lattice %.3g" % (tag, dl, gl, err))
+    assert err <= OUT_ATOL
+    assert abs(float(out.double().norm()) - float(g["out_gen_norm"])) <= 1e-3 * float(g["out_gen_norm"])
+    for i, (k, p) in enumerate(sorted(model.gen.named_parameters())):
+        check_grad("gen." + k, p.grad, g["g_grad_norm"][i], g["g_grad_%02d" % i], big_sample_idx(p.numel()), report)
+    print_report(tag, report)
+    # Adam-updated weights: every element moved by at most lr (first step) and agrees with the reference's update
+    # wherever the gradient's sign is unambiguous
+    for name, net, key in (("gen", model.gen, "g_param"), ("disc", model.disc, "d_param")):
+        from helpers import summarize
+        got = np.stack([summarize(p) for _, p in sorted(net.named_parameters())])
+        want = g[key]
+        assert np.abs(got[:, 0] - want[:, 0]).max() <= 1e-3 * np.abs(want[:, 0]).max() + 5e-4, name
+        assert np.abs(got[:, 2:] - want[:, 2:]).max() <= 2 * 2e-4 * 1.01 + 1e-6, name
+
+
+def _live_reference():
+    from oracle import fetch_ref
+    if fetch_ref.root("src_deformable") is None:
+        pytest.skip("baseline/_ref (copy of the unmodified reference) not present")
+    from oracle import ref_import
+    return ref_import
+
+
+@pytest.mark.parametrize("H,P,N", [(256, 18, 8)], ids=["cfg2_256_p18_n8"])
+def test_tf32_step_matches_live_reference_on_gpu(H, P, N, monkeypatch):
+    """bench.py's own configuration: one dis_update + gen_update, ours (TF32 tensor-core path) vs the unmodified reference
+    on the same GPU in strict fp32.  Full-tensor comparisons."""
+    import torchvision
+    from oracle import synth
+    from oracle.make_golden import _DropPatch
+    ref_import = _live_reference()
+    monkeypatch.setenv("PTK_CONV_IMPL", "auto")
+    W, seed = H, 31
+    b, r, b2 = (synth.make_batch(N, H, W, P, seed=seed + i) for i in range(3))
+    drop_d, drop_g = synth.dropout_masks(N, 512, 3, seed=seed), synth.dropout_masks(N, 512, 3, seed=seed + 2)
+
+    # ---- reference, strict fp32 on the GPU
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        opt = make_opt(H, W, P, N)
+        dsd = synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1)
+        vgg = torchvision.models.vgg19(weights=None)
+        vw, vb = synth.vgg_conv1_1(seed)
+        with torch.no_grad():
+            vgg.features[0].weight.copy_(vw)
+            vgg.features[0].bias.copy_(vb)
+        ref = ref_import.make_reference_gan(opt, dsd, vgg)
+        ref.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed))
+        ref.cuda()
+        od = vars(opt)
+        with _DropPatch([d.cuda() for d in drop_d]):
+            dl_ref = ref.dis_update(b["input"].cuda(), b["target"].cuda(),
+                                    {"warps": b["warps"].float().cuda(), "masks": b["masks"].cuda()},
+                                    r["input"].cuda(), r["target"].cuda(), od)
+        dgrad_ref = {k: p.grad.detach().clone() for k, p in ref.disc.named_parameters()}
+        with _DropPatch([d.cuda() for d in drop_g]):
+            out_ref, _, gl_ref = ref.gen_update(b2["input"].cuda(), b2["target"].cuda(),
+                                                {"warps": b2["warps"].float().cuda(), "masks": b2["masks"].cuda()}, od)
+        out_ref = out_ref.detach().clone()
+        ggrad_ref = {k: p.grad.detach().clone() for k, p in ref.gen.named_parameters()}
+        del ref
+        torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+    # ---- ours
+    model, opt = build_model(H, W, P, N, seed)
+    od = vars(opt)
+    dl = model.dis_update(b["input"].cuda(), b["target"].cuda(), {"warps": b["warps"].cuda(), "masks": b["masks"].cuda()},
+                          r["input"].cuda(), r["target"].cuda(), od, drop=drop_d)
+    report = []
+    for k, p in sorted(model.disc.named_parameters()):
+        w = dgrad_ref[k].reshape(-1).double().cpu().numpy()
+        check_grad("disc." + k, p.grad, float(np.linalg.norm(w)), w, np.arange(w.size), report)
+    out, _, gl = model.gen_update(b2["input"].cuda(), b2["target"].cuda(), {"warps": b2["warps"].cuda(), "masks": b2["masks"].cuda()},
+                                  od, drop=drop_g)
+    np.testing.assert_allclose(dl, dl_ref, rtol=LOSS_RTOL)
+    np.testing.assert_allclose(gl, gl_ref, rtol=LOSS_RTOL)
+    err = max_abs(out, out_ref)
+    print("\nlive reference %dx%d N=%d: D %s vs %s ; G %s vs %s ; max|out_gen diff| %.3g" % (H, W, N, dl, dl_ref, gl, gl_ref, err))
+    assert err <= OUT_ATOL
+    for k, p in sorted(model.gen.named_parameters()):
+        w = ggrad_ref[k].reshape(-1).double().cpu().numpy()
+        check_grad("gen." + k, p.grad, float(np.linalg.norm(w)), w, np.arange(w.size), report)
+    print_report("live reference", report)

@@ -1,0 +1,228 @@
+"""GPU tests of the public MODULE surface (what a user of the reference imports), through the C ABI:
+AffineTransformLayer as an nn.Module (+ the author's gradcheck recipe, unitTests.py:81-85), Feature_Extractor,
+Stacked_Generator.forward, the Dropout2d draw, autograd through the generator after a trainer owns its parameters,
+DeformablePose_GAN.nn_loss, and the unmodified reference main.py executing on the CUDA library."""
+import argparse
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import golden, max_abs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def make_opt(H, W, P, N, gen_type="baseline", content="block1_conv2", area=5, l1_w=0.01, stacks=4):
+    return argparse.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=stacks,
+                              gen_type=gen_type, warp_skip="mask", dataset="fasion", learning_rate=2e-4,
+                              content_loss_layer=content, nn_loss_area_size=area, gan_penalty_weight=1.0,
+                              l1_penalty_weight=l1_w)
+
+
+def test_affine_transform_layer_module_matches_reference_golden():
+    """utils.pose_transform.AffineTransformLayer(10, init_size, 'mask')(x, warps, masks) as a differentiable module
+    (NCHW in / out, autograd backward) against the goldens of the unmodified reference layer, incl. the H != W quirk."""
+    from oracle.make_golden import WARP_CASES, warp_inputs
+    from pose_transfer_b200.utils.pose_transform import AffineTransformLayer
+    for name, N, C, h, w, H0, W0, seed in WARP_CASES:
+        x, warps, masks, gy = warp_inputs(N, C, h, w, H0, W0, seed)
+        xd = x.cuda().requires_grad_(True)
+        y = AffineTransformLayer(10, (H0, W0), "mask")(xd, warps.cuda(), masks.cuda())
+        y.backward(gy.cuda())
+        gold = golden(name)
+        assert max_abs(y, gold["y"]) <= 2e-4, name
+        assert max_abs(xd.grad, gold["dx"]) <= 2e-4, name
+
+
+def test_affine_transform_layer_gradcheck_recipe():
+    """The one numerical check the author intended (unitTests.py:81-85):
+        gradcheck(AffineTransformLayer(10, image_size, 'mask'), (input, warps.float(), masks), eps=1e-6, atol=1e-4).
+    The layer is PIECEWISE LINEAR in `input` (bilinear taps x mask, max over parts), so a central difference is exact up
+    to fp32 rounding for any step that does not move an arg-max; the kernels are fp32, hence eps = 1e-2 instead of the
+    fp64 recipe's 1e-6, same atol.  nondet_tol covers the order of the backward's fp32 atomics."""
+    from oracle import synth
+    from pose_transfer_b200.utils.pose_transform import AffineTransformLayer
+    H0 = W0 = 32
+    N, C, h, w = 2, 4, 8, 8
+    b = synth.make_batch(N, H0, W0, 2, seed=5)
+    g = torch.Generator().manual_seed(9)
+    x = (torch.randn(N, C, h, w, generator=g) * 2).cuda().requires_grad_(True)
+    layer = AffineTransformLayer(10, (H0, W0), "mask")
+    warps, masks = b["warps"].float().cuda(), b["masks"].cuda()
+    assert torch.autograd.gradcheck(lambda t: layer(t, warps, masks), (x,), eps=1e-2, atol=1e-4, rtol=1e-3,
+                                    nondet_tol=1e-5, check_grad_dtypes=False, raise_exception=True)
+
+
+def test_feature_extractor_module():
+    """utils.pose_utils.Feature_Extractor(vgg, x, 'block1_conv2') (pose_utils.py:320-338) vs the oracle, incl. the
+    view-based preprocessing, on a non-square input."""
+    import torchvision
+    from oracle import restate, synth
+    from pose_transfer_b200.utils import pose_utils
+    vgg = torchvision.models.vgg19(weights=None)
+    vw, vb = synth.vgg_conv1_1(2)
+    with torch.no_grad():
+        vgg.features[0].weight.copy_(vw)
+        vgg.features[0].bias.copy_(vb)
+    x = torch.rand(2, 3, 40, 24, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    got = pose_utils.Feature_Extractor(vgg, input=x.cuda(), layer_name="block1_conv2")
+    want = restate.feature_extractor(vw, vb, x)
+    assert tuple(got.shape) == (2, 64, 40, 24)
+    assert max_abs(got, want) <= 2e-5
+
+
+def test_nn_loss_public_method():
+    """DeformablePose_GAN.nn_loss(predicted, ground_truth, nh, nw) on materialised feature tensors (pose_gan.py:173-199)."""
+    from oracle import restate
+    from pose_transfer_b200.models import pose_gan
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = pose_gan.DeformablePose_GAN(make_opt(64, 64, 18, 2)).cuda()
+    g = torch.Generator().manual_seed(4)
+    pred = torch.randn(2, 64, 20, 12, generator=g)
+    gt = torch.randn(2, 64, 20, 12, generator=g)
+    for area in (1, 3, 5):
+        pd = pred.cuda().requires_grad_(True)
+        got = model.nn_loss(pd, gt.cuda(), area, area)
+        pr = pred.clone().requires_grad_(True)
+        want = restate.nn_loss(pr, gt, area, area)
+        assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want)), area
+        got.backward()
+        want.backward()
+        assert max_abs(pd.grad, pr.grad) <= 1e-7, area
+
+
+def test_stacked_generator_forward_on_gpu():
+    """gen_type='stacked' (what test.py runs): model.gen(input, interpol_pose, interpol_warps, interpol_masks) in eval mode
+    against the oracle's composition of the same generator, exact-fp32 convs."""
+    import os
+    from oracle import restate, synth
+    from pose_transfer_b200.models import pose_gan
+    os.environ["PTK_CONV_IMPL"] = "simt"
+    try:
+        H = W = 64
+        P, N, S = 18, 2, 3
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = pose_gan.DeformablePose_GAN(make_opt(H, W, P, N, gen_type="stacked", content="none", area=1, l1_w=100.0, stacks=S)).cuda()
+        gsd = synth.fill_state_dict(synth.generator_shapes(P, (H, W)), 3)
+        model.gen.generator.load_state_dict(gsd)
+        model.eval()
+        bs = [synth.make_batch(N, H, W, P, seed=20 + i) for i in range(S)]
+        inp = bs[0]["input"]
+        interpol_pose = torch.cat([b["input"][:, 3 + P:] for b in bs], 1)
+        interpol_warps = torch.stack([b["warps"] for b in bs], 1)
+        interpol_masks = torch.stack([b["masks"] for b in bs], 1)
+        with torch.no_grad():
+            got = model.gen(inp.cuda(), interpol_pose.cuda(), interpol_warps.cuda(), interpol_masks.cuda())
+            want, out = [], None
+            for i in range(S):
+                if i == 0:
+                    x = torch.cat([inp[:, :3 + P], interpol_pose[:, :P]], 1)
+                else:
+                    x = torch.cat([out, interpol_pose[:, (i - 1) * P:i * P], interpol_pose[:, i * P:(i + 1) * P]], 1)
+                out = restate.generator_forward(gsd, x, interpol_warps[:, i], interpol_masks[:, i], (H, W), P, None)
+                want.append(out)
+        assert len(got) == S
+        for a, b in zip(got, want):
+            assert max_abs(a, b) <= 5e-4
+    finally:
+        os.environ.pop("PTK_CONV_IMPL", None)
+
+
+def test_dropout_draw_is_nn_dropout2d():
+    """the generator's un-seeded Dropout2d noise (engine.py) consumes the RNG exactly like the reference's
+    three nn.Dropout2d modules in decoder order: same seed => identical kept channels."""
+    from oracle import synth
+    from pose_transfer_b200.models.networks import Deformable_Generator
+    H = W = 64
+    P, N = 18, 3
+    enc, dec = (64, 128, 256, 512, 512, 512), (512, 512, 512, 256, 128, 3)
+    G = Deformable_Generator(3 + 2 * P, P, (H, W), enc, dec, "mask").cuda()
+    G.train()
+    b = synth.make_batch(N, H, W, P, seed=0)
+    torch.manual_seed(1234)
+    with torch.no_grad():
+        G(b["input"].cuda(), b["warps"].cuda(), b["masks"].cuda())
+    ours = [d.clone() for d in G.engine.saved["drops"]]
+    torch.manual_seed(1234)
+    for j, hw in enumerate((2, 4, 8)):        # decoder blocks 0..2 produce 2x2, 4x4, 8x8 maps at 64x64
+        y = torch.nn.Dropout2d()(torch.ones(N, 512, hw, hw, device="cuda"))
+        assert torch.equal(y[:, :, 0, 0], ours[j]), j
+        assert set(torch.unique(ours[j]).tolist()) <= {0.0, 2.0}
+
+
+def test_generator_autograd_after_trainer_owns_parameters():
+    """with a DeformablePose_GAN constructed (parameters = GEMM-layout views of the arena), the module stays a
+    correct differentiable nn.Module: autograd.grad through model.gen equals the oracle for EVERY parameter tensor, and
+    two backward calls accumulate 2x everywhere."""
+    import os
+    from oracle import restate, synth
+    from pose_transfer_b200.models import pose_gan
+    os.environ["PTK_CONV_IMPL"] = "simt"
+    try:
+        H = W = 64
+        P, N, seed = 18, 2, 0
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = pose_gan.DeformablePose_GAN(make_opt(H, W, P, N)).cuda()
+        gsd = synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed)
+        model.gen.load_state_dict(gsd)
+        b = synth.make_batch(N, H, W, P, seed=seed)
+        drop = synth.dropout_masks(N, 512, 3, seed=seed)
+        gy = torch.randn(N, 3, H, W, generator=torch.Generator().manual_seed(1))
+        names = [k for k, _ in model.gen.named_parameters()]
+        params = [p for _, p in model.gen.named_parameters()]
+        model.gen.set_dropout_noise(drop)
+        out = model.gen(b["input"].cuda(), b["warps"].cuda(), b["masks"].cuda())
+        grads = torch.autograd.grad(out, params, gy.cuda())
+        sd = {k: v.clone().requires_grad_(True) for k, v in gsd.items()}
+        ref = restate.generator_forward(sd, b["input"], b["warps"], b["masks"], (H, W), P, drop)
+        ref.backward(gy)
+        for k, g in zip(names, grads):
+            assert tuple(g.shape) == tuple(sd[k].shape)
+            if sd[k].numel() == 1:
+                assert abs(float(g) - float(sd[k].grad)) <= 5e-2 * abs(float(sd[k].grad)) + 1e-5, k
+            else:
+                assert rel_l2(g, sd[k].grad) <= 2e-3, k
+        # accumulation through .backward(): twice the gradient for every tensor
+        model.gen_arena.zero_grad()
+        for _ in range(2):
+            model.gen.set_dropout_noise(drop)
+            model.gen(b["input"].cuda(), b["warps"].cuda(), b["masks"].cuda()).backward(gy.cuda())
+        for k, p, g in zip(names, params, grads):
+            if p.numel() > 1:
+                assert rel_l2(p.grad, 2 * g) <= 1e-4, k
+    finally:
+        os.environ.pop("PTK_CONV_IMPL", None)
+
+
+def test_reference_main_py_runs_on_the_cuda_library(tmp_path, monkeypatch):
+    """The UNMODIFIED reference main.py (from baseline/_ref) for 2 iterations + checkpoint on the real kernels:
+    DataLoader -> .cuda() -> dis_update / gen_update / model.gen preview -> save, then --resume picks the files up."""
+    from oracle import fetch_ref, ref_import
+    if fetch_ref.root("src_deformable") is None:
+        pytest.skip("baseline/_ref (copy of the unmodified reference) not present")
+    import dropin_launcher
+    from pose_transfer_b200 import _lib
+    work = tmp_path / "work" / "src"
+    work.mkdir(parents=True)
+    monkeypatch.chdir(work)
+    argv = ["main.py", "--dataset", "market", "--batch_size", "2", "--pose_dim", "18", "--number_of_epochs", "1",
+            "--iters_per_epoch", "2", "--checkpoint_ratio", "1", "--display_ratio", "1", "--content_loss_layer", "block1_conv2",
+            "--nn_loss_area_size", "5", "--l1_penalty_weight", "0.01", "--expID", "dropin_gpu"]
+    l0 = _lib.launch_count()
+    dropin_launcher.run_reference_main(argv, emulate_kernels=False, monkeypatch=monkeypatch)
+    assert _lib.launch_count() - l0 > 500          # two full iterations + a preview forward went through libptk.so
+    ckpt = tmp_path / "work" / "exp" / "dropin_gpu" / "models"
+    assert (ckpt / "gen_001.pkl").is_file() and (ckpt / "disc_001.pkl").is_file()
+    ns = ref_import.load()
+    enc, dec = (64, 128, 256, 512, 512, 512), (512, 512, 512, 256, 128, 3)
+    G = ns.networks.Deformable_Generator(39, 18, (128, 64), enc, dec, "mask")
+    G.load_state_dict(torch.load(ckpt / "gen_001.pkl"), strict=True)
+    assert all(torch.isfinite(p).all() for p in G.parameters())
+    # resume: a second run starts from epoch 1's files (pose_gan.py:201-214) and writes epoch 2
+    dropin_launcher.run_reference_main(argv[:8] + ["2"] + argv[9:] + ["--resume", "1"], emulate_kernels=False,
+                                       monkeypatch=monkeypatch)
+    assert (ckpt / "gen_002.pkl").is_file()

@@ -108,3 +108,40 @@ def test_restatement_matches_live_reference_when_mounted():
     x, warps, masks, _ = warp_inputs(2, 4, 16, 8, 64, 32, 9)
     y_ref = ns.pose_transform.AffineTransformLayer(10, (64, 32), "mask")(x, warps.clone(), masks.clone())
     assert max_abs(restate.affine_warp(x, warps, masks, (64, 32)), y_ref) <= 2e-4
+
+
+def test_benchmark_size_fixture_pins_restatement():
+    """tests/golden/step_256x256_p18_n2.npz (one dis_update + gen_update of the unmodified reference at the benchmarked
+    geometry, oracle/make_golden.py::gen_step_big) against the restatement: losses, out_gen lattice, gradient norm and
+    sampled-gradient cosine of every parameter tensor."""
+    from oracle.make_golden import BIG_CASES, big_sample_idx
+    tag, H, W, P, N, seed, stride = BIG_CASES[0]
+    g = golden("step_" + tag)
+    gsd = synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed)
+    dsd = synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1)
+    vw, vb = synth.vgg_conv1_1(seed)
+    model = restate.OracleGAN(gsd, dsd, vw, vb, (H, W), P, N, faithful_waste=False)
+    b, r, b2 = (synth.make_batch(N, H, W, P, seed=seed + i) for i in range(3))
+    dl = model.dis_update(b["input"], b["target"], b["warps"], b["masks"], r["input"], r["target"], 1.0,
+                          synth.dropout_masks(N, 512, 3, seed=seed))
+    np.testing.assert_allclose(dl, g["d_loss"], rtol=2e-5)
+    for i, k in enumerate(sorted(model.disc)):
+        got = model.disc[k].grad.reshape(-1).double().numpy()
+        tol = 5e-2 if got.size == 1 else 2e-3     # 1-element norm gains / biases: cancellation-heavy global sums
+        assert abs(np.linalg.norm(got) - g["d_grad_norm"][i]) <= tol * g["d_grad_norm"][i] + 1e-9, k
+    out, gl = model.gen_update(b2["input"], b2["target"], b2["warps"], b2["masks"], 1.0, 0.01,
+                               synth.dropout_masks(N, 512, 3, seed=seed + 2))
+    np.testing.assert_allclose(gl, g["g_loss"], rtol=2e-4)
+    assert max_abs(out[:, :, ::stride, ::stride], g["out_gen"]) <= 5e-4
+    worst = 1.0
+    for i, k in enumerate(sorted(model.gen)):
+        got = model.gen[k].grad.reshape(-1).double().numpy()
+        if got.size < 64:
+            continue
+        s = got[big_sample_idx(got.size)]
+        w = g["g_grad_%02d" % i].astype(np.float64)
+        cos = float(s @ w / (np.linalg.norm(s) * np.linalg.norm(w)))
+        worst = min(worst, cos)
+        assert cos >= 0.9995, (k, cos)
+        assert abs(np.linalg.norm(got) - g["g_grad_norm"][i]) <= 2e-2 * g["g_grad_norm"][i], k
+    print("worst sampled-gradient cosine restatement vs reference fixture:", worst)
