@@ -31,9 +31,19 @@ PER_GPU_BATCH = 8
 # SURVEY 8d work model (256^2, P=18): necessary conv FLOPs per image per iteration and warp bytes per image
 CONV_GFLOP_PER_IMG = 582.3
 WARP_FWD_BYTES_PER_IMG = 66.40e6
-# dram__bytes_read.sum + dram__bytes_write.sum of the 4 warp_forward launches of one generator forward at batch 8, from
-# the committed `ncu --set full` capture (profiles/r1b_ncu_summary.txt): 255.6 + 97.7 + 32.2 + 14.5 MB
-WARP_FWD_TRAFFIC_BATCH8 = 400.0e6
+
+
+def measured_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (set) of a kernel, from the committed `ncu --set full`
+    capture of the CURRENT kernel (profiles/traffic.json, written by tools/ncu_extract.py from the capture named there);
+    None when no capture of the current kernel is committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.isfile(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    e = d.get(key)
+    return e.get("bytes") if isinstance(e, dict) and e.get("batch") == PER_GPU_BATCH else None
 
 
 def make_opt(N, content="block1_conv2", area=5, l1_w=0.01):
@@ -44,12 +54,13 @@ def make_opt(N, content="block1_conv2", area=5, l1_w=0.01):
 
 
 def measured_peaks():
+    """(HBM GB/s, bf16 TFLOP/s sustained, bf16 TFLOP/s burst, source)"""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
         with open(p) as f:
             d = json.load(f)
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
-    return 6650.0, 1400.0, "fallback"
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1400.0, 1590.0, "fallback"
 
 
 class ClockSampler:
@@ -104,46 +115,129 @@ def dist_info():
 
 
 # --------------------------------------------------------------------------------------- reference arm (CPU)
-def cpu_reference_iteration(model, batches, N):
-    from oracle import synth
-    b, r, b2 = batches
-    t0 = time.perf_counter()
-    model.dis_update(b["input"], b["target"], b["warps"], b["masks"], r["input"], r["target"], 1.0,
-                     synth.dropout_masks(N, 512, 3, seed=0))
-    model.gen_update(b2["input"], b2["target"], b2["warps"], b2["masks"], 1.0, 0.01, synth.dropout_masks(N, 512, 3, seed=1))
-    return time.perf_counter() - t0
+class _RealReference:
+    """The UNMODIFIED reference (src_deformable DeformablePose_GAN imported from baseline/_ref, or /root/reference in the
+    build container) with its two file loads patched to seeded in-memory objects (oracle/ref_import.py).  device='cpu':
+    its hard-coded .cuda() calls become the identity, i.e. the reference's own torch CPU path."""
+    kind = "reference"
+
+    def __init__(self, N, device="cpu"):
+        import torchvision
+        from oracle import ref_import, synth
+        self.ri, self.N, self.device = ref_import, N, device
+        self.opt = make_opt(N)
+        vgg = torchvision.models.vgg19(weights=None)
+        vw, vb = synth.vgg_conv1_1(0)
+        with torch.no_grad():
+            vgg.features[0].weight.copy_(vw)
+            vgg.features[0].bias.copy_(vb)
+        dsd = synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), 1)
+        with self._ctx():
+            self.model = ref_import.make_reference_gan(self.opt, dsd, vgg)
+            self.model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), 0))
+        self.batches = [synth.make_batch(N, H, W, P, seed=s) for s in (0, 1, 2)]
+        if device != "cpu":
+            self.batches = [{k: v.to(device) for k, v in b.items()} for b in self.batches]
+
+    def _ctx(self):
+        import contextlib
+        return self.ri.cpu_only() if self.device == "cpu" else contextlib.nullcontext()
+
+    def iteration(self):
+        b, r, b2 = self.batches
+        od = vars(self.opt)
+        t0 = time.perf_counter()
+        with self._ctx():
+            self.model.dis_update(b["input"], b["target"], {"warps": b["warps"].float(), "masks": b["masks"]},
+                                  r["input"], r["target"], od)
+            self.model.gen_update(b2["input"], b2["target"], {"warps": b2["warps"].float(), "masks": b2["masks"]}, od)
+        if self.device != "cpu":
+            torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+
+class _PortReference:
+    """Fallback when no copy of the reference is available: oracle/restate.py (the reference's torch CPU op sequence incl.
+    its wasted generator backward in dis_update)."""
+    kind = "port"
+
+    def __init__(self, N, device="cpu"):
+        from oracle import restate, synth
+        vw, vb = synth.vgg_conv1_1(0)
+        self.N = N
+        self.model = restate.OracleGAN(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), 0),
+                                       synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), 1), vw, vb, (H, W), P, N,
+                                       faithful_waste=True)
+        self.batches = [synth.make_batch(N, H, W, P, seed=s) for s in (0, 1, 2)]
+
+    def iteration(self):
+        from oracle import synth
+        b, r, b2 = self.batches
+        N = self.N
+        t0 = time.perf_counter()
+        self.model.dis_update(b["input"], b["target"], b["warps"], b["masks"], r["input"], r["target"], 1.0,
+                              synth.dropout_masks(N, 512, 3, seed=0))
+        self.model.gen_update(b2["input"], b2["target"], b2["warps"], b2["masks"], 1.0, 0.01, synth.dropout_masks(N, 512, 3, seed=1))
+        return time.perf_counter() - t0
 
 
 def make_cpu_reference(N):
-    from oracle import restate, synth
+    from oracle import fetch_ref
     torch.set_num_threads(os.cpu_count() or 1)
-    vw, vb = synth.vgg_conv1_1(0)
-    model = restate.OracleGAN(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), 0),
-                              synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), 1), vw, vb, (H, W), P, N,
-                              faithful_waste=True)
-    batches = [synth.make_batch(N, H, W, P, seed=s) for s in (0, 1, 2)]
-    return model, batches
+    if fetch_ref.root("src_deformable") is not None:
+        return _RealReference(N, "cpu")
+    return _PortReference(N)
+
+
+def cpu_reference_iteration(ref):
+    return ref.iteration()
+
+
+def reference_on_gpu(dev, N, iters=3):
+    """Informative column: the unmodified reference on the SAME B200 through its stock ATen/cuDNN path
+    (torch defaults: cudnn.allow_tf32 = True, i.e. TF32 convs like ours).  None when baseline/_ref is absent."""
+    from oracle import fetch_ref
+    if fetch_ref.root("src_deformable") is None:
+        return None
+    import contextlib
+    import io
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = _RealReference(N, dev)
+            ref.iteration()
+            ref.iteration()
+            torch.cuda.synchronize()
+            t = sum(ref.iteration() for _ in range(iters)) / iters
+        out = {"value": N / t, "unit": "img/s", "ms_per_step": 1e3 * t, "batch": N,
+               "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+               "what": "unmodified reference DeformablePose_GAN.dis_update + gen_update on this GPU (ATen/cuDNN), inputs resident"}
+        del ref
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:      # the column is informative: never fail the bench on it
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
 
 def run_reference(args):
-    """The reference algorithm (oracle/restate.py: the reference's own torch CPU op sequence, incl. its wasted
-    generator backward in dis_update) on the host cores.  Each step is a bounded sample: one iteration at N=2
-    (the smallest batch the reference supports, models/networks.py:169) of the 256x256 workload."""
+    """The reference's own CPU implementation of the path on the host cores: the UNMODIFIED reference modules from
+    baseline/_ref (kind "reference"; oracle/restate.py, kind "port", only where no copy exists).  Each step is a bounded
+    sample: one iteration at N=2 (the smallest batch the reference supports, models/networks.py:169) of the 256x256
+    workload."""
     rank, world, _ = dist_info()
     if rank != 0:
         return
     N = 2
-    model, batches = make_cpu_reference(N)
+    ref = make_cpu_reference(N)
     # Bounded run: one CPU iteration takes seconds, so warm-up + timed iterations are capped to ~4 minutes of wall time
     # (at least one of each); the line reports how many timed iterations actually ran.
     budget_s = 240.0
-    t_first = cpu_reference_iteration(model, batches, N)
+    t_first = cpu_reference_iteration(ref)
     fit = max(int(budget_s / max(t_first, 1e-3)), 2)
     warm = max(min(args.warmup, fit // 4) - 1, 0)
     for _ in range(warm):
-        cpu_reference_iteration(model, batches, N)
+        cpu_reference_iteration(ref)
     steps = max(min(args.steps, fit - 1 - warm), 1)
-    times = [cpu_reference_iteration(model, batches, N) for _ in range(steps)]
+    times = [cpu_reference_iteration(ref) for _ in range(steps)]
     total = sum(times)
     v = N * steps / total
     args.steps = steps
@@ -153,7 +247,7 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "src_deformable warp_skip=mask, fasion 256x256, 18 kpts (BASELINE configs[1])",
                        "per_step_sample": "1 iteration (dis_update+gen_update) at batch 2"},
-            "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": ref.kind,
                              "sample": "%d iterations at batch 2, 256x256, torch CPU fp32, %d threads" % (args.steps, cores)},
             "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -263,6 +357,27 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    if args.diag:
+        # host-bound or GPU-bound?  Time the host spends blocked in the two loss read-backs of a step: ~0 => the GPU waits
+        # for the host's launches; large => the host runs ahead and only the read-back latency is exposed.
+        wait = [0.0]
+        orig = torch.Tensor.tolist
+
+        def timed_tolist(self):
+            t0 = time.perf_counter()
+            r = orig(self)
+            wait[0] += time.perf_counter() - t0
+            return r
+        torch.Tensor.tolist = timed_tolist
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            step_resident()
+        torch.cuda.synchronize()
+        total = time.perf_counter() - t0
+        torch.Tensor.tolist = orig
+        print("diag: %.2f ms/step wall, of which %.2f ms blocked in loss read-backs (host enqueue time %.2f ms/step)"
+              % (100 * total, 100 * wait[0], 100 * (total - wait[0])), file=sys.stderr)
     if args.ncu_step:
         # for `ncu --profile-from-start off`: exactly one resident step inside the profiler range, nothing else
         torch.cuda.synchronize()
@@ -304,12 +419,21 @@ def run_ours(args):
             for t, kind, geo, flop, n in rows:
                 f.write("%-13s %-40s x%d  %8.3f ms  %7.1f TFLOP/s\n" % (kind, geo, n, t, flop / t / 1e9))
         prof = {k: v for k, v in prof.items() if "|" not in k}
-    hbm_peak, tf_peak, peak_src = measured_peaks()
+    hbm_peak, tf_peak, tf_burst, peak_src = measured_peaks()
+    pbytes = dict(K.PROFILE_BYTES)
     wl, wms = prof.get("warp_forward", (0, 0.0))
-    # 2 generator forwards per step (dis_update + gen_update), 4 warped levels each
+    # 2 generator forwards per step (dis_update + gen_update), one launch set (the 4 warped levels) each
     warp_bytes_per_launch_set = WARP_FWD_BYTES_PER_IMG * N
-    warp_sets = max(wl // 4, 1)
+    warp_sets = 2 * prof_steps
     warp_gbs = warp_bytes_per_launch_set * warp_sets / (wms * 1e-3) / 1e9 if wms > 0 else 0.0
+
+    def hbm_roofline(family, kernel):
+        n, t = prof.get(family, (0, 0.0))
+        b = pbytes.get(family, 0)
+        gbs = b / (t * 1e-3) / 1e9 if t > 0 else 0.0
+        return {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                "algorithmic_bytes_per_step": b / prof_steps, "ms_per_step": t / prof_steps, "launches_per_step": n // prof_steps,
+                "peak_source": peak_src}
     conv_ms = sum(prof.get(k, (0, 0.0))[1] for k in ("conv_forward", "conv_wgrad")) / prof_steps
     conv_tflops = CONV_GFLOP_PER_IMG * N / (conv_ms * 1e-3) / 1e3 if conv_ms > 0 else 0.0
 
@@ -317,7 +441,8 @@ def run_ours(args):
     e2e_value = world * N * args.steps / (ms_e2e * 1e-3)
     line = {"metric": "training images/sec at 256x256 warp_skip=mask", "value": value, "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 operands / f32 accumulate on the tensor-core convs (cuDNN's default for the reference too); f32 elsewhere",
             "data": "synthetic",
             "config": {"workload": "src_deformable warp_skip=mask, fasion 256x256, 18 kpts, batch %d/GPU (BASELINE configs[1])" % N,
                        "global_batch": N * world, "parallelism": "dp%d" % world, "step": "dis_update + gen_update",
@@ -329,12 +454,16 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "warp_forward_tile_kernel (one launch set = the 4 warped skip levels of one generator forward)", "achieved": warp_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": warp_gbs / hbm_peak,
-                         "traffic": WARP_FWD_TRAFFIC_BATCH8 if N == 8 else None, "peak_source": peak_src,
+                         "traffic": measured_traffic("warp_forward_launch_set") if N == PER_GPU_BATCH else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch_set": warp_bytes_per_launch_set,
                          "ms_per_launch_set": wms / warp_sets if warp_sets else None},
-            "conv_roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": tf_peak / 2, "unit": "TFLOP/s",
-                              "frac": conv_tflops / (tf_peak / 2), "peak_source": peak_src + " bf16 sustained / 2 (tf32)",
+            "conv_roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": tf_burst / 2, "unit": "TFLOP/s",
+                              "frac": conv_tflops / (tf_burst / 2), "frac_of_sustained": conv_tflops / (tf_peak / 2),
+                              "peak_source": peak_src + " bf16 burst / 2 (tf32); frac_of_sustained uses bf16 sustained / 2",
                               "algorithmic_gflop_per_img": CONV_GFLOP_PER_IMG, "conv_ms_per_step": conv_ms},
+            "warp_backward_roofline": hbm_roofline("warp_backward", "warp_backward kernels (4 levels, gen_update only)"),
+            "gn_roofline": hbm_roofline("gn", "gn_apply / gn_bwd_reduce / gn_bwd_apply / gn_stats (all launches of the step)"),
+            "adam_roofline": hbm_roofline("adam", "adam_kernel (generator buckets + discriminator)"),
             "kernel_ms_per_step": {k: v[1] / prof_steps for k, v in sorted(prof.items())},
             "kernel_timing_note": "per-kernel CUDA-event times (roofline, conv_roofline, kernel_ms_per_step) come from extra steps run "
                                   "with the side-stream overlap switched off; value / e2e are measured with it on"}
@@ -344,9 +473,10 @@ def run_ours(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             torch.cuda.synchronize()
-            cm, cb = make_cpu_reference(2)
-            t = cpu_reference_iteration(cm, cb, 2)
-            line["cpu_baseline"] = {"value": 2 / t, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+            line["reference_cudnn_on_this_gpu"] = reference_on_gpu(dev, N)
+            cref = make_cpu_reference(2)
+            t = cpu_reference_iteration(cref)
+            line["cpu_baseline"] = {"value": 2 / t, "unit": "img/s", "cores": torch.get_num_threads(), "kind": cref.kind,
                                     "sample": "1 iteration (dis_update+gen_update) at batch 2, 256x256, torch CPU fp32"}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -362,6 +492,7 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE configs[1]: 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", default="", help="write a per-conv-geometry timing table (CUDA events) to this file")
+    ap.add_argument("--diag", action="store_true", help="print host-vs-GPU-bound diagnostics to stderr")
     ap.add_argument("--ncu-step", action="store_true", help="profiling aid: warm up, then run ONE step inside "
                     "cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off); prints no result line")
     args = ap.parse_args()

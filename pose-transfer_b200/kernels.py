@@ -47,6 +47,7 @@ PROFILE = None
 def profile_start():
     global PROFILE
     PROFILE = {}
+    PROFILE_BYTES.clear()
 
 
 def profile_stop():
@@ -67,7 +68,11 @@ def _conv_label(name, g):
                                                    "T" if g.transposed else "C", flop)
 
 
-def _timed(name):
+PROFILE_BYTES = {}       # family -> algorithmic bytes moved by the profiled launches (HBM-bound families only)
+
+
+def _timed(name, nbytes=None):
+    """nbytes(*args, **kw) -> algorithmic bytes of the call (what the kernel must read + write once), for the rooflines."""
     def deco(fn):
         def wrapper(*a, **kw):
             if PROFILE is None:
@@ -77,6 +82,8 @@ def _timed(name):
             r = fn(*a, **kw)
             e1.record()
             PROFILE.setdefault(name, []).append((e0, e1))
+            if nbytes is not None:
+                PROFILE_BYTES[name] = PROFILE_BYTES.get(name, 0) + nbytes(*a, **kw)
             if PROFILE_DETAIL and name in ("conv_forward", "conv_wgrad"):
                 PROFILE.setdefault(_conv_label(name, a[0]), []).append((e0, e1))
             return r
@@ -221,13 +228,14 @@ def bias_grad(dy, ld, pixels, C, dbias):
     check(_lib.lib().ptk_bias_grad(_p(dy), ld, pixels, C, _p(dbias), _stream()), "ptk_bias_grad")
 
 
-@_timed("gn")
+@_timed("gn", lambda z, N, HW, C, stats: 4 * N * HW * C)
 def gn_stats(z, N, HW, C, stats):
     z = _as_slice(z)
     check(_lib.lib().ptk_gn_stats(z.ptr, z.ld, N, HW, C, _p(stats), _stream()), "ptk_gn_stats")
 
 
-@_timed("gn")
+@_timed("gn", lambda z, stats, gamma, beta, drop, N, HW, C, out1, act1, out2=None, act2=ACT_NONE:
+        4 * N * HW * C * (2 + (out2 is not None)))
 def gn_apply(z, stats, gamma, beta, drop, N, HW, C, out1, act1, out2=None, act2=ACT_NONE):
     z, out1 = _as_slice(z), _as_slice(out1)
     o2 = _as_slice(out2) if out2 is not None else None
@@ -235,7 +243,8 @@ def gn_apply(z, stats, gamma, beta, drop, N, HW, C, out1, act1, out2=None, act2=
                                   o2.ptr if o2 else None, o2.ld if o2 else 0, act2, _stream()), "ptk_gn_apply")
 
 
-@_timed("gn")
+@_timed("gn", lambda g1, a1, act1, g2, a2, act2, drop, z, stats, N, HW, C, dy, sums:
+        4 * N * HW * C * (2 + (a1 is not None) + (g2 is not None) + (a2 is not None) + (sums is not None)))
 def gn_bwd_reduce(g1, a1, act1, g2, a2, act2, drop, z, stats, N, HW, C, dy, sums):
     g1 = _as_slice(g1)
     a1 = _as_slice(a1) if a1 is not None else None
@@ -248,7 +257,7 @@ def gn_bwd_reduce(g1, a1, act1, g2, a2, act2, drop, z, stats, N, HW, C, dy, sums
                                        _p(stats), N, HW, C, _p(dy), _p(sums), _stream()), "ptk_gn_bwd_reduce")
 
 
-@_timed("gn")
+@_timed("gn", lambda dy, z, stats, sums, gamma, N, HW, C, dgamma, dbeta: 4 * N * HW * C * 3)
 def gn_bwd_apply(dy, z, stats, sums, gamma, N, HW, C, dgamma, dbeta):
     z = _as_slice(z)
     check(_lib.lib().ptk_gn_bwd_apply(_p(dy), z.ptr, z.ld, _p(stats), _p(sums), _p(gamma), N, HW, C, _p(dgamma), _p(dbeta),
@@ -264,14 +273,16 @@ def mask_pyramid(masks, out):
     check(_lib.lib().ptk_mask_pyramid(_p(masks), N, K, H0, W0, _p(out), h, w, _stream()), "ptk_mask_pyramid")
 
 
-@_timed("warp_forward")
+@_timed("warp_forward", lambda x, warps, mask_lvl, y, argk, N, C, h, w, K, H0, W0, act=ACT_NONE, align_corners=False:
+        N * h * w * (4 * C * 2 + 4 * K))      # read X + write Y + read masks
 def warp_forward(x, warps, mask_lvl, y, argk, N, C, h, w, K, H0, W0, act=ACT_NONE, align_corners=False):
     x, y = _as_slice(x), _as_slice(y)
     check(_lib.lib().ptk_warp_forward(x.ptr, x.ld, _p(warps), _p(mask_lvl), y.ptr, y.ld, _p(argk), N, C, h, w, K, H0, W0,
                                       int(align_corners), act, _stream()), "ptk_warp_forward")
 
 
-@_timed("warp_backward")
+@_timed("warp_backward", lambda dy, y, act, warps, mask_lvl, argk, dx, N, C, h, w, K, H0, W0, align_corners=False:
+        N * h * w * (4 * C * 2 + 4 * K))      # read dY + write dX + read masks (argk and y excluded)
 def warp_backward(dy, y, act, warps, mask_lvl, argk, dx, N, C, h, w, K, H0, W0, align_corners=False):
     dy = _as_slice(dy)
     yy = _as_slice(y) if y is not None else None
@@ -322,7 +333,7 @@ def tanh_bwd_combine(g_nchw, g_nhwc, out_nchw, dz, ld, N, C, H, W):
                                           N, C, H, W, _stream()), "ptk_tanh_bwd_combine")
 
 
-@_timed("adam")
+@_timed("adam", lambda p, g, m, v, *a, **k: 28 * p.numel())     # read p, g, m, v; write p, m, v
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     check(_lib.lib().ptk_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale,
                                    _stream()), "ptk_adam_step")
