@@ -159,7 +159,8 @@ int ptk_gn_bwd_apply(float* dy, const float* z, int ldz, const double* stats, co
 int ptk_mask_pyramid(const double* masks, int N, int K, int H0, int W0, float* out, int h, int w,
                      void* stream);
 /* y[n,y,x,c] = act(max_k m[n,y,x,k] * bilinear(x[n,:,:,c]; theta_k(y,x))).  warps = raw [N,K,8] rows
- * (first 6 used, :28).  argk[n,y,x,c] = winning part (255 = zero winner).  H0,W0 = init_image_size. */
+ * (first 6 used, :28).  argk = opaque record of the winning part per element (capacity N*h*w*C bytes; the layout is
+ * private to the library: bytes, or 4-bit codes on the fast path).  H0,W0 = init_image_size. */
 int ptk_warp_forward(const float* x, int ldx, const float* warps, const float* mask_lvl, float* y, int ldy,
                      uint8_t* argk, int N, int C, int h, int w, int K, int H0, int W0, int align_corners,
                      int act, void* stream);
@@ -167,6 +168,24 @@ int ptk_warp_forward(const float* x, int ldx, const float* warps, const float* m
 int ptk_warp_backward(const float* dy, int lddy, const float* y, int ldy, int act, const float* warps,
                       const float* mask_lvl, const uint8_t* argk, float* dx, int N, int C, int h, int w,
                       int K, int H0, int W0, int align_corners, void* stream);
+
+/* All warped skip levels of one generator pass in ONE launch (models/networks.py:279-288 calls the layer once per level).
+ * Forward uses x, ldx, mask, y, ldy, argk; backward uses dy, lddy, mask, argk, dx (dense, ld = C) and, for act = LeakyReLU,
+ * y / ldy.  argk is an opaque winner record owned by the caller (N*h*w*C bytes of capacity per level) that must be passed
+ * unchanged from the forward to the backward call.  zero_dx != 0: the library zero-fills every dx first. */
+typedef struct {
+  const float* x; int ldx;
+  const float* mask;
+  float* y; int ldy;
+  uint8_t* argk;
+  const float* dy; int lddy;
+  float* dx;
+  int C, h, w;
+} ptk_warp_level;
+int ptk_warp_forward_levels(const ptk_warp_level* levels, int nlevels, const float* warps, int N, int K, int H0, int W0,
+                            int act, void* stream);
+int ptk_warp_backward_levels(const ptk_warp_level* levels, int nlevels, const float* warps, int N, int K, int H0, int W0,
+                             int act, int zero_dx, void* stream);
 
 /* ---------------------------------------------------------------- losses (models/pose_gan.py:90-98,140-199) */
 /* logits [rows][J] (pre-sigmoid).  rows < n_true: -mean_j log(sig+1e-7); other rows: -mean_j log(1-sig+1e-7);

@@ -210,6 +210,50 @@ def gen_step_big(ns, tag, H, W, P, N, seed, stride):
     np.savez_compressed(os.path.join(GOLDEN_DIR, "step_%s.npz" % tag), **rec)
 
 
+STACKED_CASE = ("stacked_64x64_p18_s2", 64, 64, 18, 2, 2, 41)     # tag, H, W, P, N, num_stacks, seed
+
+
+def stacked_inputs(H, W, P, N, S, seed):
+    """(input, target, interpol_pose [N,S*P,H,W], interpol_warps [N,S,10,8], interpol_masks [N,S,10,H,W]) from S batches."""
+    bs = [synth.make_batch(N, H, W, P, seed=seed + i) for i in range(S)]
+    return (bs[0]["input"], bs[0]["target"], torch.cat([b["input"][:, 3 + P:] for b in bs], 1),
+            torch.stack([b["warps"] for b in bs], 1), torch.stack([b["masks"] for b in bs], 1))
+
+
+def gen_step_stacked(tag, H, W, P, N, S, seed):
+    """gen_type='stacked' (SURVEY 8f-3): one dis_update + gen_update of the unmodified reference trainer with num_stacks = S
+    (L1 content loss), incl. the gradient that flows from stack i back into stack i-1 through the generated image."""
+    import argparse as ap
+    opt = ap.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=S,
+                       gen_type="stacked", warp_skip="mask", dataset="fasion", learning_rate=2e-4,
+                       content_loss_layer="none", nn_loss_area_size=1, gan_penalty_weight=1.0, l1_penalty_weight=100.0)
+    dsd = synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1)
+    gsd = synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed)
+    model = ref_import.make_reference_gan(opt, dsd, None, gen_state=gsd)
+    od = vars(opt)
+    rec = {"seed": np.int64(seed)}
+    inp, tgt, ipose, iwarps, imasks = stacked_inputs(H, W, P, N, S, seed)
+    r = synth.make_batch(N, H, W, P, seed=seed + 50)
+    inp2, tgt2, ipose2, iwarps2, imasks2 = stacked_inputs(H, W, P, N, S, seed + 100)
+    drop_d = [m for i in range(S) for m in synth.dropout_masks(N, 512, 3, seed=seed + i)]
+    drop_g = [m for i in range(S) for m in synth.dropout_masks(N, 512, 3, seed=seed + 10 + i)]
+    with _DropPatch(drop_d):
+        dl = model.dis_update(inp, tgt, {"interpol_pose": ipose, "interpol_warps": iwarps.clone(), "interpol_masks": imasks.clone()},
+                              r["input"], r["target"], od)
+    rec["d_loss"] = np.array(dl)
+    rec["d_grad"] = np.stack([summarize(p.grad) for _, p in sorted(model.disc.named_parameters())])
+    with _DropPatch(drop_g):
+        out, outs, gl = model.gen_update(inp2, tgt2, {"interpol_pose": ipose2, "interpol_warps": iwarps2.clone(),
+                                                      "interpol_masks": imasks2.clone()}, od)
+    rec["g_loss"] = np.array(gl)
+    rec["out_gen"] = out.detach().numpy()
+    rec["out_first"] = outs[0].detach().numpy()
+    rec["g_grad"] = np.stack([summarize(p.grad) for _, p in sorted(model.gen.named_parameters())])
+    rec["g_param"] = np.stack([summarize(p) for _, p in sorted(model.gen.named_parameters())])
+    print("stacked step", tag, dl, gl)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "step_%s.npz" % tag), **rec)
+
+
 def gen_step_baseline(H, W, P, N, seed, tag, l1_w=100.0):
     """BASELINE configs[0]: src_baseline Pose_GAN (single-encoder Generator, L1 + adversarial), one iteration.  Weights:
     the reference's own xavier initialisation under torch.manual_seed(seed); they are stored so the product starts from
@@ -292,6 +336,8 @@ def main():
             if a.only.startswith("big:") and a.only[4:] != case[0]:
                 continue
             gen_step_big(ns, *case)
+    if a.only in ("", "stacked"):
+        gen_step_stacked(*STACKED_CASE)
     if a.only in ("", "baseline"):
         gen_step_baseline(128, 64, 18, 4, 11, "baseline_128x64_p18")
     if a.only in ("", "params"):

@@ -129,12 +129,13 @@ class cpu_only:
         torch.Tensor.cuda, torch.nn.Module.cuda = self.saved
 
 
-def make_reference_gan(opt, disc_state, vgg):
-    """Instantiate the reference DeformablePose_GAN with the two file loads patched."""
+def make_reference_gan(opt, disc_state, vgg, gen_state=None):
+    """Instantiate the reference DeformablePose_GAN with its file loads patched (disc_090.pkl, pose_gan.py:40-42; for
+    gen_type='stacked' also gen_090.pkl, :31-32; vgg19(pretrained=True), :56)."""
     ns = load()
     pg = ns.pose_gan
     old_load, old_vgg = pg.torch.load, pg.vgg19
-    pg.torch.load = lambda path, *a, **k: disc_state
+    pg.torch.load = lambda path, *a, **k: gen_state if "gen_" in os.path.basename(str(path)) else disc_state
     pg.vgg19 = lambda pretrained=True: vgg
     try:
         import contextlib, io

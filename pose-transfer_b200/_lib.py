@@ -15,6 +15,12 @@ class ConvGeom(ctypes.Structure):
                                    "transposed", "impl")]
 
 
+class WarpLevel(ctypes.Structure):
+    """Mirror of ptk_warp_level (include/ptk.h)."""
+    _fields_ = [("x", vp), ("ldx", i32), ("mask", vp), ("y", vp), ("ldy", i32), ("argk", vp), ("dy", vp), ("lddy", i32),
+                ("dx", vp), ("C", i32), ("h", i32), ("w", i32)]
+
+
 # name -> argtypes (everything returns int unless listed in _RESTYPES)
 SIGNATURES = {
     "ptk_version": [],
@@ -48,6 +54,8 @@ SIGNATURES = {
     "ptk_mask_pyramid": [vp, i32, i32, i32, i32, vp, i32, i32, vp],
     "ptk_warp_forward": [vp, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "ptk_warp_backward": [vp, i32, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "ptk_warp_forward_levels": [ctypes.POINTER(WarpLevel), i32, vp, i32, i32, i32, i32, i32, vp],
+    "ptk_warp_backward_levels": [ctypes.POINTER(WarpLevel), i32, vp, i32, i32, i32, i32, i32, i32, vp],
     "ptk_adv_loss": [vp, i32, i32, i32, f32, vp, vp, i32, vp],
     "ptk_l1_loss": [vp, vp, i64, f32, vp, vp, vp],
     "ptk_nnloss_forward": [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp],

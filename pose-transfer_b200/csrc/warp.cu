@@ -165,173 +165,56 @@ warp_backward_kernel(const float* __restrict__ dy, int lddy, const float* __rest
 }
 
 
-// ---------------------------------------------------------------- cooperative kernels (C >= 64)
-// A group of G = min(32, C/4) lanes owns one output pixel (a warp handles 32/G pixels at a time).  The per-part
-// geometry (mask value, bilinear footprint) is computed ONCE per pixel by lane k of the group and broadcast with
-// shuffles, so the per-element instruction stream is just the gather itself; parts whose mask is zero at the pixel
-// (or whose footprint is outside the image) are skipped -- they all contribute the same candidate "0, no gradient".
-struct PartGeom { float m; int x0, y0; float w00, w01, w10, w11; };
+// ---------------------------------------------------------------- fast path (C % 64 == 0, K <= 15)
+// Lane mapping: G = 16 or 32 lanes own ONE pixel, lane gl holding channels [cb + 4 G q + 4 gl, +4) for q < NV, so that
+// every 128-bit request of a group is one contiguous run of 16 G bytes = whole 128-byte lines (an "8-16 channels per
+// lane" mapping touches half-used lines and doubles the L1 wavefronts per byte: ncu showed the L1/TEX pipe at 57 % busy
+// at only 0.42 of the HBM roofline).  A group carries PX = 4 / NV horizontally adjacent pixels, i.e. 16 independent
+// 128-bit loads in flight per lane and part.
+// Per row the geometry of every (pixel, part) pair is evaluated ONCE by lane gl == part (mask value, affine grid point,
+// bilinear weights incl. the mask factor, clamped tap offsets), parked in shared memory and read back as two broadcast
+// 128-bit loads, so the 16-32 lanes of a pixel do not redo the coordinate arithmetic.  Parts whose mask is zero at the
+// pixel (or whose footprint lies outside the image) are skipped: they all contribute the same candidate "0, no gradient".
+// The winner record is packed to 4 bits per element (15 = "0, no gradient").
+constexpr int kNoPart = 15;
 
-__device__ __forceinline__ PartGeom shfl_geom(const PartGeom& g, int src) {
-  PartGeom r;
-  r.m = __shfl_sync(0xffffffffu, g.m, src);
-  r.x0 = __shfl_sync(0xffffffffu, g.x0, src);
-  r.y0 = __shfl_sync(0xffffffffu, g.y0, src);
-  r.w00 = __shfl_sync(0xffffffffu, g.w00, src);
-  r.w01 = __shfl_sync(0xffffffffu, g.w01, src);
-  r.w10 = __shfl_sync(0xffffffffu, g.w10, src);
-  r.w11 = __shfl_sync(0xffffffffu, g.w11, src);
-  return r;
+struct WarpLevelDev {
+  const float* x; const float* mask; float* y; uint8_t* argk; const float* dy; float* dx;
+  int ldx, ldy, lddy, C, h, w, TH, strips_x, strips_y, cta_begin, cfg;     // cfg: 0 = (G16,NV1) 1 = (G16,NV2) 2 = (G32,NV2) 3 = (G32,NV4)
+};
+struct WarpLaunchDev {
+  WarpLevelDev lv[4];
+  int nlevels, K, H0, W0, act, ctas_per_image;
+};
+
+// geometry of part `gl` at output pixel (i, j); returns false for "0, no gradient" (mask 0 / footprint outside)
+__device__ __forceinline__ bool part_geometry(const Theta& t, float m, int i, int j, int h, int w, int ld, float4& wgt, int4& off) {
+  if (m == 0.f) return false;
+  // explicit rounding intrinsics: forward and backward must take bit-identical decisions whatever the inlining context
+  const float fw = (float)w, fh = (float)h;
+  const float gx = __fsub_rn(__fdiv_rn(__fmaf_rn(2.f, (float)j, 1.f), fw), 1.f);
+  const float gy = __fsub_rn(__fdiv_rn(__fmaf_rn(2.f, (float)i, 1.f), fh), 1.f);
+  const float sx = __fmaf_rn(t.a, gx, __fmaf_rn(t.b, gy, t.tx)), sy = __fmaf_rn(t.c, gx, __fmaf_rn(t.d, gy, t.ty));
+  const float px = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(sx, 1.f), fw), 1.f), 0.5f);
+  const float py = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(sy, 1.f), fh), 1.f), 0.5f);
+  const float fx0 = floorf(px), fy0 = floorf(py);
+  const int x0 = (int)fminf(fmaxf(fx0, -2.f), fw), y0 = (int)fminf(fmaxf(fy0, -2.f), fh);
+  if (!(x0 >= -1 && x0 < w && y0 >= -1 && y0 < h)) return false;
+  const float fx = __fsub_rn(px, fx0), fy = __fsub_rn(py, fy0);
+  // out-of-image taps: weight 0 at a clamped (valid) address, so that all loads are unconditional
+  const bool xin0 = x0 >= 0, xin1 = x0 + 1 < w, yin0 = y0 >= 0, yin1 = y0 + 1 < h;
+  const float wy0 = yin0 ? __fmul_rn(__fsub_rn(1.f, fy), m) : 0.f, wy1 = yin1 ? __fmul_rn(fy, m) : 0.f;
+  const float wx0 = xin0 ? __fsub_rn(1.f, fx) : 0.f, wx1 = xin1 ? fx : 0.f;
+  wgt = make_float4(__fmul_rn(wy0, wx0), __fmul_rn(wy0, wx1), __fmul_rn(wy1, wx0), __fmul_rn(wy1, wx1));
+  const int xa = max(x0, 0), xc = min(x0 + 1, w - 1), ya = max(y0, 0), yc = min(y0 + 1, h - 1);
+  off = make_int4((ya * w + xa) * ld, (ya * w + xc) * ld, (yc * w + xa) * ld, (yc * w + xc) * ld);
+  return true;
 }
 
 __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
   a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
 }
 
-// Packed per-(pixel, part) geometry that travels through the shuffles: 4 registers.
-struct PackedGeom { float m, fx, fy; int xy; };   // xy = (y0 + 2) << 16 | (x0 + 2)   (x0, y0 in [-2, 32765])
-
-__device__ __forceinline__ PackedGeom shfl_packed(const PackedGeom& g, int src) {
-  PackedGeom r;
-  r.m = __shfl_sync(0xffffffffu, g.m, src);
-  r.fx = __shfl_sync(0xffffffffu, g.fx, src);
-  r.fy = __shfl_sync(0xffffffffu, g.fy, src);
-  r.xy = __shfl_sync(0xffffffffu, g.xy, src);
-  return r;
-}
-
-// Forward, G lanes per pixel, 8 channels (two float4) per lane and chunk: C = 64 -> G = 8 (4 pixels per warp),
-// C = 128 -> G = 16, C % 256 == 0 -> G = 32.  Lane gl of a group evaluates parts gl, gl + G, ... of its pixel.
-template <int G>
-__global__ void __launch_bounds__(256)
-warp_forward_coop_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ warps,
-                         const float* __restrict__ mask_lvl, float* __restrict__ y, int ldy, uint8_t* __restrict__ argk,
-                         int C, int h, int w, int K, int H0, int W0, int act) {
-  __shared__ Theta s_theta[kMaxParts];
-  const int n = blockIdx.y;
-  if (threadIdx.x < K) s_theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * K + threadIdx.x) * 8, h, w, H0, W0);
-  __syncthreads();
-  constexpr int PPW = 32 / G;                        // pixels per warp iteration
-  constexpr int SLOTS = (kMaxParts + G - 1) / G;     // parts evaluated per lane
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % G, gbase = lane - gl, grp = lane / G;
-  const int HW = h * w;
-  const float inv_w = 1.f / (float)w, inv_h = 1.f / (float)h;
-  const float* xb = x + (int64_t)n * HW * ldx;
-  const float* mb = mask_lvl + (int64_t)n * HW * K;
-  float* yb = y + (int64_t)n * HW * ldy;
-  uint8_t* ab = argk + (int64_t)n * HW * C;
-  const int warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * (blockDim.x >> 5);
-  const int iters = (HW + PPW - 1) / PPW;
-  const unsigned kmask = (1u << K) - 1u;
-  for (int it = warp_id; it < iters; it += nwarps) {
-    const int p = it * PPW + grp;
-    const bool pvalid = p < HW;
-    const int i = pvalid ? p / w : 0, j = pvalid ? p - i * w : 0;
-    PackedGeom mine[SLOTS];
-    unsigned my_active = 0;                          // bit s: slot s is an active part
-#pragma unroll
-    for (int sl = 0; sl < SLOTS; ++sl) {
-      const int k = gl + sl * G;
-      mine[sl].m = 0.f; mine[sl].fx = 0.f; mine[sl].fy = 0.f; mine[sl].xy = 0;
-      if (pvalid && k < K) {
-        const float m = __ldg(mb + p * K + k);
-        if (m != 0.f) {
-          const Theta t = s_theta[k];
-          const float gx = (2.f * (float)j + 1.f) * inv_w - 1.f, gy = (2.f * (float)i + 1.f) * inv_h - 1.f;
-          const float px = ((t.a * gx + t.b * gy + t.tx + 1.f) * (float)w - 1.f) * 0.5f;
-          const float py = ((t.c * gx + t.d * gy + t.ty + 1.f) * (float)h - 1.f) * 0.5f;
-          const float fx0 = floorf(px), fy0 = floorf(py);
-          const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)w), y0 = (int)fminf(fmaxf(fy0, -2.f), (float)h);
-          if (x0 >= -1 && x0 < w && y0 >= -1 && y0 < h) {     // at least one neighbour inside the image
-            my_active |= 1u << sl;
-            mine[sl].m = m; mine[sl].fx = px - fx0; mine[sl].fy = py - fy0;
-            mine[sl].xy = ((y0 + 2) << 16) | (x0 + 2);
-          }
-        }
-      }
-    }
-    // active-part bit mask of every group (bit k), and their union over the warp
-    unsigned active = 0, uni = 0;
-#pragma unroll
-    for (int sl = 0; sl < SLOTS; ++sl) {
-      const unsigned ball = __ballot_sync(0xffffffffu, (my_active >> sl) & 1u);
-      active |= ((ball >> gbase) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u))) << (sl * G);
-      unsigned u = ball;
-      if (G <= 16) u |= u >> 16;
-      if (G <= 8) u |= u >> 8;
-      u &= (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
-      uni |= u << (sl * G);
-    }
-    active &= kmask; uni &= kmask;
-    const unsigned inactive = ~active & kmask;
-    const int kz = inactive ? __ffs(inactive) - 1 : 1 << 20;   // where the (single) "0, no gradient" candidate sits
-    // Each lane owns two float4 per chunk of G*8 channels: channels [cb + 4 gl, +4) and [cb + 4 G + 4 gl, +4), so that
-    // every 128-bit load / store instruction of a group covers one CONTIGUOUS run of 16*G bytes (whole L1 lines and
-    // full sectors per request instead of the half-used sectors of an "8 consecutive channels per lane" mapping).
-    for (int cb = 0; cb < C; cb += G * 8) {
-      const int c0 = cb + gl * 4, c1 = c0 + G * 4;
-      float best[8];
-      unsigned char arg[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; arg[q] = 255; }
-      bool zero_done = false;
-      unsigned rem = uni;
-      while (rem) {
-        const int k = __ffs(rem) - 1;
-        rem &= rem - 1;
-        const int sl = k / G;
-        PackedGeom g = shfl_packed(SLOTS == 1 ? mine[0] : (sl == 0 ? mine[0] : mine[SLOTS - 1]), gbase + (k - sl * G));
-        if (!((active >> k) & 1u)) continue;           // active only for another pixel of this warp
-        if (!zero_done && k > kz) {
-          zero_done = true;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) if (0.f > best[q]) { best[q] = 0.f; arg[q] = 255; }
-        }
-        const int x0 = (g.xy & 0xffff) - 2, y0 = (g.xy >> 16) - 2;
-        const bool xin0 = x0 >= 0, xin1 = x0 + 1 < w, yin0 = y0 >= 0, yin1 = y0 + 1 < h;
-        const float w00 = (yin0 && xin0) ? (1.f - g.fy) * (1.f - g.fx) * g.m : 0.f;
-        const float w01 = (yin0 && xin1) ? (1.f - g.fy) * g.fx * g.m : 0.f;
-        const float w10 = (yin1 && xin0) ? g.fy * (1.f - g.fx) * g.m : 0.f;
-        const float w11 = (yin1 && xin1) ? g.fy * g.fx * g.m : 0.f;
-        const float* r0 = xb + (y0 * w + x0) * ldx;
-        const float* r1 = r0 + w * ldx;
-        float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), cc = ca;
-        if (yin0 && xin0) { fma4(ca, w00, __ldg(reinterpret_cast<const float4*>(r0 + c0))); fma4(cc, w00, __ldg(reinterpret_cast<const float4*>(r0 + c1))); }
-        if (yin0 && xin1) { fma4(ca, w01, __ldg(reinterpret_cast<const float4*>(r0 + ldx + c0))); fma4(cc, w01, __ldg(reinterpret_cast<const float4*>(r0 + ldx + c1))); }
-        if (yin1 && xin0) { fma4(ca, w10, __ldg(reinterpret_cast<const float4*>(r1 + c0))); fma4(cc, w10, __ldg(reinterpret_cast<const float4*>(r1 + c1))); }
-        if (yin1 && xin1) { fma4(ca, w11, __ldg(reinterpret_cast<const float4*>(r1 + ldx + c0))); fma4(cc, w11, __ldg(reinterpret_cast<const float4*>(r1 + ldx + c1))); }
-        const float cand[8] = {ca.x, ca.y, ca.z, ca.w, cc.x, cc.y, cc.z, cc.w};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) if (cand[q] > best[q]) { best[q] = cand[q]; arg[q] = (unsigned char)k; }
-      }
-      if (!zero_done && inactive) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) if (0.f > best[q]) { best[q] = 0.f; arg[q] = 255; }
-      }
-      if (pvalid) {
-        float* dst = yb + p * ldy;
-        *reinterpret_cast<float4*>(dst + c0) = make_float4(apply_act(best[0], act), apply_act(best[1], act), apply_act(best[2], act), apply_act(best[3], act));
-        *reinterpret_cast<float4*>(dst + c1) = make_float4(apply_act(best[4], act), apply_act(best[5], act), apply_act(best[6], act), apply_act(best[7], act));
-        *reinterpret_cast<uint32_t*>(ab + p * C + c0) = arg[0] | (arg[1] << 8) | (arg[2] << 16) | ((unsigned)arg[3] << 24);
-        *reinterpret_cast<uint32_t*>(ab + p * C + c1) = arg[4] | (arg[5] << 8) | (arg[6] << 16) | ((unsigned)arg[7] << 24);
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------- tiled forward (K == KP parts, C >= 64)
-// One CTA owns a strip of XW = 8 * (32 / G) pixels x TH rows of one image and walks it row by row, so that the two
-// source rows a bilinear footprint touches stay in this SM's L1 from one row to the next (the row-major grid-stride
-// order of the kernel above re-fetched every source row from L2: 37 % L1 hit rate, 2.8x the input bytes over the
-// crossbar).  The strip's mask values are staged once in shared memory together with a per-pixel bit set of the
-// parts whose mask is non-zero; the row loop then iterates over set bits only and reads mask value and transform
-// from shared memory, which leaves the gather as the only global load on the dependent chain.  Every lane of a
-// pixel's group evaluates the (cheap) footprint itself: no shuffles, no ballots.
-// max over parts with torch.max's first-maximum rule: parts whose mask is zero (or whose footprint lies outside the
-// image) all contribute the same candidate "0, no gradient" (argk = 255); the first of them is merged into the bit
-// loop as a pseudo part at its own index kz, so real candidates before / after it keep their tie-breaking order.
 template <int ACT>
 __device__ __forceinline__ float warp_act(float v) {
   if (ACT == PTK_ACT_RELU) return fmaxf(v, 0.f);
@@ -339,443 +222,268 @@ __device__ __forceinline__ float warp_act(float v) {
   return v;
 }
 
-// G lanes per pixel, NV float4 (4 NV channels) per lane and channel chunk: lane gl owns channels
-// [cb + 4 G q + 4 gl, +4) for q < NV, so every 128-bit request of a group is one contiguous run of 16 G bytes.
-// ACT == ReLU (the only way the network uses this layer: the warped skip is stored post-ReLU and the backward masks the
-// gradient with y > 0) folds the "0, no gradient" candidates into the initial value max(., 0) -- no pseudo part.
-template <int G, int NV, int KP, int ACT>
-__global__ void __launch_bounds__(256, (NV > 2 ? 2 : 4))
-warp_forward_tile_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ warps,
-                         const float* __restrict__ mask_lvl, float* __restrict__ y, int ldy, uint8_t* __restrict__ argk,
-                         int C, int h, int w, int H0, int W0, int TH, int strips_x, int PD) {
-  static_assert(KP % 2 == 0 && KP <= kMaxParts, "mask rows are staged as float2");
-  constexpr int PPW = 32 / G, XW = 8 * PPW, NC = 4 * NV;   // PD: L1 prefetch distance in rows (0 = off)
+// geometry phase of one output row for the PX pixels of this lane's group: fills s_geo[(px * 16 + k) * 2 + {0, 1}] and
+// returns the per-pixel bit sets of real candidates.
+template <int G, int PX>
+__device__ __forceinline__ void row_geometry(const Theta* s_theta, const float* __restrict__ mrow, int K, int i, int j0, int h, int w,
+                                             int ld, int gl, int grp, float4* __restrict__ geo, unsigned (&bits)[PX]) {
+#pragma unroll
+  for (int px = 0; px < PX; ++px) {
+    const int j = j0 + px;
+    bool valid = false;
+    float4 wgt;
+    int4 off;
+    if (gl < K && j < w) {
+      const float m = __ldg(mrow + j * K + gl);
+      valid = part_geometry(s_theta[gl], m, i, j, h, w, ld, wgt, off);
+    }
+    if (valid) {
+      geo[(px * 16 + gl) * 2] = wgt;
+      geo[(px * 16 + gl) * 2 + 1] = make_float4(__int_as_float(off.x), __int_as_float(off.y), __int_as_float(off.z), __int_as_float(off.w));
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, valid);
+    bits[px] = (ball >> (grp * G)) & 0xffffu;
+  }
+}
+
+template <int G, int NV, int PX, int ACT>
+__device__ __forceinline__ void warp_fwd_strip(const WarpLevelDev& L, const Theta* s_theta, float4* s_geo_warp, int K, int n, int tile) {
+  constexpr int PPW = 32 / G, XW = 8 * PPW * PX, CH = 4 * G * NV;
   constexpr bool kRelu = ACT == PTK_ACT_RELU;
-  extern __shared__ float s_dyn[];                       // [TH * XW][KP] mask values, then [TH * XW] part bit sets
-  __shared__ Theta s_theta[KP];
-  float* s_m = s_dyn;
-  unsigned* s_bits = reinterpret_cast<unsigned*>(s_dyn + TH * XW * KP);
-  const int n = blockIdx.y;
-  const int sx = blockIdx.x % strips_x, sy = blockIdx.x / strips_x;
-  const int x_begin = sx * XW, y_begin = sy * TH;
-  const int rows = min(TH, h - y_begin), cols = min(XW, w - x_begin);
-  const int tid = threadIdx.x;
-  const int HW = h * w;
-  if (tid < KP) s_theta[tid] = normalized_theta(warps + ((int64_t)n * KP + tid) * 8, h, w, H0, W0);
-  // stage: one thread per pixel of the strip (KP floats = KP/2 float2, 8-byte aligned because KP is even)
-  const float* mb = mask_lvl + (int64_t)n * HW * KP;
-  for (int t = tid; t < rows * XW; t += 256) {
-    const int r = t / XW, cx = t - r * XW;
-    unsigned bits = 0u;
-    if (cx < cols) {
-      const float2* src = reinterpret_cast<const float2*>(mb + ((y_begin + r) * w + x_begin + cx) * KP);
-      float2 v[KP / 2];
-#pragma unroll
-      for (int q = 0; q < KP / 2; ++q) v[q] = __ldg(src + q);
-#pragma unroll
-      for (int q = 0; q < KP / 2; ++q) {
-        *reinterpret_cast<float2*>(s_m + t * KP + 2 * q) = v[q];
-        bits |= ((v[q].x != 0.f ? 1u : 0u) | (v[q].y != 0.f ? 2u : 0u)) << (2 * q);
-      }
-    }
-    s_bits[t] = bits;
-  }
-  __syncthreads();
-
-  const int lane = tid & 31, wi = tid >> 5;
+  const int sx = tile % L.strips_x, sy = tile / L.strips_x;
+  const int y_begin = sy * L.TH;
+  const int h = L.h, w = L.w, C = L.C;
+  const int rows = min(L.TH, h - y_begin);
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const int gl = lane % G, grp = lane / G;
-  const int lx = wi * PPW + grp;                           // pixel column inside the strip
-  const int j = x_begin + lx;
-  if (j >= w) return;
-  const float fw = (float)w, fh = (float)h;
-  const float gx = (2.f * (float)j + 1.f) / fw - 1.f;
-  const float* xb = x + (int64_t)n * HW * ldx + gl * 4;
-  float* yrow = y + ((int64_t)n * HW + (int64_t)y_begin * w + j) * ldy + gl * 4;
-  uint8_t* arow = argk + ((int64_t)n * HW + (int64_t)y_begin * w + j) * C + gl * 4;
-  const int ystep = w * ldy, astep = w * C;
-  constexpr unsigned kmask = (1u << KP) - 1u;
-  for (int r = 0; r < rows; ++r, yrow += ystep, arow += astep) {
-    const int lp = r * XW + lx;
-    const unsigned bits = s_bits[lp];
-    const float gy = (2.f * (float)(y_begin + r) + 1.f) / fh - 1.f;
-    if (PD > 0 && y_begin + r + PD < h) {
-      // L1 prefetch of the first part's footprint PD rows ahead: holds no registers, so the gather of row r + PD finds
-      // its lines on chip and the row loop stops being bound by one DRAM round trip per row.  Rows past the end of the
-      // strip (another CTA's) are prefetched with this row's part set as a guess: that warms L2 for the neighbour.
-      const unsigned pb = r + PD < rows ? s_bits[lp + PD * XW] : bits;
-      if (pb) {
-        const int k = __ffs(pb) - 1;
-        const Theta t = s_theta[k];
-        const float gy2 = (2.f * (float)(y_begin + r + PD) + 1.f) / fh - 1.f;
-        const float px = ((t.a * gx + t.b * gy2 + t.tx + 1.f) * fw - 1.f) * 0.5f;
-        const float py = ((t.c * gx + t.d * gy2 + t.ty + 1.f) * fh - 1.f) * 0.5f;
-        const int x0 = (int)fminf(fmaxf(floorf(px), -2.f), fw), y0 = (int)fminf(fmaxf(floorf(py), -2.f), fh);
-        if (x0 >= -1 && x0 < w && y0 >= -1 && y0 < h) {
-          const int xa = max(x0, 0), xc = min(x0 + 1, w - 1), yc = min(y0 + 1, h - 1);
-          // the upper footprint row was (for near-identity transforms) the lower row of an earlier output row
-          const float* p10 = xb + (yc * w + xa) * ldx;
-          const float* p11 = xb + (yc * w + xc) * ldx;
-          for (int cb = 0; cb < C; cb += G * NC) {
+  const int j0 = sx * XW + (wi * PPW + grp) * PX;
+  const int64_t img = (int64_t)n * h * w;
+  const float* xb = L.x + img * L.ldx + gl * 4;
+  const float* mb = L.mask + img * K;
+  float4* geo = s_geo_warp + grp * (PX * 32);
+  const unsigned kmask = (1u << K) - 1u;
+  for (int r = 0; r < rows; ++r) {
+    const int i = y_begin + r;
+    unsigned bits[PX];
+    row_geometry<G, PX>(s_theta, mb + (int64_t)i * w * K, K, i, j0, h, w, L.ldx, gl, grp, geo, bits);
+    __syncwarp();
+    // max over parts with torch.max's first-maximum rule.  ReLU epilogue: max(., 0) is the initial value.  Otherwise the
+    // first "0, no gradient" candidate takes part in the loop as a pseudo part at its own index kz.
+    unsigned uni = 0u;
+    int kz[PX];
 #pragma unroll
-            for (int q = 0; q < NV; ++q) {
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(p10 + cb + q * G * 4));
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(p11 + cb + q * G * 4));
-            }
-          }
-        }
-      }
+    for (int px = 0; px < PX; ++px) {
+      const unsigned inactive = ~bits[px] & kmask;
+      kz[px] = (!kRelu && inactive) ? __ffs(inactive) - 1 : -1;
+      uni |= bits[px] | ((!kRelu && inactive) ? (inactive & (0u - inactive)) : 0u);
     }
-    const unsigned inactive = ~bits & kmask;
-    const int kz = (!kRelu && inactive) ? __ffs(inactive) - 1 : -1;
-    // ReLU: real parts only.  Otherwise: real parts + the first zero candidate as a pseudo part at its own index.
-    const unsigned todo = kRelu ? bits : (bits | (inactive & (0u - inactive)));
-    const float* mrow = s_m + lp * KP;
-    for (int cb = 0; cb < C; cb += G * NC) {
-      float best[NC];
-      int arg[NC];
+    float* yrow = L.y + (img + (int64_t)i * w + j0) * L.ldy + gl * 4;
+    uint8_t* arow = L.argk + (((img + (int64_t)i * w + j0) * C) >> 1) + gl * 2;
+    for (int cb = 0; cb < C; cb += CH) {
+      float best[PX][NV * 4];
+      int arg[PX][NV * 4];
 #pragma unroll
-      for (int q = 0; q < NC; ++q) { best[q] = kRelu ? 0.f : -INFINITY; arg[q] = 255; }
-      unsigned rem = todo;
+      for (int px = 0; px < PX; ++px)
+#pragma unroll
+        for (int q = 0; q < NV * 4; ++q) { best[px][q] = kRelu ? 0.f : -INFINITY; arg[px][q] = kNoPart; }
+      unsigned rem = uni;
       while (rem) {
         const int k = __ffs(rem) - 1;
         rem &= rem - 1;
-        float4 acc[NV];
+        float4 wv[PX];
+        float4 v[PX][NV][4];
 #pragma unroll
-        for (int q = 0; q < NV; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int tag = 255;
-        if (kRelu || k != kz) {
-          const Theta t = s_theta[k];
-          const float m = mrow[k];
-          const float px = ((t.a * gx + t.b * gy + t.tx + 1.f) * fw - 1.f) * 0.5f;
-          const float py = ((t.c * gx + t.d * gy + t.ty + 1.f) * fh - 1.f) * 0.5f;
-          const float fx0 = floorf(px), fy0 = floorf(py);
-          const int x0 = (int)fminf(fmaxf(fx0, -2.f), fw), y0 = (int)fminf(fmaxf(fy0, -2.f), fh);
-          if (x0 >= -1 && x0 < w && y0 >= -1 && y0 < h) {        // otherwise: footprint outside = "0, no gradient"
-            tag = k;
-            const float fx = px - fx0, fy = py - fy0;
-            // Out-of-image taps: weight 0 at a clamped (valid) address, so that all 4 NV loads are unconditional and
-            // issue back to back (one memory round trip per part instead of one per tap).
-            const bool xin0 = x0 >= 0, xin1 = x0 + 1 < w, yin0 = y0 >= 0, yin1 = y0 + 1 < h;
-            const float wy0 = yin0 ? (1.f - fy) * m : 0.f, wy1 = yin1 ? fy * m : 0.f;
-            const float wx0 = xin0 ? 1.f - fx : 0.f, wx1 = xin1 ? fx : 0.f;
-            const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
-            const int xa = max(x0, 0), xc = min(x0 + 1, w - 1), ya = max(y0, 0), yc = min(y0 + 1, h - 1);
-            const float* p00 = xb + (ya * w + xa) * ldx + cb;
-            const float* p01 = xb + (ya * w + xc) * ldx + cb;
-            const float* p10 = xb + (yc * w + xa) * ldx + cb;
-            const float* p11 = xb + (yc * w + xc) * ldx + cb;
-            float4 v00[NV], v01[NV], v10[NV], v11[NV];
+        for (int px = 0; px < PX; ++px) {
+          const bool on = (bits[px] >> k) & 1u;
+          wv[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+          int4 o = make_int4(0, 0, 0, 0);
+          if (on) {
+            wv[px] = geo[(px * 16 + k) * 2];
+            const float4 of = geo[(px * 16 + k) * 2 + 1];
+            o = make_int4(__float_as_int(of.x), __float_as_int(of.y), __float_as_int(of.z), __float_as_int(of.w));
+          }
 #pragma unroll
-            for (int q = 0; q < NV; ++q) {
-              v00[q] = __ldg(reinterpret_cast<const float4*>(p00 + q * G * 4));
-              v01[q] = __ldg(reinterpret_cast<const float4*>(p01 + q * G * 4));
-              v10[q] = __ldg(reinterpret_cast<const float4*>(p10 + q * G * 4));
-              v11[q] = __ldg(reinterpret_cast<const float4*>(p11 + q * G * 4));
-            }
-#pragma unroll
-            for (int q = 0; q < NV; ++q) {
-              fma4(acc[q], w00, v00[q]); fma4(acc[q], w01, v01[q]); fma4(acc[q], w10, v10[q]); fma4(acc[q], w11, v11[q]);
-            }
+          for (int q = 0; q < NV; ++q) {
+            const float* p = xb + cb + q * G * 4;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[px][q][0] = on ? __ldg(reinterpret_cast<const float4*>(p + o.x)) : z;
+            v[px][q][1] = on ? __ldg(reinterpret_cast<const float4*>(p + o.y)) : z;
+            v[px][q][2] = on ? __ldg(reinterpret_cast<const float4*>(p + o.z)) : z;
+            v[px][q][3] = on ? __ldg(reinterpret_cast<const float4*>(p + o.w)) : z;
           }
         }
 #pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          if (acc[q].x > best[4 * q + 0]) { best[4 * q + 0] = acc[q].x; arg[4 * q + 0] = tag; }
-          if (acc[q].y > best[4 * q + 1]) { best[4 * q + 1] = acc[q].y; arg[4 * q + 1] = tag; }
-          if (acc[q].z > best[4 * q + 2]) { best[4 * q + 2] = acc[q].z; arg[4 * q + 2] = tag; }
-          if (acc[q].w > best[4 * q + 3]) { best[4 * q + 3] = acc[q].w; arg[4 * q + 3] = tag; }
+        for (int px = 0; px < PX; ++px) {
+          const bool on = (bits[px] >> k) & 1u;
+          const bool zero = !kRelu && k == kz[px];
+          if (!on && !zero) continue;
+          const int tag = on ? k : kNoPart;
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            fma4(acc, wv[px].x, v[px][q][0]); fma4(acc, wv[px].y, v[px][q][1]);
+            fma4(acc, wv[px].z, v[px][q][2]); fma4(acc, wv[px].w, v[px][q][3]);
+            if (acc.x > best[px][4 * q + 0]) { best[px][4 * q + 0] = acc.x; arg[px][4 * q + 0] = tag; }
+            if (acc.y > best[px][4 * q + 1]) { best[px][4 * q + 1] = acc.y; arg[px][4 * q + 1] = tag; }
+            if (acc.z > best[px][4 * q + 2]) { best[px][4 * q + 2] = acc.z; arg[px][4 * q + 2] = tag; }
+            if (acc.w > best[px][4 * q + 3]) { best[px][4 * q + 3] = acc.w; arg[px][4 * q + 3] = tag; }
+          }
         }
       }
 #pragma unroll
-      for (int q = 0; q < NV; ++q) {
-        *reinterpret_cast<float4*>(yrow + cb + q * G * 4) = make_float4(warp_act<ACT>(best[4 * q]), warp_act<ACT>(best[4 * q + 1]),
-                                                                        warp_act<ACT>(best[4 * q + 2]), warp_act<ACT>(best[4 * q + 3]));
-        *reinterpret_cast<uint32_t*>(arow + cb + q * G * 4) = (unsigned)arg[4 * q] | ((unsigned)arg[4 * q + 1] << 8) |
-                                                              ((unsigned)arg[4 * q + 2] << 16) | ((unsigned)arg[4 * q + 3] << 24);
+      for (int px = 0; px < PX; ++px) {
+        if (j0 + px >= w) continue;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          *reinterpret_cast<float4*>(yrow + px * L.ldy + cb + q * G * 4) =
+              make_float4(warp_act<ACT>(best[px][4 * q]), warp_act<ACT>(best[px][4 * q + 1]), warp_act<ACT>(best[px][4 * q + 2]),
+                          warp_act<ACT>(best[px][4 * q + 3]));
+          *reinterpret_cast<uint16_t*>(arow + ((px * C + cb + q * G * 4) >> 1)) =
+              (uint16_t)(arg[px][4 * q] | (arg[px][4 * q + 1] << 4) | (arg[px][4 * q + 2] << 8) | (arg[px][4 * q + 3] << 12));
+        }
       }
     }
+    __syncwarp();   // the next row's geometry phase overwrites s_geo
   }
 }
 
-// ---------------------------------------------------------------- tiled forward with an asynchronous row pipeline
-// EXPERIMENT (PTK_WARP_PF=1, off by default): measured 10 % SLOWER than warp_forward_tile_kernel on B200 -- ncu shows
-// the extra LDGSTS + LDS traffic pushing the L1/TEX pipe to 80 % busy, so the kernel trades a latency bound for an L1
-// bound.  Kept as the documented negative result (profiles/README.md).
-// Same strip walk as warp_forward_tile_kernel (ReLU epilogue only), but the gather of the FIRST active part of row r + 1
-// (the body part, present at every pixel) is issued with cp.async into a lane-private shared-memory slot while row r is
-// still being reduced and stored: the copies hold no registers, so every warp keeps two rows of loads in flight and the
-// row loop is no longer bound by one DRAM round trip per row.  Further parts of a pixel (sparse) use direct loads.
-__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-
-template <int G, int NV, int KP>
-__global__ void __launch_bounds__(256, 2)
-warp_forward_pf_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ warps,
-                       const float* __restrict__ mask_lvl, float* __restrict__ y, int ldy, uint8_t* __restrict__ argk,
-                       int C, int h, int w, int H0, int W0, int TH, int strips_x) {
-  static_assert(KP % 2 == 0 && KP <= kMaxParts, "mask rows are staged as float2");
-  constexpr int PPW = 32 / G, XW = 8 * PPW, NC = 4 * NV;
-  extern __shared__ __align__(16) float s_dyn[];           // [4 NV][256] float4 gather slots, [TH*XW][KP] masks, [TH*XW] bit sets
-  __shared__ Theta s_theta[KP];
-  float4* s_slot = reinterpret_cast<float4*>(s_dyn);
-  float* s_m = s_dyn + 4 * NV * 256 * 4;
-  unsigned* s_bits = reinterpret_cast<unsigned*>(s_m + TH * XW * KP);
-  const int n = blockIdx.y;
-  const int sx = blockIdx.x % strips_x, sy = blockIdx.x / strips_x;
-  const int x_begin = sx * XW, y_begin = sy * TH;
-  const int rows = min(TH, h - y_begin), cols = min(XW, w - x_begin);
-  const int tid = threadIdx.x;
-  const int HW = h * w;
-  if (tid < KP) s_theta[tid] = normalized_theta(warps + ((int64_t)n * KP + tid) * 8, h, w, H0, W0);
-  const float* mb = mask_lvl + (int64_t)n * HW * KP;
-  for (int t = tid; t < rows * XW; t += 256) {
-    const int r = t / XW, cx = t - r * XW;
-    unsigned bits = 0u;
-    if (cx < cols) {
-      const float2* src = reinterpret_cast<const float2*>(mb + ((y_begin + r) * w + x_begin + cx) * KP);
-      float2 v[KP / 2];
-#pragma unroll
-      for (int q = 0; q < KP / 2; ++q) v[q] = __ldg(src + q);
-#pragma unroll
-      for (int q = 0; q < KP / 2; ++q) {
-        *reinterpret_cast<float2*>(s_m + t * KP + 2 * q) = v[q];
-        bits |= ((v[q].x != 0.f ? 1u : 0u) | (v[q].y != 0.f ? 2u : 0u)) << (2 * q);
-      }
-    }
-    s_bits[t] = bits;
-  }
-  __syncthreads();
-
-  const int lane = tid & 31, wi = tid >> 5;
+// Backward of the same tiling: dx[taps of the winner] += dy * (mask * bilinear weight).  A lane's 4 channels usually
+// share their winner (the body part wins most pixels): one 128-bit vector reduction per tap; channels with other winners
+// go out as further vector reductions with the foreign channels zeroed.  ACT = ReLU / none need no look at y: "no
+// winner" (15) == zero candidate == y <= 0 == no gradient.
+template <int G, int NV, int PX>
+__device__ __forceinline__ void warp_bwd_strip(const WarpLevelDev& L, const Theta* s_theta, float4* s_geo_warp, int K, int n, int tile,
+                                               int act) {
+  constexpr int PPW = 32 / G, XW = 8 * PPW * PX, CH = 4 * G * NV;
+  const int sx = tile % L.strips_x, sy = tile / L.strips_x;
+  const int y_begin = sy * L.TH;
+  const int h = L.h, w = L.w, C = L.C;
+  const int rows = min(L.TH, h - y_begin);
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const int gl = lane % G, grp = lane / G;
-  const int lx = wi * PPW + grp;
-  const int j = x_begin + lx;
-  if (j >= w) return;
-  const float fw = (float)w, fh = (float)h;
-  const float gx = (2.f * (float)j + 1.f) / fw - 1.f;
-  const float* xb = x + (int64_t)n * HW * ldx + gl * 4;
-  float* yrow = y + ((int64_t)n * HW + (int64_t)y_begin * w + j) * ldy + gl * 4;
-  uint8_t* arow = argk + ((int64_t)n * HW + (int64_t)y_begin * w + j) * C + gl * 4;
-  const int ystep = w * ldy, astep = w * C;
-  const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(s_slot + tid);      // slot s of this lane: + s * 256 float4
-
-  // footprint of part k at row (y_begin + r): returns false if it lies outside the image
-  struct Geo { int x0, y0; float fx, fy; };
-  auto footprint_of = [&](int k, int r, Geo& g) -> bool {
-    const Theta t = s_theta[k];
-    const float gy = (2.f * (float)(y_begin + r) + 1.f) / fh - 1.f;
-    const float px = ((t.a * gx + t.b * gy + t.tx + 1.f) * fw - 1.f) * 0.5f;
-    const float py = ((t.c * gx + t.d * gy + t.ty + 1.f) * fh - 1.f) * 0.5f;
-    const float fx0 = floorf(px), fy0 = floorf(py);
-    g.x0 = (int)fminf(fmaxf(fx0, -2.f), fw); g.y0 = (int)fminf(fmaxf(fy0, -2.f), fh);
-    g.fx = px - fx0; g.fy = py - fy0;
-    return g.x0 >= -1 && g.x0 < w && g.y0 >= -1 && g.y0 < h;
-  };
-  // issue the asynchronous gather of the first active part of row r (channel chunk 0); returns its index or -1
-  auto prefetch_row = [&](int r, Geo& g) -> int {
-    const unsigned b = s_bits[r * XW + lx];
-    if (!b) return -1;
-    const int k = __ffs(b) - 1;
-    if (!footprint_of(k, r, g)) return -1;
-    const int xa = max(g.x0, 0), xc = min(g.x0 + 1, w - 1), ya = max(g.y0, 0), yc = min(g.y0 + 1, h - 1);
-    const float* p00 = xb + (ya * w + xa) * ldx;
-    const float* p01 = xb + (ya * w + xc) * ldx;
-    const float* p10 = xb + (yc * w + xa) * ldx;
-    const float* p11 = xb + (yc * w + xc) * ldx;
+  const int j0 = sx * XW + (wi * PPW + grp) * PX;
+  const int64_t img = (int64_t)n * h * w;
+  float* dxb = L.dx + img * C + gl * 4;
+  const float* mb = L.mask + img * K;
+  float4* geo = s_geo_warp + grp * (PX * 32);
+  for (int r = 0; r < rows; ++r) {
+    const int i = y_begin + r;
+    unsigned bits[PX];
+    row_geometry<G, PX>(s_theta, mb + (int64_t)i * w * K, K, i, j0, h, w, C, gl, grp, geo, bits);
+    __syncwarp();
+    const float* dyrow = L.dy + (img + (int64_t)i * w + j0) * L.lddy + gl * 4;
+    const float* yrow = L.y ? L.y + (img + (int64_t)i * w + j0) * L.ldy + gl * 4 : nullptr;
+    const uint8_t* arow = L.argk + (((img + (int64_t)i * w + j0) * C) >> 1) + gl * 2;
+    for (int cb = 0; cb < C; cb += CH) {
+      uint32_t a16[PX][NV];
+      float4 g[PX][NV];
 #pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      cp_async16(slot0 + (uint32_t)((0 * NV + q) * 256 * 16), p00 + q * G * 4);
-      cp_async16(slot0 + (uint32_t)((1 * NV + q) * 256 * 16), p01 + q * G * 4);
-      cp_async16(slot0 + (uint32_t)((2 * NV + q) * 256 * 16), p10 + q * G * 4);
-      cp_async16(slot0 + (uint32_t)((3 * NV + q) * 256 * 16), p11 + q * G * 4);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    return k;
-  };
-
-  Geo gcur;
-  int pk = prefetch_row(0, gcur);
-  for (int r = 0; r < rows; ++r, yrow += ystep, arow += astep) {
-    const int lp = r * XW + lx;
-    const unsigned bits = s_bits[lp];
-    const float* mrow = s_m + lp * KP;
-    float best[NC];
-    int arg[NC];
-#pragma unroll
-    for (int q = 0; q < NC; ++q) { best[q] = 0.f; arg[q] = 255; }      // ReLU: max(., 0), "no gradient"
-    unsigned rem = bits;
-    Geo gnext;
-    int pk_next = -1;
-    if (pk >= 0) {
-      // ---- first part: operands arrive through the lane-private shared-memory slots
-      rem &= rem - 1;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      float4 acc[NV];
-      {
-        const float m = mrow[pk];
-        const bool xin0 = gcur.x0 >= 0, xin1 = gcur.x0 + 1 < w, yin0 = gcur.y0 >= 0, yin1 = gcur.y0 + 1 < h;
-        const float wy0 = yin0 ? (1.f - gcur.fy) * m : 0.f, wy1 = yin1 ? gcur.fy * m : 0.f;
-        const float wx0 = xin0 ? 1.f - gcur.fx : 0.f, wx1 = xin1 ? gcur.fx : 0.f;
-        const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+      for (int px = 0; px < PX; ++px)
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
-          acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          fma4(acc[q], w00, s_slot[(0 * NV + q) * 256 + tid]);
-          fma4(acc[q], w01, s_slot[(1 * NV + q) * 256 + tid]);
-          fma4(acc[q], w10, s_slot[(2 * NV + q) * 256 + tid]);
-          fma4(acc[q], w11, s_slot[(3 * NV + q) * 256 + tid]);
+          const bool live = j0 + px < w;
+          a16[px][q] = live ? *reinterpret_cast<const uint16_t*>(arow + ((px * C + cb + q * G * 4) >> 1)) : 0xffffu;
+          g[px][q] = (live && a16[px][q] != 0xffffu) ? __ldg(reinterpret_cast<const float4*>(dyrow + px * L.lddy + cb + q * G * 4))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      }
-      // the slots are consumed (the FMAs above depend on every shared-memory read): refill them for the next row
-      if (r + 1 < rows) pk_next = prefetch_row(r + 1, gnext);
 #pragma unroll
-      for (int q = 0; q < NV; ++q) {
-        if (acc[q].x > best[4 * q + 0]) { best[4 * q + 0] = acc[q].x; arg[4 * q + 0] = pk; }
-        if (acc[q].y > best[4 * q + 1]) { best[4 * q + 1] = acc[q].y; arg[4 * q + 1] = pk; }
-        if (acc[q].z > best[4 * q + 2]) { best[4 * q + 2] = acc[q].z; arg[4 * q + 2] = pk; }
-        if (acc[q].w > best[4 * q + 3]) { best[4 * q + 3] = acc[q].w; arg[4 * q + 3] = pk; }
-      }
-    } else if (r + 1 < rows) {
-      pk_next = prefetch_row(r + 1, gnext);
-    }
-    // ---- remaining parts (and every part of further channel chunks): direct loads
-    for (int cb = 0; cb < C; cb += G * NC) {
-      if (cb > 0) {
-        // store the finished chunk, restart the reduction for the next one with ALL parts
-        const int co = cb - G * NC;
+      for (int px = 0; px < PX; ++px)
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
-          *reinterpret_cast<float4*>(yrow + co + q * G * 4) = make_float4(best[4 * q], best[4 * q + 1], best[4 * q + 2], best[4 * q + 3]);
-          *reinterpret_cast<uint32_t*>(arow + co + q * G * 4) = (unsigned)arg[4 * q] | ((unsigned)arg[4 * q + 1] << 8) |
-                                                                ((unsigned)arg[4 * q + 2] << 16) | ((unsigned)arg[4 * q + 3] << 24);
-        }
+          const uint32_t a = a16[px][q];
+          if (a == 0xffffu) continue;
+          float4 gv = g[px][q];
+          if (act == PTK_ACT_LEAKY && yrow != nullptr) {
+            const float4 yv = __ldg(reinterpret_cast<const float4*>(yrow + px * L.ldy + cb + q * G * 4));
+            gv.x *= act_grad_from_output(yv.x, act); gv.y *= act_grad_from_output(yv.y, act);
+            gv.z *= act_grad_from_output(yv.z, act); gv.w *= act_grad_from_output(yv.w, act);
+          }
+          const int k0 = a & 15, k1 = (a >> 4) & 15, k2 = (a >> 8) & 15, k3 = (a >> 12) & 15;
+          unsigned done = 1u << kNoPart;
+          const int ks[4] = {k0, k1, k2, k3};
 #pragma unroll
-        for (int q = 0; q < NC; ++q) { best[q] = 0.f; arg[q] = 255; }
-        rem = bits;
-      }
-      while (rem) {
-        const int k = __ffs(rem) - 1;
-        rem &= rem - 1;
-        Geo g;
-        if (!footprint_of(k, r, g)) continue;
-        const float m = mrow[k];
-        const bool xin0 = g.x0 >= 0, xin1 = g.x0 + 1 < w, yin0 = g.y0 >= 0, yin1 = g.y0 + 1 < h;
-        const float wy0 = yin0 ? (1.f - g.fy) * m : 0.f, wy1 = yin1 ? g.fy * m : 0.f;
-        const float wx0 = xin0 ? 1.f - g.fx : 0.f, wx1 = xin1 ? g.fx : 0.f;
-        const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
-        const int xa = max(g.x0, 0), xc = min(g.x0 + 1, w - 1), ya = max(g.y0, 0), yc = min(g.y0 + 1, h - 1);
-        const float* p00 = xb + (ya * w + xa) * ldx + cb;
-        const float* p01 = xb + (ya * w + xc) * ldx + cb;
-        const float* p10 = xb + (yc * w + xa) * ldx + cb;
-        const float* p11 = xb + (yc * w + xc) * ldx + cb;
-        float4 v00[NV], v01[NV], v10[NV], v11[NV];
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          v00[q] = __ldg(reinterpret_cast<const float4*>(p00 + q * G * 4));
-          v01[q] = __ldg(reinterpret_cast<const float4*>(p01 + q * G * 4));
-          v10[q] = __ldg(reinterpret_cast<const float4*>(p10 + q * G * 4));
-          v11[q] = __ldg(reinterpret_cast<const float4*>(p11 + q * G * 4));
+          for (int c = 0; c < 4; ++c) {
+            const int kk = ks[c];
+            if ((done >> kk) & 1u) continue;
+            done |= 1u << kk;
+            const float4 gm = make_float4(k0 == kk ? gv.x : 0.f, k1 == kk ? gv.y : 0.f, k2 == kk ? gv.z : 0.f, k3 == kk ? gv.w : 0.f);
+            const float4 wv = geo[(px * 16 + kk) * 2];
+            const float4 of = geo[(px * 16 + kk) * 2 + 1];
+            float* p = dxb + cb + q * G * 4;
+            if (wv.x != 0.f) atomicAdd(reinterpret_cast<float4*>(p + __float_as_int(of.x)), make_float4(gm.x * wv.x, gm.y * wv.x, gm.z * wv.x, gm.w * wv.x));
+            if (wv.y != 0.f) atomicAdd(reinterpret_cast<float4*>(p + __float_as_int(of.y)), make_float4(gm.x * wv.y, gm.y * wv.y, gm.z * wv.y, gm.w * wv.y));
+            if (wv.z != 0.f) atomicAdd(reinterpret_cast<float4*>(p + __float_as_int(of.z)), make_float4(gm.x * wv.z, gm.y * wv.z, gm.z * wv.z, gm.w * wv.z));
+            if (wv.w != 0.f) atomicAdd(reinterpret_cast<float4*>(p + __float_as_int(of.w)), make_float4(gm.x * wv.w, gm.y * wv.w, gm.z * wv.w, gm.w * wv.w));
+          }
         }
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          fma4(a, w00, v00[q]); fma4(a, w01, v01[q]); fma4(a, w10, v10[q]); fma4(a, w11, v11[q]);
-          if (a.x > best[4 * q + 0]) { best[4 * q + 0] = a.x; arg[4 * q + 0] = k; }
-          if (a.y > best[4 * q + 1]) { best[4 * q + 1] = a.y; arg[4 * q + 1] = k; }
-          if (a.z > best[4 * q + 2]) { best[4 * q + 2] = a.z; arg[4 * q + 2] = k; }
-          if (a.w > best[4 * q + 3]) { best[4 * q + 3] = a.w; arg[4 * q + 3] = k; }
-        }
-      }
     }
-    {
-      const int co = ((C - 1) / (G * NC)) * (G * NC);
-#pragma unroll
-      for (int q = 0; q < NV; ++q) {
-        *reinterpret_cast<float4*>(yrow + co + q * G * 4) = make_float4(best[4 * q], best[4 * q + 1], best[4 * q + 2], best[4 * q + 3]);
-        *reinterpret_cast<uint32_t*>(arow + co + q * G * 4) = (unsigned)arg[4 * q] | ((unsigned)arg[4 * q + 1] << 8) |
-                                                              ((unsigned)arg[4 * q + 2] << 16) | ((unsigned)arg[4 * q + 3] << 24);
-      }
-    }
-    pk = pk_next;
-    gcur = gnext;
+    __syncwarp();
   }
 }
 
-template <int G>
-__global__ void __launch_bounds__(256)
-warp_backward_coop_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, int act,
-                          const float* __restrict__ warps, const float* __restrict__ mask_lvl,
-                          const uint8_t* __restrict__ argk, float* __restrict__ dx, int C, int h, int w, int K, int H0,
-                          int W0, int align_corners) {
+constexpr int kGeoPerWarp = 8 * 32;      // float4 slots: (pixels per warp <= 8) x 16 parts x 2
+
+// ONE launch for all warped levels of a generator pass: blockIdx.x enumerates the strips of every level (largest level
+// first; all strips carry the same number of bytes), blockIdx.y the image.
+// VAR 0: 16 loads of 128 bits in flight per lane and part (2 CTAs / SM); VAR 1: 8 loads (3 CTAs / SM).
+template <int ACT, int VAR>
+__global__ void __launch_bounds__(256, VAR == 0 ? 2 : 3)
+warp_forward_levels_kernel(const __grid_constant__ WarpLaunchDev P, const float* __restrict__ warps) {
   __shared__ Theta s_theta[kMaxParts];
+  __shared__ float4 s_geo[8 * kGeoPerWarp];
   const int n = blockIdx.y;
-  if (threadIdx.x < K) s_theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * K + threadIdx.x) * 8, h, w, H0, W0);
-  __syncthreads();
-  constexpr int PPW = 32 / G;
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % G, gbase = lane - gl;
-  const int64_t HW = (int64_t)h * w;
-  const float* mb = mask_lvl + (int64_t)n * HW * K;
-  float* dxb = dx + (int64_t)n * HW * C;
-  const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int64_t iters = (HW + PPW - 1) / PPW;
-  for (int64_t it = warp_id; it < iters; it += nwarps) {
-    const int64_t p = it * PPW + lane / G;
-    const bool pvalid = p < HW;
-    const int i = pvalid ? (int)(p / w) : 0, j = pvalid ? (int)(p - (int64_t)i * w) : 0;
-    PartGeom mine;
-    mine.m = 0.f; mine.x0 = 0; mine.y0 = 0; mine.w00 = mine.w01 = mine.w10 = mine.w11 = 0.f;
-    if (pvalid && gl < K) {
-      mine.m = __ldg(mb + p * K + gl);
-      if (mine.m != 0.f) {
-        const Footprint f = footprint(s_theta[gl], i, j, h, w, align_corners);
-        mine.x0 = f.x0; mine.y0 = f.y0; mine.w00 = f.w00; mine.w01 = f.w01; mine.w10 = f.w10; mine.w11 = f.w11;
-      }
-    }
-    for (int c0 = gl * 4; c0 < C; c0 += G * 4) {
-      uchar4 a4 = make_uchar4(255, 255, 255, 255);
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pvalid) {
-        a4 = *reinterpret_cast<const uchar4*>(argk + ((int64_t)n * HW + p) * C + c0);
-        g = __ldg(reinterpret_cast<const float4*>(dy + ((int64_t)n * HW + p) * lddy + c0));
-        if (act != PTK_ACT_NONE) {
-          const float4 yv = __ldg(reinterpret_cast<const float4*>(y + ((int64_t)n * HW + p) * ldy + c0));
-          g.x *= act_grad_from_output(yv.x, act); g.y *= act_grad_from_output(yv.y, act);
-          g.z *= act_grad_from_output(yv.z, act); g.w *= act_grad_from_output(yv.w, act);
-        }
-      }
-      const unsigned char as[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float gs[4] = {g.x, g.y, g.z, g.w};
-      const bool uniform = a4.x == a4.y && a4.y == a4.z && a4.z == a4.w;
-      // every lane takes part in the shuffles; lanes without a winner read part 0 and add nothing
+  int li = 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = as[q] == 255 ? 0 : as[q];
-        const PartGeom f = shfl_geom(mine, gbase + k);
-        if (as[q] == 255) continue;
-        if (uniform) {
-          if (q > 0) continue;
-          float* r0 = dxb + ((int64_t)f.y0 * w + f.x0) * C + c0;
-          float* r1 = r0 + (int64_t)w * C;
-          const float4 gm = make_float4(g.x * f.m, g.y * f.m, g.z * f.m, g.w * f.m);
-          if (f.w00 != 0.f) atomicAdd(reinterpret_cast<float4*>(r0), make_float4(gm.x * f.w00, gm.y * f.w00, gm.z * f.w00, gm.w * f.w00));
-          if (f.w01 != 0.f) atomicAdd(reinterpret_cast<float4*>(r0 + C), make_float4(gm.x * f.w01, gm.y * f.w01, gm.z * f.w01, gm.w * f.w01));
-          if (f.w10 != 0.f) atomicAdd(reinterpret_cast<float4*>(r1), make_float4(gm.x * f.w10, gm.y * f.w10, gm.z * f.w10, gm.w * f.w10));
-          if (f.w11 != 0.f) atomicAdd(reinterpret_cast<float4*>(r1 + C), make_float4(gm.x * f.w11, gm.y * f.w11, gm.z * f.w11, gm.w * f.w11));
-        } else if (gs[q] != 0.f) {
-          const float gm = gs[q] * f.m;
-          float* r0 = dxb + ((int64_t)f.y0 * w + f.x0) * C + c0 + q;
-          float* r1 = r0 + (int64_t)w * C;
-          if (f.w00 != 0.f) atomicAdd(r0, gm * f.w00);
-          if (f.w01 != 0.f) atomicAdd(r0 + C, gm * f.w01);
-          if (f.w10 != 0.f) atomicAdd(r1, gm * f.w10);
-          if (f.w11 != 0.f) atomicAdd(r1 + C, gm * f.w11);
-        }
-      }
+  for (int q = 1; q < 4; ++q) if (q < P.nlevels && (int)blockIdx.x >= P.lv[q].cta_begin) li = q;
+  const WarpLevelDev& L = P.lv[li];
+  if (threadIdx.x < P.K) s_theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * P.K + threadIdx.x) * 8, L.h, L.w, P.H0, P.W0);
+  __syncthreads();
+  const int tile = blockIdx.x - L.cta_begin;
+  float4* geo = s_geo + (threadIdx.x >> 5) * kGeoPerWarp;
+  if (VAR == 0) {
+    switch (L.cfg) {
+      case 0: warp_fwd_strip<16, 1, 4, ACT>(L, s_theta, geo, P.K, n, tile); break;
+      case 1: warp_fwd_strip<16, 2, 2, ACT>(L, s_theta, geo, P.K, n, tile); break;
+      case 2: warp_fwd_strip<32, 2, 2, ACT>(L, s_theta, geo, P.K, n, tile); break;
+      default: warp_fwd_strip<32, 4, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
+    }
+  } else {
+    switch (L.cfg) {
+      case 0: warp_fwd_strip<16, 1, 2, ACT>(L, s_theta, geo, P.K, n, tile); break;
+      case 1: warp_fwd_strip<16, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
+      default: warp_fwd_strip<32, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
     }
   }
+}
+
+__global__ void __launch_bounds__(256, 2)
+warp_backward_levels_kernel(const __grid_constant__ WarpLaunchDev P, const float* __restrict__ warps) {
+  __shared__ Theta s_theta[kMaxParts];
+  __shared__ float4 s_geo[8 * kGeoPerWarp];
+  const int n = blockIdx.y;
+  int li = 0;
+#pragma unroll
+  for (int q = 1; q < 4; ++q) if (q < P.nlevels && (int)blockIdx.x >= P.lv[q].cta_begin) li = q;
+  const WarpLevelDev& L = P.lv[li];
+  if (threadIdx.x < P.K) s_theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * P.K + threadIdx.x) * 8, L.h, L.w, P.H0, P.W0);
+  __syncthreads();
+  const int tile = blockIdx.x - L.cta_begin;
+  float4* geo = s_geo + (threadIdx.x >> 5) * kGeoPerWarp;
+  switch (L.cfg) {
+    case 0: warp_bwd_strip<16, 1, 4>(L, s_theta, geo, P.K, n, tile, P.act); break;
+    case 1: warp_bwd_strip<16, 2, 2>(L, s_theta, geo, P.K, n, tile, P.act); break;
+    case 2: warp_bwd_strip<32, 2, 2>(L, s_theta, geo, P.K, n, tile, P.act); break;
+    default: warp_bwd_strip<32, 4, 1>(L, s_theta, geo, P.K, n, tile, P.act); break;
+  }
+}
+
+// zero-fill of up to four buffers in one launch (the dx targets of the backward scatter)
+struct Fill4 { float4* p[4]; long long n4[4]; };
+__global__ void __launch_bounds__(256) fill4_kernel(const __grid_constant__ Fill4 f) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < f.n4[q]; i += (long long)gridDim.x * blockDim.x) f.p[q][i] = z;
 }
 
 // cv2.resize(INTER_LINEAR) == half-pixel bilinear; computed in double like the reference (masks are f64).
@@ -841,100 +549,165 @@ extern "C" int ptk_mask_pyramid(const double* masks, int N, int K, int H0, int W
   return 0;
 }
 
+// configuration of the fast path for a level, or -1 (=> generic kernels, byte-sized winner record)
+static int warp_fast_cfg(int C, int h, int w, int K, int ld_max, int align_corners) {
+  if (align_corners || K > 15 || h >= 32000 || w >= 32000 || (int64_t)h * w * ld_max >= (1ll << 31)) return -1;
+  if (C == 64) return 0;
+  if (C == 128) return 1;
+  if (C > 0 && C % 512 == 0) return 3;
+  if (C > 0 && C % 256 == 0) return 2;
+  return -1;
+}
+
+static int warp_rows_per_strip() {
+  const char* e = getenv("PTK_WARP_TH");      // (read per call: tests and sweeps switch it inside one process)
+  int th = e ? atoi(e) : 8;
+  if (th < 1 || th > 64) th = 8;
+  return th;
+}
+
+// fills the device-side launch description; returns false if some level cannot take the fast path
+static int warp_variant() {
+  const char* e = getenv("PTK_WARP_VAR");
+  return (e && atoi(e) == 1) ? 1 : 0;
+}
+
+static bool warp_plan(const ptk_warp_level* lv, int nlevels, int K, int H0, int W0, int act, bool backward, WarpLaunchDev& P) {
+  memset(&P, 0, sizeof(P));
+  P.nlevels = nlevels; P.K = K; P.H0 = H0; P.W0 = W0; P.act = act;
+  int ctas = 0;
+  for (int q = 0; q < nlevels; ++q) {
+    const ptk_warp_level& s = lv[q];
+    const int ld_max = backward ? (s.lddy > s.C ? s.lddy : s.C) : (s.ldx > s.ldy ? s.ldx : s.ldy);
+    const int cfg = warp_fast_cfg(s.C, s.h, s.w, K, ld_max, 0);
+    if (cfg < 0) return false;
+    WarpLevelDev& d = P.lv[q];
+    d.x = s.x; d.mask = s.mask; d.y = s.y; d.argk = s.argk; d.dy = s.dy; d.dx = s.dx;
+    d.ldx = s.ldx; d.ldy = s.ldy; d.lddy = s.lddy; d.C = s.C; d.h = s.h; d.w = s.w; d.cfg = cfg;
+    const int var = backward ? 0 : warp_variant();
+    const int nv = cfg == 0 ? 1 : ((cfg == 3 && var == 0) ? 4 : 2), g = cfg <= 1 ? 16 : 32;
+    const int xw = 8 * (32 / g) * ((var == 0 ? 4 : 2) / nv);
+    d.TH = warp_rows_per_strip() < s.h ? warp_rows_per_strip() : s.h;
+    d.strips_x = (s.w + xw - 1) / xw;
+    d.strips_y = (s.h + d.TH - 1) / d.TH;
+    d.cta_begin = ctas;
+    ctas += d.strips_x * d.strips_y;
+  }
+  P.ctas_per_image = ctas;
+  return true;
+}
+
+static int warp_check_level(const ptk_warp_level& s, bool backward) {
+  PTK_REQUIRE(s.C > 0 && s.C % 4 == 0 && s.h > 0 && s.w > 0, "warp: C must be a positive multiple of 4");
+  if (!backward) PTK_REQUIRE(s.x && s.y && s.mask && s.argk && s.ldx % 4 == 0 && s.ldy % 4 == 0, "warp_forward: x / y / mask / argk and 4-float strides required");
+  else PTK_REQUIRE(s.dy && s.dx && s.mask && s.argk && s.lddy % 4 == 0, "warp_backward: dy / dx / mask / argk and 4-float strides required");
+  return 0;
+}
+
+static int warp_forward_generic(const ptk_warp_level& s, const float* warps, int N, int K, int H0, int W0, int align_corners, int act,
+                                cudaStream_t st) {
+  warp_forward_kernel<<<warp_grid((int64_t)s.h * s.w * (s.C / 4), N), 256, 0, st>>>(s.x, s.ldx, warps, s.mask, s.y, s.ldy, s.argk, s.C,
+                                                                                  s.h, s.w, K, H0, W0, align_corners, act);
+  PTK_LAUNCH_CHECK("warp_forward_kernel");
+  return 0;
+}
+
+static int warp_backward_generic(const ptk_warp_level& s, const float* warps, int N, int K, int H0, int W0, int align_corners, int act,
+                                 cudaStream_t st) {
+  warp_backward_kernel<<<warp_grid((int64_t)s.h * s.w * (s.C / 4), N), 256, 0, st>>>(s.dy, s.lddy, s.y, s.ldy, act, warps, s.mask, s.argk,
+                                                                                   s.dx, s.C, s.h, s.w, K, H0, W0, align_corners);
+  PTK_LAUNCH_CHECK("warp_backward_kernel");
+  return 0;
+}
+
+extern "C" int ptk_warp_forward_levels(const ptk_warp_level* lv, int nlevels, const float* warps, int N, int K, int H0, int W0,
+                                       int act, void* stream) {
+  PTK_REQUIRE(nlevels >= 1 && nlevels <= 4 && N > 0 && N <= 65535, "warp_forward_levels: 1..4 levels, N in [1,65535]");
+  PTK_REQUIRE(K > 0 && K <= kMaxParts, "warp_forward: K must be in [1,%d]", kMaxParts);
+  PTK_REQUIRE(act == PTK_ACT_NONE || act == PTK_ACT_RELU || act == PTK_ACT_LEAKY, "warp_forward: bad act");
+  for (int q = 0; q < nlevels; ++q) { int rc = warp_check_level(lv[q], false); if (rc) return rc; }
+  cudaStream_t st = (cudaStream_t)stream;
+  WarpLaunchDev P;
+  if (!warp_plan(lv, nlevels, K, H0, W0, act, false, P)) {
+    for (int q = 0; q < nlevels; ++q) { int rc = warp_forward_generic(lv[q], warps, N, K, H0, W0, 0, act, st); if (rc) return rc; }
+    return 0;
+  }
+  dim3 grid((unsigned)P.ctas_per_image, (unsigned)N);
+  if (warp_variant() == 0) {
+    if (act == PTK_ACT_RELU) warp_forward_levels_kernel<PTK_ACT_RELU, 0><<<grid, 256, 0, st>>>(P, warps);
+    else if (act == PTK_ACT_LEAKY) warp_forward_levels_kernel<PTK_ACT_LEAKY, 0><<<grid, 256, 0, st>>>(P, warps);
+    else warp_forward_levels_kernel<PTK_ACT_NONE, 0><<<grid, 256, 0, st>>>(P, warps);
+  } else {
+    if (act == PTK_ACT_RELU) warp_forward_levels_kernel<PTK_ACT_RELU, 1><<<grid, 256, 0, st>>>(P, warps);
+    else if (act == PTK_ACT_LEAKY) warp_forward_levels_kernel<PTK_ACT_LEAKY, 1><<<grid, 256, 0, st>>>(P, warps);
+    else warp_forward_levels_kernel<PTK_ACT_NONE, 1><<<grid, 256, 0, st>>>(P, warps);
+  }
+  PTK_LAUNCH_CHECK("warp_forward_levels_kernel");
+  return 0;
+}
+
+extern "C" int ptk_warp_backward_levels(const ptk_warp_level* lv, int nlevels, const float* warps, int N, int K, int H0, int W0,
+                                        int act, int zero_dx, void* stream) {
+  PTK_REQUIRE(nlevels >= 1 && nlevels <= 4 && N > 0 && N <= 65535, "warp_backward_levels: 1..4 levels, N in [1,65535]");
+  PTK_REQUIRE(K > 0 && K <= kMaxParts, "warp_backward: K must be in [1,%d]", kMaxParts);
+  for (int q = 0; q < nlevels; ++q) {
+    int rc = warp_check_level(lv[q], true);
+    if (rc) return rc;
+    PTK_REQUIRE(act == PTK_ACT_NONE || (lv[q].y != nullptr && lv[q].ldy % 4 == 0), "warp_backward: y required for act backward");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (zero_dx) {
+    Fill4 f;
+    memset(&f, 0, sizeof(f));
+    long long most = 0;
+    for (int q = 0; q < nlevels; ++q) {
+      PTK_REQUIRE((reinterpret_cast<uintptr_t>(lv[q].dx) & 15) == 0, "warp_backward: dx must be 16-byte aligned");
+      f.p[q] = reinterpret_cast<float4*>(lv[q].dx);
+      f.n4[q] = (long long)N * lv[q].h * lv[q].w * lv[q].C / 4;
+      if (f.n4[q] > most) most = f.n4[q];
+    }
+    long long blocks = (most + 255) / 256;
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    fill4_kernel<<<(unsigned)blocks, 256, 0, st>>>(f);
+    PTK_LAUNCH_CHECK("fill4_kernel");
+  }
+  WarpLaunchDev P;
+  if (!warp_plan(lv, nlevels, K, H0, W0, act, true, P)) {
+    for (int q = 0; q < nlevels; ++q) { int rc = warp_backward_generic(lv[q], warps, N, K, H0, W0, 0, act, st); if (rc) return rc; }
+    return 0;
+  }
+  if (act != PTK_ACT_LEAKY) for (int q = 0; q < nlevels; ++q) P.lv[q].y = nullptr;   // ReLU / none: the winner record says it all
+  dim3 grid((unsigned)P.ctas_per_image, (unsigned)N);
+  warp_backward_levels_kernel<<<grid, 256, 0, st>>>(P, warps);
+  PTK_LAUNCH_CHECK("warp_backward_levels_kernel");
+  return 0;
+}
+
 extern "C" int ptk_warp_forward(const float* x, int ldx, const float* warps, const float* mask_lvl, float* y,
                                 int ldy, uint8_t* argk, int N, int C, int h, int w, int K, int H0, int W0,
                                 int align_corners, int act, void* stream) {
-  PTK_REQUIRE(N > 0 && N <= 65535 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "warp_forward: C/ld must be multiples of 4");
-  PTK_REQUIRE(K > 0 && K <= kMaxParts, "warp_forward: K must be in [1,%d]", kMaxParts);
+  ptk_warp_level s;
+  memset(&s, 0, sizeof(s));
+  s.x = x; s.ldx = ldx; s.mask = mask_lvl; s.y = y; s.ldy = ldy; s.argk = argk; s.C = C; s.h = h; s.w = w;
+  if (!align_corners) return ptk_warp_forward_levels(&s, 1, warps, N, K, H0, W0, act, stream);
+  PTK_REQUIRE(N > 0 && N <= 65535 && K > 0 && K <= kMaxParts, "warp_forward: bad N / K");
   PTK_REQUIRE(act == PTK_ACT_NONE || act == PTK_ACT_RELU || act == PTK_ACT_LEAKY, "warp_forward: bad act");
-  // the cooperative kernel uses 32-bit element offsets inside one image and packs (x0, y0) in 16 bits each
-  const bool coop_ok = !align_corners && h < 32000 && w < 32000 && (int64_t)h * w * (ldx > ldy ? ldx : ldy) < (1ll << 31);
-  if (coop_ok && K == 10 && (C == 64 || C == 128 || C == 256 || C % 512 == 0)) {
-    // NV float4 per lane and chunk (PTK_WARP_NV = 2 | 4, default 4): G = C / (4 NV) lanes per pixel, at most 32
-    static int pd_env = -1;
-    if (pd_env < 0) { const char* e = getenv("PTK_WARP_PD"); pd_env = e ? atoi(e) : 0; if (pd_env < 0 || pd_env > 8) pd_env = 0; }
-    static int nv_env = -1;
-    if (nv_env < 0) { const char* e = getenv("PTK_WARP_NV"); nv_env = (e && atoi(e) == 2) ? 2 : 4; }
-    const int NV = nv_env;
-    const int G = C / (4 * NV) >= 32 ? 32 : C / (4 * NV);
-    const int XW = 8 * (32 / G);
-    const int strips_x = (w + XW - 1) / XW;
-    // rows per strip: 3..8, chosen for the fullest last wave
-    const int occ = NV == 4 ? 2 : 4;
-    int TH = 8;
-    double best_eff = -1.0;
-    for (int th = 8; th >= 3; --th) {
-      if (th > h) continue;
-      const int64_t blocks = (int64_t)strips_x * ((h + th - 1) / th) * N, slots = (int64_t)num_sms() * occ;
-      const double eff = (double)blocks / (double)((blocks + slots - 1) / slots * slots) * (th / (th + 1.0));
-      if (eff > best_eff) { best_eff = eff; TH = th; }
-    }
-    if (TH > h) TH = h;
-    const int strips_y = (h + TH - 1) / TH;
-    const size_t smem = (size_t)TH * XW * (10 + 1) * sizeof(float);
-    dim3 grid((unsigned)(strips_x * strips_y), (unsigned)N);
-#define PTK_WARP_TILE(G_, NV_, A_) warp_forward_tile_kernel<G_, NV_, 10, A_><<<grid, 256, smem, (cudaStream_t)stream>>>(x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, H0, W0, TH, strips_x, pd_env)
-#define PTK_WARP_TILE_G(G_, NV_) do { if (act == PTK_ACT_RELU) PTK_WARP_TILE(G_, NV_, PTK_ACT_RELU); else if (act == PTK_ACT_LEAKY) PTK_WARP_TILE(G_, NV_, PTK_ACT_LEAKY); else PTK_WARP_TILE(G_, NV_, PTK_ACT_NONE); } while (0)
-    static int pf_env = -1;
-    if (pf_env < 0) { const char* e = getenv("PTK_WARP_PF"); pf_env = (e && atoi(e) == 1) ? 1 : 0; }   // measured slower: opt-in
-    if (NV == 4 && act == PTK_ACT_RELU && pf_env) {
-      const size_t smem_pf = smem + (size_t)4 * 4 * 256 * 16;
-#define PTK_WARP_PF(G_)                                                                                                   \
-  do {                                                                                                                    \
-    static bool attr = false;                                                                                             \
-    if (!attr) { cudaFuncSetAttribute(warp_forward_pf_kernel<G_, 4, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
-    warp_forward_pf_kernel<G_, 4, 10><<<grid, 256, smem_pf, (cudaStream_t)stream>>>(x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, H0, W0, TH, strips_x); \
-  } while (0)
-      if (G == 4) PTK_WARP_PF(4);
-      else if (G == 8) PTK_WARP_PF(8);
-      else if (G == 16) PTK_WARP_PF(16);
-      else PTK_WARP_PF(32);
-#undef PTK_WARP_PF
-    } else if (NV == 4) {
-      if (G == 4) PTK_WARP_TILE_G(4, 4);
-      else if (G == 8) PTK_WARP_TILE_G(8, 4);
-      else if (G == 16) PTK_WARP_TILE_G(16, 4);
-      else PTK_WARP_TILE_G(32, 4);
-    } else {
-      if (G == 8) PTK_WARP_TILE_G(8, 2);
-      else if (G == 16) PTK_WARP_TILE_G(16, 2);
-      else PTK_WARP_TILE_G(32, 2);
-    }
-#undef PTK_WARP_TILE_G
-#undef PTK_WARP_TILE
-  } else if (coop_ok && C == 64) {
-    warp_forward_coop_kernel<8><<<warp_grid((int64_t)h * w * 8, N), 256, 0, (cudaStream_t)stream>>>(
-        x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, K, H0, W0, act);
-  } else if (coop_ok && C == 128) {
-    warp_forward_coop_kernel<16><<<warp_grid((int64_t)h * w * 16, N), 256, 0, (cudaStream_t)stream>>>(
-        x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, K, H0, W0, act);
-  } else if (coop_ok && C % 256 == 0) {
-    warp_forward_coop_kernel<32><<<warp_grid((int64_t)h * w * 32, N), 256, 0, (cudaStream_t)stream>>>(
-        x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, K, H0, W0, act);
-  } else {
-    warp_forward_kernel<<<warp_grid((int64_t)h * w * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(
-        x, ldx, warps, mask_lvl, y, ldy, argk, C, h, w, K, H0, W0, align_corners, act);
-  }
-  PTK_LAUNCH_CHECK("warp_forward_kernel");
-  return 0;
+  int rc = warp_check_level(s, false);
+  if (rc) return rc;
+  return warp_forward_generic(s, warps, N, K, H0, W0, 1, act, (cudaStream_t)stream);
 }
 
 extern "C" int ptk_warp_backward(const float* dy, int lddy, const float* y, int ldy, int act, const float* warps,
                                  const float* mask_lvl, const uint8_t* argk, float* dx, int N, int C, int h, int w,
                                  int K, int H0, int W0, int align_corners, void* stream) {
-  PTK_REQUIRE(N > 0 && N <= 65535 && C > 0 && C % 4 == 0 && lddy % 4 == 0, "warp_backward: C/ld must be multiples of 4");
-  PTK_REQUIRE(K > 0 && K <= kMaxParts, "warp_backward: K must be in [1,%d]", kMaxParts);
+  ptk_warp_level s;
+  memset(&s, 0, sizeof(s));
+  s.dy = dy; s.lddy = lddy; s.y = const_cast<float*>(y); s.ldy = ldy; s.mask = mask_lvl; s.argk = const_cast<uint8_t*>(argk);
+  s.dx = dx; s.C = C; s.h = h; s.w = w;
+  if (!align_corners) return ptk_warp_backward_levels(&s, 1, warps, N, K, H0, W0, act, 0, stream);
+  PTK_REQUIRE(N > 0 && N <= 65535 && K > 0 && K <= kMaxParts, "warp_backward: bad N / K");
   PTK_REQUIRE(act == PTK_ACT_NONE || (y != nullptr && ldy % 4 == 0), "warp_backward: y required for act backward");
-  if (C == 64) {
-    warp_backward_coop_kernel<16><<<warp_grid((int64_t)h * w * 16, N), 256, 0, (cudaStream_t)stream>>>(
-        dy, lddy, y, ldy, act, warps, mask_lvl, argk, dx, C, h, w, K, H0, W0, align_corners);
-  } else if (C % 128 == 0) {
-    warp_backward_coop_kernel<32><<<warp_grid((int64_t)h * w * 32, N), 256, 0, (cudaStream_t)stream>>>(
-        dy, lddy, y, ldy, act, warps, mask_lvl, argk, dx, C, h, w, K, H0, W0, align_corners);
-  } else {
-    warp_backward_kernel<<<warp_grid((int64_t)h * w * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(
-        dy, lddy, y, ldy, act, warps, mask_lvl, argk, dx, C, h, w, K, H0, W0, align_corners);
-  }
-  PTK_LAUNCH_CHECK("warp_backward_kernel");
-  return 0;
+  int rc = warp_check_level(s, true);
+  if (rc) return rc;
+  return warp_backward_generic(s, warps, N, K, H0, W0, 1, act, (cudaStream_t)stream);
 }

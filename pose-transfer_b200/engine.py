@@ -150,8 +150,10 @@ class ConvLayer:
         assert ceil4(cout_dx) == self.cin_pad
         K.conv_forward(g, dy, self.w_bwd, self.w_dgrad_k, None, ACT_NONE, dx, None, None)
 
-    def wgrad(self, x, dy, N, H, W, scratch, grad_w):
-        """grad_w (torch layout, fp32 view into the gradient arena) += dW."""
+    def wgrad(self, x, dy, N, H, W, scratch, grad_w, accumulate=False):
+        """grad_w (torch layout, fp32 view into the gradient arena) += dW.  On the trainer's in-place path (grad_w is the
+        zero-filled GEMM-layout arena gradient) the kernel OVERWRITES unless accumulate=True (stacked generator: the same
+        weights receive one contribution per stack)."""
         OH, OW = self.out_hw(H, W)
         g = K.conv_geom(N, H, W, self.cin_pad, x.ld, OH, OW, self.cout if self.cout <= 4 else self.cout_pad, dy.ld, self.k,
                         self.stride, self.pad, self.transposed, self.impl)
@@ -172,12 +174,12 @@ class ConvLayer:
             nparts = self._plans.get(key)
             if nparts is None:
                 nparts = self._plans[key] = K.conv_wgrad_plan(g, scratch.numel())
-            if nparts == 1:
+            if nparts == 1 and not accumulate:
                 got = K.conv_wgrad_parts(g, x, dy, gflat)           # capacity == one gradient => written in place
                 assert got == 1
             else:
                 got = K.conv_wgrad_parts(g, x, dy, scratch)
-                K.sum_parts(scratch, got, n, gflat, n, False)
+                K.sum_parts(scratch, got, n, gflat, n, accumulate)
         elif a_rows == A:
             # split-K partial gradients land back to back in the scratch and are summed (fixed order) by the unpack
             assert grad_w.is_contiguous(), "wgrad: grad_w must be a contiguous torch-layout tensor (or the arena gradient)"
@@ -234,6 +236,13 @@ class GeneratorEngine:
         self.ws = None
         self.layers_built = False
         self.saved = None
+
+    def fork(self):
+        """A second execution context over the SAME layers and weight packs with a private workspace and saved state, so
+        that several forward passes can be alive at once (stacked generator: one context per stack)."""
+        ctx = _ForkedGeneratorEngine.__new__(_ForkedGeneratorEngine)
+        ctx._parent, ctx.ws, ctx.saved = self, None, None
+        return ctx
 
     # ------------------------------------------------------------------ parameter binding
     def _build_layers(self):
@@ -325,16 +334,22 @@ class GeneratorEngine:
     # ------------------------------------------------------------------ forward
     def forward(self, inp, warps, masks, drop=None, repack=True, d_input=None):
         """inp [N,3+2P,H,W] f32, warps [N,K,8] f32, masks [N,K,H,W] f64 -> out_gen [N,3,H,W] (fresh tensor).
+        `inp` may also be a list of (tensor, first channel, channels) pieces whose concatenation along C is the input
+        (the stacked generator feeds [previous output | pose_{i-1} | pose_i] without materialising the cat,
+        models/networks.py:315-323).
         `drop`: list of three [N,512] (or [N,512,1,1]) Dropout2d noise tensors or None (=> drawn here).
         `d_input`: optional Slice of a discriminator input buffer that also receives out_gen (NHWC)."""
-        assert inp.dtype == torch.float32 and inp.dim() == 4   # device is enforced by the kernel wrappers
-        N, Ct, H, W = inp.shape
+        pieces = [(inp, 0, inp.shape[1])] if torch.is_tensor(inp) else list(inp)
+        pieces = [(t.contiguous(), c0, C) for t, c0, C in pieces]
+        inp = pieces[0][0]
+        assert all(t.dtype == torch.float32 and t.dim() == 4 for t, _, _ in pieces)   # device is enforced by the kernel wrappers
+        N, _, H, W = inp.shape
+        Ct = sum(C for _, _, C in pieces)
         assert N >= 2, "the reference's .squeeze() (models/networks.py:169) makes N=1 unsupported"
         L = self.L
         assert Ct == self.in_channels
         self._ensure(inp.device)
         ws = self.ws
-        inp = inp.contiguous()
         any_warp = any(sp[4] for sp in self.specs)
         if any_warp:
             warps = warps.contiguous().float()
@@ -395,8 +410,14 @@ class GeneratorEngine:
         for e_idx, (name, _, c_src0, cin, warped_branch) in enumerate(self.specs):
             with (torch.cuda.stream(side) if (side is not None and e_idx == 1) else contextlib.nullcontext()):
                 convs, norms = self.enc_conv[name], self.enc_norm[name]
+                warp_levels = []
                 xin = ws.get("xin_%s_%s" % (name, tag), (N, H, W, convs[0].cin_pad))
-                K.nchw_to_nhwc(inp, c_src0, cin, Slice(xin, 0, cin))
+                lo = 0
+                for t, t0, tc in pieces:        # channel range [c_src0, c_src0 + cin) of the (virtual) concatenation
+                    a, b = max(lo, c_src0), min(lo + tc, c_src0 + cin)
+                    if a < b:
+                        K.nchw_to_nhwc(t, t0 + a - lo, b - a, Slice(xin, a - c_src0, b - a))
+                    lo += tc
                 sv["xin"][name] = xin
                 for i in range(L):
                     j = L - 1 - i
@@ -430,8 +451,11 @@ class GeneratorEngine:
                         K.gn_apply(z, st, gam, bet, None, N, HW, c, cat_slice, ACT_RELU)
                     if warped:
                         argk = ws.get("argk%d_%s" % (i, tag), (N, hs[i], wsz[i], c), torch.uint8)
-                        K.warp_forward(sv["yraw"][i], warps, mlv[i], cat_slice, argk, N, c, hs[i], wsz[i], Kp, H0, W0, ACT_RELU)
                         sv["argk"][i] = argk
+                        warp_levels.append(dict(x=Slice(sv["yraw"][i]), mask=mlv[i], y=cat_slice, argk=argk, C=c, h=hs[i], w=wsz[i]))
+                        if i == min(4, L) - 1:
+                            # all warped skip levels of this forward in ONE launch (utils/pose_transform.py:16-92 x 4)
+                            K.warp_forward_levels(warp_levels, warps, N, Kp, H0, W0, ACT_RELU)
         if side is not None:
             main.wait_stream(side)
 
@@ -463,12 +487,15 @@ class GeneratorEngine:
         return out
 
     # ------------------------------------------------------------------ backward
-    def backward(self, grads, dout_nchw=None, dout_nhwc=None, on_stage=None):
+    def backward(self, grads, dout_nchw=None, dout_nhwc=None, on_stage=None, accumulate=False, need_image_grad=False):
         """Accumulate parameter gradients into `grads` (dict: parameter -> fp32 tensor of the same shape).
         Uses the weight packs of the preceding forward().
         dout_nchw [N,3,H,W] and/or dout_nhwc (Slice over [N,H,W,*]) are gradients w.r.t. out_gen.
         on_stage(name) is called once every gradient of a sub-network ("decoder", "app", "pose") has been enqueued
-        (the data-parallel trainer starts that bucket's all-reduce there)."""
+        (the data-parallel trainer starts that bucket's all-reduce there).
+        accumulate: add to the arena gradients instead of overwriting them (second and later stacks).
+        need_image_grad: also return d loss / d input[:, 0:3] as NCHW [N,3,H,W] (the previous stack's output feeds these
+        channels, models/networks.py:320-323); None otherwise."""
         sv = self.saved
         assert sv is not None, "forward() must run before backward()"
         ws, L = self.ws, self.L
@@ -498,11 +525,12 @@ class GeneratorEngine:
         else:
             dzf = ws.get("dzf" + tag, (N, H, W, fc.dy_pad))      # channels 3.. stay zero (padding for the dgrad GEMM)
             K.tanh_bwd_combine(dout_nchw, dout_nhwc, sv["out"], dzf, fc.dy_pad, N, 3, H, W)
-            fc.wgrad(Slice(cats[L - 1]), Slice(dz4), N, H, W, scratch, grads[fc.weight])
+            fc.wgrad(Slice(cats[L - 1]), Slice(dz4), N, H, W, scratch, grads[fc.weight], accumulate)
             K.bias_grad(dz4, 4, N * H * W, 3, grads[fc.bias])
             fc.dgrad(Slice(dzf), N, H, W, Slice(dcat))
         dcats = {L - 1: dcat}
 
+        image_grad = None
         side = self._side_stream(dcat.device)
         main = torch.cuda.current_stream() if side is not None else None
         scratch_side = ws.get("wgrad_scratch_side", (max(4 * max_w, 1 << 24),)) if side is not None else scratch
@@ -523,7 +551,7 @@ class GeneratorEngine:
             if side is not None:
                 side.wait_stream(main)
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-                cv.wgrad(Slice(cats[j]), Slice(dy), N, hs[i], wsz[i], scratch_side, grads[cv.weight])
+                cv.wgrad(Slice(cats[j]), Slice(dy), N, hs[i], wsz[i], scratch_side, grads[cv.weight], accumulate)
             dc = ws.get("dcat%d_%s" % (j, tag), tuple(cats[j].shape))
             cv.dgrad(Slice(dy), N, hs[i], wsz[i], Slice(dc))
             dcats[j] = dc
@@ -541,6 +569,19 @@ class GeneratorEngine:
             with (torch.cuda.stream(side) if on_side else contextlib.nullcontext()):
                 convs, norms = self.enc_conv[name], self.enc_norm[name]
                 dact_next = None
+                dwarps = {}
+                if warped_branch:
+                    # gradient of all warped skip levels in ONE launch (zero fill of the scatter targets included)
+                    lv = []
+                    for i in range(min(4, L)):
+                        j = L - 1 - i
+                        _, dprev, _ = self._cat_layout(j)
+                        c = self.enc[i]
+                        off = dprev + e_idx * c
+                        dwarps[i] = ws.get("dwarp%d_%s" % (i, tag), (N, hs[i], wsz[i], c))
+                        lv.append(dict(dy=Slice(dcats[j], off, c), y=Slice(cats[j], off, c), mask=sv["mlv"][i], argk=sv["argk"][i],
+                                       dx=dwarps[i], C=c, h=hs[i], w=wsz[i]))
+                    K.warp_backward_levels(lv, sv["warps"], N, sv["K"], H0, W0, ACT_RELU, True)
                 for i in range(L - 1, -1, -1):
                     j = L - 1 - i
                     _, dprev, _ = self._cat_layout(j)
@@ -549,10 +590,7 @@ class GeneratorEngine:
                     off = dprev + e_idx * c
                     warped = warped_branch and i < 4
                     if warped:
-                        dwarp = ws.get("dwarp%d_%s" % (i, tag), (N, hs[i], wsz[i], c))
-                        K.fill(dwarp, 0.0)
-                        K.warp_backward(Slice(dcats[j], off, c), Slice(cats[j], off, c), ACT_RELU, sv["warps"], sv["mlv"][i],
-                                        sv["argk"][i], dwarp, N, c, hs[i], wsz[i], sv["K"], H0, W0)
+                        dwarp = dwarps[i]
                         skip_g, skip_a, skip_act = Slice(dwarp), None, ACT_NONE
                     else:
                         skip_g, skip_a, skip_act = Slice(dcats[j], off, c), Slice(cats[j], off, c), ACT_RELU
@@ -572,10 +610,16 @@ class GeneratorEngine:
                         K.gn_bwd_apply(dy, z, st, sm, norm.weight.detach(), N, HW, c, grads[norm.weight], grads[norm.bias])
                     cv = convs[i]
                     if i == 0:
-                        cv.wgrad(Slice(sv["xin"][name]), Slice(dy), N, H, W, scratch_e, grads[cv.weight])
+                        cv.wgrad(Slice(sv["xin"][name]), Slice(dy), N, H, W, scratch_e, grads[cv.weight], accumulate)
                         K.bias_grad(dy, c, N * HW, c, grads[cv.bias])
+                        if need_image_grad and e_idx == 0:
+                            # gradient w.r.t. the stem's input; channels 0..2 are the image (pose channels are data)
+                            dxin = ws.get("dxin_%s_%s" % (name, tag), (N, H, W, cv.cin_pad))
+                            cv.dgrad(Slice(dy), N, H, W, Slice(dxin), dx_channels=cv.cin_pad)
+                            image_grad = torch.empty(N, 3, H, W, device=dxin.device)
+                            K.nhwc_to_nchw(Slice(dxin, 0, 3), image_grad)
                     else:
-                        cv.wgrad(Slice(sv["act"][(name, i - 1)]), Slice(dy), N, hs[i - 1], wsz[i - 1], scratch_e, grads[cv.weight])
+                        cv.wgrad(Slice(sv["act"][(name, i - 1)]), Slice(dy), N, hs[i - 1], wsz[i - 1], scratch_e, grads[cv.weight], accumulate)
                         dact = ws.get("dact_%s%d_%s" % (name, i - 1, tag), (N, hs[i - 1], wsz[i - 1], self.enc[i - 1]))
                         cv.dgrad(Slice(dy), N, hs[i - 1], wsz[i - 1], Slice(dact))
                         dact_next = dact
@@ -585,6 +629,16 @@ class GeneratorEngine:
             main.wait_stream(side)
         if on_stage is not None and len(self.specs) > 1:
             on_stage(self.specs[1][0])
+        return image_grad
+
+
+class _ForkedGeneratorEngine(GeneratorEngine):
+    """GeneratorEngine.fork(): own `ws` / `saved`, everything else (layers, weight packs, streams) read from the parent."""
+
+    def __getattr__(self, name):        # only reached when the attribute is not set on the fork itself
+        if name == "_parent":
+            raise AttributeError(name)
+        return getattr(self._parent, name)
 
 
 class DiscriminatorEngine:

@@ -291,6 +291,40 @@ def warp_backward(dy, y, act, warps, mask_lvl, argk, dx, N, C, h, w, K, H0, W0, 
           "ptk_warp_backward")
 
 
+def _warp_levels(levels):
+    arr = (_lib.WarpLevel * len(levels))()
+    for a, lv in zip(arr, levels):
+        for k in ("x", "y", "dy"):
+            s = lv.get(k)
+            if s is not None:
+                s = _as_slice(s)
+                setattr(a, k, s.ptr)
+                setattr(a, {"x": "ldx", "y": "ldy", "dy": "lddy"}[k], s.ld)
+        a.mask, a.argk = _p(lv["mask"]), _p(lv["argk"])
+        a.dx = _p(lv.get("dx"))
+        a.C, a.h, a.w = lv["C"], lv["h"], lv["w"]
+    return arr
+
+
+def _warp_levels_bytes(levels, warps, N, K, *a, **kw):
+    return sum(N * lv["h"] * lv["w"] * (8 * lv["C"] + 4 * K) for lv in levels)
+
+
+@_timed("warp_forward", _warp_levels_bytes)
+def warp_forward_levels(levels, warps, N, K, H0, W0, act=ACT_NONE):
+    """All warped levels of a generator forward in one launch.  levels: list of dict(x=Slice, mask=t, y=Slice, argk=t, C, h, w)."""
+    arr = _warp_levels(levels)
+    check(_lib.lib().ptk_warp_forward_levels(arr, len(levels), _p(warps), N, K, H0, W0, act, _stream()), "ptk_warp_forward_levels")
+
+
+@_timed("warp_backward", _warp_levels_bytes)
+def warp_backward_levels(levels, warps, N, K, H0, W0, act=ACT_NONE, zero_dx=True):
+    """levels: list of dict(dy=Slice, mask=t, argk=t, dx=t (dense [N,h,w,C]), y=Slice (LeakyReLU only), C, h, w)."""
+    arr = _warp_levels(levels)
+    check(_lib.lib().ptk_warp_backward_levels(arr, len(levels), _p(warps), N, K, H0, W0, act, int(zero_dx), _stream()),
+          "ptk_warp_backward_levels")
+
+
 def adv_loss(logits, rows, J, n_true, scale, loss, dlogits=None, ldd=1):
     check(_lib.lib().ptk_adv_loss(_p(logits), rows, J, n_true, float(scale), _p(loss), _p(dlogits), ldd, _stream()),
           "ptk_adv_loss")

@@ -146,22 +146,34 @@ class decoder(nn.Module):
 
 
 class _GeneratorFn(torch.autograd.Function):
-    """Makes the fused schedule differentiable for external callers (main.py / test.py style use)."""
+    """Makes the fused schedule differentiable for external callers (main.py / test.py style use).  `engine` is the
+    execution context that holds this call's activations (the module's own engine, or one fork per stack of the stacked
+    generator).  Gradients: every parameter, and the IMAGE channels 0..2 of `inp` (what a previous stack's output feeds,
+    models/networks.py:320-323); the pose heat-map channels are data and get zeros."""
 
     @staticmethod
-    def forward(ctx, gen, inp, warps, masks, *params):
-        ctx.gen = gen
+    def forward(ctx, gen, engine, inp, warps, masks, *params):
+        ctx.engine = engine
         ctx.params = params
-        out = gen.engine.forward(inp, warps, masks, drop=gen._next_drop())
+        out = engine.forward(inp, warps, masks, drop=gen._next_drop())
+        ctx.token = engine.saved
+        ctx.inp_shape = tuple(inp.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        gen = ctx.gen
+        engine = ctx.engine
+        if engine.saved is not ctx.token:
+            raise RuntimeError("the generator was run again before this backward: its saved activations are gone")
         # fresh contiguous tensors (zeros_like would inherit the GEMM-layout strides of arena-backed parameters)
         grads = {p: torch.zeros(p.shape, device=p.device) for p in ctx.params}
-        gen.engine.backward(grads, dout_nchw=dout.contiguous())
-        return (None, None, None, None) + tuple(grads[p] if p.requires_grad else None for p in ctx.params)
+        need_inp = ctx.needs_input_grad[2]
+        ig = engine.backward(grads, dout_nchw=dout.contiguous(), need_image_grad=need_inp)
+        dinp = None
+        if need_inp:
+            dinp = torch.zeros(ctx.inp_shape, device=dout.device)
+            dinp[:, :3] = ig
+        return (None, None, dinp, None, None) + tuple(grads[p] if p.requires_grad else None for p in ctx.params)
 
 
 class Deformable_Generator(nn.Module):
@@ -199,8 +211,8 @@ class Deformable_Generator(nn.Module):
     def forward(self, input, warps, masks):
         _require_cuda(input, "Deformable_Generator")
         params = tuple(self.parameters())
-        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return _GeneratorFn.apply(self, input, warps, masks, *params)
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params)):
+            return _GeneratorFn.apply(self, self.engine, input, warps, masks, *params)
         return self.engine.forward(input, warps, masks, drop=self._next_drop())
 
 
@@ -234,13 +246,16 @@ class Generator(nn.Module):
     def forward(self, input):
         _require_cuda(input, "Generator")
         params = tuple(self.parameters())
-        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return _GeneratorFn.apply(self, input, None, None, *params)
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params)):
+            return _GeneratorFn.apply(self, self.engine, input, None, None, *params)
         return self.engine.forward(input, None, None, drop=self._next_drop())
 
 
 class Stacked_Generator(nn.Module):
-    """models/networks.py:290-327 -- pure composition of Deformable_Generator."""
+    """models/networks.py:290-327: the same Deformable_Generator applied `num_stacks` times, stack i reading
+    [previous output | pose_{i-1} | pose_i] with its own warps / masks.  One engine context per stack (shared layers and
+    weight packs, private activations) keeps every stack's forward alive for the backward pass, which walks the stacks in
+    reverse and hands the gradient of the image channels from stack i to stack i-1."""
 
     def __init__(self, input_nc, num_stacks, image_size, pose_dim, nfilters_enc, nfilters_dec, warp_skip=False,
                  use_input_pose=True):
@@ -254,17 +269,62 @@ class Stacked_Generator(nn.Module):
         self.image_size = image_size
         self.generator = Deformable_Generator(input_nc, pose_dim, image_size, nfilters_enc, nfilters_dec, warp_skip,
                                               use_input_pose)
+        self._contexts = []
+
+    @property
+    def engine(self):
+        return self.generator.engine
+
+    def contexts(self, n):
+        """Engine contexts of the first n stacks (stack 0 = the generator's own engine)."""
+        while len(self._contexts) < n:
+            self._contexts.append(self.generator.engine if not self._contexts else self.generator.engine.fork())
+        return self._contexts[:n]
+
+    def stack_input(self, i, input, target_pose, prev_out):
+        """Pieces of stack i's input (models/networks.py:312-323), never concatenated in memory."""
+        P = self.pose_dim
+        if i == 0:
+            return [(input, 0, 3 + P), (target_pose, 0, P)]
+        return [(prev_out, 0, 3), (target_pose, (i - 1) * P, P), (target_pose, i * P, P)]
+
+    def run_stacks(self, input, target_pose, target_warps, target_masks, drops=None, d_input=None, repack=None):
+        """Trainer path (no autograd graph): returns the list of stack outputs; d_input receives the LAST output."""
+        S = self.num_stacks
+        ctxs = self.contexts(S)
+        outs = []
+        for i, eng in enumerate(ctxs):
+            pieces = self.stack_input(i, input, target_pose, outs[-1] if outs else None)
+            outs.append(eng.forward(pieces, target_warps[:, i].contiguous(), target_masks[:, i].contiguous(),
+                                    drop=drops[i] if drops is not None else None, repack=repack if i == 0 else False,
+                                    d_input=d_input if i == S - 1 else None))
+        return outs
+
+    def backward_stacks(self, grads, dout_nchw, dout_nhwc, on_stage=None):
+        """Gradients of a loss on the last stack's output w.r.t. the shared parameters (summed over the stacks)."""
+        S = self.num_stacks
+        ctxs = self.contexts(S)
+        g, g2 = dout_nchw, dout_nhwc
+        for i in range(S - 1, -1, -1):
+            g = ctxs[i].backward(grads, dout_nchw=g, dout_nhwc=g2, on_stage=on_stage if i == 0 else None,
+                                 accumulate=i < S - 1, need_image_grad=i > 0)
+            g2 = None
 
     def forward(self, input, target_pose, target_warps, target_masks):
-        init_input, init_pose, _ = pose_utils.get_imgpose(input, self.use_input_pose, self.pose_dim)
+        _require_cuda(input, "Stacked_Generator")
+        gen = self.generator
+        params = tuple(gen.parameters())
+        track = torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params))
         outputs = []
-        P = self.pose_dim
-        for i in range(self.num_stacks):
-            if i == 0:
-                inp = torch.cat([init_input, init_pose, target_pose[:, i * P:(i + 1) * P]], dim=1)
+        for i, eng in enumerate(self.contexts(self.num_stacks)):
+            w, m = target_warps[:, i].contiguous(), target_masks[:, i].contiguous()
+            if track:
+                # autograd needs ONE input tensor per stack: materialise the concatenation (module-surface use only)
+                inp = torch.cat([t[:, c0:c0 + C] for t, c0, C in self.stack_input(i, input, target_pose, outputs[-1] if outputs else None)], 1)
+                out = _GeneratorFn.apply(gen, eng, inp, w, m, *params)
             else:
-                inp = torch.cat([out, target_pose[:, (i - 1) * P:i * P], target_pose[:, i * P:(i + 1) * P]], dim=1)
-            out = self.generator(inp, target_warps[:, i].contiguous(), target_masks[:, i].contiguous())
+                out = eng.forward(self.stack_input(i, input, target_pose, outputs[-1] if outputs else None), w, m,
+                                  drop=gen._next_drop(), repack=True if i == 0 else False)
             outputs.append(out)
         return outputs
 

@@ -35,8 +35,11 @@ class ParamArena:
         self.bind()
 
     def bump(self):
-        """Weights changed: the engines' GEMM-layout copies are stale."""
-        self.module._ptk_weights_version = getattr(self.module, "_ptk_weights_version", 0) + 1
+        """Weights changed: the engines' GEMM-layout copies are stale (every sub-module that owns an engine is told:
+        a Stacked_Generator wraps the Deformable_Generator whose engine holds the packs)."""
+        for m in self.module.modules():
+            if hasattr(m, "_ptk_weights_version"):
+                m._ptk_weights_version += 1
 
     @staticmethod
     def _gemm_master(p):
@@ -184,9 +187,8 @@ class DeformablePose_GAN(nn.Module):
         self.pose_dim = opt.pose_dim
         self.image_size = tuple(opt.image_size)
         if opt.gen_type == 'stacked':
-            # the stacked generator is a composition of the same Deformable_Generator; its forward (what
-            # test.py runs: model.gen(input, interpol_pose, interpol_warps, interpol_masks)) is on the B200 path, its
-            # training branches (pose_gan.py:72-77,120-125) are not (gen_update / dis_update raise).
+            # the stacked generator is a composition of the same Deformable_Generator (one engine context per
+            # stack); forward (test.py) and both training branches (pose_gan.py:72-77,120-125) run on the B200 path.
             self.gen = Stacked_Generator(input_nc, opt.num_stacks, opt.image_size, opt.pose_dim, nfilters_encoder,
                                          nfilters_decoder, opt.warp_skip, use_input_pose=opt.use_input_pose)
             pretrained_gen_path = '../exp/' + 'full_' + opt.dataset + '/models/gen_090.pkl'   # pose_gan.py:31-32
@@ -282,11 +284,26 @@ class DeformablePose_GAN(nn.Module):
 
     # ------------------------------------------------------------------ updates
     def gen_update(self, input, target, other_inputs, opt, drop=None):
-        if opt['gen_type'] != 'baseline':
-            raise NotImplementedError("gen_type='stacked' is outside the B200 hot path")
+        """pose_gan.py:69-115.  gen_type='stacked' (pose_gan.py:72-77): other_inputs carries interpol_pose [N,S*P,H,W],
+        interpol_warps [N,S,10,8], interpol_masks [N,S,10,H,W]; `drop` is then a list of S noise triples (test hook)."""
+        if opt['gen_type'] == 'stacked':
+            stacked = (self._prep(other_inputs['interpol_pose']), other_inputs['interpol_warps'], other_inputs['interpol_masks'])
+            return self._gen_step(input, target, None, None, opt, drop, stacked=stacked)
         return self._gen_step(input, target, other_inputs['warps'], other_inputs['masks'], opt, drop)
 
-    def _gen_step(self, input, target, warps, masks, opt, drop=None):
+    def _forward_gen(self, input, warps, masks, drop, d_input, stacked):
+        """Generator forward of an update: (out_gen, outputs_gen list)."""
+        if stacked is None:
+            out = self.gen.engine.forward(input, warps, masks, drop=drop if drop is not None else self.gen._next_drop(),
+                                          repack=None, d_input=d_input)
+            return out, []
+        pose, swarps, smasks = stacked
+        swarps = swarps.cuda().float() if not swarps.is_cuda else swarps.float()
+        smasks = smasks.cuda() if not smasks.is_cuda else smasks
+        outs = self.gen.run_stacks(input, pose, swarps, smasks, drops=drop, d_input=d_input, repack=None)
+        return outs[-1], outs
+
+    def _gen_step(self, input, target, warps, masks, opt, drop=None, stacked=None):
         P = opt['pose_dim']
         input, target = self._prep(input), self._prep(target)
         N, _, H, W = input.shape
@@ -298,8 +315,7 @@ class DeformablePose_GAN(nn.Module):
 
         din = self.disc.engine.input_buffer(N, H, W, dev)
         self._fill_disc_input(din, input, None, P)
-        out_gen = self.gen.engine.forward(input, warps, masks, drop=drop if drop is not None else self.gen._next_drop(),
-                                          repack=None, d_input=Slice(din, 3 + P, 3))
+        out_gen, outputs_gen = self._forward_gen(input, warps, masks, drop, Slice(din, 3 + P, 3), stacked)
         # The content loss (VGG conv1_1 + 5x5 NN loss, FFMA-bound) and the adversarial branch (D forward + input
         # gradient, tensor-core / memory bound) only share out_gen: they run concurrently on two streams.
         dpred = self.gen.engine.ws.get("dpred_%d_%d_%d" % (N, H, W), (N, 3, H, W))
@@ -347,8 +363,11 @@ class DeformablePose_GAN(nn.Module):
                     torch.distributed.all_reduce(self.gen_arena.grad[lo:hi])
                 self.gen_opt.step_range(lo, hi)
 
-        self.gen.engine.backward(self.gen_arena.grads, dout_nchw=dpred, dout_nhwc=Slice(din_grad, 3 + P, 3),
-                                 on_stage=stage_done)
+        if stacked is None:
+            self.gen.engine.backward(self.gen_arena.grads, dout_nchw=dpred, dout_nhwc=Slice(din_grad, 3 + P, 3),
+                                     on_stage=stage_done)
+        else:
+            self.gen.backward_stacks(self.gen_arena.grads, dpred, Slice(din_grad, 3 + P, 3), on_stage=stage_done)
         assert sorted(covered)[0][0] == 0 and sorted(covered)[-1][1] == self.gen_arena.total and \
             all(a[1] == b[0] for a, b in zip(sorted(covered), sorted(covered)[1:])), "optimiser buckets do not tile the arena"
         if ost is not None:
@@ -357,14 +376,16 @@ class DeformablePose_GAN(nn.Module):
         host = loss.tolist()                                             # single device->host sync
         self.gen_ad_loss, self.gen_ll_loss = host[0], host[2]
         self.gen_total_loss = float(torch.tensor(host[0]) + torch.tensor(host[2]))
-        return out_gen, [], [self.gen_total_loss, self.gen_ll_loss, self.gen_ad_loss]
+        return out_gen, outputs_gen, [self.gen_total_loss, self.gen_ll_loss, self.gen_ad_loss]
 
     def dis_update(self, input, target, other_inputs, real_inp, real_target, opt, drop=None):
-        if opt['gen_type'] != 'baseline':
-            raise NotImplementedError("gen_type='stacked' is outside the B200 hot path")
+        """pose_gan.py:117-171 (gen_type='stacked': :120-125, the discriminator sees the LAST stack's output)."""
+        if opt['gen_type'] == 'stacked':
+            stacked = (self._prep(other_inputs['interpol_pose']), other_inputs['interpol_warps'], other_inputs['interpol_masks'])
+            return self._dis_step(input, target, None, None, real_inp, real_target, opt, drop, stacked=stacked)
         return self._dis_step(input, target, other_inputs['warps'], other_inputs['masks'], real_inp, real_target, opt, drop)
 
-    def _dis_step(self, input, target, warps, masks, real_inp, real_target, opt, drop=None):
+    def _dis_step(self, input, target, warps, masks, real_inp, real_target, opt, drop=None, stacked=None):
         P = opt['pose_dim']
         input, real_inp, real_target = self._prep(input), self._prep(real_inp), self._prep(real_target)
         N, _, H, W = input.shape
@@ -379,8 +400,7 @@ class DeformablePose_GAN(nn.Module):
         nr = real_inp.shape[0]
         self._fill_disc_input(din[:nr], real_inp, real_target, P)        # real rows first (pose_gan.py:136)
         self._fill_disc_input(din[nr:], input, None, P)
-        self.gen.engine.forward(input, warps, masks, drop=drop if drop is not None else self.gen._next_drop(),
-                                repack=None, d_input=Slice(din[nr:], 3 + P, 3))
+        self._forward_gen(input, warps, masks, drop, Slice(din[nr:], 3 + P, 3), stacked)
         logits = self.disc.engine.forward(din, repack=None)
         J = logits.shape[1]
         dlog4 = self.disc.engine.dlogits_buffer(M, J)

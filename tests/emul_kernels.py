@@ -281,6 +281,16 @@ def install(K):
         gx, = torch.autograd.grad(v, xr, g)
         dx.reshape(N, h, w, C).add_(nhwc(gx))
 
+    def warp_forward_levels(levels, warps, N, Kp, H0, W0, act=0):
+        for lv in levels:
+            warp_forward(lv["x"], warps, lv["mask"], lv["y"], lv["argk"], N, lv["C"], lv["h"], lv["w"], Kp, H0, W0, act)
+
+    def warp_backward_levels(levels, warps, N, Kp, H0, W0, act=0, zero_dx=True):
+        for lv in levels:
+            if zero_dx:
+                lv["dx"].zero_()
+            warp_backward(lv["dy"], lv.get("y"), act, warps, lv["mask"], lv["argk"], lv["dx"], N, lv["C"], lv["h"], lv["w"], Kp, H0, W0)
+
     def adv_loss(logits, rows, J, n_true, scale, loss, dlogits=None, ldd=1):
         z = logits.reshape(rows, J).clone().requires_grad_(True)
         p = torch.sigmoid(z)
@@ -336,7 +346,8 @@ def install(K):
                  conv_forward=conv_forward, conv_wgrad=conv_wgrad, conv_wgrad_parts=conv_wgrad_parts,
                  bias_grad=bias_grad, gn_stats=gn_stats, gn_apply=gn_apply, gn_bwd_reduce=gn_bwd_reduce,
                  gn_bwd_apply=gn_bwd_apply, mask_pyramid=mask_pyramid, warp_forward=warp_forward,
-                 warp_backward=warp_backward, adv_loss=adv_loss, l1_loss=l1_loss, nnloss_forward=nnloss_forward,
+                 warp_backward=warp_backward, warp_forward_levels=warp_forward_levels, warp_backward_levels=warp_backward_levels,
+                 adv_loss=adv_loss, l1_loss=l1_loss, nnloss_forward=nnloss_forward,
                  nnloss_backward=nnloss_backward, tanh_bwd_combine=tanh_bwd_combine, adam_step=adam_step)
 
     @contextlib.contextmanager

@@ -225,6 +225,64 @@ def test_warp_full_size_vs_oracle_and_relu_epilogue(K):
         assert rel_l2(dx, xr.grad) <= 2e-3   # a handful of arg-max flips at near-ties + atomics order
 
 
+@pytest.mark.parametrize("act", ["none", "relu"])
+@pytest.mark.parametrize("C,h,w,H0,W0", [(64, 37, 53, 74, 106), (128, 48, 24, 96, 48), (256, 19, 33, 152, 264), (512, 16, 16, 128, 128),
+                                         (64, 64, 64, 64, 64), (1024, 9, 7, 72, 56)])
+def test_warp_fast_path_vs_oracle(K, C, h, w, H0, W0, act):
+    """The 16/32-lanes-per-pixel kernels (C = 64 / 128 / 256 / 512 / 1024), ragged extents (strip edges in x and y),
+    non-square images (the H != W translation quirk), with and without the folded ReLU, forward and backward vs the oracle."""
+    from oracle import restate, synth
+    N = 2
+    b = synth.make_batch(N, H0, W0, 2, seed=C + h)
+    x = torch.randn(N, C, h, w, generator=gen(C + w))
+    gy = torch.randn(N, C, h, w, generator=gen(C + w + 1))
+    xr = x.clone().requires_grad_(True)
+    ref = restate.affine_warp(xr, b["warps"], b["masks"], (H0, W0))
+    if act == "relu":
+        ref = F.relu(ref)
+    ref.backward(gy)
+    y, dx, _ = _run_warp(K, x, b["warps"], b["masks"], H0, W0, gy, act=K.ACT_RELU if act == "relu" else K.ACT_NONE)
+    assert max_abs(y, ref) <= 3e-4
+    assert rel_l2(dx, xr.grad) <= 2e-3
+
+
+def test_warp_levels_api_matches_single_level_calls(K, monkeypatch):
+    """ptk_warp_forward_levels / _backward_levels (one launch for the 4 skip levels, writes into channel slices of wider
+    buffers) == four single-level calls, bit for bit on the forward; both load-depth variants of the kernel."""
+    from oracle import synth
+    N, H0 = 2, 64
+    b = synth.make_batch(N, H0, H0, 2, seed=3)
+    wr = b["warps"].float().cuda().contiguous()
+    shapes = [(64, 64), (128, 32), (256, 16), (512, 8)]
+    xs, mls, gys = [], [], []
+    for C, h in shapes:
+        xs.append(torch.randn(N, h, h, C, generator=gen(C)).cuda())
+        gys.append(torch.randn(N, h, h, C + 32, generator=gen(C + 7)).cuda())
+        ml = torch.empty(N, h, h, 10, device="cuda")
+        K.mask_pyramid(b["masks"].cuda(), ml)
+        mls.append(ml)
+    single = []
+    for (C, h), x, ml, gy in zip(shapes, xs, mls, gys):
+        y = torch.zeros(N, h, h, C + 32, device="cuda")
+        argk = torch.zeros(N, h, h, C, dtype=torch.uint8, device="cuda")
+        K.warp_forward(x, wr, ml, K.Slice(y, 32, C), argk, N, C, h, h, 10, H0, H0, K.ACT_RELU)
+        dx = torch.zeros(N, h, h, C, device="cuda")
+        K.warp_backward(K.Slice(gy, 32, C), K.Slice(y, 32, C), K.ACT_RELU, wr, ml, argk, dx, N, C, h, h, 10, H0, H0)
+        single.append((y, dx))
+    for var in ("0", "1"):
+        monkeypatch.setenv("PTK_WARP_VAR", var)
+        lv = []
+        for (C, h), x, ml, gy in zip(shapes, xs, mls, gys):
+            lv.append(dict(x=K.Slice(x), mask=ml, y=K.Slice(torch.zeros(N, h, h, C + 32, device="cuda"), 32, C),
+                           argk=torch.zeros(N, h, h, C, dtype=torch.uint8, device="cuda"), dy=K.Slice(gy, 32, C),
+                           dx=torch.full((N, h, h, C), 7.0, device="cuda"), C=C, h=h, w=h))
+        K.warp_forward_levels(lv, wr, N, 10, H0, H0, K.ACT_RELU)
+        K.warp_backward_levels(lv, wr, N, 10, H0, H0, K.ACT_RELU, True)
+        for d, (y, dx) in zip(lv, single):
+            assert torch.equal(d["y"].t, y)
+            assert rel_l2(d["dx"], dx) <= 1e-5      # fp32 atomics: order-dependent in the last bits
+
+
 # ----------------------------------------------------------------------------- losses
 def test_adv_loss(K):
     from oracle import restate

@@ -343,3 +343,24 @@ def test_src_baseline_step_matches_reference_golden(impl):
     slack = 5e-4      # Adam turns the sign of a ~0 gradient element into +-lr
     assert_summary_close(np.stack([summarize(gpar[k]) for k in gnames]), g["g_param"], what="g_param", abs_slack=slack, **T["param"])
     assert_summary_close(np.stack([summarize(dpar[k]) for k in dnames]), g["d_param"], what="d_param", abs_slack=slack, **T["param"])
+
+
+def test_stacked_training_step_matches_reference_golden(impl):
+    """SURVEY 8f-3 on the CUDA kernels: gen_type='stacked' dis_update + gen_update (2 stacks, shared weights) against the
+    golden record of the unmodified reference (tests/golden/step_stacked_64x64_p18_s2.npz)."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_logic_cpu import _stacked_step, stacked_opt
+    from oracle import synth
+    from oracle.make_golden import STACKED_CASE
+    from pose_transfer_b200.models import pose_gan
+    tag, H, W, P, N, S, seed = STACKED_CASE
+    g = golden("step_" + tag)
+    opt = stacked_opt()
+    model = pose_gan.DeformablePose_GAN(opt).cuda()
+    model.gen.generator.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed))
+    model.disc.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1))
+    T = TOL[impl]
+    _stacked_step(model, opt, g, T["loss"], T["out"], T["grad"] if impl == "auto" else dict(tol_norm=1e-2, tol_samp=5e-2, tol_scalar=0.12),
+                  dict(T["param"], abs_slack=5e-4))
