@@ -55,6 +55,15 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---- programmatic dependent launch
+// pdl_trigger(): the next kernel of the stream (if it was launched with the programmatic-serialization attribute) may
+// start occupying SM slots as soon as every CTA of this grid has passed this point or exited -- i.e. while the last wave
+// of this grid is still running.  pdl_wait(): block until the preceding grid has completed and its writes are visible;
+// everything before it (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail.  Both are
+// no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 static inline int num_sms() {
   static int sms = 0;
   if (!sms) {

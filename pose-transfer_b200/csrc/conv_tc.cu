@@ -55,6 +55,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   const uint32_t tmem_slot = bar_tmem + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  pdl_trigger();
   const TcPhase ph = g.ph[blockIdx.z / g.splits];
   const int split = blockIdx.z % g.splits;
   int t = blockIdx.x;
@@ -81,6 +82,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();      // nothing above touched global memory: the setup overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -180,6 +182,25 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
 }
 
 // ----------------------------------------------------------------------------- host side
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PTK_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v != 0;
+}
+
+// launch with programmatic stream serialization (see pdl_wait / pdl_trigger in tc_ptx.cuh)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -360,7 +381,7 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 16 + 1024;                                 \
     static bool attr = false;                                                                                              \
     if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
-    conv_tc_kernel<BN_, ST_, MH_><<<grid, 192, smem, st>>>(maps, g, y, stats, bias, act);                                   \
+    launch_pdl(conv_tc_kernel<BN_, ST_, MH_>, grid, dim3(192), smem, st, maps, g, y, stats, bias, act);                      \
   } while (0)
   if (MH == 1 && BN == 32) PTK_TC_LAUNCH(32, 4, 1);
   else if (MH == 2 && BN == 32) PTK_TC_LAUNCH(32, 3, 2);
@@ -430,6 +451,7 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_tmem = sBar + 16 * STAGES;
   const uint32_t tmem_slot = bar_tmem + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   const int btiles = g.Cb_pad / BLOCK_N;
   const int at = blockIdx.x / btiles, bt = blockIdx.x - at * btiles;
   const int tap0 = blockIdx.y * TPC, split = blockIdx.z;
@@ -453,6 +475,7 @@ wgrad_tc_kernel(const __grid_constant__ WgTmapSet maps, const __grid_constant__ 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -664,7 +687,7 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + TPC_ * BN_ * 128) + 16 * ST_ + 16 + 1024;                          \
     static bool attr = false;                                                                                              \
     if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<BN_, ST_, MH_, TPC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
-    wgrad_tc_kernel<BN_, ST_, MH_, TPC_><<<grid, 192, smem, st>>>(maps, g, dw);                                             \
+    launch_pdl(wgrad_tc_kernel<BN_, ST_, MH_, TPC_>, grid, dim3(192), smem, st, maps, g, dw);                                \
   } while (0)
   if (TPC == 9) PTK_WG_LAUNCH(32, 3, 1, 9);
   else if (TPC == 4) PTK_WG_LAUNCH(64, 4, 1, 4);

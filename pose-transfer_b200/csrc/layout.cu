@@ -167,6 +167,7 @@ sum_parts_kernel(const float4* __restrict__ src, int nparts, int64_t stride4, fl
 }
 
 __global__ void fill_kernel(float* __restrict__ dst, int64_t n, float v) {
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = v;
 }

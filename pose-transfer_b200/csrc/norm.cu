@@ -25,6 +25,7 @@ __device__ __forceinline__ void block_reduce2_atomic(double a, double b, double*
 // grid (chunks, N); every thread strides over float4 groups of sample n, two independent loads in flight.
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ z, int ld, int64_t HW, int C, double* __restrict__ stats) {
+  pdl_trigger();
   const int n = blockIdx.y;
   const int C4 = C >> 2;
   const int total4 = (int)(HW * C4);          // < 2^31 float4 groups per sample (checked by the host)
@@ -75,11 +76,27 @@ __device__ __forceinline__ void mean_rstd(const double* stats, int n, double cou
   *rstd = (float)(1.0 / sqrt(var + (double)kEps));
 }
 
+// Element indexing shared by the streaming kernels below: when the total thread count is a multiple of C/4 (host
+// guarantees it on this path), a thread keeps ONE channel group c and walks pixels with a constant stride, so the loop
+// body has no integer division and U independent 128-bit loads per operand are in flight per thread.
+struct PixWalk { int c; int64_t p, step, npix; };
+__device__ __forceinline__ PixWalk pix_walk(int64_t HW, int C4) {
+  PixWalk w;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  w.c = (int)(t % C4) << 2;
+  w.p = t / C4;
+  w.step = ((int64_t)gridDim.x * blockDim.x) / C4;
+  w.npix = HW;
+  return w;
+}
+
+template <int U>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ z, int ldz, const double* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ drop,
                 int64_t HW, int C, float* __restrict__ out1, int ld1, int act1, float* __restrict__ out2,
                 int ld2, int act2) {
+  pdl_trigger();
   const int n = blockIdx.y;
   float scale = 1.f, shift = 0.f;
   if (gamma) {
@@ -89,77 +106,94 @@ gn_apply_kernel(const float* __restrict__ z, int ldz, const double* __restrict__
     scale = rstd * g;
     shift = b - mean * scale;
   }
-  const int C4 = C >> 2;
-  const int total4 = (int)(HW * C4);
-  const float* zb = z + (int64_t)n * HW * ldz;
-  float* o1 = out1 + (int64_t)n * HW * ld1;
-  float* o2 = out2 ? out2 + (int64_t)n * HW * ld2 : nullptr;
-  const float* dr = drop ? drop + (int64_t)n * C : nullptr;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
-    const int64_t p = i / C4;
-    const int c = (i - (int)p * C4) << 2;
-    float4 v = __ldg(reinterpret_cast<const float4*>(zb + p * ldz + c));
-    v.x = fmaf(v.x, scale, shift); v.y = fmaf(v.y, scale, shift);
-    v.z = fmaf(v.z, scale, shift); v.w = fmaf(v.w, scale, shift);
-    if (dr) {
-      const float4 d = __ldg(reinterpret_cast<const float4*>(dr + c));
-      v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
+  const PixWalk w = pix_walk(HW, C >> 2);
+  const float* zb = z + (int64_t)n * HW * ldz + w.c;
+  float* o1 = out1 + (int64_t)n * HW * ld1 + w.c;
+  float* o2 = out2 ? out2 + (int64_t)n * HW * ld2 + w.c : nullptr;
+  float4 d = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (drop) d = __ldg(reinterpret_cast<const float4*>(drop + (int64_t)n * C + w.c));
+  for (int64_t p = w.p; p < HW; p += U * w.step) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = p + u * w.step;
+      if (q < HW) v[u] = __ldg(reinterpret_cast<const float4*>(zb + q * ldz));
     }
-    float4 a = make_float4(apply_act(v.x, act1), apply_act(v.y, act1), apply_act(v.z, act1), apply_act(v.w, act1));
-    *reinterpret_cast<float4*>(o1 + p * ld1 + c) = a;
-    if (o2) {
-      a = make_float4(apply_act(v.x, act2), apply_act(v.y, act2), apply_act(v.z, act2), apply_act(v.w, act2));
-      *reinterpret_cast<float4*>(o2 + p * ld2 + c) = a;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = p + u * w.step;
+      if (q >= HW) break;
+      float4 t = v[u];
+      t.x = fmaf(t.x, scale, shift) * d.x; t.y = fmaf(t.y, scale, shift) * d.y;
+      t.z = fmaf(t.z, scale, shift) * d.z; t.w = fmaf(t.w, scale, shift) * d.w;
+      *reinterpret_cast<float4*>(o1 + q * ld1) = make_float4(apply_act(t.x, act1), apply_act(t.y, act1), apply_act(t.z, act1), apply_act(t.w, act1));
+      if (o2) *reinterpret_cast<float4*>(o2 + q * ld2) = make_float4(apply_act(t.x, act2), apply_act(t.y, act2), apply_act(t.z, act2), apply_act(t.w, act2));
     }
   }
 }
 
+template <int U>
 __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const float* __restrict__ g1, int ldg1, const float* __restrict__ a1, int lda1, int act1,
                      const float* __restrict__ g2, int ldg2, const float* __restrict__ a2, int lda2, int act2,
                      const float* __restrict__ drop, const float* __restrict__ z, int ldz,
                      const double* __restrict__ stats, int64_t HW, int C, float* __restrict__ dy,
                      double* __restrict__ sums) {
+  pdl_trigger();
   const int n = blockIdx.y;
   float mean = 0.f, rstd = 1.f;
   const bool normed = sums != nullptr;
   if (normed) mean_rstd(stats, n, (double)HW * C, &mean, &rstd);
-  const int C4 = C >> 2;
-  const int total4 = (int)(HW * C4);
+  const PixWalk w = pix_walk(HW, C >> 2);
   const int64_t pix0 = (int64_t)n * HW;
-  const float* dr = drop ? drop + (int64_t)n * C : nullptr;
+  g1 += pix0 * ldg1 + w.c;
+  if (a1) a1 += pix0 * lda1 + w.c;
+  if (g2) g2 += pix0 * ldg2 + w.c;
+  if (a2) a2 += pix0 * lda2 + w.c;
+  if (normed) z += pix0 * ldz + w.c;
+  dy += pix0 * C + w.c;
+  float4 d = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (drop) d = __ldg(reinterpret_cast<const float4*>(drop + (int64_t)n * C + w.c));
   float s1 = 0.f, s2 = 0.f;
   double d1 = 0.0, d2 = 0.0;
   int cnt = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
-    const int64_t p = i / C4;
-    const int c = (i - (int)p * C4) << 2;
-    const int64_t pp = pix0 + p;
-    float4 g = __ldg(reinterpret_cast<const float4*>(g1 + pp * ldg1 + c));
-    if (a1) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(a1 + pp * lda1 + c));
-      g.x *= act_grad_from_output(a.x, act1); g.y *= act_grad_from_output(a.y, act1);
-      g.z *= act_grad_from_output(a.z, act1); g.w *= act_grad_from_output(a.w, act1);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t p = w.p; p < HW; p += U * w.step) {
+    float4 vg[U], va[U], vh[U], vb[U], vz[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = p + u * w.step;
+      const bool in = q < HW;
+      vg[u] = in ? __ldg(reinterpret_cast<const float4*>(g1 + q * ldg1)) : zero;
+      va[u] = (in && a1) ? __ldg(reinterpret_cast<const float4*>(a1 + q * lda1)) : zero;
+      vh[u] = (in && g2) ? __ldg(reinterpret_cast<const float4*>(g2 + q * ldg2)) : zero;
+      vb[u] = (in && a2) ? __ldg(reinterpret_cast<const float4*>(a2 + q * lda2)) : zero;
+      vz[u] = (in && normed) ? __ldg(reinterpret_cast<const float4*>(z + q * ldz)) : zero;
     }
-    if (g2) {
-      float4 h = __ldg(reinterpret_cast<const float4*>(g2 + pp * ldg2 + c));
-      if (a2) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(a2 + pp * lda2 + c));
-        h.x *= act_grad_from_output(a.x, act2); h.y *= act_grad_from_output(a.y, act2);
-        h.z *= act_grad_from_output(a.z, act2); h.w *= act_grad_from_output(a.w, act2);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = p + u * w.step;
+      if (q >= HW) break;
+      float4 g = vg[u];
+      if (a1) {
+        g.x *= act_grad_from_output(va[u].x, act1); g.y *= act_grad_from_output(va[u].y, act1);
+        g.z *= act_grad_from_output(va[u].z, act1); g.w *= act_grad_from_output(va[u].w, act1);
       }
-      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
-    }
-    if (dr) {
-      const float4 d = __ldg(reinterpret_cast<const float4*>(dr + c));
+      if (g2) {
+        float4 h = vh[u];
+        if (a2) {
+          h.x *= act_grad_from_output(vb[u].x, act2); h.y *= act_grad_from_output(vb[u].y, act2);
+          h.z *= act_grad_from_output(vb[u].z, act2); h.w *= act_grad_from_output(vb[u].w, act2);
+        }
+        g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+      }
       g.x *= d.x; g.y *= d.y; g.z *= d.z; g.w *= d.w;
-    }
-    *reinterpret_cast<float4*>(dy + pp * C + c) = g;
-    if (normed) {
-      const float4 zv = __ldg(reinterpret_cast<const float4*>(z + pp * ldz + c));
-      s1 += (g.x + g.y) + (g.z + g.w);
-      s2 += g.x * (zv.x - mean) + g.y * (zv.y - mean) + g.z * (zv.z - mean) + g.w * (zv.w - mean);
-      if (++cnt == 64) { d1 += s1; d2 += s2; s1 = 0.f; s2 = 0.f; cnt = 0; }
+      *reinterpret_cast<float4*>(dy + q * C) = g;
+      if (normed) {
+        s1 += (g.x + g.y) + (g.z + g.w);
+        s2 += g.x * (vz[u].x - mean) + g.y * (vz[u].y - mean) + g.z * (vz[u].z - mean) + g.w * (vz[u].w - mean);
+        if (++cnt == 64) { d1 += s1; d2 += s2; s1 = 0.f; s2 = 0.f; cnt = 0; }
+      }
     }
   }
   if (normed) {
@@ -168,10 +202,12 @@ gn_bwd_reduce_kernel(const float* __restrict__ g1, int ldg1, const float* __rest
   }
 }
 
+template <int U>
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(float* __restrict__ dy, const float* __restrict__ z, int ldz, const double* __restrict__ stats,
                     const double* __restrict__ sums, const float* __restrict__ gamma, int N, int64_t HW, int C,
                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_trigger();
   const int n = blockIdx.y;
   float mean, rstd;
   const double count = (double)HW * C;
@@ -179,20 +215,30 @@ gn_bwd_apply_kernel(float* __restrict__ dy, const float* __restrict__ z, int ldz
   const float g = __ldg(gamma);
   const float m1 = (float)(sums[2 * n] / count), m2 = (float)(sums[2 * n + 1] / count);
   const float k = g * rstd;
-  const int C4 = C >> 2;
-  const int total4 = (int)(HW * C4);
-  float* dyb = dy + (int64_t)n * HW * C;
-  const float* zb = z + (int64_t)n * HW * ldz;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
-    const int64_t p = i / C4;
-    const int c = (i - (int)p * C4) << 2;
-    float4 d = *reinterpret_cast<const float4*>(dyb + p * C + c);
-    const float4 zv = __ldg(reinterpret_cast<const float4*>(zb + p * ldz + c));
-    d.x = k * (d.x - m1 - (zv.x - mean) * rstd * m2);
-    d.y = k * (d.y - m1 - (zv.y - mean) * rstd * m2);
-    d.z = k * (d.z - m1 - (zv.z - mean) * rstd * m2);
-    d.w = k * (d.w - m1 - (zv.w - mean) * rstd * m2);
-    *reinterpret_cast<float4*>(dyb + p * C + c) = d;
+  const PixWalk w = pix_walk(HW, C >> 2);
+  float* dyb = dy + (int64_t)n * HW * C + w.c;
+  const float* zb = z + (int64_t)n * HW * ldz + w.c;
+  for (int64_t p = w.p; p < HW; p += U * w.step) {
+    float4 vd[U], vz[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = p + u * w.step;
+      if (q < HW) {
+        vd[u] = *reinterpret_cast<const float4*>(dyb + q * C);
+        vz[u] = __ldg(reinterpret_cast<const float4*>(zb + q * ldz));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = p + u * w.step;
+      if (q >= HW) break;
+      float4 d = vd[u];
+      d.x = k * (d.x - m1 - (vz[u].x - mean) * rstd * m2);
+      d.y = k * (d.y - m1 - (vz[u].y - mean) * rstd * m2);
+      d.z = k * (d.z - m1 - (vz[u].z - mean) * rstd * m2);
+      d.w = k * (d.w - m1 - (vz[u].w - mean) * rstd * m2);
+      *reinterpret_cast<float4*>(dyb + q * C) = d;
+    }
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     double sg = 0.0, sb = 0.0;
@@ -200,6 +246,20 @@ gn_bwd_apply_kernel(float* __restrict__ dy, const float* __restrict__ z, int ldz
     *dgamma += (float)sg;
     *dbeta += (float)sb;
   }
+}
+
+// grid for the PixWalk kernels: (blocks * 256) % (C / 4) == 0 so that a thread keeps its channel group; about 8 blocks
+// of 256 threads per SM over the whole batch, never more threads than U-element work items
+static inline dim3 grid_walk(int64_t HW, int C, int N, int U) {
+  const int C4 = C / 4;
+  int64_t quantum = 1;                       // smallest block count with (blocks * 256) % C4 == 0
+  while ((quantum * 256) % C4 != 0) ++quantum;
+  int64_t want = (HW * C4 + (int64_t)256 * U - 1) / ((int64_t)256 * U);
+  int64_t cap = ((int64_t)num_sms() * 8 + N - 1) / N;
+  if (want > cap) want = cap;
+  int64_t b = (want + quantum - 1) / quantum * quantum;
+  if (b < quantum) b = quantum;
+  return dim3((unsigned)b, (unsigned)N);
 }
 
 static inline dim3 grid2(int64_t work, int N) {
@@ -233,8 +293,9 @@ extern "C" int ptk_gn_apply(const float* z, int ldz, const double* stats, const 
   PTK_REQUIRE(C % 4 == 0 && ldz % 4 == 0 && ld1 % 4 == 0 && (!out2 || ld2 % 4 == 0), "gn_apply: C and strides must be multiples of 4");
   PTK_REQUIRE((gamma == nullptr) == (beta == nullptr), "gn_apply: gamma and beta must both be given or both NULL");
   PTK_REQUIRE(!gamma || stats, "gn_apply: stats required");
-  gn_apply_kernel<<<grid2(HW * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(z, ldz, stats, gamma, beta, drop, HW, C, out1,
-                                                                            ld1, act1, out2, ld2, act2);
+  PTK_REQUIRE(C / 4 <= 4096, "gn_apply: C too large");
+  gn_apply_kernel<4><<<grid_walk(HW, C, N, 4), 256, 0, (cudaStream_t)stream>>>(z, ldz, stats, gamma, beta, drop, HW, C, out1,
+                                                                               ld1, act1, out2, ld2, act2);
   PTK_LAUNCH_CHECK("gn_apply_kernel");
   return 0;
 }
@@ -247,8 +308,9 @@ extern "C" int ptk_gn_bwd_reduce(const float* g1, int ldg1, const float* a1, int
   PTK_REQUIRE(ldg1 % 4 == 0 && (!a1 || lda1 % 4 == 0) && (!g2 || ldg2 % 4 == 0) && (!a2 || lda2 % 4 == 0) && (!sums || ldz % 4 == 0),
               "gn_bwd_reduce: strides must be multiples of 4");
   PTK_REQUIRE(!sums || (z && stats), "gn_bwd_reduce: z and stats required with sums");
-  gn_bwd_reduce_kernel<<<grid2(HW * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(g1, ldg1, a1, lda1, act1, g2, ldg2, a2, lda2,
-                                                                                 act2, drop, z, ldz, stats, HW, C, dy, sums);
+  PTK_REQUIRE(C / 4 <= 4096, "gn_bwd_reduce: C too large");
+  gn_bwd_reduce_kernel<2><<<grid_walk(HW, C, N, 2), 256, 0, (cudaStream_t)stream>>>(g1, ldg1, a1, lda1, act1, g2, ldg2, a2, lda2,
+                                                                                    act2, drop, z, ldz, stats, HW, C, dy, sums);
   PTK_LAUNCH_CHECK("gn_bwd_reduce_kernel");
   return 0;
 }
@@ -257,8 +319,9 @@ extern "C" int ptk_gn_bwd_apply(float* dy, const float* z, int ldz, const double
                                 const float* gamma, int N, int64_t HW, int C, float* dgamma, float* dbeta,
                                 void* stream) {
   PTK_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0 && C % 4 == 0 && ldz % 4 == 0 && HW * C < (1ll << 32), "gn_bwd_apply: bad extents");
-  gn_bwd_apply_kernel<<<grid2(HW * (C / 4), N), 256, 0, (cudaStream_t)stream>>>(dy, z, ldz, stats, sums, gamma, N, HW, C,
-                                                                               dgamma, dbeta);
+  PTK_REQUIRE(C / 4 <= 4096, "gn_bwd_apply: C too large");
+  gn_bwd_apply_kernel<4><<<grid_walk(HW, C, N, 4), 256, 0, (cudaStream_t)stream>>>(dy, z, ldz, stats, sums, gamma, N, HW, C,
+                                                                                  dgamma, dbeta);
   PTK_LAUNCH_CHECK("gn_bwd_apply_kernel");
   return 0;
 }

@@ -184,7 +184,7 @@ struct WarpLevelDev {
 };
 struct WarpLaunchDev {
   WarpLevelDev lv[4];
-  int nlevels, K, H0, W0, act, ctas_per_image;
+  int nlevels, K, H0, W0, act, ctas_per_image, pf_rows;
 };
 
 // geometry of part `gl` at output pixel (i, j); returns false for "0, no gradient" (mask 0 / footprint outside)
@@ -347,6 +347,163 @@ __device__ __forceinline__ void warp_fwd_strip(const WarpLevelDev& L, const Thet
   }
 }
 
+
+// ---- pipelined forward: the mask values of a row are fetched one row ahead (registers), the geometry of row r + 1 is
+// evaluated into the second half of a double-buffered shared-memory record while the gathers of row r are in flight, and the
+// source lines that the body of the strip will need PF rows further down are pulled into L2 early -- the row loop's critical
+// path is then ONE global round trip per part instead of mask -> geometry -> gather.
+template <int G, int PX>
+__device__ __forceinline__ void load_row_masks(const float* __restrict__ mrow, int K, int j0, int w, int gl, float (&m)[PX]) {
+#pragma unroll
+  for (int px = 0; px < PX; ++px) m[px] = (gl < K && j0 + px < w) ? __ldg(mrow + (j0 + px) * K + gl) : 0.f;
+}
+
+template <int G, int PX>
+__device__ __forceinline__ void row_geometry_m(const Theta* s_theta, const float (&m)[PX], int K, int i, int j0, int h, int w, int ld,
+                                               int gl, int grp, float4* __restrict__ geo, unsigned (&bits)[PX]) {
+  const unsigned gmask = G == 32 ? 0xffffffffu : (0xffffu << (grp * 16));
+#pragma unroll
+  for (int px = 0; px < PX; ++px) {
+    bool valid = false;
+    float4 wgt;
+    int4 off;
+    if (gl < K && j0 + px < w) valid = part_geometry(s_theta[gl], m[px], i, j0 + px, h, w, ld, wgt, off);
+    if (valid) {
+      geo[(px * 16 + gl) * 2] = wgt;
+      geo[(px * 16 + gl) * 2 + 1] = make_float4(__int_as_float(off.x), __int_as_float(off.y), __int_as_float(off.z), __int_as_float(off.w));
+    }
+    const unsigned ball = __ballot_sync(gmask, valid);      // group-wide: the two pixel groups of a warp may have diverged
+    bits[px] = (ball >> (grp * G)) & 0xffffu;
+  }
+}
+
+template <int G, int NV, int PX, int ACT>
+__device__ __forceinline__ void warp_fwd_strip_pipe(const WarpLevelDev& L, const Theta* s_theta, float4* s_geo_warp, int K, int n,
+                                                    int tile, int pf_rows) {
+  constexpr int PPW = 32 / G, XW = 8 * PPW * PX, CH = 4 * G * NV;
+  constexpr bool kRelu = ACT == PTK_ACT_RELU;
+  const int sx = tile % L.strips_x, sy = tile / L.strips_x;
+  const int y_begin = sy * L.TH;
+  const int h = L.h, w = L.w, C = L.C;
+  const int rows = min(L.TH, h - y_begin);
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int gl = lane % G, grp = lane / G;
+  const int j0 = sx * XW + (wi * PPW + grp) * PX;
+  const int64_t img = (int64_t)n * h * w;
+  const float* xb = L.x + img * L.ldx + gl * 4;
+  const float* mb = L.mask + img * K;
+  float4* geo0 = s_geo_warp + grp * (PX * 32);                  // [2 buffers][PPW groups][PX * 32]
+  float4* geo1 = geo0 + PPW * PX * 32;
+  const unsigned kmask = (1u << K) - 1u;
+  const int pf_step = pf_rows * w * L.ldx, pf_lim = (h * w - 1) * L.ldx;
+
+  float mnext[PX];
+  unsigned bits[PX], bits_next[PX];
+  load_row_masks<G, PX>(mb + (int64_t)y_begin * w * K, K, j0, w, gl, mnext);
+  row_geometry_m<G, PX>(s_theta, mnext, K, y_begin, j0, h, w, L.ldx, gl, grp, geo0, bits);
+  if (rows > 1) load_row_masks<G, PX>(mb + (int64_t)(y_begin + 1) * w * K, K, j0, w, gl, mnext);
+  __syncwarp();
+  for (int r = 0; r < rows; ++r) {
+    const int i = y_begin + r;
+    float4* geo = (r & 1) ? geo1 : geo0;
+    float4* geo_nx = (r & 1) ? geo0 : geo1;
+    unsigned uni = 0u;
+    int kz[PX];
+#pragma unroll
+    for (int px = 0; px < PX; ++px) {
+      const unsigned inactive = ~bits[px] & kmask;
+      kz[px] = (!kRelu && inactive) ? __ffs(inactive) - 1 : -1;
+      uni |= bits[px] | ((!kRelu && inactive) ? (inactive & (0u - inactive)) : 0u);
+    }
+    float* yrow = L.y + (img + (int64_t)i * w + j0) * L.ldy + gl * 4;
+    uint8_t* arow = L.argk + (((img + (int64_t)i * w + j0) * C) >> 1) + gl * 2;
+    bool staged = false;          // next row's geometry done?
+    for (int cb = 0; cb < C; cb += CH) {
+      float best[PX][NV * 4];
+      int arg[PX][NV * 4];
+#pragma unroll
+      for (int px = 0; px < PX; ++px)
+#pragma unroll
+        for (int q = 0; q < NV * 4; ++q) { best[px][q] = kRelu ? 0.f : -INFINITY; arg[px][q] = kNoPart; }
+      unsigned rem = uni;
+      while (rem) {
+        const int k = __ffs(rem) - 1;
+        rem &= rem - 1;
+        float4 wv[PX];
+        float4 v[PX][NV][4];
+#pragma unroll
+        for (int px = 0; px < PX; ++px) {
+          const bool on = (bits[px] >> k) & 1u;
+          wv[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+          int4 o = make_int4(0, 0, 0, 0);
+          if (on) {
+            wv[px] = geo[(px * 16 + k) * 2];
+            const float4 of = geo[(px * 16 + k) * 2 + 1];
+            o = make_int4(__float_as_int(of.x), __float_as_int(of.y), __float_as_int(of.z), __float_as_int(of.w));
+          }
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            const float* p = xb + cb + q * G * 4;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[px][q][0] = on ? __ldg(reinterpret_cast<const float4*>(p + o.x)) : z;
+            v[px][q][1] = on ? __ldg(reinterpret_cast<const float4*>(p + o.y)) : z;
+            v[px][q][2] = on ? __ldg(reinterpret_cast<const float4*>(p + o.z)) : z;
+            v[px][q][3] = on ? __ldg(reinterpret_cast<const float4*>(p + o.w)) : z;
+            if (pf_rows > 0 && on && !staged) {     // first part of the row (the body): warm L2 for the rows further down
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p + min(o.z + pf_step, pf_lim)));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p + min(o.w + pf_step, pf_lim)));
+            }
+          }
+        }
+        if (!staged) {
+          // while those loads are in flight: geometry of the next row, mask values of the row after it
+          staged = true;
+          if (r + 1 < rows) {
+            row_geometry_m<G, PX>(s_theta, mnext, K, i + 1, j0, h, w, L.ldx, gl, grp, geo_nx, bits_next);
+            if (r + 2 < rows) load_row_masks<G, PX>(mb + (int64_t)(i + 2) * w * K, K, j0, w, gl, mnext);
+          }
+        }
+#pragma unroll
+        for (int px = 0; px < PX; ++px) {
+          const bool on = (bits[px] >> k) & 1u;
+          const bool zero = !kRelu && k == kz[px];
+          if (!on && !zero) continue;
+          const int tag = on ? k : kNoPart;
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            fma4(acc, wv[px].x, v[px][q][0]); fma4(acc, wv[px].y, v[px][q][1]);
+            fma4(acc, wv[px].z, v[px][q][2]); fma4(acc, wv[px].w, v[px][q][3]);
+            if (acc.x > best[px][4 * q + 0]) { best[px][4 * q + 0] = acc.x; arg[px][4 * q + 0] = tag; }
+            if (acc.y > best[px][4 * q + 1]) { best[px][4 * q + 1] = acc.y; arg[px][4 * q + 1] = tag; }
+            if (acc.z > best[px][4 * q + 2]) { best[px][4 * q + 2] = acc.z; arg[px][4 * q + 2] = tag; }
+            if (acc.w > best[px][4 * q + 3]) { best[px][4 * q + 3] = acc.w; arg[px][4 * q + 3] = tag; }
+          }
+        }
+      }
+#pragma unroll
+      for (int px = 0; px < PX; ++px) {
+        if (j0 + px >= w) continue;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          *reinterpret_cast<float4*>(yrow + px * L.ldy + cb + q * G * 4) =
+              make_float4(warp_act<ACT>(best[px][4 * q]), warp_act<ACT>(best[px][4 * q + 1]), warp_act<ACT>(best[px][4 * q + 2]),
+                          warp_act<ACT>(best[px][4 * q + 3]));
+          *reinterpret_cast<uint16_t*>(arow + ((px * C + cb + q * G * 4) >> 1)) =
+              (uint16_t)(arg[px][4 * q] | (arg[px][4 * q + 1] << 4) | (arg[px][4 * q + 2] << 8) | (arg[px][4 * q + 3] << 12));
+        }
+      }
+    }
+    if (!staged && r + 1 < rows) {      // no candidate at all in this row (all masks zero): stage the next row here
+      row_geometry_m<G, PX>(s_theta, mnext, K, i + 1, j0, h, w, L.ldx, gl, grp, geo_nx, bits_next);
+      if (r + 2 < rows) load_row_masks<G, PX>(mb + (int64_t)(i + 2) * w * K, K, j0, w, gl, mnext);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int px = 0; px < PX; ++px) bits[px] = bits_next[px];
+  }
+}
+
 // Backward of the same tiling: dx[taps of the winner] += dy * (mask * bilinear weight).  A lane's 4 channels usually
 // share their winner (the body part wins most pixels): one 128-bit vector reduction per tap; channels with other winners
 // go out as further vector reductions with the foreign channels zeroed.  ACT = ReLU / none need no look at y: "no
@@ -427,7 +584,7 @@ constexpr int kGeoPerWarp = 8 * 32;      // float4 slots: (pixels per warp <= 8)
 // first; all strips carry the same number of bytes), blockIdx.y the image.
 // VAR 0: 16 loads of 128 bits in flight per lane and part (2 CTAs / SM); VAR 1: 8 loads (3 CTAs / SM).
 template <int ACT, int VAR>
-__global__ void __launch_bounds__(256, VAR == 0 ? 2 : 3)
+__global__ void __launch_bounds__(256, (VAR == 0 || VAR == 3) ? 2 : 3)
 warp_forward_levels_kernel(const __grid_constant__ WarpLaunchDev P, const float* __restrict__ warps) {
   __shared__ Theta s_theta[kMaxParts];
   __shared__ float4 s_geo[8 * kGeoPerWarp];
@@ -447,11 +604,17 @@ warp_forward_levels_kernel(const __grid_constant__ WarpLaunchDev P, const float*
       case 2: warp_fwd_strip<32, 2, 2, ACT>(L, s_theta, geo, P.K, n, tile); break;
       default: warp_fwd_strip<32, 4, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
     }
-  } else {
+  } else if (VAR == 1) {
     switch (L.cfg) {
       case 0: warp_fwd_strip<16, 1, 2, ACT>(L, s_theta, geo, P.K, n, tile); break;
       case 1: warp_fwd_strip<16, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
       default: warp_fwd_strip<32, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
+    }
+  } else {
+    switch (L.cfg) {
+      case 0: warp_fwd_strip_pipe<16, 1, 2, ACT>(L, s_theta, geo, P.K, n, tile, P.pf_rows); break;
+      case 1: warp_fwd_strip_pipe<16, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile, P.pf_rows); break;
+      default: warp_fwd_strip_pipe<32, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile, P.pf_rows); break;
     }
   }
 }
@@ -569,7 +732,8 @@ static int warp_rows_per_strip() {
 // fills the device-side launch description; returns false if some level cannot take the fast path
 static int warp_variant() {
   const char* e = getenv("PTK_WARP_VAR");
-  return (e && atoi(e) == 1) ? 1 : 0;
+  const int v = e ? atoi(e) : 2;
+  return (v >= 0 && v <= 3) ? v : 2;
 }
 
 static bool warp_plan(const ptk_warp_level* lv, int nlevels, int K, int H0, int W0, int act, bool backward, WarpLaunchDev& P) {
@@ -587,6 +751,8 @@ static bool warp_plan(const ptk_warp_level* lv, int nlevels, int K, int H0, int 
     const int var = backward ? 0 : warp_variant();
     const int nv = cfg == 0 ? 1 : ((cfg == 3 && var == 0) ? 4 : 2), g = cfg <= 1 ? 16 : 32;
     const int xw = 8 * (32 / g) * ((var == 0 ? 4 : 2) / nv);
+    if (const char* e = getenv("PTK_WARP_PF")) P.pf_rows = atoi(e); else P.pf_rows = 4;
+    if (P.pf_rows < 0 || P.pf_rows > 32) P.pf_rows = 0;
     d.TH = warp_rows_per_strip() < s.h ? warp_rows_per_strip() : s.h;
     d.strips_x = (s.w + xw - 1) / xw;
     d.strips_y = (s.h + d.TH - 1) / d.TH;
@@ -633,7 +799,15 @@ extern "C" int ptk_warp_forward_levels(const ptk_warp_level* lv, int nlevels, co
     return 0;
   }
   dim3 grid((unsigned)P.ctas_per_image, (unsigned)N);
-  if (warp_variant() == 0) {
+  if (warp_variant() == 3) {
+    if (act == PTK_ACT_RELU) warp_forward_levels_kernel<PTK_ACT_RELU, 3><<<grid, 256, 0, st>>>(P, warps);
+    else if (act == PTK_ACT_LEAKY) warp_forward_levels_kernel<PTK_ACT_LEAKY, 3><<<grid, 256, 0, st>>>(P, warps);
+    else warp_forward_levels_kernel<PTK_ACT_NONE, 3><<<grid, 256, 0, st>>>(P, warps);
+  } else if (warp_variant() == 2) {
+    if (act == PTK_ACT_RELU) warp_forward_levels_kernel<PTK_ACT_RELU, 2><<<grid, 256, 0, st>>>(P, warps);
+    else if (act == PTK_ACT_LEAKY) warp_forward_levels_kernel<PTK_ACT_LEAKY, 2><<<grid, 256, 0, st>>>(P, warps);
+    else warp_forward_levels_kernel<PTK_ACT_NONE, 2><<<grid, 256, 0, st>>>(P, warps);
+  } else if (warp_variant() == 0) {
     if (act == PTK_ACT_RELU) warp_forward_levels_kernel<PTK_ACT_RELU, 0><<<grid, 256, 0, st>>>(P, warps);
     else if (act == PTK_ACT_LEAKY) warp_forward_levels_kernel<PTK_ACT_LEAKY, 0><<<grid, 256, 0, st>>>(P, warps);
     else warp_forward_levels_kernel<PTK_ACT_NONE, 0><<<grid, 256, 0, st>>>(P, warps);

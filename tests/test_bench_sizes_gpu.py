@@ -9,8 +9,10 @@
 
 Stated tolerances (SURVEY 8c, TF32 operands = 10-bit mantissa, fp32 accumulate): losses <= 1e-2 rel (measured 3e-4),
 out_gen <= 1e-2 abs (measured 4e-3), gradient norm <= 5 % per tensor, gradient cosine >= 0.999 for the layers that carry
-the FLOPs and sit within a few layers of the loss (decoder.3 .. decoder.5 + head, encoder level 0 / 1 incl. the stems, the
-whole discriminator) and >= 0.995 for the deep bottleneck layers.  Why the deep layers are looser: the backward pass is
+the FLOPs and sit within a few layers of the loss (decoder.3 .. decoder.5 + head, encoder levels 1 / 2, the whole
+discriminator), >= 0.997 for the two encoder stems (10k-element tensors at the far end of the backward chain; 0.9994+ at
+batch 8, 0.998 at batch 2) and >= 0.995 for the deep bottleneck layers.  Measured on B200 (batch 8, live reference): worst
+tensor 0.99743 (encoder_app level 6) where the reference's own TF32 run reaches 0.99757.  Why the deep layers are looser: the backward pass is
 piecewise linear with hard switches -- sign(gt - pred) in the NN / L1 loss, the arg-max over parts in the warp, the
 arg-min over the 5x5 window, every ReLU / LeakyReLU mask -- and a 1e-3 perturbation of the forward activations (TF32)
 flips ~0.1 % of the switches per layer it crosses; each crossed layer adds ~3 % of uncorrelated gradient noise, so the
@@ -32,7 +34,8 @@ from helpers import golden, max_abs
 pytestmark = pytest.mark.gpu
 
 COS_MIN = 0.999          # gradient direction, layers near the loss (see module docstring)
-COS_MIN_DEEP = 0.995     # bottleneck layers (encoder levels >= 2, decoder levels 0 .. 2) and tensors under 4096 elements
+COS_MIN_STEM = 0.997     # encoder stems: 10k-element tensors at the very end of the backward chain
+COS_MIN_DEEP = 0.995     # bottleneck layers (encoder levels >= 3, decoder levels 0 .. 2) and tensors under 4096 elements
 NORM_TOL = 5e-2
 LOSS_RTOL = 1e-2
 OUT_ATOL = 1e-2
@@ -77,7 +80,9 @@ def cos_floor(name, n):
     kind, lvl = m.group(1), int(m.group(2))
     if kind == "decoder":
         return COS_MIN if lvl >= 3 else COS_MIN_DEEP
-    return COS_MIN if lvl <= 1 else COS_MIN_DEEP
+    if lvl == 0:
+        return COS_MIN_STEM
+    return COS_MIN if lvl <= 2 else COS_MIN_DEEP
 
 
 def check_grad(name, got_full, want_norm, want_sample, idx, report):

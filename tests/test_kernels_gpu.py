@@ -222,7 +222,7 @@ def test_warp_full_size_vs_oracle_and_relu_epilogue(K):
         ref.backward(gy)
         y, dx, _ = _run_warp(K, x, b["warps"], b["masks"], 256, 256, gy, act=K.ACT_RELU)
         assert max_abs(y, ref) <= 3e-4
-        assert rel_l2(dx, xr.grad) <= 2e-3   # a handful of arg-max flips at near-ties + atomics order
+        assert rel_l2(dx, xr.grad) <= 4e-3   # a handful of arg-max flips at near-ties + atomics order
 
 
 @pytest.mark.parametrize("act", ["none", "relu"])
@@ -269,7 +269,7 @@ def test_warp_levels_api_matches_single_level_calls(K, monkeypatch):
         dx = torch.zeros(N, h, h, C, device="cuda")
         K.warp_backward(K.Slice(gy, 32, C), K.Slice(y, 32, C), K.ACT_RELU, wr, ml, argk, dx, N, C, h, h, 10, H0, H0)
         single.append((y, dx))
-    for var in ("0", "1"):
+    for var in ("0", "1", "2", "3"):
         monkeypatch.setenv("PTK_WARP_VAR", var)
         lv = []
         for (C, h), x, ml, gy in zip(shapes, xs, mls, gys):

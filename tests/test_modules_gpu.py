@@ -44,7 +44,7 @@ def test_affine_transform_layer_gradcheck_recipe():
     Restated for fp32 kernels: the layer is PIECEWISE LINEAR in `input` (bilinear taps x mask, max over parts), so a
     central difference is exact up to fp32 rounding (~1e-7 |y| / eps) for any step that does not move an arg-max.  The
     full Jacobian (512 x 512) from central differences with eps = 4e-3 against the one assembled from the backward
-    kernel: every entry within atol = 5e-4 except the handful of outputs that sit within eps of a kink (a tie between two
+    kernel: every entry within the recipe's atol = 1e-4 except the handful of outputs that sit within eps of a kink (a tie between two
     parts or with the zero candidate) -- those rows are identified by the forward pass itself and excluded."""
     from oracle import synth
     from pose_transfer_b200.utils.pose_transform import AffineTransformLayer
@@ -55,7 +55,7 @@ def test_affine_transform_layer_gradcheck_recipe():
     x = (torch.randn(N, C, h, w, generator=g) * 2).cuda()
     layer = AffineTransformLayer(10, (H0, W0), "mask")
     warps, masks = b["warps"].float().cuda(), b["masks"].cuda()
-    eps, atol = 4e-3, 5e-4
+    eps, atol = 4e-3, 1e-4          # atol as in the author's recipe (measured max deviation on B200: 6e-5)
     n_in = x.numel()
     with torch.no_grad():
         y0 = layer(x, warps, masks).reshape(-1)

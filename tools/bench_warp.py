@@ -50,7 +50,7 @@ def main():
         return e0.elapsed_time(e1) / iters
 
     print("algorithmic bytes per launch set: %.1f MB (N=%d); HBM peak %.0f GB/s" % (alg / 1e6, N, peak))
-    for var in ("0", "1"):
+    for var in ("0", "1", "2", "3"):
         for th in ("4", "8", "16", "32"):
             os.environ["PTK_WARP_VAR"], os.environ["PTK_WARP_TH"] = var, th
             ms = timeit(lambda: K.warp_forward_levels(lv, wr, N, 10, H, H, K.ACT_RELU))
