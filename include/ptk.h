@@ -96,6 +96,13 @@ typedef struct {
 int ptk_conv_tc_supported(const ptk_conv_geom* g);
 int ptk_conv_forward(const ptk_conv_geom* g, const float* x, const float* w_t, const float* w_k,
                      const float* bias, int act, float* y, float* y_nchw, double* stats, void* stream);
+/* Same, with a caller-owned scratch of scratch_floats floats (may be NULL / 0).  Layers with too few output tiles to fill
+ * the machine split their K loop over several CTAs; with a scratch of at least 2 * N*OH*OW*Cout floats every split stores
+ * its partial tile there and one reduction kernel sums them in a fixed order (deterministic, statistics fused); without it
+ * the splits accumulate into y with fp32 atomics. */
+int ptk_conv_forward_ws(const ptk_conv_geom* g, const float* x, const float* w_t, const float* w_k,
+                        const float* bias, int act, float* y, float* y_nchw, double* stats, float* scratch,
+                        int64_t scratch_floats, void* stream);
 /* dw[tap][A][B] = sum_pixels small[m][a] * big[m*stride+off(tap)][b]; for Conv2d small=dy,big=x
  * (result [tap][Cout][Cin]); for ConvTranspose2d small=x,big=dy (result [tap][Cin][Cout]), with Cin/Cout as given in
  * the geometry (i.e. including channel padding).  dw is scratch owned by the caller and is OVERWRITTEN (the library

@@ -34,6 +34,7 @@ SIGNATURES = {
     "ptk_fill": [vp, i64, f32, vp],
     "ptk_conv_tc_supported": [ctypes.POINTER(ConvGeom)],
     "ptk_conv_forward": [ctypes.POINTER(ConvGeom), vp, vp, vp, vp, i32, vp, vp, vp, vp],
+    "ptk_conv_forward_ws": [ctypes.POINTER(ConvGeom), vp, vp, vp, vp, i32, vp, vp, vp, vp, i64, vp],
     "ptk_conv_wgrad": [ctypes.POINTER(ConvGeom), vp, vp, vp, vp],
     "ptk_conv_wgrad_parts": [ctypes.POINTER(ConvGeom), vp, vp, vp, i64, ctypes.POINTER(i32), vp],
     "ptk_unpack_weight_grad_parts": [vp, i32, i64, vp, i32, i32, i32, i32, i32, vp],

@@ -7,7 +7,7 @@ int conv_forward_simt(const ptk_conv_geom& c, const float* x, const float* w_t, 
 int conv_wgrad_simt(const ptk_conv_geom& c, const float* x, const float* dy, float* dw, cudaStream_t st);
 bool conv_tc_supported(const ptk_conv_geom& c);
 int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, const float* bias, int act, float* y,
-                    double* stats, cudaStream_t st);
+                    double* stats, float* scratch, int64_t scratch_floats, cudaStream_t st);
 bool conv_wgrad_tc_supported(const ptk_conv_geom& c);
 int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float* dw, int64_t dw_capacity, int* nparts,
                   cudaStream_t st, bool plan_only = false);
@@ -19,6 +19,12 @@ extern "C" int ptk_conv_tc_supported(const ptk_conv_geom* g) { return conv_tc_su
 
 extern "C" int ptk_conv_forward(const ptk_conv_geom* g, const float* x, const float* w_t, const float* w_k,
                                 const float* bias, int act, float* y, float* y_nchw, double* stats, void* stream) {
+  return ptk_conv_forward_ws(g, x, w_t, w_k, bias, act, y, y_nchw, stats, nullptr, 0, stream);
+}
+
+extern "C" int ptk_conv_forward_ws(const ptk_conv_geom* g, const float* x, const float* w_t, const float* w_k,
+                                   const float* bias, int act, float* y, float* y_nchw, double* stats, float* scratch,
+                                   int64_t scratch_floats, void* stream) {
   PTK_REQUIRE(g && x && (y || y_nchw), "conv_forward: null argument");
   PTK_REQUIRE(g->N > 0 && g->H > 0 && g->W > 0 && g->OH > 0 && g->OW > 0 && g->Cin > 0 && g->Cout > 0, "conv_forward: bad extents");
   PTK_REQUIRE(g->ldx >= g->Cin && (!y || g->ldy >= g->Cout), "conv_forward: ld smaller than channel count");
@@ -33,7 +39,7 @@ extern "C" int ptk_conv_forward(const ptk_conv_geom* g, const float* x, const fl
   }
   if (use_tc) {
     PTK_REQUIRE(w_k != nullptr && y != nullptr && y_nchw == nullptr, "conv_forward(tc): needs w_k and an NHWC destination");
-    return conv_forward_tc(*g, x, w_k, bias, act, y, stats, st);
+    return conv_forward_tc(*g, x, w_k, bias, act, y, stats, scratch, scratch_floats, st);
   }
   PTK_REQUIRE(w_t != nullptr, "conv_forward(simt): w_t is NULL");
   const int cout_pad = (g->Cout + 3) & ~3;

@@ -29,7 +29,9 @@ struct TcGeom {
   int N, OH, OW, ldy, so;
   int BW, BH, BI, tiles_x, tiles_y, tiles_i;
   int kchunks;
-  int splits;      // split-K factor (k-blocks of a tile are divided over `splits` CTAs that accumulate atomically)
+  int splits;      // split-K factor: the k-blocks of a tile are divided over `splits` CTAs
+  long long part_stride;   // > 0: split z stores its partial tile into y + z * part_stride (summed in a fixed order by
+                           // splitk_reduce_kernel => deterministic); 0: the splits accumulate atomically into y
   TcPhase ph[4];
 };
 
@@ -134,14 +136,14 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
       float* dst = nullptr;
       if (valid) {
         const int oy = gy * g.so + ph.py, ox = gx * g.so + ph.px;
-        dst = y + (((int64_t)n * g.OH + oy) * g.OW + ox) * g.ldy + blockIdx.y * BLOCK_N;
+        dst = y + (int64_t)split * g.part_stride + (((int64_t)n * g.OH + oy) * g.OW + ox) * g.ldy + blockIdx.y * BLOCK_N;
       }
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         float v[32];
         tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(hm * BLOCK_N + c * 32), v);
-        if (valid && g.splits > 1) {        // split-K partial sums: accumulate into the zero-filled output
+        if (valid && g.splits > 1 && g.part_stride == 0) {        // split-K partial sums: accumulate into the zero-filled output
 #pragma unroll
           for (int q = 0; q < 32; ++q) atomicAdd(dst + c * 32 + q, v[q]);
         } else if (valid) {
@@ -161,7 +163,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
             *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
       }
-      if (stats != nullptr && g.splits == 1) {
+      if (stats != nullptr && g.splits == 1) {   // (split-K: the statistics come out of the reduction kernel)
         if (g.BW * g.BH >= 32) {          // the warp's 32 rows belong to one image
           const float a = warp_sum(s1), b = warp_sum(s2);
           const int nw = n0 + (hm * 128 + lg * 32) / (g.BW * g.BH);
@@ -178,6 +180,46 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// Deterministic split-K combine: y[i] = sum_{z < nparts} parts[z * part_stride + i] (fixed order), fused with the per-sample
+// {sum, sum of squares} that the following norm needs.  grid (chunks, N); per_sample = OH * OW * Cout (multiple of 4).
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ parts, int nparts, long long part_stride, float* __restrict__ y, long long per_sample,
+                     double* __restrict__ stats) {
+  pdl_trigger();
+  const int n = blockIdx.y;
+  const float4* src = reinterpret_cast<const float4*>(parts + (long long)n * per_sample);
+  float4* dst = reinterpret_cast<float4*>(y + (long long)n * per_sample);
+  const long long n4 = per_sample >> 2, ps4 = part_stride >> 2;
+  float s1 = 0.f, s2 = 0.f;
+  double d1 = 0.0, d2 = 0.0;
+  int cnt = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = __ldg(src + i);
+    for (int z = 1; z < nparts; ++z) {
+      const float4 b = __ldg(src + z * ps4 + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    dst[i] = a;
+    s1 += (a.x + a.y) + (a.z + a.w);
+    s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+    if (++cnt == 32) { d1 += s1; d2 += s2; s1 = 0.f; s2 = 0.f; cnt = 0; }
+  }
+  if (stats != nullptr) {
+    d1 += s1; d2 += s2;
+    __shared__ double ra[8], rb[8];
+    d1 = warp_sum(d1); d2 = warp_sum(d2);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { ra[wid] = d1; rb[wid] = d2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+      for (int q = 0; q < 8; ++q) { a += ra[q]; b += rb[q]; }
+      atomicAdd(stats + 2 * n, a);
+      atomicAdd(stats + 2 * n + 1, b);
+    }
   }
 }
 
@@ -246,7 +288,7 @@ bool conv_tc_supported(const ptk_conv_geom& c) {
 }
 
 int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, const float* bias, int act, float* y,
-                    double* stats, cudaStream_t st) {
+                    double* stats, float* scratch, int64_t scratch_floats, cudaStream_t st) {
   PTK_REQUIRE(act == PTK_ACT_NONE || act == PTK_ACT_LEAKY || act == PTK_ACT_RELU, "conv_forward(tc): unsupported activation epilogue");
   PTK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(w_k) & 15) == 0, "conv_forward(tc): pointers must be 16-byte aligned");
@@ -309,6 +351,9 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   double best_cost = 0.0;
   int best_splits = 1;
   const bool can_split = c.ldy == c.Cout && bias == nullptr && act == PTK_ACT_NONE;
+  const int64_t out_floats = (int64_t)c.N * c.OH * c.OW * c.Cout;
+  const bool use_parts = scratch != nullptr && scratch_floats >= 2 * out_floats && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0 &&
+                         out_floats % 4 == 0;
   for (const TileCfg& t : kCfgs) {
     if (c.Cout % t.bn != 0) continue;
     if (t.bn == 64 && c.Cout % 128 == 0) continue;
@@ -328,12 +373,14 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     if (can_split && ctas * 2 <= slots) {
       sp = (int)(slots / ctas);
       if (sp > min_kb / 4) sp = min_kb / 4;
+      if (use_parts && (int64_t)sp * out_floats > scratch_floats) sp = (int)(scratch_floats / out_floats);
       if (sp < 1) sp = 1;
       while (sp > 1 && (min_kb + sp - 1) / sp * (sp - 1) >= min_kb) --sp;
     }
     if (t.occ == 1 && !forced && ctas * sp < slots / 2) continue;   // big one-CTA-per-SM shapes must fill the machine
     const double tile_clk = (double)((min_kb + sp - 1) / sp) * t.mh * (t.bn / 128.0) * 256.0 / t.eff + (t.occ == 1 ? 6000.0 : 1500.0);
-    const double combine = sp > 1 ? (double)c.N * c.OH * c.OW * c.Cout * sp / 100.0 : 0.0;
+    // combining the splits: fp32 L2 atomics (~100 floats / clk chip-wide) or one streamed pass over the partial buffers
+    const double combine = sp > 1 ? (double)out_floats * sp / (use_parts ? 1500.0 : 100.0) + (use_parts ? 3000.0 : 0.0) : 0.0;
     const double cost = (double)((ctas * sp + slots - 1) / slots) * t.occ * tile_clk + combine;
     if (forced) { best = &t; best_splits = sp; break; }
     if (!best || cost < best_cost) { best = &t; best_cost = cost; best_splits = sp; }
@@ -371,8 +418,11 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   }
   const int splits = best_splits;
   g.splits = splits;
-  if (splits > 1) {
-    int rc = ptk_fill(y, (int64_t)c.N * c.OH * c.OW * c.Cout, 0.f, st);
+  const bool parts = splits > 1 && use_parts;
+  g.part_stride = parts ? out_floats : 0;
+  float* y_kernel = parts ? scratch : y;
+  if (splits > 1 && !parts) {
+    int rc = ptk_fill(y, out_floats, 0.f, st);
     if (rc) return rc;
   }
   dim3 grid((unsigned)(g.tiles_x * g.tiles_y * g.tiles_i), (unsigned)(c.Cout / BN), (unsigned)(nphases * splits));
@@ -381,7 +431,7 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 16 + 1024;                                 \
     static bool attr = false;                                                                                              \
     if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
-    launch_pdl(conv_tc_kernel<BN_, ST_, MH_>, grid, dim3(192), smem, st, maps, g, y, stats, bias, act);                      \
+    launch_pdl(conv_tc_kernel<BN_, ST_, MH_>, grid, dim3(192), smem, st, maps, g, y_kernel, stats, bias, act);               \
   } while (0)
   if (MH == 1 && BN == 32) PTK_TC_LAUNCH(32, 4, 1);
   else if (MH == 2 && BN == 32) PTK_TC_LAUNCH(32, 3, 2);
@@ -393,7 +443,17 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   else PTK_TC_LAUNCH(256, 3, 2);
 #undef PTK_TC_LAUNCH
   PTK_LAUNCH_CHECK("conv_tc_kernel");
-  if (splits > 1 && stats != nullptr)   // partial sums cannot feed the fused statistics: one extra pass over a tiny tensor
+  if (parts) {
+    const long long per_sample = (long long)c.OH * c.OW * c.Cout;
+    int blocks = (int)((per_sample / 4 + 255) / 256);
+    const int cap = (num_sms() * 8 + c.N - 1) / c.N;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    splitk_reduce_kernel<<<dim3((unsigned)blocks, (unsigned)c.N), 256, 0, st>>>(scratch, splits, (long long)out_floats, y, per_sample, stats);
+    PTK_LAUNCH_CHECK("splitk_reduce_kernel");
+    return 0;
+  }
+  if (splits > 1 && stats != nullptr)   // atomic split-K: the statistics need one extra pass over a tiny tensor
     return ptk_gn_stats(y, c.ldy, c.N, (int64_t)c.OH * c.OW, c.Cout, stats, st);
   return 0;
 }

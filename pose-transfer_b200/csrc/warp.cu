@@ -184,7 +184,7 @@ struct WarpLevelDev {
 };
 struct WarpLaunchDev {
   WarpLevelDev lv[4];
-  int nlevels, K, H0, W0, act, ctas_per_image, pf_rows;
+  int nlevels, K, H0, W0, act, ctas_per_image;
 };
 
 // geometry of part `gl` at output pixel (i, j); returns false for "0, no gradient" (mask 0 / footprint outside)
@@ -348,159 +348,203 @@ __device__ __forceinline__ void warp_fwd_strip(const WarpLevelDev& L, const Thet
 }
 
 
-// ---- pipelined forward: the mask values of a row are fetched one row ahead (registers), the geometry of row r + 1 is
-// evaluated into the second half of a double-buffered shared-memory record while the gathers of row r are in flight, and the
-// source lines that the body of the strip will need PF rows further down are pulled into L2 early -- the row loop's critical
-// path is then ONE global round trip per part instead of mask -> geometry -> gather.
-template <int G, int PX>
-__device__ __forceinline__ void load_row_masks(const float* __restrict__ mrow, int K, int j0, int w, int gl, float (&m)[PX]) {
-#pragma unroll
-  for (int px = 0; px < PX; ++px) m[px] = (gl < K && j0 + px < w) ? __ldg(mrow + (j0 + px) * K + gl) : 0.f;
-}
+// ---- forward, record-staged variant (the default).  ncu on the per-row-geometry kernel above: 160 M warp instructions per
+// launch set, 9 % of them FFMA -- the coordinate arithmetic re-done by the 16-32 lanes of every pixel, 64-bit address
+// arithmetic and divergence bookkeeping made it ISSUE-bound (66 % issue-active at 0.36 of the HBM roofline).  Here a CTA
+// owns a tile of 32 x 8 output pixels and works in two phases:
+//   A  one THREAD per pixel evaluates the geometry of that pixel's active parts once and parks it in shared memory as
+//      32-byte records (4 bilinear weights incl. the mask factor, 4 clamped tap offsets), plus one header word per pixel
+//      (count, the part index of each record, the position of the first "0, no gradient" candidate);
+//   B  one WARP per tile row gathers: G lanes own a pixel, two pixels per lane group in flight, every 128-bit request a
+//      run of whole lines; per (pixel, part) the lanes read the record with two broadcast loads and do nothing but
+//      4 NV loads, 16 NV FMAs and the running max.
+constexpr int kTileW = 32, kTileH = 8, kMaxRec = 6;     // records per pixel held in shared memory (more: inline slow path)
 
-template <int G, int PX>
-__device__ __forceinline__ void row_geometry_m(const Theta* s_theta, const float (&m)[PX], int K, int i, int j0, int h, int w, int ld,
-                                               int gl, int grp, float4* __restrict__ geo, unsigned (&bits)[PX]) {
-  const unsigned gmask = G == 32 ? 0xffffffffu : (0xffffu << (grp * 16));
-#pragma unroll
-  for (int px = 0; px < PX; ++px) {
-    bool valid = false;
-    float4 wgt;
-    int4 off;
-    if (gl < K && j0 + px < w) valid = part_geometry(s_theta[gl], m[px], i, j0 + px, h, w, ld, wgt, off);
-    if (valid) {
-      geo[(px * 16 + gl) * 2] = wgt;
-      geo[(px * 16 + gl) * 2 + 1] = make_float4(__int_as_float(off.x), __int_as_float(off.y), __int_as_float(off.z), __int_as_float(off.w));
-    }
-    const unsigned ball = __ballot_sync(gmask, valid);      // group-wide: the two pixel groups of a warp may have diverged
-    bits[px] = (ball >> (grp * G)) & 0xffffu;
-  }
-}
+struct FwdTileSmem {
+  Theta theta[kMaxParts];
+  uint32_t hdr[kTileW * kTileH];                 // bits [0,24): part index of record r at 4r; [24,27): count; 27: overflow;
+                                                 // [28,32): kz (first part that contributes the zero candidate), 15 = none
+  float4 rec[kTileW * kTileH * kMaxRec * 2];
+};
 
-template <int G, int NV, int PX, int ACT>
-__device__ __forceinline__ void warp_fwd_strip_pipe(const WarpLevelDev& L, const Theta* s_theta, float4* s_geo_warp, int K, int n,
-                                                    int tile, int pf_rows) {
-  constexpr int PPW = 32 / G, XW = 8 * PPW * PX, CH = 4 * G * NV;
+template <int G, int NV, int ACT>
+__device__ __forceinline__ void warp_fwd_tile(const WarpLevelDev& L, FwdTileSmem& S, int K, int n, int tile) {
+  constexpr int PPW = 32 / G, PX = 2, CH = 4 * G * NV;
   constexpr bool kRelu = ACT == PTK_ACT_RELU;
-  const int sx = tile % L.strips_x, sy = tile / L.strips_x;
-  const int y_begin = sy * L.TH;
-  const int h = L.h, w = L.w, C = L.C;
-  const int rows = min(L.TH, h - y_begin);
+  const int h = L.h, w = L.w, C = L.C, ldx = L.ldx, ldy = L.ldy;
+  const int tx = tile % L.strips_x, ty = tile / L.strips_x;
+  const int x0 = tx * kTileW, y0 = ty * kTileH;
+  const int64_t img = (int64_t)n * h * w;
+  const unsigned kmask = (1u << K) - 1u;
+  // ------------------------------------------------------------------ phase A: one thread per pixel
+  {
+    const int t = threadIdx.x;
+    const int i = y0 + t / kTileW, j = x0 + t % kTileW;
+    uint32_t hdr = 15u << 28;
+    if (i < h && j < w) {
+      const float* mp = L.mask + (img + (int64_t)i * w + j) * K;
+      int cnt = 0;
+      unsigned seen = 0u;
+      for (int k = 0; k < K; ++k) {
+        const float m = __ldg(mp + k);
+        float4 wgt;
+        int4 off;
+        if (part_geometry(S.theta[k], m, i, j, h, w, ldx, wgt, off)) {
+          seen |= 1u << k;
+          if (cnt < kMaxRec) {
+            S.rec[(t * kMaxRec + cnt) * 2] = wgt;
+            S.rec[(t * kMaxRec + cnt) * 2 + 1] = make_float4(__int_as_float(off.x), __int_as_float(off.y), __int_as_float(off.z), __int_as_float(off.w));
+            hdr |= (uint32_t)k << (4 * cnt);
+            ++cnt;
+          } else {
+            hdr |= 1u << 27;
+          }
+        }
+      }
+      const unsigned inactive = ~seen & kmask;
+      const uint32_t kz = inactive ? (uint32_t)(__ffs(inactive) - 1) : 15u;
+      hdr = (hdr & 0x0fffffffu) | ((uint32_t)cnt << 24) | (kz << 28);
+    }
+    S.hdr[t] = hdr;
+  }
+  __syncthreads();
+  // ------------------------------------------------------------------ phase B: one warp per tile row
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const int gl = lane % G, grp = lane / G;
-  const int j0 = sx * XW + (wi * PPW + grp) * PX;
-  const int64_t img = (int64_t)n * h * w;
-  const float* xb = L.x + img * L.ldx + gl * 4;
-  const float* mb = L.mask + img * K;
-  float4* geo0 = s_geo_warp + grp * (PX * 32);                  // [2 buffers][PPW groups][PX * 32]
-  float4* geo1 = geo0 + PPW * PX * 32;
-  const unsigned kmask = (1u << K) - 1u;
-  const int pf_step = pf_rows * w * L.ldx, pf_lim = (h * w - 1) * L.ldx;
-
-  float mnext[PX];
-  unsigned bits[PX], bits_next[PX];
-  load_row_masks<G, PX>(mb + (int64_t)y_begin * w * K, K, j0, w, gl, mnext);
-  row_geometry_m<G, PX>(s_theta, mnext, K, y_begin, j0, h, w, L.ldx, gl, grp, geo0, bits);
-  if (rows > 1) load_row_masks<G, PX>(mb + (int64_t)(y_begin + 1) * w * K, K, j0, w, gl, mnext);
-  __syncwarp();
-  for (int r = 0; r < rows; ++r) {
-    const int i = y_begin + r;
-    float4* geo = (r & 1) ? geo1 : geo0;
-    float4* geo_nx = (r & 1) ? geo0 : geo1;
-    unsigned uni = 0u;
-    int kz[PX];
+  const int i = y0 + wi;
+  if (i >= h) return;
+  const float* xb = L.x + img * ldx + gl * 4;
+  float* yb = L.y + (img + (int64_t)i * w) * ldy + gl * 4;
+  uint8_t* ab = L.argk + (((img + (int64_t)i * w) * C) >> 1) + gl * 2;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int it = 0; it < kTileW / (PPW * PX); ++it) {
+    const int c0 = it * (PPW * PX) + grp * PX;             // first tile column of this group's pixel pair
+    if (x0 + c0 >= w) break;                                 // (group-uniform; later columns are outside as well)
+    uint32_t hd[PX];
+    int cnt[PX];
 #pragma unroll
     for (int px = 0; px < PX; ++px) {
-      const unsigned inactive = ~bits[px] & kmask;
-      kz[px] = (!kRelu && inactive) ? __ffs(inactive) - 1 : -1;
-      uni |= bits[px] | ((!kRelu && inactive) ? (inactive & (0u - inactive)) : 0u);
+      hd[px] = S.hdr[wi * kTileW + c0 + px];
+      cnt[px] = (x0 + c0 + px < w) ? (int)((hd[px] >> 24) & 7u) : 0;
     }
-    float* yrow = L.y + (img + (int64_t)i * w + j0) * L.ldy + gl * 4;
-    uint8_t* arow = L.argk + (((img + (int64_t)i * w + j0) * C) >> 1) + gl * 2;
-    bool staged = false;          // next row's geometry done?
+    const int nrec = max(cnt[0], cnt[1]);
+    const float4* rbase = S.rec + (wi * kTileW + c0) * (kMaxRec * 2);
+#pragma unroll 1
     for (int cb = 0; cb < C; cb += CH) {
       float best[PX][NV * 4];
       int arg[PX][NV * 4];
+      bool zdone[PX];
 #pragma unroll
-      for (int px = 0; px < PX; ++px)
+      for (int px = 0; px < PX; ++px) {
+        zdone[px] = kRelu;
 #pragma unroll
         for (int q = 0; q < NV * 4; ++q) { best[px][q] = kRelu ? 0.f : -INFINITY; arg[px][q] = kNoPart; }
-      unsigned rem = uni;
-      while (rem) {
-        const int k = __ffs(rem) - 1;
-        rem &= rem - 1;
+      }
+#pragma unroll 1
+      for (int r = 0; r < nrec; ++r) {
         float4 wv[PX];
         float4 v[PX][NV][4];
+        int kk[PX];
 #pragma unroll
         for (int px = 0; px < PX; ++px) {
-          const bool on = (bits[px] >> k) & 1u;
-          wv[px] = make_float4(0.f, 0.f, 0.f, 0.f);
-          int4 o = make_int4(0, 0, 0, 0);
-          if (on) {
-            wv[px] = geo[(px * 16 + k) * 2];
-            const float4 of = geo[(px * 16 + k) * 2 + 1];
-            o = make_int4(__float_as_int(of.x), __float_as_int(of.y), __float_as_int(of.z), __float_as_int(of.w));
-          }
+          const bool on = r < cnt[px];
+          kk[px] = (int)((hd[px] >> (4 * r)) & 15u);
+          wv[px] = on ? rbase[(px * kMaxRec + r) * 2] : zero4;
+          const float4 of = on ? rbase[(px * kMaxRec + r) * 2 + 1] : zero4;
+          const float* p = xb + cb;
 #pragma unroll
           for (int q = 0; q < NV; ++q) {
-            const float* p = xb + cb + q * G * 4;
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            v[px][q][0] = on ? __ldg(reinterpret_cast<const float4*>(p + o.x)) : z;
-            v[px][q][1] = on ? __ldg(reinterpret_cast<const float4*>(p + o.y)) : z;
-            v[px][q][2] = on ? __ldg(reinterpret_cast<const float4*>(p + o.z)) : z;
-            v[px][q][3] = on ? __ldg(reinterpret_cast<const float4*>(p + o.w)) : z;
-            if (pf_rows > 0 && on && !staged) {     // first part of the row (the body): warm L2 for the rows further down
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p + min(o.z + pf_step, pf_lim)));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p + min(o.w + pf_step, pf_lim)));
-            }
-          }
-        }
-        if (!staged) {
-          // while those loads are in flight: geometry of the next row, mask values of the row after it
-          staged = true;
-          if (r + 1 < rows) {
-            row_geometry_m<G, PX>(s_theta, mnext, K, i + 1, j0, h, w, L.ldx, gl, grp, geo_nx, bits_next);
-            if (r + 2 < rows) load_row_masks<G, PX>(mb + (int64_t)(i + 2) * w * K, K, j0, w, gl, mnext);
+            v[px][q][0] = on ? __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.x))) : zero4;
+            v[px][q][1] = on ? __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.y))) : zero4;
+            v[px][q][2] = on ? __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.z))) : zero4;
+            v[px][q][3] = on ? __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.w))) : zero4;
           }
         }
 #pragma unroll
         for (int px = 0; px < PX; ++px) {
-          const bool on = (bits[px] >> k) & 1u;
-          const bool zero = !kRelu && k == kz[px];
-          if (!on && !zero) continue;
-          const int tag = on ? k : kNoPart;
+          if (r >= cnt[px]) continue;
+          if (!kRelu && !zdone[px] && kk[px] > (int)(hd[px] >> 28)) {      // the zero candidate sits before this part
+            zdone[px] = true;
+#pragma unroll
+            for (int q = 0; q < NV * 4; ++q) if (0.f > best[px][q]) { best[px][q] = 0.f; arg[px][q] = kNoPart; }
+          }
 #pragma unroll
           for (int q = 0; q < NV; ++q) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 acc = zero4;
             fma4(acc, wv[px].x, v[px][q][0]); fma4(acc, wv[px].y, v[px][q][1]);
             fma4(acc, wv[px].z, v[px][q][2]); fma4(acc, wv[px].w, v[px][q][3]);
-            if (acc.x > best[px][4 * q + 0]) { best[px][4 * q + 0] = acc.x; arg[px][4 * q + 0] = tag; }
-            if (acc.y > best[px][4 * q + 1]) { best[px][4 * q + 1] = acc.y; arg[px][4 * q + 1] = tag; }
-            if (acc.z > best[px][4 * q + 2]) { best[px][4 * q + 2] = acc.z; arg[px][4 * q + 2] = tag; }
-            if (acc.w > best[px][4 * q + 3]) { best[px][4 * q + 3] = acc.w; arg[px][4 * q + 3] = tag; }
+            if (acc.x > best[px][4 * q + 0]) { best[px][4 * q + 0] = acc.x; arg[px][4 * q + 0] = kk[px]; }
+            if (acc.y > best[px][4 * q + 1]) { best[px][4 * q + 1] = acc.y; arg[px][4 * q + 1] = kk[px]; }
+            if (acc.z > best[px][4 * q + 2]) { best[px][4 * q + 2] = acc.z; arg[px][4 * q + 2] = kk[px]; }
+            if (acc.w > best[px][4 * q + 3]) { best[px][4 * q + 3] = acc.w; arg[px][4 * q + 3] = kk[px]; }
           }
         }
       }
 #pragma unroll
       for (int px = 0; px < PX; ++px) {
-        if (j0 + px >= w) continue;
+        const int j = x0 + c0 + px;
+        if (j >= w) continue;
+        if (hd[px] & (1u << 27)) {
+          // more active parts than records (never seen in practice): the remaining parts, geometry evaluated inline
+          const int last = (int)((hd[px] >> (4 * (kMaxRec - 1))) & 15u);
+          for (int k = last + 1; k < K; ++k) {
+            float4 wgt;
+            int4 off;
+            const float m = __ldg(L.mask + (img + (int64_t)i * w + j) * K + k);
+            if (!part_geometry(S.theta[k], m, i, j, h, w, ldx, wgt, off)) continue;
+            if (!kRelu && !zdone[px] && k > (int)(hd[px] >> 28)) {
+              zdone[px] = true;
+#pragma unroll
+              for (int q = 0; q < NV * 4; ++q) if (0.f > best[px][q]) { best[px][q] = 0.f; arg[px][q] = kNoPart; }
+            }
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+              const float* p = xb + cb + q * G * 4;
+              float4 acc = zero4;
+              fma4(acc, wgt.x, __ldg(reinterpret_cast<const float4*>(p + off.x))); fma4(acc, wgt.y, __ldg(reinterpret_cast<const float4*>(p + off.y)));
+              fma4(acc, wgt.z, __ldg(reinterpret_cast<const float4*>(p + off.z))); fma4(acc, wgt.w, __ldg(reinterpret_cast<const float4*>(p + off.w)));
+              if (acc.x > best[px][4 * q + 0]) { best[px][4 * q + 0] = acc.x; arg[px][4 * q + 0] = k; }
+              if (acc.y > best[px][4 * q + 1]) { best[px][4 * q + 1] = acc.y; arg[px][4 * q + 1] = k; }
+              if (acc.z > best[px][4 * q + 2]) { best[px][4 * q + 2] = acc.z; arg[px][4 * q + 2] = k; }
+              if (acc.w > best[px][4 * q + 3]) { best[px][4 * q + 3] = acc.w; arg[px][4 * q + 3] = k; }
+            }
+          }
+        }
+        if (!kRelu && !zdone[px] && (hd[px] >> 28) != 15u) {      // zero candidate after the last real part
+#pragma unroll
+          for (int q = 0; q < NV * 4; ++q) if (0.f > best[px][q]) { best[px][q] = 0.f; arg[px][q] = kNoPart; }
+        }
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
-          *reinterpret_cast<float4*>(yrow + px * L.ldy + cb + q * G * 4) =
+          *reinterpret_cast<float4*>(yb + j * ldy + cb + q * G * 4) =
               make_float4(warp_act<ACT>(best[px][4 * q]), warp_act<ACT>(best[px][4 * q + 1]), warp_act<ACT>(best[px][4 * q + 2]),
                           warp_act<ACT>(best[px][4 * q + 3]));
-          *reinterpret_cast<uint16_t*>(arow + ((px * C + cb + q * G * 4) >> 1)) =
+          *reinterpret_cast<uint16_t*>(ab + ((j * C + cb + q * G * 4) >> 1)) =
               (uint16_t)(arg[px][4 * q] | (arg[px][4 * q + 1] << 4) | (arg[px][4 * q + 2] << 8) | (arg[px][4 * q + 3] << 12));
         }
       }
     }
-    if (!staged && r + 1 < rows) {      // no candidate at all in this row (all masks zero): stage the next row here
-      row_geometry_m<G, PX>(s_theta, mnext, K, i + 1, j0, h, w, L.ldx, gl, grp, geo_nx, bits_next);
-      if (r + 2 < rows) load_row_masks<G, PX>(mb + (int64_t)(i + 2) * w * K, K, j0, w, gl, mnext);
-    }
-    __syncwarp();
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256, 2)
+warp_forward_tiles_kernel(const __grid_constant__ WarpLaunchDev P, const float* __restrict__ warps) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  FwdTileSmem& S = *reinterpret_cast<FwdTileSmem*>(s_raw);
+  const int n = blockIdx.y;
+  int li = 0;
 #pragma unroll
-    for (int px = 0; px < PX; ++px) bits[px] = bits_next[px];
+  for (int q = 1; q < 4; ++q) if (q < P.nlevels && (int)blockIdx.x >= P.lv[q].cta_begin) li = q;
+  const WarpLevelDev& L = P.lv[li];
+  if (threadIdx.x < P.K) S.theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * P.K + threadIdx.x) * 8, L.h, L.w, P.H0, P.W0);
+  __syncthreads();
+  const int tile = blockIdx.x - L.cta_begin;
+  switch (L.cfg) {
+    case 0: warp_fwd_tile<16, 1, ACT>(L, S, P.K, n, tile); break;
+    case 1: warp_fwd_tile<16, 2, ACT>(L, S, P.K, n, tile); break;
+    default: warp_fwd_tile<32, 2, ACT>(L, S, P.K, n, tile); break;
   }
 }
 
@@ -582,9 +626,9 @@ constexpr int kGeoPerWarp = 8 * 32;      // float4 slots: (pixels per warp <= 8)
 
 // ONE launch for all warped levels of a generator pass: blockIdx.x enumerates the strips of every level (largest level
 // first; all strips carry the same number of bytes), blockIdx.y the image.
-// VAR 0: 16 loads of 128 bits in flight per lane and part (2 CTAs / SM); VAR 1: 8 loads (3 CTAs / SM).
+// (forward through this kernel = the per-row-geometry variant, PTK_WARP_VAR=1; the backward pass uses its sibling below)
 template <int ACT, int VAR>
-__global__ void __launch_bounds__(256, (VAR == 0 || VAR == 3) ? 2 : 3)
+__global__ void __launch_bounds__(256, 3)
 warp_forward_levels_kernel(const __grid_constant__ WarpLaunchDev P, const float* __restrict__ warps) {
   __shared__ Theta s_theta[kMaxParts];
   __shared__ float4 s_geo[8 * kGeoPerWarp];
@@ -597,25 +641,10 @@ warp_forward_levels_kernel(const __grid_constant__ WarpLaunchDev P, const float*
   __syncthreads();
   const int tile = blockIdx.x - L.cta_begin;
   float4* geo = s_geo + (threadIdx.x >> 5) * kGeoPerWarp;
-  if (VAR == 0) {
-    switch (L.cfg) {
-      case 0: warp_fwd_strip<16, 1, 4, ACT>(L, s_theta, geo, P.K, n, tile); break;
-      case 1: warp_fwd_strip<16, 2, 2, ACT>(L, s_theta, geo, P.K, n, tile); break;
-      case 2: warp_fwd_strip<32, 2, 2, ACT>(L, s_theta, geo, P.K, n, tile); break;
-      default: warp_fwd_strip<32, 4, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
-    }
-  } else if (VAR == 1) {
-    switch (L.cfg) {
-      case 0: warp_fwd_strip<16, 1, 2, ACT>(L, s_theta, geo, P.K, n, tile); break;
-      case 1: warp_fwd_strip<16, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
-      default: warp_fwd_strip<32, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
-    }
-  } else {
-    switch (L.cfg) {
-      case 0: warp_fwd_strip_pipe<16, 1, 2, ACT>(L, s_theta, geo, P.K, n, tile, P.pf_rows); break;
-      case 1: warp_fwd_strip_pipe<16, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile, P.pf_rows); break;
-      default: warp_fwd_strip_pipe<32, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile, P.pf_rows); break;
-    }
+  switch (L.cfg) {
+    case 0: warp_fwd_strip<16, 1, 2, ACT>(L, s_theta, geo, P.K, n, tile); break;
+    case 1: warp_fwd_strip<16, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
+    default: warp_fwd_strip<32, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
   }
 }
 
@@ -730,10 +759,10 @@ static int warp_rows_per_strip() {
 }
 
 // fills the device-side launch description; returns false if some level cannot take the fast path
+// forward kernel variant: 2 = record-staged tiles (default), 1 = per-row geometry strips (PTK_WARP_VAR=1, kept for comparison)
 static int warp_variant() {
   const char* e = getenv("PTK_WARP_VAR");
-  const int v = e ? atoi(e) : 2;
-  return (v >= 0 && v <= 3) ? v : 2;
+  return (e && atoi(e) == 1) ? 1 : 2;
 }
 
 static bool warp_plan(const ptk_warp_level* lv, int nlevels, int K, int H0, int W0, int act, bool backward, WarpLaunchDev& P) {
@@ -748,12 +777,20 @@ static bool warp_plan(const ptk_warp_level* lv, int nlevels, int K, int H0, int 
     WarpLevelDev& d = P.lv[q];
     d.x = s.x; d.mask = s.mask; d.y = s.y; d.argk = s.argk; d.dy = s.dy; d.dx = s.dx;
     d.ldx = s.ldx; d.ldy = s.ldy; d.lddy = s.lddy; d.C = s.C; d.h = s.h; d.w = s.w; d.cfg = cfg;
-    const int var = backward ? 0 : warp_variant();
-    const int nv = cfg == 0 ? 1 : ((cfg == 3 && var == 0) ? 4 : 2), g = cfg <= 1 ? 16 : 32;
-    const int xw = 8 * (32 / g) * ((var == 0 ? 4 : 2) / nv);
-    if (const char* e = getenv("PTK_WARP_PF")) P.pf_rows = atoi(e); else P.pf_rows = 4;
-    if (P.pf_rows < 0 || P.pf_rows > 32) P.pf_rows = 0;
-    d.TH = warp_rows_per_strip() < s.h ? warp_rows_per_strip() : s.h;
+    const int g = cfg <= 1 ? 16 : 32;
+    int xw;
+    if (backward) {                       // warp_bwd_strip<G, NV, 4 / NV>
+      const int nv = cfg == 0 ? 1 : (cfg == 3 ? 4 : 2);
+      xw = 8 * (32 / g) * (4 / nv);
+      d.TH = warp_rows_per_strip() < s.h ? warp_rows_per_strip() : s.h;
+    } else if (warp_variant() == 1) {     // warp_fwd_strip<G, NV, 2 / NV>
+      const int nv = cfg == 0 ? 1 : 2;
+      xw = 8 * (32 / g) * (2 / nv);
+      d.TH = warp_rows_per_strip() < s.h ? warp_rows_per_strip() : s.h;
+    } else {                              // warp_fwd_tile: 32 x 8 pixel tiles
+      xw = kTileW;
+      d.TH = kTileH;
+    }
     d.strips_x = (s.w + xw - 1) / xw;
     d.strips_y = (s.h + d.TH - 1) / d.TH;
     d.cta_begin = ctas;
@@ -799,22 +836,22 @@ extern "C" int ptk_warp_forward_levels(const ptk_warp_level* lv, int nlevels, co
     return 0;
   }
   dim3 grid((unsigned)P.ctas_per_image, (unsigned)N);
-  if (warp_variant() == 3) {
-    if (act == PTK_ACT_RELU) warp_forward_levels_kernel<PTK_ACT_RELU, 3><<<grid, 256, 0, st>>>(P, warps);
-    else if (act == PTK_ACT_LEAKY) warp_forward_levels_kernel<PTK_ACT_LEAKY, 3><<<grid, 256, 0, st>>>(P, warps);
-    else warp_forward_levels_kernel<PTK_ACT_NONE, 3><<<grid, 256, 0, st>>>(P, warps);
-  } else if (warp_variant() == 2) {
-    if (act == PTK_ACT_RELU) warp_forward_levels_kernel<PTK_ACT_RELU, 2><<<grid, 256, 0, st>>>(P, warps);
-    else if (act == PTK_ACT_LEAKY) warp_forward_levels_kernel<PTK_ACT_LEAKY, 2><<<grid, 256, 0, st>>>(P, warps);
-    else warp_forward_levels_kernel<PTK_ACT_NONE, 2><<<grid, 256, 0, st>>>(P, warps);
-  } else if (warp_variant() == 0) {
-    if (act == PTK_ACT_RELU) warp_forward_levels_kernel<PTK_ACT_RELU, 0><<<grid, 256, 0, st>>>(P, warps);
-    else if (act == PTK_ACT_LEAKY) warp_forward_levels_kernel<PTK_ACT_LEAKY, 0><<<grid, 256, 0, st>>>(P, warps);
-    else warp_forward_levels_kernel<PTK_ACT_NONE, 0><<<grid, 256, 0, st>>>(P, warps);
-  } else {
+  if (warp_variant() == 1) {
     if (act == PTK_ACT_RELU) warp_forward_levels_kernel<PTK_ACT_RELU, 1><<<grid, 256, 0, st>>>(P, warps);
     else if (act == PTK_ACT_LEAKY) warp_forward_levels_kernel<PTK_ACT_LEAKY, 1><<<grid, 256, 0, st>>>(P, warps);
     else warp_forward_levels_kernel<PTK_ACT_NONE, 1><<<grid, 256, 0, st>>>(P, warps);
+  } else {
+    const size_t smem = sizeof(FwdTileSmem);
+#define PTK_WARP_TILES(A_)                                                                                              \
+  do {                                                                                                                  \
+    static bool attr = false;                                                                                           \
+    if (!attr) { cudaFuncSetAttribute(warp_forward_tiles_kernel<A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
+    warp_forward_tiles_kernel<A_><<<grid, 256, smem, st>>>(P, warps);                                                   \
+  } while (0)
+    if (act == PTK_ACT_RELU) PTK_WARP_TILES(PTK_ACT_RELU);
+    else if (act == PTK_ACT_LEAKY) PTK_WARP_TILES(PTK_ACT_LEAKY);
+    else PTK_WARP_TILES(PTK_ACT_NONE);
+#undef PTK_WARP_TILES
   }
   PTK_LAUNCH_CHECK("warp_forward_levels_kernel");
   return 0;

@@ -20,6 +20,10 @@ from .kernels import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, Slice
 STREAMS = True
 
 
+# floats of split-K scratch per stream (partial output tiles of the small bottleneck layers; 64 MB)
+SPLITK_SCRATCH = 1 << 24
+
+
 def ceil4(x):
     return (x + 3) // 4 * 4
 
@@ -129,18 +133,20 @@ class ConvLayer:
         return (self.impl != K.IMPL_SIMT and not self.transposed and self.k == 3 and self.stride == 1 and self.pad == 1 and
                 self.cout == 64 and self.cin <= 24 and os.environ.get("PTK_STEM", "1") != "0")
 
-    def forward(self, x, N, H, W, y, act=ACT_NONE, stats=None, y_nchw=None):
-        """x: Slice with cin_pad readable channels; y: Slice (cout channels) or None."""
+    def forward(self, x, N, H, W, y, act=ACT_NONE, stats=None, y_nchw=None, scratch=None):
+        """x: Slice with cin_pad readable channels; y: Slice (cout channels) or None.  scratch: fp32 buffer for the
+        deterministic split-K of layers with few output tiles (one per stream that may run this layer)."""
         OH, OW = self.out_hw(H, W)
         g = K.conv_geom(N, H, W, self.cin_pad, x.ld, OH, OW, self.cout, y.ld if y is not None else self.cout, self.k,
                         self.stride, self.pad, self.transposed, self.impl)
         if self._is_stem() and act == ACT_NONE and stats is None and y is not None and y_nchw is None and self.stem_wk is not None:
             K.stem_conv(g, x, self.stem_wk, self.bias.detach() if self.bias is not None else None, y)
             return OH, OW
-        K.conv_forward(g, x, self.w_fwd, self.w_bwd, self.bias.detach() if self.bias is not None else None, act, y, y_nchw, stats)
+        K.conv_forward(g, x, self.w_fwd, self.w_bwd, self.bias.detach() if self.bias is not None else None, act, y, y_nchw, stats,
+                       scratch)
         return OH, OW
 
-    def dgrad(self, dy, N, H, W, dx, dx_channels=None):
+    def dgrad(self, dy, N, H, W, dx, dx_channels=None, scratch=None):
         """dy: Slice over the OUTPUT grid (dy_pad readable channels); dx: Slice over the input grid (H, W)."""
         OH, OW = self.out_hw(H, W)
         cout_dx = self.cin if dx_channels is None else dx_channels
@@ -148,7 +154,7 @@ class ConvLayer:
                         not self.transposed, self.impl)
         # the dgrad weights are [taps][dy_pad][cin_pad]; the kernel's inner extent is ceil4(Cout')
         assert ceil4(cout_dx) == self.cin_pad
-        K.conv_forward(g, dy, self.w_bwd, self.w_dgrad_k, None, ACT_NONE, dx, None, None)
+        K.conv_forward(g, dy, self.w_bwd, self.w_dgrad_k, None, ACT_NONE, dx, None, None, scratch)
 
     def wgrad(self, x, dy, N, H, W, scratch, grad_w, accumulate=False):
         """grad_w (torch layout, fp32 view into the gradient arena) += dW.  On the trainer's in-place path (grad_w is the
@@ -410,6 +416,7 @@ class GeneratorEngine:
         for e_idx, (name, _, c_src0, cin, warped_branch) in enumerate(self.specs):
             with (torch.cuda.stream(side) if (side is not None and e_idx == 1) else contextlib.nullcontext()):
                 convs, norms = self.enc_conv[name], self.enc_norm[name]
+                ck = ws.get("splitk_side" if (side is not None and e_idx == 1) else "splitk_main", (SPLITK_SCRATCH,))
                 warp_levels = []
                 xin = ws.get("xin_%s_%s" % (name, tag), (N, H, W, convs[0].cin_pad))
                 lo = 0
@@ -428,7 +435,7 @@ class GeneratorEngine:
                     src = Slice(xin) if i == 0 else Slice(sv["act"][(name, i - 1)])
                     norm = norms[i]
                     st = stat_for((name, i)) if norm is not None else None
-                    convs[i].forward(src, N, hs[i - 1] if i else H, wsz[i - 1] if i else W, Slice(z), ACT_NONE, st)
+                    convs[i].forward(src, N, hs[i - 1] if i else H, wsz[i - 1] if i else W, Slice(z), ACT_NONE, st, scratch=ck)
                     sv["z"][(name, i)] = z
                     HW = hs[i] * wsz[i]
                     gam = norm.weight.detach() if norm is not None else None
@@ -467,7 +474,7 @@ class GeneratorEngine:
             oh, ow = hs[i - 1], wsz[i - 1]
             z = ws.get("zd%d_%s" % (j, tag), (N, oh, ow, co))
             st = stat_for(("dec", j))
-            self.dec_conv[j].forward(Slice(cats[j]), N, hs[i], wsz[i], Slice(z), ACT_NONE, st)
+            self.dec_conv[j].forward(Slice(cats[j]), N, hs[i], wsz[i], Slice(z), ACT_NONE, st, scratch=ws.get("splitk_main", (SPLITK_SCRATCH,)))
             nl = self.dec_norm[j]
             K.gn_apply(z, st, nl.weight.detach(), nl.bias.detach(), drops[j] if j < 3 else None, N, oh * ow, co,
                        Slice(cats[j + 1], 0, co), ACT_RELU)
@@ -553,7 +560,7 @@ class GeneratorEngine:
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                 cv.wgrad(Slice(cats[j]), Slice(dy), N, hs[i], wsz[i], scratch_side, grads[cv.weight], accumulate)
             dc = ws.get("dcat%d_%s" % (j, tag), tuple(cats[j].shape))
-            cv.dgrad(Slice(dy), N, hs[i], wsz[i], Slice(dc))
+            cv.dgrad(Slice(dy), N, hs[i], wsz[i], Slice(dc), scratch=ws.get("splitk_main", (SPLITK_SCRATCH,)))
             dcats[j] = dc
 
         if side is not None:
@@ -621,7 +628,8 @@ class GeneratorEngine:
                     else:
                         cv.wgrad(Slice(sv["act"][(name, i - 1)]), Slice(dy), N, hs[i - 1], wsz[i - 1], scratch_e, grads[cv.weight], accumulate)
                         dact = ws.get("dact_%s%d_%s" % (name, i - 1, tag), (N, hs[i - 1], wsz[i - 1], self.enc[i - 1]))
-                        cv.dgrad(Slice(dy), N, hs[i - 1], wsz[i - 1], Slice(dact))
+                        cv.dgrad(Slice(dy), N, hs[i - 1], wsz[i - 1], Slice(dact),
+                                 scratch=ws.get("splitk_side" if on_side else "splitk_main", (SPLITK_SCRATCH,)))
                         dact_next = dact
             if e_idx == 0 and on_stage is not None:
                 on_stage(name)
@@ -708,7 +716,7 @@ class DiscriminatorEngine:
                 sv["act"].append(act)
             elif not last:
                 z = ws.get("dz%d_%s" % (i, tag), (M, oh, ow, cv.cout))
-                cv.forward(Slice(x), M, h, w, Slice(z), ACT_NONE, stats[i])
+                cv.forward(Slice(x), M, h, w, Slice(z), ACT_NONE, stats[i], scratch=ws.get("splitk_main", (SPLITK_SCRATCH,)))
                 act = ws.get("dact%d_%s" % (i, tag), (M, oh, ow, cv.cout))
                 nm = self.norms[i]
                 K.gn_apply(z, stats[i], nm.weight.detach(), nm.bias.detach(), None, M, oh * ow, cv.cout, act, ACT_LEAKY)
@@ -771,7 +779,7 @@ class DiscriminatorEngine:
             # gradient w.r.t. the previous block's activated output, then through its activation / norm
             pc = self.convs[i - 1]
             dact = ws.get("ddact%d_%s" % (i - 1, tag), (M, h, w, pc.cout))
-            cv.dgrad(dy_s, M, h, w, Slice(dact))
+            cv.dgrad(dy_s, M, h, w, Slice(dact), scratch=ws.get("splitk_main", (SPLITK_SCRATCH,)))
             dprev = ws.get("ddy%d_%s" % (i - 1, tag), (M, h, w, pc.cout))
             nm = self.norms[i - 1]
             if nm is not None:

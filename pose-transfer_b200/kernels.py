@@ -142,9 +142,10 @@ def conv_tc_supported(g):
 
 
 @_timed("conv_forward")
-def conv_forward(g, x, w_t, w_k, bias, act, y, y_nchw=None, stats=None):
-    check(_lib.lib().ptk_conv_forward(g, _p(x), _p(w_t), _p(w_k), _p(bias), act, _p(y), _p(y_nchw), _p(stats), _stream()),
-          "ptk_conv_forward")
+def conv_forward(g, x, w_t, w_k, bias, act, y, y_nchw=None, stats=None, scratch=None):
+    """scratch: optional fp32 buffer for the deterministic split-K of small layers (partial tiles + fixed-order reduction)."""
+    check(_lib.lib().ptk_conv_forward_ws(g, _p(x), _p(w_t), _p(w_k), _p(bias), act, _p(y), _p(y_nchw), _p(stats), _p(scratch),
+                                         scratch.numel() if scratch is not None else 0, _stream()), "ptk_conv_forward")
 
 
 @_timed("conv_wgrad")

@@ -161,7 +161,7 @@ def install(K):
         else:
             grad.copy_(v)
 
-    def conv_forward(g, x, w_t, w_k, bias, act, y, y_nchw=None, stats=None):
+    def conv_forward(g, x, w_t, w_k, bias, act, y, y_nchw=None, stats=None, scratch=None):
         xs = nchw(view(x, g.Cin)).reshape(g.N, g.Cin, g.H, g.W)
         w = _weights(g, w_t, w_k)
         if g.transposed:

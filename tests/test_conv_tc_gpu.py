@@ -379,3 +379,51 @@ def test_stem_conv_smem_im2col(shape, monkeypatch):
     got = nchw(y[..., 32:]).cpu()
     assert rel_l2(got, ref) < TF32_TOL, describe(got, ref, "stem")
     assert float((y[..., :32] - 7.0).abs().max()) == 0
+
+
+SPLITK_CASES = [
+    # name, transposed, Cin, Cout, N, H, W   (k4 s2 p1: the bottleneck layers of the U-Net at batch 8 / 2)
+    ("enc_512to512_16", False, 512, 512, 8, 16, 16),
+    ("enc_512to512_8", False, 512, 512, 8, 8, 8),
+    ("dec_1024to512_4", True, 1024, 512, 8, 4, 4),
+    ("dec_1536to512_8", True, 1536, 512, 2, 8, 8),
+    ("dgrad_like_512to1536_16", False, 512, 1536, 2, 16, 16),
+]
+
+
+@pytest.mark.parametrize("case", SPLITK_CASES, ids=[c[0] for c in SPLITK_CASES])
+def test_conv_tc_deterministic_split_k(case):
+    """Layers with few output tiles split their K loop over CTAs.  With a scratch buffer every split stores its partial
+    tile and splitk_reduce_kernel sums them in a fixed order with the norm statistics fused: correct vs torch, statistics
+    correct, and BIT-IDENTICAL from run to run (the atomic fallback without scratch is only equal to rounding)."""
+    import pose_transfer_b200  # noqa: F401
+    from pose_transfer_b200 import kernels as K
+    from pose_transfer_b200.engine import ConvLayer
+    name, tr, Cin, Cout, N, H, W = case
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    wshape = (Cin, Cout, 4, 4) if tr else (Cout, Cin, 4, 4)
+    w = (torch.rand(wshape, generator=g) * 2 - 1) / (Cin * 16 / (4 if tr else 1)) ** 0.5
+    x = torch.randn(N, Cin, H, W, generator=g)
+    z = F.conv_transpose2d(x, w, None, stride=2, padding=1) if tr else F.conv2d(x, w, None, stride=2, padding=1)
+    layer = ConvLayer(torch.nn.Parameter(w.cuda()), None, tr, 4, 2, 1)
+    layer.impl = K.IMPL_TC
+    layer.pack_forward()
+    xin = nhwc(x).cuda()
+    OH, OW = layer.out_hw(H, W)
+    scratch = torch.full((1 << 24,), float("nan"), device="cuda")
+    outs = []
+    for rep in range(3):
+        y = torch.full((N, OH, OW, Cout), 7.0, device="cuda")
+        stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+        layer.forward(K.Slice(xin), N, H, W, K.Slice(y), K.ACT_NONE, stats, scratch=scratch if rep < 2 else None)
+        torch.cuda.synchronize()
+        outs.append((y, stats))
+    got = nchw(outs[0][0]).cpu()
+    assert rel_l2(got, z) < TF32_TOL, describe(got, z, "fprop split-K")
+    assert torch.equal(outs[0][0], outs[1][0]), "deterministic split-K differs from run to run"
+    assert rel_l2(outs[2][0], outs[0][0]) < 1e-5           # atomic fallback: same numbers up to summation order
+    ref_stats = torch.stack([z.double().reshape(N, -1).sum(1), (z.double() ** 2).reshape(N, -1).sum(1)], 1)
+    for y, stats in outs:
+        assert rel_l2(stats[:, 1], ref_stats[:, 1]) < 2e-3
+        mine = torch.stack([y.double().reshape(N, -1).sum(1), (y.double() ** 2).reshape(N, -1).sum(1)], 1)
+        assert rel_l2(stats, mine) < 1e-6                  # the fused statistics describe exactly what was written
