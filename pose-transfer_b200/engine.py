@@ -243,6 +243,19 @@ class GeneratorEngine:
         self.layers_built = False
         self.saved = None
 
+    def deep_split(self):
+        """First encoder level of the 'deep' gradient bucket (0 = do not split an encoder's bucket)."""
+        return 4 if self.L >= 6 else 0
+
+    def stage_parts(self, stage, part):
+        """Sub-modules whose parameters form the gradient bucket (stage, part) announced by backward()'s on_stage."""
+        mod = self.stage_modules[stage]
+        if part is None:
+            return [mod]
+        nets = list(mod.net)
+        sp = self.deep_split()
+        return nets[sp:] if part == "deep" else nets[:sp]
+
     def fork(self):
         """A second execution context over the SAME layers and weight packs with a private workspace and saved state, so
         that several forward passes can be alive at once (stacked generator: one context per stack)."""
@@ -568,16 +581,20 @@ class GeneratorEngine:
         if on_stage is not None:
             # the decoder's weight gradients are on the side stream: issue the bucket's all-reduce behind them
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-                on_stage("decoder")
-        # encoders, deepest level first
+                on_stage("decoder", None)
+        # Encoders, deepest level first, the branches level by level in lock step (the second branch on the side stream).
+        # Levels >= DEEP_SPLIT hold most of an encoder's parameters (50 of 61 MB) and finish first: their gradient bucket is
+        # handed to on_stage as soon as both branches have enqueued them, the shallow levels' bucket at the end.
+        split = self.deep_split()
+        dact_next = {name: None for name, _, _, _, _ in self.specs}
+        dwarps = {}
+
+        def ctx(e_idx):
+            return torch.cuda.stream(side) if (side is not None and e_idx == 1) else contextlib.nullcontext()
+
         for e_idx, (name, _, _, _, warped_branch) in enumerate(self.specs):
-            on_side = side is not None and e_idx == 1
-            scratch_e = scratch_side if on_side else scratch
-            with (torch.cuda.stream(side) if on_side else contextlib.nullcontext()):
-                convs, norms = self.enc_conv[name], self.enc_norm[name]
-                dact_next = None
-                dwarps = {}
-                if warped_branch:
+            if warped_branch:
+                with ctx(e_idx):
                     # gradient of all warped skip levels in ONE launch (zero fill of the scatter targets included)
                     lv = []
                     for i in range(min(4, L)):
@@ -589,7 +606,12 @@ class GeneratorEngine:
                         lv.append(dict(dy=Slice(dcats[j], off, c), y=Slice(cats[j], off, c), mask=sv["mlv"][i], argk=sv["argk"][i],
                                        dx=dwarps[i], C=c, h=hs[i], w=wsz[i]))
                     K.warp_backward_levels(lv, sv["warps"], N, sv["K"], H0, W0, ACT_RELU, True)
-                for i in range(L - 1, -1, -1):
+        for i in range(L - 1, -1, -1):
+            for e_idx, (name, _, _, _, warped_branch) in enumerate(self.specs):
+                on_side = side is not None and e_idx == 1
+                scratch_e = scratch_side if on_side else scratch
+                with ctx(e_idx):
+                    convs, norms = self.enc_conv[name], self.enc_norm[name]
                     j = L - 1 - i
                     _, dprev, _ = self._cat_layout(j)
                     c = self.enc[i]
@@ -597,8 +619,7 @@ class GeneratorEngine:
                     off = dprev + e_idx * c
                     warped = warped_branch and i < 4
                     if warped:
-                        dwarp = dwarps[i]
-                        skip_g, skip_a, skip_act = Slice(dwarp), None, ACT_NONE
+                        skip_g, skip_a, skip_act = Slice(dwarps[i]), None, ACT_NONE
                     else:
                         skip_g, skip_a, skip_act = Slice(dcats[j], off, c), Slice(cats[j], off, c), ACT_RELU
                     norm = norms[i]
@@ -607,8 +628,8 @@ class GeneratorEngine:
                     si = st_idx[(name, i)] if norm is not None else None
                     st = stats[si] if norm is not None else None
                     sm = sums[si] if norm is not None else None
-                    if dact_next is not None:
-                        K.gn_bwd_reduce(Slice(dact_next), Slice(sv["act"][(name, i)]), ACT_LEAKY, skip_g, skip_a, skip_act,
+                    if dact_next[name] is not None:
+                        K.gn_bwd_reduce(Slice(dact_next[name]), Slice(sv["act"][(name, i)]), ACT_LEAKY, skip_g, skip_a, skip_act,
                                         None, z if norm is not None else None, st, N, HW, c, dy, sm)
                     else:
                         K.gn_bwd_reduce(skip_g, skip_a, skip_act, None, None, ACT_NONE, None, z if norm is not None else None,
@@ -630,13 +651,13 @@ class GeneratorEngine:
                         dact = ws.get("dact_%s%d_%s" % (name, i - 1, tag), (N, hs[i - 1], wsz[i - 1], self.enc[i - 1]))
                         cv.dgrad(Slice(dy), N, hs[i - 1], wsz[i - 1], Slice(dact),
                                  scratch=ws.get("splitk_side" if on_side else "splitk_main", (SPLITK_SCRATCH,)))
-                        dact_next = dact
-            if e_idx == 0 and on_stage is not None:
-                on_stage(name)
+                        dact_next[name] = dact
+                    if on_stage is not None and i == split and split > 0:
+                        on_stage(name, "deep")
+                    if on_stage is not None and i == 0:
+                        on_stage(name, "shallow" if split > 0 else None)
         if side is not None:
             main.wait_stream(side)
-        if on_stage is not None and len(self.specs) > 1:
-            on_stage(self.specs[1][0])
         return image_grad
 
 

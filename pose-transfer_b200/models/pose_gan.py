@@ -113,6 +113,13 @@ class ParamArena:
         hi = self.offsets[idx[-1] + 1] if idx[-1] + 1 < len(self.offsets) else self.total
         return lo, hi
 
+    def segment_range_of(self, modules):
+        """[lo, hi) covering every parameter of a list of sub-modules that are adjacent in the arena."""
+        rs = [self.segment_range(m) for m in modules if any(True for _ in m.parameters())]
+        rs.sort()
+        assert rs and all(a[1] == b[0] for a, b in zip(rs, rs[1:])), "sub-modules are not adjacent in the arena"
+        return rs[0][0], rs[-1][1]
+
     def segment(self, submodule):
         lo, hi = self.segment_range(submodule)
         return self.grad[lo:hi]
@@ -352,9 +359,8 @@ class DeformablePose_GAN(nn.Module):
         self.gen_opt.begin_step()
         covered = []
 
-        def stage_done(stage):
-            sub = self.gen.engine.stage_modules[stage]
-            lo, hi = self.gen_arena.segment_range(sub)
+        def stage_done(stage, part=None):
+            lo, hi = self.gen_arena.segment_range_of(self.gen.engine.stage_parts(stage, part))
             covered.append((lo, hi))
             if ost is not None:
                 ost.wait_stream(torch.cuda.current_stream())
@@ -407,9 +413,17 @@ class DeformablePose_GAN(nn.Module):
         # rows < opt['batch_size'] are "true", the rest "fake"; both * gan_w / self.batch_size (pose_gan.py:140-163)
         K.adv_loss(logits, M, J, opt['batch_size'], opt['gan_penalty_weight'] / self.batch_size, loss[0:2], dlog4, dlog4.shape[1])
         self.disc.engine.backward(dlog4, grads=self.disc_arena.grads, need_input_grad=False)
-        self._allreduce(self.disc_arena)
-        self.disc_opt.step()
+        # all-reduce + Adam of the discriminator on the optimiser stream: they run while the host is blocked in the loss
+        # read-back below and sets up the next update; the compute stream re-joins (device-side dependency, no host sync)
+        ost = self._opt_stream(dev)
+        if ost is not None:
+            ost.wait_stream(torch.cuda.current_stream())
+        with (torch.cuda.stream(ost) if ost is not None else contextlib.nullcontext()):
+            self._allreduce(self.disc_arena)
+            self.disc_opt.step()
         host = loss.tolist()
+        if ost is not None:
+            torch.cuda.current_stream().wait_stream(ost)
         self.dis_true_loss, self.dis_fake_loss = host[0], host[1]
         self.dis_total_loss = float(torch.tensor(host[0]) + torch.tensor(host[1]))
         return [self.dis_total_loss, self.dis_true_loss, self.dis_fake_loss]
