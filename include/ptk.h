@@ -225,6 +225,17 @@ int ptk_nnloss_features_backward(const float* pred, const float* gt, const uint8
 int ptk_tanh_bwd_combine(const float* g_nchw, const float* g_nhwc, int ldg, const float* out_nchw,
                          float* dz, int ld, int N, int C, int H, int W, void* stream);
 
+/* ---------------------------------------------------------------- device-side data path
+ * Replaces the per-sample numpy / skimage work of datasets/PoseTransfer_Dataset.py:78-109 on the host.
+ * kp: int32 [N,P,2] key-points as (y, x), -1 = missing (utils/pose_utils.py:42). */
+/* out[n, c0+p, y, x] = exp(-((y-ky)^2 + (x-kx)^2) / (2 sigma^2)) (zero plane if missing); out is NCHW with C_total
+ * channels (utils/pose_utils.py:79-86 cords_to_map, sigma = 6). */
+int ptk_pose_heatmaps(const int* kp, int N, int P, int H, int W, float sigma, float* out, int C_total, int c0, void* stream);
+/* masks[N,10,H,W] float64: body (all ones), head rectangle, eight limb quadrilaterals (utils/pose_transform.py:143-214
+ * pose_masks / estimate_polygon / mask_from_kp_array; point-in-polygon = skimage.measure.grid_points_in_poly).  P = 16 or 18.
+ * The caller must have checked that Rhip, Lhip, Rsho, Lsho are present (the reference raises KeyError otherwise). */
+int ptk_pose_masks(const int* kp, int N, int P, int H, int W, double* masks, void* stream);
+
 /* ---------------------------------------------------------------- optimiser (models/pose_gan.py:49-51) */
 /* torch.optim.Adam (no weight decay, no amsgrad) on a flat fp32 arena. step >= 1. grad_scale multiplies g
  * first (1/world for data-parallel averaging). */

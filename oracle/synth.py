@@ -72,6 +72,60 @@ def make_batch(N, H, W, P, seed=0, K=10):
     return {"input": inp, "target": target, "warps": warps, "masks": masks}
 
 
+def make_keypoints(N, H, W, P, seed=0, missing=0.1):
+    """[N, P, 2] int64 (y, x; -1 = missing): a plausible upright skeleton per sample for the 18-joint (OpenPose / PAF) or the
+    16-joint (stacked-hourglass) label set of the reference (utils/pose_utils.py:27,36-37).  The four torso joints are
+    always present (the reference's pose geometry dereferences them unconditionally)."""
+    g = _gen(2000003 * (seed + 1) + 31 * N + H + 5 * W + 11 * P)
+    names18 = ['nose', 'neck', 'Rsho', 'Relb', 'Rwri', 'Lsho', 'Lelb', 'Lwri', 'Rhip', 'Rkne', 'Rank', 'Lhip', 'Lkne', 'Lank',
+               'Leye', 'Reye', 'Lear', 'Rear']
+    names16 = ['Rank', 'Rknee', 'Rhip', 'Lhip', 'Lknee', 'Lank', 'pelv', 'spine', 'neck', 'head', 'Rwri', 'Relb', 'Rsho', 'Lsho',
+               'Lelb', 'Lwri']
+    names = names18 if P == 18 else names16
+    out = torch.full((N, P, 2), -1, dtype=torch.int64)
+
+    def rnd(a=1.0):
+        return float(torch.rand(1, generator=g)) * a
+
+    for n in range(N):
+        s = H * (0.16 + 0.08 * rnd())                        # shoulder-to-hip length
+        cy, cx = H * (0.30 + 0.1 * rnd()), W * (0.35 + 0.3 * rnd())
+        lean = (rnd() - 0.5) * 0.5
+        pts = {}
+        pts['neck'] = (cy - 0.15 * s, cx)
+        pts['Rsho'] = (cy, cx - 0.45 * s)
+        pts['Lsho'] = (cy, cx + 0.45 * s)
+        pts['Rhip'] = (cy + s, cx - 0.3 * s + lean * s)
+        pts['Lhip'] = (cy + s, cx + 0.3 * s + lean * s)
+        pts['pelv'] = (cy + s, cx + lean * s)
+        pts['spine'] = (cy + 0.5 * s, cx + 0.5 * lean * s)
+        pts['nose'] = pts['head'] = (cy - 0.55 * s, cx + (rnd() - 0.5) * 0.2 * s)
+        pts['Reye'] = (cy - 0.62 * s, cx - 0.1 * s)
+        pts['Leye'] = (cy - 0.62 * s, cx + 0.1 * s)
+        pts['Rear'] = (cy - 0.58 * s, cx - 0.22 * s)
+        pts['Lear'] = (cy - 0.58 * s, cx + 0.22 * s)
+        for side, sx in (('R', -1), ('L', 1)):
+            a1, a2 = (rnd() - 0.5) * 1.6, (rnd() - 0.5) * 1.6
+            sy, sxx = pts[side + 'sho']
+            ey, ex = sy + 0.6 * s * math.cos(a1), sxx + sx * 0.15 * s + 0.6 * s * math.sin(a1)
+            wy, wx = ey + 0.55 * s * math.cos(a1 + a2), ex + 0.55 * s * math.sin(a1 + a2)
+            pts[side + 'elb'], pts[side + 'wri'] = (ey, ex), (wy, wx)
+            b1, b2 = (rnd() - 0.5) * 0.8, (rnd() - 0.5) * 0.6
+            hy, hx = pts[side + 'hip']
+            ky, kx = hy + 0.85 * s * math.cos(b1), hx + 0.85 * s * math.sin(b1)
+            ay, ax = ky + 0.8 * s * math.cos(b1 + b2), kx + 0.8 * s * math.sin(b1 + b2)
+            pts[side + 'kne'] = pts[side + 'knee'] = (ky, kx)
+            pts[side + 'ank'] = (ay, ax)
+        for i, name in enumerate(names):
+            y, x = pts[name]
+            keep = name in ('Rhip', 'Lhip', 'Rsho', 'Lsho') or rnd() >= missing
+            if keep and 0 <= y < H and 0 <= x < W:
+                out[n, i, 0], out[n, i, 1] = int(y), int(x)
+            elif name in ('Rhip', 'Lhip', 'Rsho', 'Lsho'):
+                out[n, i, 0], out[n, i, 1] = int(min(max(y, 0), H - 1)), int(min(max(x, 0), W - 1))
+    return out
+
+
 def fill_state_dict(shapes, seed=0):
     """Deterministic weights for a {key: shape} mapping (keys visited in sorted order).
 

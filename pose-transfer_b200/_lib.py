@@ -64,6 +64,8 @@ SIGNATURES = {
     "ptk_nnloss_features_forward": [vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp],
     "ptk_nnloss_features_backward": [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp],
     "ptk_tanh_bwd_combine": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp],
+    "ptk_pose_heatmaps": [vp, i32, i32, i32, i32, f32, vp, i32, i32, vp],
+    "ptk_pose_masks": [vp, i32, i32, i32, i32, vp, vp],
     "ptk_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
 }
 _RESTYPES = {"ptk_last_error": ctypes.c_char_p, "ptk_launch_count": i64}

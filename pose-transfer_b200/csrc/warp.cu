@@ -371,10 +371,10 @@ struct FwdTileSmem {
 // levels of a pass balance over the machine: TH = 8 / 4 / 2 / 1 for C = 64 / 128 / 256 / >= 512.  A warp owns a run of
 // 32 * TH / 8 pixels of one tile row; G lanes hold one pixel (16 NV-byte... 4 NV channels per lane at stride 4 G: every
 // 128-bit request of the group is whole lines), 32 / G pixels per warp are in flight.
-template <int G, int NV, int TH, int ACT>
+template <int G, int NV, int TH, int PX, int ACT>
 __device__ __forceinline__ void warp_fwd_tile(const WarpLevelDev& L, FwdTileSmem& S, int K, int n, int tile, int prefetch) {
-  constexpr int PPW = 32 / G, CH = 4 * G * NV, SPR = 8 / TH, SEG = kTileW / SPR, ITERS = SEG / PPW;
-  static_assert(SEG % PPW == 0 && ITERS >= 1, "segment must be a whole number of warp iterations");
+  constexpr int PPW = 32 / G, CH = 4 * G * NV, SPR = 8 / TH, SEG = kTileW / SPR, ITERS = SEG / (PPW * PX);
+  static_assert(SEG % (PPW * PX) == 0 && ITERS >= 1, "segment must be a whole number of warp iterations");
   constexpr bool kRelu = ACT == PTK_ACT_RELU;
   const int h = L.h, w = L.w, C = L.C, ldx = L.ldx, ldy = L.ldy;
   const int tx = tile % L.strips_x, ty = tile / L.strips_x;
@@ -425,95 +425,125 @@ __device__ __forceinline__ void warp_fwd_tile(const WarpLevelDev& L, FwdTileSmem
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
   for (int it = 0; it < ITERS; ++it) {
-    const int col = seg * SEG + it * PPW + grp;             // tile column of this group's pixel
-    const int j = x0 + col;
-    if (j >= w) continue;
-    const int t = row * kTileW + col;
-    const uint32_t hd = S.hdr[t];
-    const int cnt = (int)((hd >> 24) & 7u);
-    const int kz = (int)(hd >> 28);
-    const float4* rbase = S.rec + t * (kMaxRec * 2);
-    if (prefetch && it + 1 < ITERS && j + PPW < w) {
-      // warm L2 with the lower tap row of the first (body) part of the pixel this group handles next
-      const uint32_t hn = S.hdr[t + PPW];
-      if ((hn >> 24) & 7u) {
-        const float4 of = S.rec[(t + PPW) * (kMaxRec * 2) + 1];
+    // PX pixels per lane group in flight: tile columns col0 + px * PPW (the groups of a warp interleave, so that one
+    // 128-bit request of the warp still covers PPW adjacent pixels)
+    const int col0 = seg * SEG + it * (PPW * PX) + grp;
+    if (x0 + col0 >= w) continue;
+    uint32_t hd[PX];
+    int cnt[PX], nrec = 0;
 #pragma unroll
-        for (int q = 0; q < NV; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + q * G * 4 + __float_as_int(of.w)));
+    for (int px = 0; px < PX; ++px) {
+      const int col = col0 + px * PPW;
+      hd[px] = S.hdr[row * kTileW + col];
+      cnt[px] = (x0 + col < w) ? (int)((hd[px] >> 24) & 7u) : 0;
+      nrec = max(nrec, cnt[px]);
+    }
+    const float4* rbase = S.rec + (row * kTileW + col0) * (kMaxRec * 2);
+    if (prefetch && it + 1 < ITERS && x0 + col0 + PPW * PX < w) {
+      // warm L2 with the lower tap row of the first (body) part of the pixels this group handles next
+#pragma unroll
+      for (int px = 0; px < PX; ++px) {
+        const int tn = row * kTileW + col0 + (PX + px) * PPW;
+        if ((S.hdr[tn] >> 24) & 7u) {
+          const float4 of = S.rec[tn * (kMaxRec * 2) + 1];
+#pragma unroll
+          for (int q = 0; q < NV; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + q * G * 4 + __float_as_int(of.w)));
+        }
       }
     }
 #pragma unroll 1
     for (int cb = 0; cb < C; cb += CH) {
-      float best[NV * 4];
-      int arg[NV * 4];
-      bool zdone = kRelu;
+      float best[PX][NV * 4];
+      int arg[PX][NV * 4];
+      bool zdone[PX];
 #pragma unroll
-      for (int q = 0; q < NV * 4; ++q) { best[q] = kRelu ? 0.f : -INFINITY; arg[q] = kNoPart; }
-#pragma unroll 1
-      for (int r = 0; r < cnt; ++r) {
-        const int kk = (int)((hd >> (4 * r)) & 15u);
-        const float4 wv = rbase[r * 2];
-        const float4 of = rbase[r * 2 + 1];
-        const float* p = xb + cb;
-        float4 v[NV][4];
+      for (int px = 0; px < PX; ++px) {
+        zdone[px] = kRelu;
 #pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          v[q][0] = __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.x)));
-          v[q][1] = __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.y)));
-          v[q][2] = __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.z)));
-          v[q][3] = __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.w)));
-        }
-        if (!kRelu && !zdone && kk > kz) {      // the zero candidate sits before this part
-          zdone = true;
-#pragma unroll
-          for (int q = 0; q < NV * 4; ++q) if (0.f > best[q]) { best[q] = 0.f; arg[q] = kNoPart; }
-        }
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          float4 acc = zero4;
-          fma4(acc, wv.x, v[q][0]); fma4(acc, wv.y, v[q][1]); fma4(acc, wv.z, v[q][2]); fma4(acc, wv.w, v[q][3]);
-          if (acc.x > best[4 * q + 0]) { best[4 * q + 0] = acc.x; arg[4 * q + 0] = kk; }
-          if (acc.y > best[4 * q + 1]) { best[4 * q + 1] = acc.y; arg[4 * q + 1] = kk; }
-          if (acc.z > best[4 * q + 2]) { best[4 * q + 2] = acc.z; arg[4 * q + 2] = kk; }
-          if (acc.w > best[4 * q + 3]) { best[4 * q + 3] = acc.w; arg[4 * q + 3] = kk; }
-        }
+        for (int q = 0; q < NV * 4; ++q) { best[px][q] = kRelu ? 0.f : -INFINITY; arg[px][q] = kNoPart; }
       }
-      if (hd & (1u << 27)) {
-        // more active parts than records (never seen in practice): the remaining parts, geometry evaluated inline
-        const int last = (int)((hd >> (4 * (kMaxRec - 1))) & 15u);
-        for (int k = last + 1; k < K; ++k) {
-          float4 wgt;
-          int4 off;
-          const float m = __ldg(L.mask + (img + (int64_t)i * w + j) * K + k);
-          if (!part_geometry(S.theta[k], m, i, j, h, w, ldx, wgt, off)) continue;
-          if (!kRelu && !zdone && k > kz) {
-            zdone = true;
+#pragma unroll 1
+      for (int r = 0; r < nrec; ++r) {
+        float4 wv[PX];
+        float4 v[PX][NV][4];
 #pragma unroll
-            for (int q = 0; q < NV * 4; ++q) if (0.f > best[q]) { best[q] = 0.f; arg[q] = kNoPart; }
+        for (int px = 0; px < PX; ++px) {
+          const bool on = r < cnt[px];
+          wv[px] = on ? rbase[(px * PPW * kMaxRec + r) * 2] : zero4;
+          const float4 of = on ? rbase[(px * PPW * kMaxRec + r) * 2 + 1] : zero4;
+          const float* p = xb + cb;
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            v[px][q][0] = on ? __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.x))) : zero4;
+            v[px][q][1] = on ? __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.y))) : zero4;
+            v[px][q][2] = on ? __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.z))) : zero4;
+            v[px][q][3] = on ? __ldg(reinterpret_cast<const float4*>(p + q * G * 4 + __float_as_int(of.w))) : zero4;
+          }
+        }
+#pragma unroll
+        for (int px = 0; px < PX; ++px) {
+          if (r >= cnt[px]) continue;
+          const int kk = (int)((hd[px] >> (4 * r)) & 15u);
+          if (!kRelu && !zdone[px] && kk > (int)(hd[px] >> 28)) {      // the zero candidate sits before this part
+            zdone[px] = true;
+#pragma unroll
+            for (int q = 0; q < NV * 4; ++q) if (0.f > best[px][q]) { best[px][q] = 0.f; arg[px][q] = kNoPart; }
           }
 #pragma unroll
           for (int q = 0; q < NV; ++q) {
-            const float* p = xb + cb + q * G * 4;
             float4 acc = zero4;
-            fma4(acc, wgt.x, __ldg(reinterpret_cast<const float4*>(p + off.x))); fma4(acc, wgt.y, __ldg(reinterpret_cast<const float4*>(p + off.y)));
-            fma4(acc, wgt.z, __ldg(reinterpret_cast<const float4*>(p + off.z))); fma4(acc, wgt.w, __ldg(reinterpret_cast<const float4*>(p + off.w)));
-            if (acc.x > best[4 * q + 0]) { best[4 * q + 0] = acc.x; arg[4 * q + 0] = k; }
-            if (acc.y > best[4 * q + 1]) { best[4 * q + 1] = acc.y; arg[4 * q + 1] = k; }
-            if (acc.z > best[4 * q + 2]) { best[4 * q + 2] = acc.z; arg[4 * q + 2] = k; }
-            if (acc.w > best[4 * q + 3]) { best[4 * q + 3] = acc.w; arg[4 * q + 3] = k; }
+            fma4(acc, wv[px].x, v[px][q][0]); fma4(acc, wv[px].y, v[px][q][1]);
+            fma4(acc, wv[px].z, v[px][q][2]); fma4(acc, wv[px].w, v[px][q][3]);
+            if (acc.x > best[px][4 * q + 0]) { best[px][4 * q + 0] = acc.x; arg[px][4 * q + 0] = kk; }
+            if (acc.y > best[px][4 * q + 1]) { best[px][4 * q + 1] = acc.y; arg[px][4 * q + 1] = kk; }
+            if (acc.z > best[px][4 * q + 2]) { best[px][4 * q + 2] = acc.z; arg[px][4 * q + 2] = kk; }
+            if (acc.w > best[px][4 * q + 3]) { best[px][4 * q + 3] = acc.w; arg[px][4 * q + 3] = kk; }
           }
         }
       }
-      if (!kRelu && !zdone && kz != 15) {      // zero candidate after the last real part
 #pragma unroll
-        for (int q = 0; q < NV * 4; ++q) if (0.f > best[q]) { best[q] = 0.f; arg[q] = kNoPart; }
-      }
+      for (int px = 0; px < PX; ++px) {
+        const int j = x0 + col0 + px * PPW;
+        if (j >= w) continue;
+        const int kz = (int)(hd[px] >> 28);
+        if (hd[px] & (1u << 27)) {
+          // more active parts than records (never seen in practice): the remaining parts, geometry evaluated inline
+          const int last = (int)((hd[px] >> (4 * (kMaxRec - 1))) & 15u);
+          for (int k = last + 1; k < K; ++k) {
+            float4 wgt;
+            int4 off;
+            const float m = __ldg(L.mask + (img + (int64_t)i * w + j) * K + k);
+            if (!part_geometry(S.theta[k], m, i, j, h, w, ldx, wgt, off)) continue;
+            if (!kRelu && !zdone[px] && k > kz) {
+              zdone[px] = true;
 #pragma unroll
-      for (int q = 0; q < NV; ++q) {
-        *reinterpret_cast<float4*>(yb + j * ldy + cb + q * G * 4) =
-            make_float4(warp_act<ACT>(best[4 * q]), warp_act<ACT>(best[4 * q + 1]), warp_act<ACT>(best[4 * q + 2]), warp_act<ACT>(best[4 * q + 3]));
-        *reinterpret_cast<uint16_t*>(ab + ((j * C + cb + q * G * 4) >> 1)) =
-            (uint16_t)(arg[4 * q] | (arg[4 * q + 1] << 4) | (arg[4 * q + 2] << 8) | (arg[4 * q + 3] << 12));
+              for (int q = 0; q < NV * 4; ++q) if (0.f > best[px][q]) { best[px][q] = 0.f; arg[px][q] = kNoPart; }
+            }
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+              const float* p = xb + cb + q * G * 4;
+              float4 acc = zero4;
+              fma4(acc, wgt.x, __ldg(reinterpret_cast<const float4*>(p + off.x))); fma4(acc, wgt.y, __ldg(reinterpret_cast<const float4*>(p + off.y)));
+              fma4(acc, wgt.z, __ldg(reinterpret_cast<const float4*>(p + off.z))); fma4(acc, wgt.w, __ldg(reinterpret_cast<const float4*>(p + off.w)));
+              if (acc.x > best[px][4 * q + 0]) { best[px][4 * q + 0] = acc.x; arg[px][4 * q + 0] = k; }
+              if (acc.y > best[px][4 * q + 1]) { best[px][4 * q + 1] = acc.y; arg[px][4 * q + 1] = k; }
+              if (acc.z > best[px][4 * q + 2]) { best[px][4 * q + 2] = acc.z; arg[px][4 * q + 2] = k; }
+              if (acc.w > best[px][4 * q + 3]) { best[px][4 * q + 3] = acc.w; arg[px][4 * q + 3] = k; }
+            }
+          }
+        }
+        if (!kRelu && !zdone[px] && kz != 15) {      // zero candidate after the last real part
+#pragma unroll
+          for (int q = 0; q < NV * 4; ++q) if (0.f > best[px][q]) { best[px][q] = 0.f; arg[px][q] = kNoPart; }
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          *reinterpret_cast<float4*>(yb + j * ldy + cb + q * G * 4) =
+              make_float4(warp_act<ACT>(best[px][4 * q]), warp_act<ACT>(best[px][4 * q + 1]), warp_act<ACT>(best[px][4 * q + 2]),
+                          warp_act<ACT>(best[px][4 * q + 3]));
+          *reinterpret_cast<uint16_t*>(ab + ((j * C + cb + q * G * 4) >> 1)) =
+              (uint16_t)(arg[px][4 * q] | (arg[px][4 * q + 1] << 4) | (arg[px][4 * q + 2] << 8) | (arg[px][4 * q + 3] << 12));
+        }
       }
     }
   }
@@ -533,10 +563,10 @@ warp_forward_tiles_kernel(const __grid_constant__ WarpLaunchDev P, const float* 
   __syncthreads();
   const int tile = blockIdx.x - L.cta_begin;
   switch (L.cfg) {
-    case 0: warp_fwd_tile<8, 2, 8, ACT>(L, S, P.K, n, tile, P.prefetch); break;      // C = 64
-    case 1: warp_fwd_tile<8, 4, 4, ACT>(L, S, P.K, n, tile, P.prefetch); break;      // C = 128
-    case 2: warp_fwd_tile<16, 4, 2, ACT>(L, S, P.K, n, tile, P.prefetch); break;     // C = 256 (and 768, ...)
-    default: warp_fwd_tile<32, 4, 1, ACT>(L, S, P.K, n, tile, P.prefetch); break;    // C % 512 == 0
+    case 0: warp_fwd_tile<8, 2, 8, 2, ACT>(L, S, P.K, n, tile, P.prefetch); break;      // C = 64: two pixels per lane group
+    case 1: warp_fwd_tile<8, 4, 4, 1, ACT>(L, S, P.K, n, tile, P.prefetch); break;      // C = 128
+    case 2: warp_fwd_tile<16, 4, 2, 1, ACT>(L, S, P.K, n, tile, P.prefetch); break;     // C = 256 (and 768, ...)
+    default: warp_fwd_tile<32, 4, 1, 1, ACT>(L, S, P.K, n, tile, P.prefetch); break;    // C % 512 == 0
   }
 }
 

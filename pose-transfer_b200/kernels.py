@@ -368,6 +368,24 @@ def tanh_bwd_combine(g_nchw, g_nhwc, out_nchw, dz, ld, N, C, H, W):
                                           N, C, H, W, _stream()), "ptk_tanh_bwd_combine")
 
 
+@_timed("pose_data")
+def pose_heatmaps(kp, out, c0, sigma=6.0):
+    """kp int32 [N,P,2] (y, x; -1 missing) -> out[:, c0:c0+P] (NCHW fp32) Gaussian heat-maps (pose_utils.py:79-86)."""
+    N, P, _ = kp.shape
+    _, C_total, H, W = out.shape
+    assert kp.dtype == torch.int32 and out.dtype == torch.float32
+    check(_lib.lib().ptk_pose_heatmaps(_p(kp), N, P, H, W, float(sigma), _p(out), C_total, c0, _stream()), "ptk_pose_heatmaps")
+
+
+@_timed("pose_data")
+def pose_masks(kp, masks):
+    """kp int32 [N,P,2] -> masks [N,10,H,W] float64 (pose_transform.py:143-214)."""
+    N, P, _ = kp.shape
+    _, K10, H, W = masks.shape
+    assert kp.dtype == torch.int32 and masks.dtype == torch.float64 and K10 == 10
+    check(_lib.lib().ptk_pose_masks(_p(kp), N, P, H, W, _p(masks), _stream()), "ptk_pose_masks")
+
+
 @_timed("adam", lambda p, g, m, v, *a, **k: 28 * p.numel())     # read p, g, m, v; write p, m, v
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     check(_lib.lib().ptk_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale,
