@@ -38,12 +38,17 @@ struct TcGeom {
 struct TmapSet {
   CUtensorMap a[4];
   CUtensorMap b;
+  CUtensorMap b_half;    // box of BLOCK_N / 2 weight rows: what one CTA of a pair fetches and multicasts to both
 };
 
 // MH = number of 128-pixel halves of the CTA's M tile (1 or 2): with MH = 2 the same weight (B) stage feeds two
 // M = 128 MMAs, and BLOCK_N = 256 lets one activation (A) stage feed a twice-as-wide MMA -- both raise the MACs per
 // byte fetched from L2, which (not the tensor pipe) is what bounds fp32-operand tiles.  TMEM: MH * BLOCK_N columns.
-template <int BLOCK_N, int STAGES, int MH>
+// CL = CTAs per cluster (1 or 2).  CL = 2: two CTAs that are neighbours along the pixel (M) dimension need the SAME weight
+// tile; each fetches half of it and multicasts it into both shared memories, so the L2 -> SM weight traffic per CTA halves
+// (fp32 operands make these kernels L2-bandwidth bound).  A stage may be refilled only when the MMAs of BOTH CTAs have
+// consumed it: the empty barriers count CL arrivals and every MMA issuer commits to its own and to its peer's barrier.
+template <int BLOCK_N, int STAGES, int MH, int CL>
 __global__ void __launch_bounds__(192)
 conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcGeom g, float* __restrict__ y,
                double* __restrict__ stats, const float* __restrict__ bias, int act) {
@@ -70,8 +75,9 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   const int kb0 = split * kb_per;
   const int KB = (kb0 + kb_per < KB_all ? kb0 + kb_per : KB_all) - kb0;   // k-blocks of this CTA (may be <= 0)
 
+  const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
     mbar_init(bar_tmem, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -82,6 +88,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL == 2) cluster_sync_all();      // the peer's barriers exist before anything is multicast into them
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_wait();      // nothing above touched global memory: the setup overlapped the previous kernel's tail
@@ -96,7 +103,11 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
         const int c0 = ((kb0 + kb) - tap * g.kchunks) * 32;
         mbar_expect_tx(bar_full + 8 * s, A_BYTES + B_BYTES);
         tma_load_4d(sA + s * A_BYTES, &maps.a[ph.map[tap]], bar_full + 8 * s, c0, gx0 + ph.cx[tap], gy0 + ph.cy[tap], n0);
-        tma_load_3d(sB + s * B_BYTES, &maps.b, bar_full + 8 * s, c0, blockIdx.y * BLOCK_N, ph.wt[tap]);
+        if (CL == 2)
+          tma_load_3d_mc(sB + s * B_BYTES + crank * (B_BYTES / 2), &maps.b_half, bar_full + 8 * s, c0,
+                         blockIdx.y * BLOCK_N + (int)crank * (BLOCK_N / 2), ph.wt[tap], (uint16_t)0x3);
+        else
+          tma_load_3d(sB + s * B_BYTES, &maps.b, bar_full + 8 * s, c0, blockIdx.y * BLOCK_N, ph.wt[tap]);
       }
     }
     __syncwarp();
@@ -115,7 +126,9 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
           for (int hm = 0; hm < MH; ++hm)   // pixel rows [128 hm, 128 hm + 128) of the stage -> accumulator hm
             tc_mma_tf32(tmem_base + (uint32_t)(hm * BLOCK_N), da + (uint64_t)(hm * (16384 >> 4)) + 2 * k, db + 2 * k, idesc,
                         (kb > 0 || k > 0) ? 1u : 0u);
-        tc_commit(bar_empty + 8 * s);   // frees the smem stage once these MMAs have read it
+        // frees the smem stage once these MMAs have read it (CL = 2: in both CTAs, the peer multicasts into this stage too)
+        if (CL == 2) tc_commit_mc(bar_empty + 8 * s, (uint16_t)0x3);
+        else tc_commit(bar_empty + 8 * s);
       }
       if (KB > 0) tc_commit(bar_tmem);  // accumulator complete
     }
@@ -181,6 +194,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+  if (CL == 2) cluster_sync_all();      // the peer may still be arriving on this CTA's barriers
 }
 
 // Deterministic split-K combine: y[i] = sum_{z < nparts} parts[z * part_stride + i] (fixed order), fused with the per-sample
@@ -232,14 +246,19 @@ static bool pdl_enabled() {
 
 // launch with programmatic stream serialization (see pdl_wait / pdl_trigger in tc_ptx.cuh)
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (cluster_x > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)cluster_x; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -425,13 +444,30 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     int rc = ptk_fill(y, out_floats, 0.f, st);
     if (rc) return rc;
   }
-  dim3 grid((unsigned)(g.tiles_x * g.tiles_y * g.tiles_i), (unsigned)(c.Cout / BN), (unsigned)(nphases * splits));
+  // CTA pairs along the pixel dimension share their weight tile through a TMA multicast (PTK_TC_CLUSTER=0 disables)
+  static int cl_env = -1;
+  if (cl_env < 0) { const char* e = getenv("PTK_TC_CLUSTER"); cl_env = (e && atoi(e) == 0) ? 0 : 1; }
+  const int mtiles = g.tiles_x * g.tiles_y * g.tiles_i;
+  const bool pair = cl_env && mtiles >= 2 && BN >= 64;
+  if (pair) {
+    const uint64_t dims[3] = {(uint64_t)c.Cin, (uint64_t)c.Cout, (uint64_t)(k * k)};
+    const uint64_t str[2] = {(uint64_t)c.Cin * 4, (uint64_t)c.Cin * c.Cout * 4};
+    const uint32_t boxH[3] = {32u, (uint32_t)(BN / 2), 1u};
+    int rc = encode(&maps.b_half, w_k, 3, dims, str, boxH);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)(pair ? (mtiles + 1) / 2 * 2 : mtiles), (unsigned)(c.Cout / BN), (unsigned)(nphases * splits));
 #define PTK_TC_LAUNCH(BN_, ST_, MH_)                                                                                       \
   do {                                                                                                                     \
     const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 16 + 1024;                                 \
     static bool attr = false;                                                                                              \
-    if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
-    launch_pdl(conv_tc_kernel<BN_, ST_, MH_>, grid, dim3(192), smem, st, maps, g, y_kernel, stats, bias, act);               \
+    if (!attr) {                                                                                                           \
+      cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MH_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+      cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MH_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+      attr = true;                                                                                                         \
+    }                                                                                                                      \
+    if (pair) launch_pdl(conv_tc_kernel<BN_, ST_, MH_, 2>, grid, dim3(192), smem, st, 2, maps, g, y_kernel, stats, bias, act); \
+    else launch_pdl(conv_tc_kernel<BN_, ST_, MH_, 1>, grid, dim3(192), smem, st, 1, maps, g, y_kernel, stats, bias, act);    \
   } while (0)
   if (MH == 1 && BN == 32) PTK_TC_LAUNCH(32, 4, 1);
   else if (MH == 2 && BN == 32) PTK_TC_LAUNCH(32, 3, 2);
@@ -747,7 +783,7 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + TPC_ * BN_ * 128) + 16 * ST_ + 16 + 1024;                          \
     static bool attr = false;                                                                                              \
     if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<BN_, ST_, MH_, TPC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
-    launch_pdl(wgrad_tc_kernel<BN_, ST_, MH_, TPC_>, grid, dim3(192), smem, st, maps, g, dw);                                \
+    launch_pdl(wgrad_tc_kernel<BN_, ST_, MH_, TPC_>, grid, dim3(192), smem, st, 1, maps, g, dw);                                \
   } while (0)
   if (TPC == 9) PTK_WG_LAUNCH(32, 3, 1, 9);
   else if (TPC == 4) PTK_WG_LAUNCH(64, 4, 1, 4);
