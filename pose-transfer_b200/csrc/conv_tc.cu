@@ -444,9 +444,12 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     int rc = ptk_fill(y, out_floats, 0.f, st);
     if (rc) return rc;
   }
-  // CTA pairs along the pixel dimension share their weight tile through a TMA multicast (PTK_TC_CLUSTER=0 disables)
+  // CTA pairs along the pixel dimension can share their weight tile through a TMA multicast (PTK_TC_CLUSTER=1).  Measured on
+  // B200 (profiles/README.md, r2f): correct, but 3 % SLOWER over the conv stack (decoder.5 0.577 -> 0.604 ms, Cout = 64
+  // dgrads 0.156 -> 0.189 ms): the pair's lock-step stage recycling and the two cluster barriers cost more than the halved
+  // weight traffic saves, so it stays opt-in.
   static int cl_env = -1;
-  if (cl_env < 0) { const char* e = getenv("PTK_TC_CLUSTER"); cl_env = (e && atoi(e) == 0) ? 0 : 1; }
+  if (cl_env < 0) { const char* e = getenv("PTK_TC_CLUSTER"); cl_env = (e && atoi(e) == 1) ? 1 : 0; }
   const int mtiles = g.tiles_x * g.tiles_y * g.tiles_i;
   const bool pair = cl_env && mtiles >= 2 && BN >= 64;
   if (pair) {

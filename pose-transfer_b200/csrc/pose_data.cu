@@ -107,7 +107,8 @@ pose_masks_kernel(const int* __restrict__ kps, int P, int H, int W, const __grid
         frx = frx + (frx - tox) * inc_from; fry = fry + (fry - toy) * inc_from;
         tox = tox + (tox - frx) * inc_to;   toy = toy + (toy - fry) * inc_to;
         double nx = -(fry - toy), ny = frx - tox;
-        const double norm = sqrt(nx * nx + ny * ny);
+        // np.linalg.norm = sqrt(dot(v, v)); the BLAS dot accumulates with a fused multiply-add: sqrt(fma(v1, v1, v0 * v0))
+        const double norm = sqrt(fma(ny, ny, nx * nx));
         double vx[4], vy[4];       // polygon vertices (x, y)
         if (norm == 0.0) {
           vx[0] = frx + 1; vy[0] = fry + 1; vx[1] = frx - 1; vy[1] = fry - 1;
