@@ -197,6 +197,175 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   if (CL == 2) cluster_sync_all();      // the peer may still be arriving on this CTA's barriers
 }
 
+
+// ----------------------------------------------------------------------------- persistent variant
+// Same tile arithmetic as conv_tc_kernel, but a CTA stays resident and walks tiles T = blockIdx.x, + gridDim.x, ... of the
+// whole launch (pixel tile fastest, then output-channel tile, then output-parity phase).  The TMA producer and the MMA
+// issuer run ahead across tile boundaries (one shared-memory ring for the whole CTA lifetime) and the accumulator is
+// DOUBLE-BUFFERED in tensor memory: while the four epilogue warps drain tile i (tcgen05.ld -> bias / statistics /
+// activation -> global), the MMAs of tile i + 1 already fill the other buffer.  For the layers with short K loops (stems,
+// encoder level 1, the 1x1 head GEMMs, the PatchGAN) the setup (barrier init, TMEM allocation) and the epilogue were
+// 30-60 % of a one-tile CTA's life; here they are paid once per SM / hidden behind the next tile.  No split-K.
+template <int BLOCK_N, int STAGES, int MH>
+__global__ void __launch_bounds__(192)
+conv_tc_persist_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcGeom g, float* __restrict__ y,
+                       double* __restrict__ stats, const float* __restrict__ bias, int act, int ntile_n, int nphases) {
+  constexpr uint32_t A_BYTES = MH * 128 * 128, B_BYTES = BLOCK_N * 128, ACC_COLS = MH * BLOCK_N, TMEM_COLS = 2 * ACC_COLS;
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "two accumulators must fit tensor memory");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + STAGES * A_BYTES, sBar = sB + STAGES * B_BYTES;
+  // barriers: full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]; then the TMEM base-address slot
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_accf = sBar + 16 * STAGES, bar_acce = bar_accf + 16;
+  const uint32_t tmem_slot = bar_acce + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_accf + 8 * a, 1); mbar_init(bar_acce + 8 * a, 4); }    // 4 epilogue warps release a buffer
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
+
+  const int mtiles = g.tiles_x * g.tiles_y * g.tiles_i;
+  const int ntiles = mtiles * ntile_n * nphases;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;                                   // k-blocks issued by this CTA so far (ring position)
+      for (int T = blockIdx.x; T < ntiles; T += gridDim.x) {
+        int t = T % mtiles;
+        const int nt = (T / mtiles) % ntile_n;
+        const TcPhase& ph = g.ph[T / (mtiles * ntile_n)];
+        const int tx = t % g.tiles_x; t /= g.tiles_x;
+        const int ty = t % g.tiles_y;
+        const int ti = t / g.tiles_y;
+        const int gx0 = tx * g.BW, gy0 = ty * g.BH, n0 = ti * g.BI;
+        const int KB = ph.ntaps * g.kchunks;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % STAGES, par = (it / STAGES) & 1u;
+          mbar_wait(bar_empty + 8 * s, par ^ 1u);
+          const int tap = kb / g.kchunks;
+          const int c0 = (kb - tap * g.kchunks) * 32;
+          mbar_expect_tx(bar_full + 8 * s, A_BYTES + B_BYTES);
+          tma_load_4d(sA + s * A_BYTES, &maps.a[ph.map[tap]], bar_full + 8 * s, c0, gx0 + ph.cx[tap], gy0 + ph.cy[tap], n0);
+          tma_load_3d(sB + s * B_BYTES, &maps.b, bar_full + 8 * s, c0, nt * BLOCK_N, ph.wt[tap]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(128, BLOCK_N);
+      uint32_t it = 0, tile_i = 0;
+      for (int T = blockIdx.x; T < ntiles; T += gridDim.x, ++tile_i) {
+        const int KB = g.ph[T / (mtiles * ntile_n)].ntaps * g.kchunks;
+        const uint32_t acc = tile_i & 1u, use = tile_i >> 1;          // use-th time this buffer is filled
+        mbar_wait(bar_acce + 8 * acc, (use & 1u) ^ 1u);                // the epilogue has drained its previous contents
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * ACC_COLS;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % STAGES, par = (it / STAGES) & 1u;
+          mbar_wait(bar_full + 8 * s, par);
+          tc_fence_after();
+          const uint64_t da = smem_desc_k_sw128(sA + s * A_BYTES), db = smem_desc_k_sw128(sB + s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int hm = 0; hm < MH; ++hm)
+              tc_mma_tf32(tacc + (uint32_t)(hm * BLOCK_N), da + (uint64_t)(hm * (16384 >> 4)) + 2 * k, db + 2 * k, idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(bar_empty + 8 * s);
+        }
+        tc_commit(bar_accf + 8 * acc);                                  // accumulator of this tile complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int lg = warp & 3;
+    uint32_t tile_i = 0;
+    for (int T = blockIdx.x; T < ntiles; T += gridDim.x, ++tile_i) {
+      int t = T % mtiles;
+      const int nt = (T / mtiles) % ntile_n;
+      const TcPhase& ph = g.ph[T / (mtiles * ntile_n)];
+      const int tx = t % g.tiles_x; t /= g.tiles_x;
+      const int ty = t % g.tiles_y;
+      const int ti = t / g.tiles_y;
+      const int gx0 = tx * g.BW, gy0 = ty * g.BH, n0 = ti * g.BI;
+      const uint32_t acc = tile_i & 1u, use = tile_i >> 1;
+      mbar_wait(bar_accf + 8 * acc, use & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + acc * ACC_COLS;
+#pragma unroll 1
+      for (int hm = 0; hm < MH; ++hm) {
+        const int row = hm * 128 + lg * 32 + lane;
+        const int x = row % g.BW;
+        const int yy = (row / g.BW) % g.BH;
+        const int ii = row / (g.BW * g.BH);
+        const int gx = gx0 + x, gy = gy0 + yy, n = n0 + ii;
+        const bool valid = gx < ph.GW && gy < ph.GH && n < g.N;
+        float* dst = nullptr;
+        if (valid) {
+          const int oy = gy * g.so + ph.py, ox = gx * g.so + ph.px;
+          dst = y + (((int64_t)n * g.OH + oy) * g.OW + ox) * g.ldy + nt * BLOCK_N;
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          float v[32];
+          tc_ld32(tacc + ((uint32_t)(lg * 32) << 16) + (uint32_t)(hm * BLOCK_N + c * 32), v);
+          if (valid) {
+            if (bias != nullptr) {
+              const float* bp = bias + nt * BLOCK_N + c * 32;
+#pragma unroll
+              for (int q = 0; q < 32; ++q) v[q] += __ldg(bp + q);
+            }
+#pragma unroll
+            for (int q = 0; q < 32; ++q) { s1 += v[q]; s2 = fmaf(v[q], v[q], s2); }
+            if (act != PTK_ACT_NONE) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) v[q] = apply_act(v[q], act);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+        if (stats != nullptr) {
+          if (g.BW * g.BH >= 32) {          // the warp's 32 rows belong to one image
+            const float a = warp_sum(s1), b = warp_sum(s2);
+            const int nw = n0 + (hm * 128 + lg * 32) / (g.BW * g.BH);
+            if (lane == 0 && nw < g.N) { atomicAdd(stats + 2 * nw, (double)a); atomicAdd(stats + 2 * nw + 1, (double)b); }
+          } else if (valid) {
+            atomicAdd(stats + 2 * n, (double)s1);
+            atomicAdd(stats + 2 * n + 1, (double)s2);
+          }
+        }
+      }
+      // this warp has read everything it needs from the buffer: one arrival per warp hands it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * acc) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // Deterministic split-K combine: y[i] = sum_{z < nparts} parts[z * part_stride + i] (fixed order), fused with the per-sample
 // {sum, sum of squares} that the following norm needs.  grid (chunks, N); per_sample = OH * OW * Cout (multiple of 4).
 __global__ void __launch_bounds__(256)
@@ -460,6 +629,16 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     if (rc) return rc;
   }
   dim3 grid((unsigned)(pair ? (mtiles + 1) / 2 * 2 : mtiles), (unsigned)(c.Cout / BN), (unsigned)(nphases * splits));
+  // Persistent CTAs with a double-buffered accumulator (conv_tc_persist_kernel) when every resident CTA gets several tiles:
+  // PTK_TC_PERSIST=0 disables, =2 forces it whenever the tile shape allows (tests).
+  int ps_env = 1;
+  if (const char* e = getenv("PTK_TC_PERSIST")) ps_env = atoi(e);      // (read per call: the tests switch it inside one process)
+  const int64_t all_tiles = (int64_t)mtiles * (c.Cout / BN) * nphases;
+  const int occ_ps = (size_t)best->stages * (MH * 128 * 128 + BN * 128) > 100 * 1024 ? 1 : 2;
+  const int64_t slots_ps = (int64_t)num_sms() * occ_ps;
+  const bool persist = splits == 1 && !pair && 2 * MH * BN <= 512 && all_tiles < (1 << 30) &&
+                       (ps_env == 2 ? all_tiles >= 2 : (ps_env == 1 && all_tiles >= 3 * slots_ps));
+  const unsigned grid_ps = (unsigned)(ps_env == 2 ? (all_tiles + 1) / 2 : (all_tiles < slots_ps ? all_tiles : slots_ps));
 #define PTK_TC_LAUNCH(BN_, ST_, MH_)                                                                                       \
   do {                                                                                                                     \
     const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 16 + 1024;                                 \
@@ -472,6 +651,26 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     if (pair) launch_pdl(conv_tc_kernel<BN_, ST_, MH_, 2>, grid, dim3(192), smem, st, 2, maps, g, y_kernel, stats, bias, act); \
     else launch_pdl(conv_tc_kernel<BN_, ST_, MH_, 1>, grid, dim3(192), smem, st, 1, maps, g, y_kernel, stats, bias, act);    \
   } while (0)
+#define PTK_TC_LAUNCH_PS(BN_, ST_, MH_)                                                                                    \
+  do {                                                                                                                     \
+    const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 48 + 1024;                                 \
+    static bool attr = false;                                                                                              \
+    if (!attr) { cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, ST_, MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
+    launch_pdl(conv_tc_persist_kernel<BN_, ST_, MH_>, dim3(grid_ps), dim3(192), smem, st, 1, maps, g, y_kernel, stats, bias, act, \
+               c.Cout / BN_, nphases);                                                                                     \
+  } while (0)
+  if (persist) {
+    if (MH == 1 && BN == 32) PTK_TC_LAUNCH_PS(32, 4, 1);
+    else if (MH == 2 && BN == 32) PTK_TC_LAUNCH_PS(32, 3, 2);
+    else if (MH == 1 && BN == 64) PTK_TC_LAUNCH_PS(64, 4, 1);
+    else if (MH == 2 && BN == 64) PTK_TC_LAUNCH_PS(64, 4, 2);
+    else if (MH == 1 && BN == 128) PTK_TC_LAUNCH_PS(128, 3, 1);
+    else if (MH == 1 && BN == 256) PTK_TC_LAUNCH_PS(256, 4, 1);
+    else PTK_TC_LAUNCH_PS(128, 4, 2);
+    PTK_LAUNCH_CHECK("conv_tc_persist_kernel");
+    return 0;
+  }
+#undef PTK_TC_LAUNCH_PS
   if (MH == 1 && BN == 32) PTK_TC_LAUNCH(32, 4, 1);
   else if (MH == 2 && BN == 32) PTK_TC_LAUNCH(32, 3, 2);
   else if (MH == 1 && BN == 64) PTK_TC_LAUNCH(64, 4, 1);

@@ -427,3 +427,52 @@ def test_conv_tc_deterministic_split_k(case):
         assert rel_l2(stats[:, 1], ref_stats[:, 1]) < 2e-3
         mine = torch.stack([y.double().reshape(N, -1).sum(1), (y.double() ** 2).reshape(N, -1).sum(1)], 1)
         assert rel_l2(stats, mine) < 1e-6                  # the fused statistics describe exactly what was written
+
+
+PERSIST_CASES = [
+    # name, transposed, k, s, p, Cin, Cout, N, H, W, bias, act
+    ("enc1_like", False, 4, 2, 1, 64, 128, 2, 64, 96, False, "none"),
+    ("dec_like_T", True, 4, 2, 1, 128, 64, 2, 24, 40, False, "none"),
+    ("head_1x1_to32", False, 1, 1, 0, 256, 32, 2, 40, 56, False, "none"),
+    ("head_1x1_from32", False, 1, 1, 0, 32, 256, 2, 40, 56, False, "none"),
+    ("k3_bias_leaky", False, 3, 1, 1, 32, 64, 3, 33, 47, True, "leaky"),
+    ("odd_extent_p0", False, 4, 2, 0, 64, 64, 3, 31, 45, True, "leaky"),
+]
+
+
+@pytest.mark.parametrize("case", PERSIST_CASES, ids=[c[0] for c in PERSIST_CASES])
+def test_conv_tc_persistent_double_buffered(case, monkeypatch):
+    """conv_tc_persist_kernel (resident CTAs walking several tiles, two TMEM accumulators: the epilogue of tile i overlaps
+    the MMAs of tile i + 1) forced on (PTK_TC_PERSIST=2) must reproduce the one-tile-per-CTA kernel BIT FOR BIT (same
+    tile arithmetic, same accumulation order) -- output, bias / activation epilogue and the fused statistics."""
+    import pose_transfer_b200  # noqa: F401
+    from pose_transfer_b200 import kernels as K
+    from pose_transfer_b200.engine import ConvLayer
+    name, tr, k, s, p, Cin, Cout, N, H, W, with_bias, act = case
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    wshape = (Cin, Cout, k, k) if tr else (Cout, Cin, k, k)
+    w = (torch.rand(wshape, generator=g) * 2 - 1) / (Cin * k * k) ** 0.5
+    b = (torch.rand(Cout, generator=g) - 0.5) if with_bias else None
+    x = torch.randn(N, Cin, H, W, generator=g)
+    z = F.conv_transpose2d(x, w, b, stride=s, padding=p) if tr else F.conv2d(x, w, b, stride=s, padding=p)
+    layer = ConvLayer(torch.nn.Parameter(w.cuda()), torch.nn.Parameter(b.cuda()) if with_bias else None, tr, k, s, p)
+    layer.impl = K.IMPL_TC
+    layer.pack_forward()
+    xin = nhwc(x).cuda()
+    OH, OW = layer.out_hw(H, W)
+    code = K.ACT_LEAKY if act == "leaky" else K.ACT_NONE
+    outs = []
+    for mode in ("0", "2"):
+        monkeypatch.setenv("PTK_TC_PERSIST", mode)
+        y = torch.full((N, OH, OW, Cout + 32), 7.0, device="cuda")
+        stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+        layer.forward(K.Slice(xin), N, H, W, K.Slice(y, 32, Cout), code, stats if not with_bias else None)
+        torch.cuda.synchronize()
+        outs.append((y, stats))
+    ref = F.leaky_relu(z, 0.2) if act == "leaky" else z
+    got = nchw(outs[1][0][..., 32:]).cpu()
+    assert rel_l2(got, ref) < TF32_TOL, describe(got, ref, "persistent fprop")
+    assert torch.equal(outs[0][0], outs[1][0]), "persistent kernel differs from the one-tile kernel"
+    assert float((outs[1][0][..., :32] - 7.0).abs().max()) == 0
+    if not with_bias:
+        assert rel_l2(outs[1][1], outs[0][1]) < 1e-12        # fp64 atomics: equal up to summation order
