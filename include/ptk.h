@@ -118,13 +118,6 @@ int ptk_conv_wgrad_parts(const ptk_conv_geom* g, const float* x, const float* dy
  * its arguments; with dw_capacity == one gradient the answer is always 1, i.e. the kernel writes the final result). */
 int ptk_conv_wgrad_plan(const ptk_conv_geom* g, int64_t dw_capacity, int* nparts);
 /* dbias[c] += sum_pixels dy[pixel][c] */
-/* ---- encoder stem Conv2d(Cin <= 24 -> 64, k3, s1, p1, bias) (models/networks.py:186) with the im2col assembled in shared
- * memory (csrc/stem.cu).  wk [64][224]: K = tap*24 + c, produced by ptk_stem_pack from the tap-major weight
- * [tap][64][cin_pad] (the layout the parameter arena / ptk_pack_weight_dual hold). */
-int ptk_stem_pack(const float* w_tap_major, int cin, int cin_pad, float* wk, void* stream);
-int ptk_stem_conv(const float* x, int ldx, const float* wk, const float* bias, float* y, int ldy, int N, int H, int W,
-                  void* stream);
-
 /* ---- narrow 3x3 output head (ReLU -> Conv2d(C -> Co<=3, k3, p1) -> Tanh, models/networks.py:227-232) as three 1x1 GEMMs
  * on a 32-column "tap x channel" tensor, so that the C-channel operand is read / written once per pass (csrc/head.cu).
  * wk [32][Cin] / wd [Cin][32]: the two GEMM layouts of the torch weight [Co][Cin][3][3]. */

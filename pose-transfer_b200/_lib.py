@@ -41,8 +41,6 @@ SIGNATURES = {
     "ptk_conv_wgrad_plan": [ctypes.POINTER(ConvGeom), i64, ctypes.POINTER(i32)],
     "ptk_transpose_weight": [vp, vp, i32, i32, i32, vp],
     "ptk_sum_parts": [vp, i32, i64, vp, i64, i32, vp],
-    "ptk_stem_pack": [vp, i32, i32, vp, vp],
-    "ptk_stem_conv": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp],
     "ptk_head_pack_weights": [vp, i32, i32, vp, vp, vp],
     "ptk_head_shift_add": [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp],
     "ptk_head_shift_gather": [vp, i32, i32, i32, i32, i32, vp, vp],

@@ -206,7 +206,11 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
 // activation -> global), the MMAs of tile i + 1 already fill the other buffer.  For the layers with short K loops (stems,
 // encoder level 1, the 1x1 head GEMMs, the PatchGAN) the setup (barrier init, TMEM allocation) and the epilogue were
 // 30-60 % of a one-tile CTA's life; here they are paid once per SM / hidden behind the next tile.  No split-K.
-template <int BLOCK_N, int STAGES, int MH>
+// CO = coalescing epilogue: the accumulator block is transposed through shared memory so that every store instruction
+// writes whole 128-byte lines (a thread owns a ROW of the accumulator; storing it directly touches 32 partial lines per
+// instruction).  Costs 19 KB of shared memory: enabled for the tile shapes that are one CTA per SM anyway; the small
+// shapes keep two resident CTAs and store directly.
+template <int BLOCK_N, int STAGES, int MH, bool CO>
 __global__ void __launch_bounds__(192)
 conv_tc_persist_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcGeom g, float* __restrict__ y,
                        double* __restrict__ stats, const float* __restrict__ bias, int act, int ntile_n, int nphases) {
@@ -218,6 +222,10 @@ conv_tc_persist_kernel(const __grid_constant__ TmapSet maps, const __grid_consta
   // barriers: full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]; then the TMEM base-address slot
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * STAGES, bar_accf = sBar + 16 * STAGES, bar_acce = bar_accf + 16;
   const uint32_t tmem_slot = bar_acce + 16;
+  // epilogue staging (one 32 x 32 fp32 block per epilogue warp, rows padded to 36 floats: conflict-free 128-bit accesses)
+  // and the global element offset of each of the warp's 32 rows (-1: row outside the tensor)
+  float* s_stage = reinterpret_cast<float*>(smem_raw + (sBar + 16 * STAGES + 64 - smem_u32(smem_raw)));
+  long long* s_rowoff = reinterpret_cast<long long*>(s_stage + 4 * 32 * 36);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
   if (threadIdx.x == 0) {
@@ -306,6 +314,8 @@ conv_tc_persist_kernel(const __grid_constant__ TmapSet maps, const __grid_consta
       mbar_wait(bar_accf + 8 * acc, use & 1u);
       tc_fence_after();
       const uint32_t tacc = tmem_base + acc * ACC_COLS;
+      float* stg = CO ? s_stage + lg * (32 * 36) : nullptr;
+      long long* roff = CO ? s_rowoff + lg * 32 : nullptr;
 #pragma unroll 1
       for (int hm = 0; hm < MH; ++hm) {
         const int row = hm * 128 + lg * 32 + lane;
@@ -314,31 +324,48 @@ conv_tc_persist_kernel(const __grid_constant__ TmapSet maps, const __grid_consta
         const int ii = row / (g.BW * g.BH);
         const int gx = gx0 + x, gy = gy0 + yy, n = n0 + ii;
         const bool valid = gx < ph.GW && gy < ph.GH && n < g.N;
-        float* dst = nullptr;
+        long long off = -1;
         if (valid) {
           const int oy = gy * g.so + ph.py, ox = gx * g.so + ph.px;
-          dst = y + (((int64_t)n * g.OH + oy) * g.OW + ox) * g.ldy + nt * BLOCK_N;
+          off = (((long long)n * g.OH + oy) * g.OW + ox) * g.ldy + nt * BLOCK_N;
         }
+        if (CO) { __syncwarp(); roff[lane] = off; }
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           float v[32];
           tc_ld32(tacc + ((uint32_t)(lg * 32) << 16) + (uint32_t)(hm * BLOCK_N + c * 32), v);
-          if (valid) {
-            if (bias != nullptr) {
-              const float* bp = bias + nt * BLOCK_N + c * 32;
+          if (bias != nullptr) {
+            const float* bp = bias + nt * BLOCK_N + c * 32;
 #pragma unroll
-              for (int q = 0; q < 32; ++q) v[q] += __ldg(bp + q);
-            }
+            for (int q = 0; q < 32; ++q) v[q] += __ldg(bp + q);
+          }
+          if (valid) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) { s1 += v[q]; s2 = fmaf(v[q], v[q], s2); }
-            if (act != PTK_ACT_NONE) {
+          }
+          if (act != PTK_ACT_NONE) {
 #pragma unroll
-              for (int q = 0; q < 32; ++q) v[q] = apply_act(v[q], act);
-            }
+            for (int q = 0; q < 32; ++q) v[q] = apply_act(v[q], act);
+          }
+          if (CO) {
+            // 8 lanes per row of 128 contiguous bytes: 4 whole lines per store instruction
+            __syncwarp();
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              *reinterpret_cast<float4*>(stg + lane * 36 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const int r = i4 * 4 + (lane >> 3);
+              const long long o = roff[r];
+              const float4 w4 = *reinterpret_cast<const float4*>(stg + r * 36 + (lane & 7) * 4);
+              if (o >= 0) *reinterpret_cast<float4*>(y + o + c * 32 + (lane & 7) * 4) = w4;
+            }
+          } else if (valid) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(y + off + c * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         }
         if (stats != nullptr) {
@@ -630,14 +657,15 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   }
   dim3 grid((unsigned)(pair ? (mtiles + 1) / 2 * 2 : mtiles), (unsigned)(c.Cout / BN), (unsigned)(nphases * splits));
   // Persistent CTAs with a double-buffered accumulator (conv_tc_persist_kernel) when every resident CTA gets several tiles:
-  // PTK_TC_PERSIST=0 disables, =2 forces it whenever the tile shape allows (tests).
+  // PTK_TC_PERSIST=0 disables, =2 forces it whenever the tile shape allows (tests), =k >= 3 requires more than (k - 2) tiles
+  // per resident CTA (default: more tiles than resident CTAs).
   int ps_env = 1;
   if (const char* e = getenv("PTK_TC_PERSIST")) ps_env = atoi(e);      // (read per call: the tests switch it inside one process)
   const int64_t all_tiles = (int64_t)mtiles * (c.Cout / BN) * nphases;
   const int occ_ps = (size_t)best->stages * (MH * 128 * 128 + BN * 128) > 100 * 1024 ? 1 : 2;
   const int64_t slots_ps = (int64_t)num_sms() * occ_ps;
   const bool persist = splits == 1 && !pair && 2 * MH * BN <= 512 && all_tiles < (1 << 30) &&
-                       (ps_env == 2 ? all_tiles >= 2 : (ps_env == 1 && all_tiles >= 3 * slots_ps));
+                       (ps_env == 2 ? all_tiles >= 2 : (ps_env >= 1 && all_tiles > (int64_t)(ps_env >= 3 ? ps_env - 2 : 1) * slots_ps));
   const unsigned grid_ps = (unsigned)(ps_env == 2 ? (all_tiles + 1) / 2 : (all_tiles < slots_ps ? all_tiles : slots_ps));
 #define PTK_TC_LAUNCH(BN_, ST_, MH_)                                                                                       \
   do {                                                                                                                     \
@@ -651,22 +679,22 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     if (pair) launch_pdl(conv_tc_kernel<BN_, ST_, MH_, 2>, grid, dim3(192), smem, st, 2, maps, g, y_kernel, stats, bias, act); \
     else launch_pdl(conv_tc_kernel<BN_, ST_, MH_, 1>, grid, dim3(192), smem, st, 1, maps, g, y_kernel, stats, bias, act);    \
   } while (0)
-#define PTK_TC_LAUNCH_PS(BN_, ST_, MH_)                                                                                    \
+#define PTK_TC_LAUNCH_PS(BN_, ST_, MH_, CO_)                                                                               \
   do {                                                                                                                     \
-    const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 48 + 1024;                                 \
+    const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 64 + (CO_ ? 18432 + 1024 : 0) + 1024 + 64;  \
     static bool attr = false;                                                                                              \
-    if (!attr) { cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, ST_, MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
-    launch_pdl(conv_tc_persist_kernel<BN_, ST_, MH_>, dim3(grid_ps), dim3(192), smem, st, 1, maps, g, y_kernel, stats, bias, act, \
+    if (!attr) { cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, ST_, MH_, CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
+    launch_pdl(conv_tc_persist_kernel<BN_, ST_, MH_, CO_>, dim3(grid_ps), dim3(192), smem, st, 1, maps, g, y_kernel, stats, bias, act, \
                c.Cout / BN_, nphases);                                                                                     \
   } while (0)
   if (persist) {
-    if (MH == 1 && BN == 32) PTK_TC_LAUNCH_PS(32, 4, 1);
-    else if (MH == 2 && BN == 32) PTK_TC_LAUNCH_PS(32, 3, 2);
-    else if (MH == 1 && BN == 64) PTK_TC_LAUNCH_PS(64, 4, 1);
-    else if (MH == 2 && BN == 64) PTK_TC_LAUNCH_PS(64, 4, 2);
-    else if (MH == 1 && BN == 128) PTK_TC_LAUNCH_PS(128, 3, 1);
-    else if (MH == 1 && BN == 256) PTK_TC_LAUNCH_PS(256, 4, 1);
-    else PTK_TC_LAUNCH_PS(128, 4, 2);
+    if (MH == 1 && BN == 32) PTK_TC_LAUNCH_PS(32, 4, 1, false);
+    else if (MH == 2 && BN == 32) PTK_TC_LAUNCH_PS(32, 3, 2, false);
+    else if (MH == 1 && BN == 64) PTK_TC_LAUNCH_PS(64, 4, 1, false);
+    else if (MH == 2 && BN == 64) PTK_TC_LAUNCH_PS(64, 4, 2, true);
+    else if (MH == 1 && BN == 128) PTK_TC_LAUNCH_PS(128, 3, 1, false);
+    else if (MH == 1 && BN == 256) PTK_TC_LAUNCH_PS(256, 4, 1, true);
+    else PTK_TC_LAUNCH_PS(128, 4, 2, true);
     PTK_LAUNCH_CHECK("conv_tc_persist_kernel");
     return 0;
   }

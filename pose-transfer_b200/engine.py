@@ -51,7 +51,6 @@ class ConvLayer:
         self.w_fwd = None    # [taps][cin_pad][cout_pad]
         self.w_bwd = None    # [taps][dy_pad][cin_pad]  (weights of the dgrad gather-conv)
         self.w_dgrad_k = None  # [taps][cin_pad][dy_pad]: K-major tensor-core operand of the dgrad (== w_fwd unless narrow)
-        self.stem_wk = None    # encoder stems: [64][224] K = tap*24 + c operand of csrc/stem.cu
         self._derived = None   # GEMM-layout master weights: the transposed copy
         self._plans = {}       # wgrad geometry -> number of split-K partial gradients
         self.impl = {"auto": K.IMPL_AUTO, "simt": K.IMPL_SIMT, "tc": K.IMPL_AUTO}[os.environ.get("PTK_CONV_IMPL", "auto")]
@@ -81,10 +80,6 @@ class ConvLayer:
 
     def pack_forward(self):
         self._pack_layouts()
-        if self._is_stem():
-            if self.stem_wk is None or self.stem_wk.device != self.weight.device:
-                self.stem_wk = torch.zeros(64 * 224, device=self.weight.device)
-            K.stem_pack(self.w_bwd, self.cin, self.cin_pad, self.stem_wk)     # w_bwd = [tap][64][cin_pad]
 
     def _pack_layouts(self):
         """Both GEMM layouts are refreshed in one pass: w_fwd = [tap][cin][cout] is the CUDA-core fprop operand AND the
@@ -127,21 +122,12 @@ class ConvLayer:
             return (H - 1) * self.stride - 2 * self.pad + self.k, (W - 1) * self.stride - 2 * self.pad + self.k
         return (H + 2 * self.pad - self.k) // self.stride + 1, (W + 2 * self.pad - self.k) // self.stride + 1
 
-    def _is_stem(self):
-        """Conv2d(Cin <= 24 -> 64, k3, s1, p1): the encoder stems run on csrc/stem.cu (im2col assembled in shared memory;
-        0.139 ms vs 0.153 ms for the generic implicit-GEMM kernel at 256x256, N=8).  PTK_STEM=0 falls back."""
-        return (self.impl != K.IMPL_SIMT and not self.transposed and self.k == 3 and self.stride == 1 and self.pad == 1 and
-                self.cout == 64 and self.cin <= 24 and os.environ.get("PTK_STEM", "1") != "0")
-
     def forward(self, x, N, H, W, y, act=ACT_NONE, stats=None, y_nchw=None, scratch=None):
         """x: Slice with cin_pad readable channels; y: Slice (cout channels) or None.  scratch: fp32 buffer for the
         deterministic split-K of layers with few output tiles (one per stream that may run this layer)."""
         OH, OW = self.out_hw(H, W)
         g = K.conv_geom(N, H, W, self.cin_pad, x.ld, OH, OW, self.cout, y.ld if y is not None else self.cout, self.k,
                         self.stride, self.pad, self.transposed, self.impl)
-        if self._is_stem() and act == ACT_NONE and stats is None and y is not None and y_nchw is None and self.stem_wk is not None:
-            K.stem_conv(g, x, self.stem_wk, self.bias.detach() if self.bias is not None else None, y)
-            return OH, OW
         K.conv_forward(g, x, self.w_fwd, self.w_bwd, self.bias.detach() if self.bias is not None else None, act, y, y_nchw, stats,
                        scratch)
         return OH, OW

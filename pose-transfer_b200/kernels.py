@@ -188,18 +188,6 @@ def unpack_weight_grad_parts(src, nparts, part_stride, grad, A, B, taps, B_pad, 
 
 
 @_timed("pack")
-def stem_pack(w_tap_major, cin, cin_pad, wk):
-    check(_lib.lib().ptk_stem_pack(_p(w_tap_major), cin, cin_pad, _p(wk), _stream()), "ptk_stem_pack")
-
-
-@_timed("conv_forward")
-def stem_conv(g, x, wk, bias, y):
-    """Encoder stem (k3, Cin <= 24 -> 64) with the im2col assembled in shared memory; g only labels the timing row."""
-    x, y = _as_slice(x), _as_slice(y)
-    check(_lib.lib().ptk_stem_conv(x.ptr, x.ld, _p(wk), _p(bias), y.ptr, y.ld, g.N, g.H, g.W, _stream()), "ptk_stem_conv")
-
-
-@_timed("pack")
 def head_pack_weights(w, wk, wd):
     Co, Cin = w.shape[0], w.shape[1]
     check(_lib.lib().ptk_head_pack_weights(_p(w), Co, Cin, _p(wk), _p(wd), _stream()), "ptk_head_pack_weights")

@@ -105,18 +105,6 @@ def install(K):
         w = w_t[:k * k * g.Cin * cout_pad].reshape(k, k, g.Cin, cout_pad)[..., :g.Cout]
         return w   # [kh][kw][ci][co]
 
-    def stem_pack(w_tap_major, cin, cin_pad, wk):
-        w = w_tap_major[:9 * 64 * cin_pad].reshape(9, 64, cin_pad)[:, :, :cin]          # [tap][co][c]
-        full = torch.zeros(64, 9, 24)
-        full[:, :, :cin] = w.permute(1, 0, 2)
-        wk[:64 * 224].zero_()
-        wk[:64 * 224].reshape(64, 224)[:, :216] = full.reshape(64, 216)
-
-    def stem_conv(g, x, wk, bias, y):
-        xs = nchw(view(x, 24)).reshape(g.N, 24, g.H, g.W)
-        w = wk[:64 * 224].reshape(64, 224)[:, :216].reshape(64, 3, 3, 24).permute(0, 3, 1, 2)
-        view(y, 64).copy_(nhwc(F.conv2d(xs, w, bias, padding=1)))
-
     def head_pack_weights(w, wk, wd):
         Co, Cin = w.shape[0], w.shape[1]
         full = torch.zeros(32, Cin)
@@ -341,7 +329,7 @@ def install(K):
     table = dict(nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, pack_weight=pack_weight, pack_weight_dual=pack_weight_dual,
                  unpack_weight_grad=unpack_weight_grad, unpack_weight_grad_parts=unpack_weight_grad_parts, fill=fill,
                  transpose_weight=transpose_weight, sum_parts=sum_parts, conv_wgrad_plan=conv_wgrad_plan,
-                 stem_pack=stem_pack, stem_conv=stem_conv, head_pack_weights=head_pack_weights, head_shift_add=head_shift_add, head_shift_gather=head_shift_gather,
+                 head_pack_weights=head_pack_weights, head_shift_add=head_shift_add, head_shift_gather=head_shift_gather,
                  head_wgrad_scatter=head_wgrad_scatter,
                  conv_forward=conv_forward, conv_wgrad=conv_wgrad, conv_wgrad_parts=conv_wgrad_parts,
                  bias_grad=bias_grad, gn_stats=gn_stats, gn_apply=gn_apply, gn_bwd_reduce=gn_bwd_reduce,

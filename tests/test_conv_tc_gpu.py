@@ -355,32 +355,6 @@ def test_head_as_1x1_gemms(shape):
     assert float((dx[..., :32] - 5).abs().max()) == 0
 
 
-@pytest.mark.parametrize("shape", [(2, 21, 24, 40), (3, 18, 19, 37), (2, 24, 8, 16)], ids=["c21", "c18_ragged", "c24_one_tile"])
-def test_stem_conv_smem_im2col(shape, monkeypatch):
-    """csrc/stem.cu: Conv2d(Cin <= 24 -> 64, k3, p1, bias) with the im2col assembled in shared memory vs torch CPU fp32."""
-    monkeypatch.setenv("PTK_STEM", "1")
-    import pose_transfer_b200  # noqa: F401
-    from pose_transfer_b200 import kernels as K
-    from pose_transfer_b200.engine import ConvLayer
-    N, C, H, W = shape
-    g = torch.Generator().manual_seed(C * 100 + H)
-    w = (torch.rand(64, C, 3, 3, generator=g) * 2 - 1) / (9 * C) ** 0.5
-    b = torch.rand(64, generator=g) - 0.5
-    x = torch.randn(N, C, H, W, generator=g)
-    ref = F.conv2d(x, w, b, padding=1)
-    layer = ConvLayer(torch.nn.Parameter(w.cuda()), torch.nn.Parameter(b.cuda()), False, 3, 1, 1)
-    assert layer._is_stem()
-    layer.pack_forward()
-    xin = torch.zeros(N, H, W, 32, device="cuda")
-    xin[..., :C] = nhwc(x).cuda()
-    y = torch.full((N, H, W, 64 + 32), 7.0, device="cuda")
-    layer.forward(K.Slice(xin), N, H, W, K.Slice(y, 32, 64), K.ACT_NONE, None)
-    torch.cuda.synchronize()
-    got = nchw(y[..., 32:]).cpu()
-    assert rel_l2(got, ref) < TF32_TOL, describe(got, ref, "stem")
-    assert float((y[..., :32] - 7.0).abs().max()) == 0
-
-
 SPLITK_CASES = [
     # name, transposed, Cin, Cout, N, H, W   (k4 s2 p1: the bottleneck layers of the U-Net at batch 8 / 2)
     ("enc_512to512_16", False, 512, 512, 8, 16, 16),
