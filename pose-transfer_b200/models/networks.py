@@ -128,13 +128,13 @@ class decoder(nn.Module):
         for i, nf in enumerate(nfilters_dec):
             if i == 0:
                 model_dec.append(Block(self.num_skips * self.nfilters_enc[-1], nf, down=False, leaky=False, dropout=True))
-            elif 0 < i < 3:
-                model_dec.append(Block(self.num_skips * self.nfilters_enc[-(i + 1)] + nfilters_dec[i - 1], nf, down=False,
-                                       leaky=False, dropout=True))
             elif i == len(nfilters_dec) - 1:
                 model_dec.append(nn.ReLU())
                 model_dec.append(nn.Conv2d(self.num_skips * self.nfilters_enc[-(i + 1)] + nfilters_dec[i - 1], nf,
                                            kernel_size=3, padding=1, bias=True))
+            elif 0 < i < 3:
+                model_dec.append(Block(self.num_skips * self.nfilters_enc[-(i + 1)] + nfilters_dec[i - 1], nf, down=False,
+                                       leaky=False, dropout=True))
             else:
                 model_dec.append(Block(self.num_skips * self.nfilters_enc[-(i + 1)] + nfilters_dec[i - 1], nf, down=False,
                                        leaky=False))
@@ -267,9 +267,11 @@ class Stacked_Generator(nn.Module):
         self.use_input_pose = use_input_pose
         self.pose_dim = pose_dim
         self.image_size = image_size
-        self.generator = Deformable_Generator(input_nc, pose_dim, image_size, nfilters_enc, nfilters_dec, warp_skip,
-                                              use_input_pose)
+        self.generator = self._make_generator(input_nc, pose_dim, image_size, nfilters_enc, nfilters_dec, warp_skip, use_input_pose)
         self._contexts = []
+
+    def _make_generator(self, input_nc, pose_dim, image_size, nfilters_enc, nfilters_dec, warp_skip, use_input_pose):
+        return Deformable_Generator(input_nc, pose_dim, image_size, nfilters_enc, nfilters_dec, warp_skip, use_input_pose)
 
     @property
     def engine(self):
@@ -295,9 +297,10 @@ class Stacked_Generator(nn.Module):
         outs = []
         for i, eng in enumerate(ctxs):
             pieces = self.stack_input(i, input, target_pose, outs[-1] if outs else None)
-            outs.append(eng.forward(pieces, target_warps[:, i].contiguous(), target_masks[:, i].contiguous(),
-                                    drop=drops[i] if drops is not None else None, repack=repack if i == 0 else False,
-                                    d_input=d_input if i == S - 1 else None))
+            w = target_warps[:, i].contiguous() if target_warps is not None else None
+            m = target_masks[:, i].contiguous() if target_masks is not None else None
+            outs.append(eng.forward(pieces, w, m, drop=drops[i] if drops is not None else None,
+                                    repack=repack if i == 0 else False, d_input=d_input if i == S - 1 else None))
         return outs
 
     def backward_stacks(self, grads, dout_nchw, dout_nhwc, on_stage=None):
@@ -310,14 +313,15 @@ class Stacked_Generator(nn.Module):
                                  accumulate=i < S - 1, need_image_grad=i > 0)
             g2 = None
 
-    def forward(self, input, target_pose, target_warps, target_masks):
+    def forward(self, input, target_pose, target_warps=None, target_masks=None):
         _require_cuda(input, "Stacked_Generator")
         gen = self.generator
         params = tuple(gen.parameters())
         track = torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params))
         outputs = []
         for i, eng in enumerate(self.contexts(self.num_stacks)):
-            w, m = target_warps[:, i].contiguous(), target_masks[:, i].contiguous()
+            w = target_warps[:, i].contiguous() if target_warps is not None else None
+            m = target_masks[:, i].contiguous() if target_masks is not None else None
             if track:
                 # autograd needs ONE input tensor per stack: materialise the concatenation (module-surface use only)
                 inp = torch.cat([t[:, c0:c0 + C] for t, c0, C in self.stack_input(i, input, target_pose, outputs[-1] if outputs else None)], 1)
@@ -327,6 +331,20 @@ class Stacked_Generator(nn.Module):
                                   drop=gen._next_drop(), repack=True if i == 0 else False)
             outputs.append(out)
         return outputs
+
+
+class Stacked_Baseline_Generator(Stacked_Generator):
+    """Drop-in for src_baseline/models/networks.py:255-298: the same stacking over the single-encoder, un-warped Generator;
+    called as gen(input, interpol_pose)."""
+
+    def __init__(self, input_nc, num_stacks, pose_dim, nfilters_enc, nfilters_dec, num_skips=1, warp_skip=False,
+                 use_input_pose=True):
+        self._num_skips = num_skips
+        super(Stacked_Baseline_Generator, self).__init__(input_nc, num_stacks, None, pose_dim, nfilters_enc, nfilters_dec,
+                                                         warp_skip, use_input_pose)
+
+    def _make_generator(self, input_nc, pose_dim, image_size, nfilters_enc, nfilters_dec, warp_skip, use_input_pose):
+        return Generator(input_nc, nfilters_enc, nfilters_dec, self._num_skips, warp_skip, use_input_pose)
 
 
 class _DiscriminatorFn(torch.autograd.Function):
@@ -362,24 +380,28 @@ class _DiscriminatorFn(torch.autograd.Function):
 class Discriminator(nn.Module):
     """models/networks.py:329-357."""
 
-    def __init__(self, input_nc, warp_skip=False, use_input_pose=True, checkMode=0):
+    def __init__(self, input_nc, warp_skip=False, use_input_pose=True, checkMode=0, baseline_tree=False):
         super(Discriminator, self).__init__()
         self.input_nc = input_nc
         self.use_input_pose = use_input_pose
         self.warp_skip = warp_skip
         self.checkMode = checkMode
+        # the two trees reduce the PatchGAN differently under --checkMode: src_deformable keeps Block(128, 256) and ends with
+        # Block(256, 1) (networks.py:341-351), src_baseline ends with Block(128, 1) (src_baseline/models/networks.py:312-319)
+        self.baseline_tree = baseline_tree
         self.net = self.build_net()
         self.engine = DiscriminatorEngine(self)
         self._ptk_weights_version = 0
         self.register_load_state_dict_post_hook(_bump_weights_version)
 
     def build_net(self):
-        model = [nn.Conv2d(self.input_nc, 64, kernel_size=4, stride=2), Block(64, 128), Block(128, 256)]
+        model = [nn.Conv2d(self.input_nc, 64, kernel_size=4, stride=2), Block(64, 128)]
         if self.checkMode == 0:
-            model.append(Block(256, 512))
-            model.append(Block(512, 1, bn=False))
+            model += [Block(128, 256), Block(256, 512), Block(512, 1, bn=False)]
+        elif self.baseline_tree:
+            model.append(Block(128, 1, bn=False))
         else:
-            model.append(Block(256, 1, bn=False))
+            model += [Block(128, 256), Block(256, 1, bn=False)]
         model.append(nn.Sigmoid())
         model.append(Flatten())
         return nn.Sequential(*model)

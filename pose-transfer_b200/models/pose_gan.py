@@ -22,7 +22,8 @@ from torchvision.models import vgg19
 from .. import kernels as K
 from ..kernels import Slice
 from ..utils import pose_utils
-from .networks import Deformable_Generator, Discriminator, Generator, Stacked_Generator, xavier_weights_init  # noqa: F401
+from .networks import (Deformable_Generator, Discriminator, Generator, Stacked_Baseline_Generator, Stacked_Generator,  # noqa: F401
+                       xavier_weights_init)
 
 
 class ParamArena:
@@ -305,8 +306,9 @@ class DeformablePose_GAN(nn.Module):
                                           repack=None, d_input=d_input)
             return out, []
         pose, swarps, smasks = stacked
-        swarps = swarps.cuda().float() if not swarps.is_cuda else swarps.float()
-        smasks = smasks.cuda() if not smasks.is_cuda else smasks
+        if swarps is not None:
+            swarps = swarps.cuda().float() if not swarps.is_cuda else swarps.float()
+            smasks = smasks.cuda() if not smasks.is_cuda else smasks
         outs = self.gen.run_stacks(input, pose, swarps, smasks, drops=drop, d_input=d_input, repack=None)
         return outs[-1], outs
 
@@ -471,10 +473,13 @@ class Pose_GAN(DeformablePose_GAN):
 
     def __init__(self, opt):
         nn.Module.__init__(self)
-        if getattr(opt, "checkMode", 0) != 0:
-            raise NotImplementedError("src_baseline --checkMode nets are outside the B200 path")
-        nfilters_decoder = (512, 512, 512, 256, 128, 3) if max(opt.image_size) < 256 else (512, 512, 512, 512, 256, 128, 3)
-        nfilters_encoder = (64, 128, 256, 512, 512, 512) if max(opt.image_size) < 256 else (64, 128, 256, 512, 512, 512, 512)
+        check_mode = getattr(opt, "checkMode", 0)
+        if check_mode == 0:
+            nfilters_decoder = (512, 512, 512, 256, 128, 3) if max(opt.image_size) < 256 else (512, 512, 512, 512, 256, 128, 3)
+            nfilters_encoder = (64, 128, 256, 512, 512, 512) if max(opt.image_size) < 256 else (64, 128, 256, 512, 512, 512, 512)
+        else:       # --checkMode: reduced nets for over-fitting checks (src_baseline/models/pose_gan.py:16-21)
+            nfilters_decoder = (128, 3) if max(opt.image_size) < 256 else (256, 128, 3)
+            nfilters_encoder = (64, 128) if max(opt.image_size) < 256 else (64, 128, 256)
         input_nc = 3 + 2 * opt.pose_dim if opt.use_input_pose else 3 + opt.pose_dim
         if not opt.use_input_pose:
             raise NotImplementedError("only use_input_pose=True is on the B200 path")
@@ -482,24 +487,26 @@ class Pose_GAN(DeformablePose_GAN):
         self.batch_size = opt.batch_size
         self.pose_dim = opt.pose_dim
         self.image_size = tuple(opt.image_size)
-        if opt.gen_type != 'baseline':
-            raise NotImplementedError("src_baseline gen_type='stacked' is outside the B200 path")
-        self.gen = Generator(input_nc, nfilters_encoder, nfilters_decoder, use_input_pose=opt.use_input_pose)
-        self.disc = Discriminator(input_nc + 3, use_input_pose=opt.use_input_pose)
+        if opt.gen_type == 'stacked':
+            self.gen = Stacked_Baseline_Generator(input_nc, opt.num_stacks, opt.pose_dim, nfilters_encoder, nfilters_decoder,
+                                                  use_input_pose=opt.use_input_pose)
+        elif opt.gen_type == 'baseline':
+            self.gen = Generator(input_nc, nfilters_encoder, nfilters_decoder, use_input_pose=opt.use_input_pose)
+        else:
+            raise Exception('Invalid gen_type')
+        self.disc = Discriminator(input_nc + 3, use_input_pose=opt.use_input_pose, checkMode=check_mode, baseline_tree=True)
         self.disc.apply(xavier_weights_init)            # src_baseline/models/pose_gan.py:51-52
         self.gen.apply(xavier_weights_init)
         base = argparse_like(opt, content_loss_layer='none', nn_loss_area_size=1)
         self._finish_init(base)
 
     def gen_update(self, input, target, interpol_pose, opt, drop=None):
-        if opt['gen_type'] != 'baseline':
-            raise NotImplementedError("src_baseline gen_type='stacked' is outside the B200 path")
-        return self._gen_step(input, target, None, None, opt, drop)
+        stacked = (self._prep(interpol_pose), None, None) if opt['gen_type'] == 'stacked' else None
+        return self._gen_step(input, target, None, None, opt, drop, stacked=stacked)
 
     def dis_update(self, input, target, interpol_pose, real_inp, real_target, opt, drop=None):
-        if opt['gen_type'] != 'baseline':
-            raise NotImplementedError("src_baseline gen_type='stacked' is outside the B200 path")
-        return self._dis_step(input, target, None, None, real_inp, real_target, opt, drop)
+        stacked = (self._prep(interpol_pose), None, None) if opt['gen_type'] == 'stacked' else None
+        return self._dis_step(input, target, None, None, real_inp, real_target, opt, drop, stacked=stacked)
 
 
 def argparse_like(opt, **overrides):

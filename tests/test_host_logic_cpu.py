@@ -322,3 +322,57 @@ def test_stacked_training_step_matches_reference_golden(monkeypatch):
         # with the live reference to 1e-3 .. 8e-3 rel-L2 (cosine >= 0.99997), the scalar norm gains to a few per cent
         _stacked_step(model, opt, g, 5e-5, 5e-5, dict(tol_norm=1e-2, tol_samp=5e-2, tol_scalar=0.12),
                       dict(tol_norm=1e-4, tol_samp=2e-3, tol_scalar=2e-3, abs_slack=4.1e-4))
+
+
+@pytest.mark.parametrize("gen_type,check_mode", [("baseline", 1), ("stacked", 0), ("stacked", 1)],
+                         ids=["checkMode", "stacked", "stacked_checkMode"])
+def test_src_baseline_variants_match_reference(gen_type, check_mode, monkeypatch):
+    """SURVEY 8f-4 remainder: src_baseline --checkMode nets (reduced U-Net / 3-conv PatchGAN, src_baseline/models/pose_gan.py:
+    16-21, networks.py:314-319) and the src_baseline stacked generator (networks.py:255-298), one dis_update + gen_update each
+    against the LIVE reference classes from identical weights, inputs and dropout noise (emulated kernels)."""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not available")
+    from pose_transfer_b200.models import pose_gan, networks
+    import contextlib, io
+    ns = ref_import.load_baseline()
+    H, W, P, N, S = 128, 64, 18, 2, 2
+    opt = argparse.Namespace(image_size=(H, W), use_input_pose=True, pose_dim=P, batch_size=N, num_stacks=S, checkMode=check_mode,
+                             gen_type=gen_type, dataset="fasion128", learning_rate=2e-4, gan_penalty_weight=1.0, l1_penalty_weight=100.0)
+    with _CpuGAN():
+        with contextlib.redirect_stdout(io.StringIO()):
+            torch.manual_seed(7)
+            ref = ns.pose_gan.Pose_GAN(opt)
+        gsd = {k: v.clone() for k, v in ref.gen.state_dict().items()}
+        dsd = {k: v.clone() for k, v in ref.disc.state_dict().items()}
+        bs = [synth.make_batch(N, H, W, P, seed=30 + i) for i in range(S)]
+        r = synth.make_batch(N, H, W, P, seed=40)
+        inp, tgt = bs[0]["input"], bs[0]["target"]
+        ipose = torch.cat([b["input"][:, 3 + P:] for b in bs], 1) if gen_type == "stacked" else None
+        nstack = S if gen_type == "stacked" else 1
+        ndrop = len([m for m in ref.gen.modules() if isinstance(m, torch.nn.Dropout2d)])
+        drops = [synth.dropout_masks(N, 128 if check_mode else 512, ndrop, seed=50 + i) for i in range(nstack)]
+        od = vars(opt)
+        from oracle.make_golden import _DropPatch
+        flat = [m for d in drops for m in d]
+        with _DropPatch(flat):
+            dl_ref = ref.dis_update(inp, tgt, ipose, r["input"], r["target"], od)
+        with _DropPatch(flat):
+            out_ref, outs_ref, gl_ref = ref.gen_update(inp, tgt, ipose, od)
+        monkeypatch.setattr(networks, "_require_cuda", lambda t, who: None)
+        with emul_kernels.install(K), contextlib.redirect_stdout(io.StringIO()):
+            model = pose_gan.Pose_GAN(opt)
+            model.gen.load_state_dict(gsd)
+            model.disc.load_state_dict(dsd)
+            dr = drops if gen_type == "stacked" else drops[0]
+            dl = model.dis_update(inp, tgt, ipose, r["input"], r["target"], od, drop=dr)
+            out, outs, gl = model.gen_update(inp, tgt, ipose, od, drop=dr)
+    np.testing.assert_allclose(dl, dl_ref, rtol=2e-4)
+    np.testing.assert_allclose(gl, gl_ref, rtol=2e-4)
+    assert max_abs(out, out_ref.detach()) <= 2e-4
+    assert len(outs) == len(outs_ref)
+    got = model.gen.state_dict()
+    for k, v in ref.gen.state_dict().items():
+        d = (got[k].double() - v.double()).abs()
+        assert float(d.max()) <= 4.1e-4, (k, float(d.max()))
+        assert float((d > 1e-5).double().mean()) <= 5e-3, (k, float((d > 1e-5).double().mean()))
