@@ -26,6 +26,19 @@ def rows(path):
         lines = [ln for ln in f if ln.startswith('"')]
     rd = csv.reader(lines)
     header = next(rd)
+    if "Metric Name" in header:            # long format (`--csv` without `--page raw`): one row per launch and metric
+        kn, mn, mu, mv = (header.index(k) for k in ("Kernel Name", "Metric Name", "Metric Unit", "Metric Value"))
+        grid = header.index("Grid Size")
+        launches = {}
+        for r in rd:
+            if len(r) <= mv:
+                continue
+            d = launches.setdefault(r[0], {"kernel": re.sub(r"^void |ptk::|\(.*$", "", r[kn]), "grid": r[grid]})
+            for want, label, kind in COLS:
+                if r[mn] == want:
+                    d[label] = float(r[mv].replace(",", "")) * (UNIT[kind].get(r[mu], 1.0) if kind else 1.0)
+        yield from launches.values()
+        return
     units = next(rd)
     idx = {}
     for want, label, _ in COLS:
