@@ -218,6 +218,21 @@ int ptk_nnloss_features_backward(const float* pred, const float* gt, const uint8
 int ptk_tanh_bwd_combine(const float* g_nchw, const float* g_nhwc, int ldg, const float* out_nchw,
                          float* dz, int ld, int N, int C, int H, int W, void* stream);
 
+/* ---------------------------------------------------------------- VGG-19 prefix deeper than block1_conv2
+ * (utils/pose_utils.py:320-338 Feature_Extractor with content_loss_layer = blockB_convC: the convolutions run through
+ * ptk_conv_forward; these are the remaining torchvision ops of the prefix.)
+ * ptk_vgg_preprocess: backward == 0: out NHWC [N,H,W,ld] channels 0..2 = preprocess_for_vgg(x NCHW [N,3,H,W]) -- the
+ *   reference re-views the NCHW buffer as NHWC, so flat per-sample element i uses mean[i % 3], std[i % 3];
+ *   backward != 0: x is the NHWC gradient [N,H,W,ld], out the NCHW gradient [N,3,H,W] (divided by the same std).
+ * ptk_maxpool2_*: nn.MaxPool2d(kernel_size=2, stride=2) on NHWC; the backward routes to the first maximum of the window
+ *   and writes every element of dx (even H, W required).
+ * ptk_relu_backward: dy *= (y > 0) in place from the saved output. */
+int ptk_vgg_preprocess(const float* x, float* out, int ld, int N, int H, int W, int backward, void* stream);
+int ptk_maxpool2_forward(const float* x, int ldx, float* y, int ldy, int N, int H, int W, int C, void* stream);
+int ptk_maxpool2_backward(const float* dy, int lddy, const float* x, int ldx, float* dx, int lddx, int N, int H, int W,
+                          int C, void* stream);
+int ptk_relu_backward(const float* y, int ldy, float* dy, int lddy, int64_t pixels, int C, void* stream);
+
 /* ---------------------------------------------------------------- device-side data path
  * Replaces the per-sample numpy / skimage work of datasets/PoseTransfer_Dataset.py:78-109 on the host.
  * kp: int32 [N,P,2] key-points as (y, x), -1 = missing (utils/pose_utils.py:42). */

@@ -111,10 +111,13 @@ def gen_step(ns, H, W, P, N, seed, tag, content="block1_conv2", area=5, l1_w=0.0
                        l1_penalty_weight=l1_w)
     dsd = synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1)
     vgg = torchvision.models.vgg19(weights=None)
-    vw, vb = synth.vgg_conv1_1(seed)
-    with torch.no_grad():
-        vgg.features[0].weight.copy_(vw)
-        vgg.features[0].bias.copy_(vb)
+    if content in ("none", "block1_conv2"):
+        vw, vb = synth.vgg_conv1_1(seed)
+        with torch.no_grad():
+            vgg.features[0].weight.copy_(vw)
+            vgg.features[0].bias.copy_(vb)
+    else:
+        synth.fill_vgg(vgg, seed)
     model = ref_import.make_reference_gan(opt, dsd, vgg)
     model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, image_size), seed))
     od = vars(opt)
@@ -331,6 +334,11 @@ def main():
     if a.only in ("", "step"):
         gen_step(ns, 64, 64, 18, 2, 0, "64x64_p18_nn5")
         gen_step(ns, 64, 64, 18, 2, 3, "64x64_p18_l1", content="none", area=1, l1_w=100.0, steps=1)
+    if a.only in ("", "step", "vggdeep"):
+        # content_loss_layer deeper than block1_conv2: conv2_1 without its ReLU (features[0..5]) and relu(conv3_2) after
+        # two max-pools (features[0..13]); seeded weights in every VGG conv
+        gen_step(ns, 64, 64, 18, 2, 5, "64x64_p18_b2c1", content="block2_conv1", area=3, l1_w=0.01, steps=1)
+        gen_step(ns, 64, 64, 18, 2, 6, "64x64_p18_b3c4", content="block3_conv4", area=3, l1_w=0.01, steps=1)
     if a.only in ("", "big") or a.only.startswith("big:"):
         for case in BIG_CASES:
             if a.only.startswith("big:") and a.only[4:] != case[0]:

@@ -193,6 +193,33 @@ def feature_extractor(vgg_w, vgg_b, x):
     return F.relu(F.conv2d(vgg_preprocess(x), vgg_w, vgg_b, padding=1))
 
 
+VGG19_CFG = (64, 64, 'M', 128, 128, 'M', 256, 256, 256, 256, 'M', 512, 512, 512, 512, 'M', 512, 512, 512, 512, 'M')
+
+
+def feature_extractor_prefix(convs, x, layer_ind):
+    """Feature_Extractor for ANY content_loss_layer (pose_utils.py:320-338): torchvision vgg19.features[0..layer_ind]
+    (configuration 'E': 3x3/pad-1 convs each followed by ReLU, 'M' = MaxPool2d(2, 2)) on the view-normalised image.
+    convs: [(weight, bias)] of the VGG convolutions in order (as many as the prefix needs)."""
+    x = vgg_preprocess(x)
+    it, ci = 0, 0
+    for v in VGG19_CFG:
+        if it > layer_ind:
+            break
+        if v == 'M':
+            x = F.max_pool2d(x, 2, 2)
+            it += 1
+            continue
+        w, b = convs[ci]
+        ci += 1
+        x = F.conv2d(x, w, b, padding=1)
+        it += 1
+        if it > layer_ind:
+            break
+        x = F.relu(x)
+        it += 1
+    return x
+
+
 # ----------------------------------------------------------------------------- a11
 def nn_loss(pred, gt, nh, nw):
     """DeformablePose_GAN.nn_loss (models/pose_gan.py:173-199), without materialising the 25x stack."""

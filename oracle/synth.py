@@ -157,6 +157,28 @@ def vgg_conv1_1(seed=0):
     return w, b
 
 
+def fill_vgg(vgg, seed=0):
+    """Seeded weights for EVERY conv of a torchvision vgg19 (deeper content_loss_layer fixtures): features[0] keeps
+    vgg_conv1_1(seed); the others get uniform(+-sqrt(6 / fan_in)) so that activations keep their scale through ReLUs."""
+    import torch.nn as nn
+    w0, b0 = vgg_conv1_1(seed)
+    k = 0
+    with torch.no_grad():
+        for m in vgg.features:
+            if not isinstance(m, nn.Conv2d):
+                continue
+            if k == 0:
+                m.weight.copy_(w0)
+                m.bias.copy_(b0)
+            else:
+                g = _gen(7919 * (seed + 1) + 31 * k)
+                fan_in = m.weight.shape[1] * 9
+                m.weight.copy_((torch.rand(m.weight.shape, generator=g) * 2 - 1) * math.sqrt(6.0 / fan_in))
+                m.bias.copy_(torch.rand(m.bias.shape, generator=g) * 0.2 - 0.1)
+            k += 1
+    return vgg
+
+
 def dropout_masks(N, C, count, seed=0):
     """`count` Dropout2d(0.5) noise tensors [N,C,1,1] with values in {0, 2} (networks.py:161)."""
     g = _gen(15485863 * (seed + 1))

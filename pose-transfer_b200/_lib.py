@@ -62,6 +62,10 @@ SIGNATURES = {
     "ptk_nnloss_features_forward": [vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp],
     "ptk_nnloss_features_backward": [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp],
     "ptk_tanh_bwd_combine": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp],
+    "ptk_vgg_preprocess": [vp, vp, i32, i32, i32, i32, i32, vp],
+    "ptk_maxpool2_forward": [vp, i32, vp, i32, i32, i32, i32, i32, vp],
+    "ptk_maxpool2_backward": [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp],
+    "ptk_relu_backward": [vp, i32, vp, i32, i64, i32, vp],
     "ptk_pose_heatmaps": [vp, i32, i32, i32, i32, f32, vp, i32, i32, vp],
     "ptk_pose_masks": [vp, i32, i32, i32, i32, vp, vp],
     "ptk_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],

@@ -270,3 +270,126 @@ extern "C" int ptk_fill(float* dst, int64_t n, float value, void* stream) {
   PTK_LAUNCH_CHECK("fill_kernel");
   return 0;
 }
+
+// ---------------------------------------------------------------- VGG prefix helpers (content_loss_layer deeper than block1_conv2)
+namespace ptk {
+
+// utils/pose_utils.py:324-331: the NCHW buffer is re-viewed as NHWC without a permute, so the element with flat per-sample
+// index i is normalised with mean[i % 3], std[i % 3].  Output: NHWC with `ld` channels (3 used, the rest left untouched).
+__global__ void vgg_preprocess_kernel(const float* __restrict__ x, float* __restrict__ out, int ld, int64_t HW, int64_t total, int backward) {
+  pdl_trigger();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / (3 * HW), flat = i - n * 3 * HW;      // NCHW order: flat = c*HW + p
+    const int c = (int)(flat / HW);
+    const int64_t p = flat - (int64_t)c * HW;
+    const int r = (int)(flat % 3);
+    const float mean = r == 0 ? 0.485f : (r == 1 ? 0.456f : 0.406f);
+    const float sd = r == 0 ? 0.229f : (r == 1 ? 0.224f : 0.225f);
+    if (!backward) out[(n * HW + p) * ld + c] = (x[i] - mean) / sd;
+    else out[i] = x[(n * HW + p) * ld + c] / sd;               // x = gradient w.r.t. the NHWC preprocessed tensor, out = NCHW
+  }
+}
+
+// nn.MaxPool2d(2, 2) on NHWC (floor mode).  Backward routes the gradient to the first maximum of the window (row-major).
+__global__ void maxpool2_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int H, int W, int C, int64_t total) {
+  pdl_trigger();
+  const int OH = H / 2, OW = W / 2, C4 = C >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) << 2;
+    int64_t t = i / C4;
+    const int ox = (int)(t % OW); t /= OW;
+    const int oy = (int)(t % OH);
+    const int64_t n = t / OH;
+    const float* p = x + ((n * H + 2 * oy) * W + 2 * ox) * (int64_t)ldx + c;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + ldx));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(p + (int64_t)W * ldx)), e = __ldg(reinterpret_cast<const float4*>(p + (int64_t)W * ldx + ldx));
+    *reinterpret_cast<float4*>(y + ((n * OH + oy) * OW + ox) * (int64_t)ldy + c) =
+        make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
+                    fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
+  }
+}
+
+__device__ __forceinline__ void route4(float g, float a, float b, float d, float e, float& ga, float& gb, float& gd, float& ge) {
+  const float m = fmaxf(fmaxf(a, b), fmaxf(d, e));
+  ga = gb = gd = ge = 0.f;
+  if (a == m) ga = g; else if (b == m) gb = g; else if (d == m) gd = g; else ge = g;
+}
+
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx, float* __restrict__ dx,
+                                    int lddx, int H, int W, int C, int64_t total) {
+  pdl_trigger();
+  const int OH = H / 2, OW = W / 2, C4 = C >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) << 2;
+    int64_t t = i / C4;
+    const int ox = (int)(t % OW); t /= OW;
+    const int oy = (int)(t % OH);
+    const int64_t n = t / OH;
+    const int64_t pix = (n * H + 2 * oy) * W + 2 * ox;
+    const float* p = x + pix * ldx + c;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + ldx));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(p + (int64_t)W * ldx)), e = __ldg(reinterpret_cast<const float4*>(p + (int64_t)W * ldx + ldx));
+    const float4 g = __ldg(reinterpret_cast<const float4*>(dy + ((n * OH + oy) * OW + ox) * (int64_t)lddy + c));
+    float4 ga, gb, gd, ge;
+    route4(g.x, a.x, b.x, d.x, e.x, ga.x, gb.x, gd.x, ge.x);
+    route4(g.y, a.y, b.y, d.y, e.y, ga.y, gb.y, gd.y, ge.y);
+    route4(g.z, a.z, b.z, d.z, e.z, ga.z, gb.z, gd.z, ge.z);
+    route4(g.w, a.w, b.w, d.w, e.w, ga.w, gb.w, gd.w, ge.w);
+    float* q = dx + pix * lddx + c;
+    *reinterpret_cast<float4*>(q) = ga;
+    *reinterpret_cast<float4*>(q + lddx) = gb;
+    *reinterpret_cast<float4*>(q + (int64_t)W * lddx) = gd;
+    *reinterpret_cast<float4*>(q + (int64_t)W * lddx + lddx) = ge;
+  }
+}
+
+// dy *= (y > 0) in place (nn.ReLU backward from the saved OUTPUT), NHWC float4 lanes
+__global__ void relu_bwd_kernel(const float* __restrict__ y, int ldy, float* __restrict__ dy, int lddy, int C, int64_t total) {
+  pdl_trigger();
+  const int C4 = C >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / C4;
+    const int c = (int)(i - p * C4) << 2;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y + p * ldy + c));
+    float4* gp = reinterpret_cast<float4*>(dy + p * lddy + c);
+    float4 g = *gp;
+    g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f; g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
+    *gp = g;
+  }
+}
+
+}  // namespace ptk
+
+extern "C" int ptk_relu_backward(const float* y, int ldy, float* dy, int lddy, int64_t pixels, int C, void* stream) {
+  PTK_REQUIRE(y && dy && pixels > 0 && C > 0 && C % 4 == 0 && ldy % 4 == 0 && lddy % 4 == 0, "relu_backward: bad arguments");
+  const int64_t total = pixels * (C / 4);
+  ptk::relu_bwd_kernel<<<ptk::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, dy, lddy, C, total);
+  PTK_LAUNCH_CHECK("relu_bwd_kernel");
+  return 0;
+}
+
+extern "C" int ptk_vgg_preprocess(const float* x, float* out, int ld, int N, int H, int W, int backward, void* stream) {
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * 3 * HW;
+  PTK_REQUIRE(x && out && total > 0 && ld >= 3, "vgg_preprocess: bad arguments");
+  ptk::vgg_preprocess_kernel<<<ptk::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, ld, HW, total, backward);
+  PTK_LAUNCH_CHECK("vgg_preprocess_kernel");
+  return 0;
+}
+
+extern "C" int ptk_maxpool2_forward(const float* x, int ldx, float* y, int ldy, int N, int H, int W, int C, void* stream) {
+  PTK_REQUIRE(x && y && N > 0 && H >= 2 && W >= 2 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "maxpool2: bad arguments");
+  const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 4);
+  ptk::maxpool2_kernel<<<ptk::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, H, W, C, total);
+  PTK_LAUNCH_CHECK("maxpool2_kernel");
+  return 0;
+}
+
+extern "C" int ptk_maxpool2_backward(const float* dy, int lddy, const float* x, int ldx, float* dx, int lddx, int N, int H, int W, int C,
+                                     void* stream) {
+  PTK_REQUIRE(dy && x && dx && N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 &&
+              lddy % 4 == 0 && lddx % 4 == 0, "maxpool2_backward: even extents and 4-float strides required");
+  const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 4);
+  ptk::maxpool2_bwd_kernel<<<ptk::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, dx, lddx, H, W, C, total);
+  PTK_LAUNCH_CHECK("maxpool2_bwd_kernel");
+  return 0;
+}

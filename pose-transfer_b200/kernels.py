@@ -356,6 +356,37 @@ def tanh_bwd_combine(g_nchw, g_nhwc, out_nchw, dz, ld, N, C, H, W):
                                           N, C, H, W, _stream()), "ptk_tanh_bwd_combine")
 
 
+@_timed("vgg_misc")
+def vgg_preprocess(x_nchw, out_nhwc):
+    """out_nhwc[..., 0:3] = preprocess_for_vgg(x_nchw) (utils/pose_utils.py:324-331, view-based normalisation)."""
+    N, _, H, W = x_nchw.shape
+    check(_lib.lib().ptk_vgg_preprocess(_p(x_nchw), _p(out_nhwc), out_nhwc.shape[-1], N, H, W, 0, _stream()), "ptk_vgg_preprocess")
+
+
+@_timed("vgg_misc")
+def vgg_preprocess_backward(g_nhwc, dx_nchw):
+    N, _, H, W = dx_nchw.shape
+    check(_lib.lib().ptk_vgg_preprocess(_p(g_nhwc), _p(dx_nchw), g_nhwc.shape[-1], N, H, W, 1, _stream()), "ptk_vgg_preprocess")
+
+
+@_timed("vgg_misc")
+def maxpool2_forward(x, y, N, H, W, C):
+    x, y = _as_slice(x), _as_slice(y)
+    check(_lib.lib().ptk_maxpool2_forward(x.ptr, x.ld, y.ptr, y.ld, N, H, W, C, _stream()), "ptk_maxpool2_forward")
+
+
+@_timed("vgg_misc")
+def maxpool2_backward(dy, x, dx, N, H, W, C):
+    dy, x, dx = _as_slice(dy), _as_slice(x), _as_slice(dx)
+    check(_lib.lib().ptk_maxpool2_backward(dy.ptr, dy.ld, x.ptr, x.ld, dx.ptr, dx.ld, N, H, W, C, _stream()), "ptk_maxpool2_backward")
+
+
+@_timed("vgg_misc")
+def relu_backward(y, dy, pixels, C):
+    y, dy = _as_slice(y), _as_slice(dy)
+    check(_lib.lib().ptk_relu_backward(y.ptr, y.ld, dy.ptr, dy.ld, pixels, C, _stream()), "ptk_relu_backward")
+
+
 @_timed("pose_data")
 def pose_heatmaps(kp, out, c0, sigma=6.0):
     """kp int32 [N,P,2] (y, x; -1 missing) -> out[:, c0:c0+P] (NCHW fp32) Gaussian heat-maps (pose_utils.py:79-86)."""

@@ -258,11 +258,20 @@ class DeformablePose_GAN(nn.Module):
 
     # ------------------------------------------------------------------ helpers
     def _vgg_params(self, device):
-        if self._vgg_dev is None or self._vgg_dev[0].device != device:
-            conv = self.content_model.features[0]
+        conv = self.content_model.features[0]
+        ver = (conv.weight._version, conv.bias._version)
+        if self._vgg_dev is None or self._vgg_dev[0].device != device or self._vgg_ver != ver:
+            self._vgg_ver = ver
             self._vgg_dev = (conv.weight.detach().to(device, torch.float32).contiguous(),
                              conv.bias.detach().to(device, torch.float32).contiguous())
         return self._vgg_dev
+
+    def _vgg_prefix(self, device):
+        vp = getattr(self, "_vgg_pre", None)
+        if vp is None or vp.device != device or vp.stale():
+            from .vgg_prefix import VggPrefix
+            vp = self._vgg_pre = VggPrefix(self.content_model, pose_utils.get_layer_ind(self.content_loss_layer), device)
+        return vp
 
     def _opt_stream(self, dev):
         """Stream for the per-bucket all-reduce + Adam (None on CPU / with PTK_STREAMS=0)."""
@@ -333,14 +342,25 @@ class DeformablePose_GAN(nn.Module):
         if side is not None:
             side.wait_stream(main)
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-            if self.content_loss_layer != 'none':
-                if pose_utils.get_layer_ind(self.content_loss_layer) != 1:
-                    raise NotImplementedError("only content_loss_layer='block1_conv2' is on the B200 hot path")
+            if self.content_loss_layer != 'none' and pose_utils.get_layer_ind(self.content_loss_layer) == 1:
+                # block1_conv2 (the north-star configuration): extractor fused into the loss kernels
                 vw, vb = self._vgg_params(dev)
                 area = self.nn_loss_area_size
                 argmin = self.gen.engine.ws.get("nn_argmin_%d_%d_%d" % (N, H, W), (N, H, W), torch.uint8)
                 K.nnloss_forward(out_gen, target, vw, vb, area, opt['l1_penalty_weight'], loss[2:3], argmin)
                 K.nnloss_backward(out_gen, target, vw, vb, argmin, area, opt['l1_penalty_weight'], dpred)
+            elif self.content_loss_layer != 'none':
+                # any other depth: materialised VGG prefix (models/vgg_prefix.py) + nn_loss on its features
+                vp = self._vgg_prefix(dev)
+                f_tgt = vp.forward(target, "tgt")
+                f_gen = vp.forward(out_gen, "gen")
+                area = self.nn_loss_area_size
+                fN, fC, fH, fW = f_gen.shape
+                argmin = vp.ws.get("nn_argmin", (fN, fH, fW), torch.uint8)
+                dfeat = vp.ws.get("dfeat", (fN, fC, fH, fW))
+                K.nnloss_features_forward(f_gen, f_tgt, area, opt['l1_penalty_weight'], loss[2:3], argmin)
+                K.nnloss_features_backward(f_gen, f_tgt, argmin, area, opt['l1_penalty_weight'], dfeat)
+                dpred.copy_(vp.backward(dfeat, "gen"))
             else:
                 K.l1_loss(out_gen, target, opt['l1_penalty_weight'], loss[2:3], dpred)
 

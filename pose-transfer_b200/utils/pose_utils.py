@@ -45,14 +45,16 @@ VGG_STD = (0.229, 0.224, 0.225)
 
 
 def Feature_Extractor(model, input=None, layer_name=None):
-    """utils/pose_utils.py:320-338 for layer index 1 (the only depth the north-star path uses): relu(conv1_1(pre(x)))
-    with the reference's view-based preprocessing.  Runs the ptk conv kernel; returns NCHW [N,64,H,W].
-    (The training step never calls this: ptk_nnloss_* fuse the extractor into the loss.)"""
+    """utils/pose_utils.py:320-338: model.features[0..layer] on the view-normalised image, NCHW in / NCHW out.
+    Layer index 1 ('block1_conv2' = relu(conv1_1), the north-star depth) is one ptk conv; deeper layers run the
+    VggPrefix (models/vgg_prefix.py).  (The training step at 'block1_conv2' never calls this: ptk_nnloss_* fuse the
+    extractor into the loss.)"""
     layer = get_layer_ind(layer_name)
-    if layer != 1:
-        raise NotImplementedError("only content_loss_layer='block1_conv2' (features[0..1]) is on the B200 hot path")
     if not input.is_cuda:
         raise RuntimeError("Feature_Extractor: CUDA tensors required (no CPU fallback)")
+    if layer != 1:
+        from ..models.vgg_prefix import VggPrefix
+        return VggPrefix(model, layer, input.device).forward(input.float(), "fx").clone()
     conv = model.features[0]
     w = conv.weight.detach().to(input.device, torch.float32).contiguous()
     b = conv.bias.detach().to(input.device, torch.float32).contiguous()

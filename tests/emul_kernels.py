@@ -311,6 +311,41 @@ def install(K):
         l.backward()
         dpred.copy_(pr.grad)
 
+    def nnloss_features_forward(pred, gt, area, scale, loss, argmin):
+        with torch.no_grad():
+            loss[0] += restate.nn_loss(pred, gt, area, area) * scale
+
+    def nnloss_features_backward(pred, gt, argmin, area, scale, dpred):
+        pr = pred.clone().requires_grad_(True)
+        (restate.nn_loss(pr, gt, area, area) * scale).backward()
+        dpred.copy_(pr.grad)
+
+    def _vgg_consts(C, H, W):
+        idx = torch.arange(C * H * W) % 3
+        mean = torch.tensor([0.485, 0.456, 0.406])[idx].view(1, C, H, W)
+        std = torch.tensor([0.229, 0.224, 0.225])[idx].view(1, C, H, W)
+        return mean, std
+
+    def vgg_preprocess(x_nchw, out_nhwc):
+        mean, std = _vgg_consts(*x_nchw.shape[1:])
+        out_nhwc[..., :3].copy_(nhwc((x_nchw - mean) / std))
+
+    def vgg_preprocess_backward(g_nhwc, dx_nchw):
+        _, std = _vgg_consts(*dx_nchw.shape[1:])
+        dx_nchw.copy_(nchw(g_nhwc[..., :3]) / std)
+
+    def maxpool2_forward(x, y, N, H, W, C):
+        view(y, C).copy_(nhwc(F.max_pool2d(nchw(view(x, C)), 2, 2)))
+
+    def maxpool2_backward(dy, x, dx, N, H, W, C):
+        xi = nchw(view(x, C)).clone().requires_grad_(True)
+        F.max_pool2d(xi, 2, 2).backward(nchw(view(dy, C)))
+        view(dx, C).copy_(nhwc(xi.grad))
+
+    def relu_backward(y, dy, pixels, C):
+        g = view(dy, C)
+        g.mul_((view(y, C) > 0).float())
+
     def tanh_bwd_combine(g_nchw, g_nhwc, out_nchw, dz, ld, N, C, H, W):
         g = torch.zeros(N, C, H, W)
         if g_nchw is not None:
@@ -336,7 +371,10 @@ def install(K):
                  gn_bwd_apply=gn_bwd_apply, mask_pyramid=mask_pyramid, warp_forward=warp_forward,
                  warp_backward=warp_backward, warp_forward_levels=warp_forward_levels, warp_backward_levels=warp_backward_levels,
                  adv_loss=adv_loss, l1_loss=l1_loss, nnloss_forward=nnloss_forward,
-                 nnloss_backward=nnloss_backward, tanh_bwd_combine=tanh_bwd_combine, adam_step=adam_step)
+                 nnloss_backward=nnloss_backward, nnloss_features_forward=nnloss_features_forward,
+                 nnloss_features_backward=nnloss_features_backward, vgg_preprocess=vgg_preprocess,
+                 vgg_preprocess_backward=vgg_preprocess_backward, maxpool2_forward=maxpool2_forward,
+                 maxpool2_backward=maxpool2_backward, relu_backward=relu_backward, tanh_bwd_combine=tanh_bwd_combine, adam_step=adam_step)
 
     @contextlib.contextmanager
     def ctx():

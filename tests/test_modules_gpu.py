@@ -103,6 +103,54 @@ def test_feature_extractor_module():
     assert max_abs(got, want) <= 2e-5
 
 
+@pytest.mark.parametrize("layer_name,ind", [("block1_conv1", 0), ("block2_conv1", 5), ("block2_conv2", 8), ("block3_conv4", 13),
+                                            ("block4_conv1", 19)])
+def test_feature_extractor_deeper_layers(layer_name, ind, monkeypatch):
+    """Feature_Extractor at other depths (conv endings without ReLU, ReLU endings, 1..3 max-pools, odd extents that the
+    pooling floors) vs the oracle's restatement of vgg19.features[0..ind]; strict-fp32 convs for a tight bound, then
+    the default TF32 path."""
+    import torchvision
+    from oracle import restate, synth
+    from pose_transfer_b200.utils import pose_utils
+    assert pose_utils.get_layer_ind(layer_name) == ind
+    vgg = synth.fill_vgg(torchvision.models.vgg19(weights=None), 7)
+    convs = [(m.weight.detach(), m.bias.detach()) for m in vgg.features if isinstance(m, torch.nn.Conv2d)]
+    x = torch.rand(2, 3, 44, 28, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    want = restate.feature_extractor_prefix(convs, x, ind)
+    for mode, tol in (("simt", 2e-5), ("auto", 4e-3)):
+        monkeypatch.setenv("PTK_CONV_IMPL", mode)
+        got = pose_utils.Feature_Extractor(vgg, input=x.cuda(), layer_name=layer_name)
+        assert tuple(got.shape) == tuple(want.shape)
+        assert rel_l2(got, want) <= tol, (mode, rel_l2(got, want))
+
+
+def test_vgg_prefix_input_gradient(monkeypatch):
+    """VggPrefix.backward (dgrad chain, ReLU masks, max-pool routing, pre-processing) vs autograd through the oracle."""
+    import torchvision
+    from oracle import restate, synth
+    from pose_transfer_b200.models.vgg_prefix import VggPrefix
+    vgg = synth.fill_vgg(torchvision.models.vgg19(weights=None), 8)
+    convs = [(m.weight.detach(), m.bias.detach()) for m in vgg.features if isinstance(m, torch.nn.Conv2d)]
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 32, 48, generator=g) * 2 - 1
+    for ind in (5, 13):
+        xr = x.clone().requires_grad_(True)
+        f = restate.feature_extractor_prefix(convs, xr, ind)
+        df = torch.randn(f.shape, generator=g)
+        f.backward(df)
+        for mode, tol in (("simt", 5e-5), ("auto", 6e-3)):
+            monkeypatch.setenv("PTK_CONV_IMPL", mode)
+            vp = VggPrefix(vgg, ind, torch.device("cuda"))
+            got_f = vp.forward(x.cuda(), "gen")
+            assert rel_l2(got_f, f) <= tol
+            got = vp.backward(df.cuda(), "gen")
+            assert rel_l2(got, xr.grad) <= tol, (ind, mode, rel_l2(got, xr.grad))
+        assert not vp.stale()
+        with torch.no_grad():
+            vgg.features[0].weight.mul_(1.0)
+        assert vp.stale()
+
+
 def test_nn_loss_public_method():
     """DeformablePose_GAN.nn_loss(predicted, ground_truth, nh, nw) on materialised feature tensors (pose_gan.py:173-199)."""
     from oracle import restate

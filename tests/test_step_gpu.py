@@ -118,11 +118,13 @@ def _run_steps(tag, content, area, l1_w, steps, seed, impl):
     model = pose_gan.DeformablePose_GAN(opt).cuda()
     model.gen.load_state_dict(synth.fill_state_dict(synth.generator_shapes(P, (H, W)), seed))
     model.disc.load_state_dict(synth.fill_state_dict(synth.discriminator_shapes(3 + 2 * P + 3), seed + 1))
-    if content != "none":
+    if content == "block1_conv2":
         vw, vb = synth.vgg_conv1_1(seed)
         with torch.no_grad():
             model.content_model.features[0].weight.copy_(vw)
             model.content_model.features[0].bias.copy_(vb)
+    elif content != "none":
+        synth.fill_vgg(model.content_model, seed)
     od = vars(opt)
     for s in range(steps):
         b = synth.make_batch(N, H, W, P, seed=seed + 10 * s)
@@ -157,6 +159,13 @@ def _run_steps(tag, content, area, l1_w, steps, seed, impl):
 
 def test_train_step_nn_loss_matches_reference_golden(impl):
     _run_steps("64x64_p18_nn5", "block1_conv2", 5, 0.01, 2, 0, impl)
+
+
+@pytest.mark.parametrize("tag,content,seed", [("64x64_p18_b2c1", "block2_conv1", 5), ("64x64_p18_b3c4", "block3_conv4", 6)])
+def test_train_step_deeper_content_layer_matches_reference_golden(tag, content, seed, impl):
+    """content_loss_layer beyond block1_conv2 (pose_utils.py:312-338): the VGG prefix (tcgen05 convs, max-pool, ReLU,
+    view-based pre-processing) and its input gradient inside gen_update, against the live reference's fixture."""
+    _run_steps(tag, content, 3, 0.01, 1, seed, impl)
 
 
 def test_train_step_l1_matches_reference_golden(impl):
