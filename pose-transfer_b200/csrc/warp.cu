@@ -367,26 +367,23 @@ struct FwdTileSmem {
   float4 rec[kTileW * kTileH * kMaxRec * 2];
 };
 
-// TH = tile rows: every CTA carries the same number of bytes (32 x TH pixels x C channels = 64 KB of output), so the four
-// levels of a pass balance over the machine: TH = 8 / 4 / 2 / 1 for C = 64 / 128 / 256 / >= 512.  A warp owns a run of
-// 32 * TH / 8 pixels of one tile row; G lanes hold one pixel (16 NV-byte... 4 NV channels per lane at stride 4 G: every
-// 128-bit request of the group is whole lines), 32 / G pixels per warp are in flight.
-template <int G, int NV, int TH, int PX, int ACT>
-__device__ __forceinline__ void warp_fwd_tile(const WarpLevelDev& L, FwdTileSmem& S, int K, int n, int tile, int prefetch) {
-  constexpr int PPW = 32 / G, CH = 4 * G * NV, SPR = 8 / TH, SEG = kTileW / SPR, ITERS = SEG / (PPW * PX);
-  static_assert(SEG % (PPW * PX) == 0 && ITERS >= 1, "segment must be a whole number of warp iterations");
-  constexpr bool kRelu = ACT == PTK_ACT_RELU;
-  const int h = L.h, w = L.w, C = L.C, ldx = L.ldx, ldy = L.ldy;
-  const int tx = tile % L.strips_x, ty = tile / L.strips_x;
-  const int x0 = tx * kTileW, y0 = ty * TH;
-  const int64_t img = (int64_t)n * h * w;
+// Phase A of the record-staged kernels: every warp evaluates the geometry of ITS OWN run of pixels (32 * TH / 8 of one
+// tile row, one lane per pixel) and parks it in shared memory; only a __syncwarp() separates it from the warp's gather /
+// scatter phase, so the warps of a CTA drift apart and the ALU-bound geometry of one overlaps the memory phase of the
+// others (ncu on the CTA-wide variant with a __syncthreads(): 1.5 barrier-stall cycles per issued instruction).
+// ld = pixel stride of the tensor the tap offsets address (x in the forward pass, dx in the backward pass).
+template <int TH>
+__device__ __forceinline__ void tile_records(const WarpLevelDev& L, FwdTileSmem& S, int K, int64_t img, int x0, int y0, int ld) {
+  constexpr int SPR = 8 / TH, SEG = kTileW / SPR;
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int row = wi / SPR, col = (wi % SPR) * SEG + lane;
+  const int i = y0 + row, j = x0 + col;
+  const int h = L.h, w = L.w;
   const unsigned kmask = (1u << K) - 1u;
-  // ------------------------------------------------------------------ phase A: one thread per pixel
-  {
-    const int t = threadIdx.x;
-    const int i = y0 + t / kTileW, j = x0 + t % kTileW;
+  if (lane < SEG) {
+    const int t = row * kTileW + col;
     uint32_t hdr = 15u << 28;
-    if (t < kTileW * TH && i < h && j < w) {
+    if (i < h && j < w) {
       const float* mp = L.mask + (img + (int64_t)i * w + j) * K;
       int cnt = 0;
       unsigned seen = 0u;
@@ -394,7 +391,7 @@ __device__ __forceinline__ void warp_fwd_tile(const WarpLevelDev& L, FwdTileSmem
         const float m = __ldg(mp + k);
         float4 wgt;
         int4 off;
-        if (part_geometry(S.theta[k], m, i, j, h, w, ldx, wgt, off)) {
+        if (part_geometry(S.theta[k], m, i, j, h, w, ld, wgt, off)) {
           seen |= 1u << k;
           if (cnt < kMaxRec) {
             S.rec[(t * kMaxRec + cnt) * 2] = wgt;
@@ -410,9 +407,26 @@ __device__ __forceinline__ void warp_fwd_tile(const WarpLevelDev& L, FwdTileSmem
       const uint32_t kz = inactive ? (uint32_t)(__ffs(inactive) - 1) : 15u;
       hdr = (hdr & 0x0fffffffu) | ((uint32_t)cnt << 24) | (kz << 28);
     }
-    if (t < kTileW * TH) S.hdr[t] = hdr;
+    S.hdr[t] = hdr;
   }
-  __syncthreads();
+  __syncwarp();
+}
+
+// TH = tile rows: every CTA carries the same number of bytes (32 x TH pixels x C channels = 64 KB of output), so the four
+// levels of a pass balance over the machine: TH = 8 / 4 / 2 / 1 for C = 64 / 128 / 256 / >= 512.  A warp owns a run of
+// 32 * TH / 8 pixels of one tile row; G lanes hold one pixel (16 NV-byte... 4 NV channels per lane at stride 4 G: every
+// 128-bit request of the group is whole lines), 32 / G pixels per warp are in flight.
+template <int G, int NV, int TH, int PX, int ACT>
+__device__ __forceinline__ void warp_fwd_tile(const WarpLevelDev& L, FwdTileSmem& S, int K, int n, int tile, int prefetch) {
+  constexpr int PPW = 32 / G, CH = 4 * G * NV, SPR = 8 / TH, SEG = kTileW / SPR, ITERS = SEG / (PPW * PX);
+  static_assert(SEG % (PPW * PX) == 0 && ITERS >= 1, "segment must be a whole number of warp iterations");
+  constexpr bool kRelu = ACT == PTK_ACT_RELU;
+  const int h = L.h, w = L.w, C = L.C, ldx = L.ldx, ldy = L.ldy;
+  const int tx = tile % L.strips_x, ty = tile / L.strips_x;
+  const int x0 = tx * kTileW, y0 = ty * TH;
+  const int64_t img = (int64_t)n * h * w;
+  // ------------------------------------------------------------------ phase A: geometry records of this warp's pixels
+  tile_records<TH>(L, S, K, img, x0, y0, ldx);
   // ------------------------------------------------------------------ phase B: gather
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const int gl = lane % G, grp = lane / G;
@@ -546,6 +560,136 @@ __device__ __forceinline__ void warp_fwd_tile(const WarpLevelDev& L, FwdTileSmem
         }
       }
     }
+  }
+}
+
+// Backward on the same tiles and records (tap offsets address dx): dx[taps of the winner] += dy * (mask * bilinear weight).
+// A lane's 4 channels usually share their winner: one 128-bit vector reduction per tap and record, with the channels won by
+// other parts zeroed; zero-weight taps are skipped.  ReLU / none need no look at y: "no winner" (15) == zero candidate
+// == no gradient.  (ncu on the per-row-geometry predecessor: 167 M warp instructions per launch, 2.5x the forward pass.)
+__device__ __forceinline__ void scatter4(float* p, const float4& wv, const int4& of, const float4& gm) {
+  if (wv.x != 0.f) atomicAdd(reinterpret_cast<float4*>(p + of.x), make_float4(gm.x * wv.x, gm.y * wv.x, gm.z * wv.x, gm.w * wv.x));
+  if (wv.y != 0.f) atomicAdd(reinterpret_cast<float4*>(p + of.y), make_float4(gm.x * wv.y, gm.y * wv.y, gm.z * wv.y, gm.w * wv.y));
+  if (wv.z != 0.f) atomicAdd(reinterpret_cast<float4*>(p + of.z), make_float4(gm.x * wv.z, gm.y * wv.z, gm.z * wv.z, gm.w * wv.z));
+  if (wv.w != 0.f) atomicAdd(reinterpret_cast<float4*>(p + of.w), make_float4(gm.x * wv.w, gm.y * wv.w, gm.z * wv.w, gm.w * wv.w));
+}
+
+template <int G, int NV, int TH, int PX>
+__device__ __forceinline__ void warp_bwd_tile(const WarpLevelDev& L, FwdTileSmem& S, int K, int n, int tile, int act) {
+  constexpr int PPW = 32 / G, CH = 4 * G * NV, SPR = 8 / TH, SEG = kTileW / SPR, ITERS = SEG / (PPW * PX);
+  static_assert(SEG % (PPW * PX) == 0 && ITERS >= 1, "segment must be a whole number of warp iterations");
+  const int h = L.h, w = L.w, C = L.C;
+  const int tx = tile % L.strips_x, ty = tile / L.strips_x;
+  const int x0 = tx * kTileW, y0 = ty * TH;
+  const int64_t img = (int64_t)n * h * w;
+  tile_records<TH>(L, S, K, img, x0, y0, C);
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int gl = lane % G, grp = lane / G;
+  const int row = wi / SPR, seg = wi % SPR;
+  const int i = y0 + row;
+  if (i >= h) return;
+  float* dxb = L.dx + img * C + gl * 4;
+  const float* dyb = L.dy + (img + (int64_t)i * w) * L.lddy + gl * 4;
+  const float* yb = (act == PTK_ACT_LEAKY && L.y) ? L.y + (img + (int64_t)i * w) * L.ldy + gl * 4 : nullptr;
+  const uint8_t* ab = L.argk + (((img + (int64_t)i * w) * C) >> 1) + gl * 2;
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+    const int col0 = seg * SEG + it * (PPW * PX) + grp;
+    if (x0 + col0 >= w) continue;
+    uint32_t hd[PX];
+    int cnt[PX];
+#pragma unroll
+    for (int px = 0; px < PX; ++px) {
+      const int col = col0 + px * PPW;
+      hd[px] = S.hdr[row * kTileW + col];
+      cnt[px] = (x0 + col < w) ? (int)((hd[px] >> 24) & 7u) : 0;
+    }
+    const float4* rbase = S.rec + (row * kTileW + col0) * (kMaxRec * 2);
+#pragma unroll 1
+    for (int cb = 0; cb < C; cb += CH) {
+      uint32_t a16[PX][NV];
+      float4 g[PX][NV];
+#pragma unroll
+      for (int px = 0; px < PX; ++px) {
+        const int j = x0 + col0 + px * PPW;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          a16[px][q] = j < w ? *reinterpret_cast<const uint16_t*>(ab + ((j * C + cb + q * G * 4) >> 1)) : 0xffffu;
+          g[px][q] = a16[px][q] != 0xffffu ? __ldg(reinterpret_cast<const float4*>(dyb + j * L.lddy + cb + q * G * 4))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (yb != nullptr) {
+#pragma unroll
+        for (int px = 0; px < PX; ++px) {
+          const int j = x0 + col0 + px * PPW;
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            if (a16[px][q] == 0xffffu) continue;
+            const float4 yv = __ldg(reinterpret_cast<const float4*>(yb + j * L.ldy + cb + q * G * 4));
+            g[px][q].x *= act_grad_from_output(yv.x, act); g[px][q].y *= act_grad_from_output(yv.y, act);
+            g[px][q].z *= act_grad_from_output(yv.z, act); g[px][q].w *= act_grad_from_output(yv.w, act);
+          }
+        }
+      }
+#pragma unroll
+      for (int px = 0; px < PX; ++px) {
+        const int j = x0 + col0 + px * PPW;
+#pragma unroll 1
+        for (int r = 0; r < cnt[px]; ++r) {
+          const uint32_t kk = (hd[px] >> (4 * r)) & 15u;
+          const float4 wv = rbase[(px * PPW * kMaxRec + r) * 2];
+          const float4 ofv = rbase[(px * PPW * kMaxRec + r) * 2 + 1];
+          const int4 of = make_int4(__float_as_int(ofv.x), __float_as_int(ofv.y), __float_as_int(ofv.z), __float_as_int(ofv.w));
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            const uint32_t a = a16[px][q];
+            const bool m0 = (a & 15u) == kk, m1 = ((a >> 4) & 15u) == kk, m2 = ((a >> 8) & 15u) == kk, m3 = ((a >> 12) & 15u) == kk;
+            if (!(m0 || m1 || m2 || m3)) continue;
+            const float4 gv = g[px][q];
+            scatter4(dxb + cb + q * G * 4, wv, of, make_float4(m0 ? gv.x : 0.f, m1 ? gv.y : 0.f, m2 ? gv.z : 0.f, m3 ? gv.w : 0.f));
+          }
+        }
+        if (hd[px] & (1u << 27)) {
+          // more active parts than records (never seen in practice): winners beyond the last record, geometry inline
+          const int last = (int)((hd[px] >> (4 * (kMaxRec - 1))) & 15u);
+          for (int k = last + 1; k < K; ++k) {
+            float4 wgt;
+            int4 off;
+            const float m = __ldg(L.mask + (img + (int64_t)i * w + j) * K + k);
+            if (j >= w || !part_geometry(S.theta[k], m, i, j, h, w, C, wgt, off)) continue;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+              const uint32_t a = a16[px][q], kk = (uint32_t)k;
+              const bool m0 = (a & 15u) == kk, m1 = ((a >> 4) & 15u) == kk, m2 = ((a >> 8) & 15u) == kk, m3 = ((a >> 12) & 15u) == kk;
+              if (!(m0 || m1 || m2 || m3)) continue;
+              const float4 gv = g[px][q];
+              scatter4(dxb + cb + q * G * 4, wgt, off, make_float4(m0 ? gv.x : 0.f, m1 ? gv.y : 0.f, m2 ? gv.z : 0.f, m3 ? gv.w : 0.f));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 3)
+warp_backward_tiles_kernel(const __grid_constant__ WarpLaunchDev P, const float* __restrict__ warps) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  FwdTileSmem& S = *reinterpret_cast<FwdTileSmem*>(s_raw);
+  const int n = blockIdx.y;
+  int li = 0;
+#pragma unroll
+  for (int q = 1; q < 4; ++q) if (q < P.nlevels && (int)blockIdx.x >= P.lv[q].cta_begin) li = q;
+  const WarpLevelDev& L = P.lv[li];
+  if (threadIdx.x < P.K) S.theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * P.K + threadIdx.x) * 8, L.h, L.w, P.H0, P.W0);
+  __syncthreads();
+  const int tile = blockIdx.x - L.cta_begin;
+  switch (L.cfg) {
+    case 0: warp_bwd_tile<8, 2, 8, 2>(L, S, P.K, n, tile, P.act); break;
+    case 1: warp_bwd_tile<8, 4, 4, 1>(L, S, P.K, n, tile, P.act); break;
+    case 2: warp_bwd_tile<16, 4, 2, 1>(L, S, P.K, n, tile, P.act); break;
+    default: warp_bwd_tile<32, 4, 1, 1>(L, S, P.K, n, tile, P.act); break;
   }
 }
 
@@ -787,6 +931,12 @@ static int warp_variant() {
   return (e && atoi(e) == 1) ? 1 : 2;
 }
 
+// backward kernel variant: 2 = record-staged tiles (default), 1 = per-row geometry strips (PTK_WARP_BWD=1, kept for comparison)
+static int warp_bwd_variant() {
+  const char* e = getenv("PTK_WARP_BWD");
+  return (e && atoi(e) == 1) ? 1 : 2;
+}
+
 static bool warp_plan(const ptk_warp_level* lv, int nlevels, int K, int H0, int W0, int act, bool backward, WarpLaunchDev& P) {
   memset(&P, 0, sizeof(P));
   P.nlevels = nlevels; P.K = K; P.H0 = H0; P.W0 = W0; P.act = act;
@@ -801,7 +951,10 @@ static bool warp_plan(const ptk_warp_level* lv, int nlevels, int K, int H0, int 
     d.ldx = s.ldx; d.ldy = s.ldy; d.lddy = s.lddy; d.C = s.C; d.h = s.h; d.w = s.w; d.cfg = cfg;
     const int g = cfg <= 1 ? 16 : 32;
     int xw;
-    if (backward) {                       // warp_bwd_strip<G, NV, 4 / NV>
+    if (backward && warp_bwd_variant() == 2) {   // warp_bwd_tile: the forward pass' tiles
+      xw = kTileW;
+      d.TH = cfg == 0 ? 8 : (cfg == 1 ? 4 : (cfg == 2 ? 2 : 1));
+    } else if (backward) {                // warp_bwd_strip<G, NV, 4 / NV>
       const int nv = cfg == 0 ? 1 : (cfg == 3 ? 4 : 2);
       xw = 8 * (32 / g) * (4 / nv);
       d.TH = warp_rows_per_strip() < s.h ? warp_rows_per_strip() : s.h;
@@ -913,7 +1066,14 @@ extern "C" int ptk_warp_backward_levels(const ptk_warp_level* lv, int nlevels, c
   }
   if (act != PTK_ACT_LEAKY) for (int q = 0; q < nlevels; ++q) P.lv[q].y = nullptr;   // ReLU / none: the winner record says it all
   dim3 grid((unsigned)P.ctas_per_image, (unsigned)N);
-  warp_backward_levels_kernel<<<grid, 256, 0, st>>>(P, warps);
+  if (warp_bwd_variant() == 2) {
+    const size_t smem = sizeof(FwdTileSmem);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(warp_backward_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    warp_backward_tiles_kernel<<<grid, 256, smem, st>>>(P, warps);
+  } else {
+    warp_backward_levels_kernel<<<grid, 256, 0, st>>>(P, warps);
+  }
   PTK_LAUNCH_CHECK("warp_backward_levels_kernel");
   return 0;
 }

@@ -225,12 +225,13 @@ def test_warp_full_size_vs_oracle_and_relu_epilogue(K):
         assert rel_l2(dx, xr.grad) <= 4e-3   # a handful of arg-max flips at near-ties + atomics order
 
 
-@pytest.mark.parametrize("act", ["none", "relu"])
+@pytest.mark.parametrize("act", ["none", "relu", "leaky"])
 @pytest.mark.parametrize("C,h,w,H0,W0", [(64, 37, 53, 74, 106), (128, 48, 24, 96, 48), (256, 19, 33, 152, 264), (512, 16, 16, 128, 128),
                                          (64, 64, 64, 64, 64), (1024, 9, 7, 72, 56)])
 def test_warp_fast_path_vs_oracle(K, C, h, w, H0, W0, act):
-    """The 16/32-lanes-per-pixel kernels (C = 64 / 128 / 256 / 512 / 1024), ragged extents (strip edges in x and y),
-    non-square images (the H != W translation quirk), with and without the folded ReLU, forward and backward vs the oracle."""
+    """The record-staged tile kernels (C = 64 / 128 / 256 / 512 / 1024), ragged extents (tile edges in x and y),
+    non-square images (the H != W translation quirk), with the folded ReLU / LeakyReLU or none, forward and backward vs
+    the oracle."""
     from oracle import restate, synth
     N = 2
     b = synth.make_batch(N, H0, W0, 2, seed=C + h)
@@ -240,10 +241,31 @@ def test_warp_fast_path_vs_oracle(K, C, h, w, H0, W0, act):
     ref = restate.affine_warp(xr, b["warps"], b["masks"], (H0, W0))
     if act == "relu":
         ref = F.relu(ref)
+    elif act == "leaky":
+        ref = F.leaky_relu(ref, 0.2)
     ref.backward(gy)
-    y, dx, _ = _run_warp(K, x, b["warps"], b["masks"], H0, W0, gy, act=K.ACT_RELU if act == "relu" else K.ACT_NONE)
+    y, dx, _ = _run_warp(K, x, b["warps"], b["masks"], H0, W0, gy, act={"relu": K.ACT_RELU, "leaky": K.ACT_LEAKY, "none": K.ACT_NONE}[act])
     assert max_abs(y, ref) <= 3e-4
     assert rel_l2(dx, xr.grad) <= 2e-3
+
+
+@pytest.mark.parametrize("C,h", [(64, 40), (256, 20)])
+def test_warp_more_active_parts_than_records(K, C, h):
+    """Every pixel covered by ALL ten part masks (fractional values): more live candidates per pixel than the six
+    shared-memory records of the tile kernels -> the inline slow path of the forward gather and the backward scatter."""
+    from oracle import restate, synth
+    N, H0 = 2, 80
+    b = synth.make_batch(N, H0, H0, 2, seed=9)
+    g = gen(77)
+    masks = (torch.rand(N, 10, H0, H0, generator=g) * 0.75 + 0.25).double()
+    x = torch.randn(N, C, h, h, generator=g)
+    gy = torch.randn(N, C, h, h, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = restate.affine_warp(xr, b["warps"], masks, (H0, H0))
+    ref.backward(gy)
+    y, dx, _ = _run_warp(K, x, b["warps"], masks, H0, H0, gy)
+    assert max_abs(y, ref) <= 3e-4
+    assert rel_l2(dx, xr.grad) <= 4e-3
 
 
 def test_warp_levels_api_matches_single_level_calls(K, monkeypatch):

@@ -50,17 +50,19 @@ def main():
         return e0.elapsed_time(e1) / iters
 
     print("algorithmic bytes per launch set: %.1f MB (N=%d); HBM peak %.0f GB/s" % (alg / 1e6, N, peak))
-    for var in ("1", "2"):
-        for th in ("4", "8"):
-            os.environ["PTK_WARP_VAR"], os.environ["PTK_WARP_TH"] = var, th
-            ms = timeit(lambda: K.warp_forward_levels(lv, wr, N, 10, H, H, K.ACT_RELU))
-            print("forward  var=%s TH=%-2s  %.4f ms  %.0f GB/s  frac %.3f" % (var, th, ms, alg / ms / 1e6, alg / ms / 1e6 / peak))
-    os.environ["PTK_WARP_VAR"] = "0"
-    for th in ("4", "8", "16"):
-        os.environ["PTK_WARP_TH"] = th
-        K.warp_forward_levels(lv, wr, N, 10, H, H, K.ACT_RELU)
+    for var, th in (("1", "8"), ("2", "8")):
+        os.environ["PTK_WARP_VAR"], os.environ["PTK_WARP_TH"] = var, th
+        ms = timeit(lambda: K.warp_forward_levels(lv, wr, N, 10, H, H, K.ACT_RELU))
+        print("forward  var=%s  %.4f ms  %.0f GB/s  frac %.3f" % (var, ms, alg / ms / 1e6, alg / ms / 1e6 / peak))
+    os.environ["PTK_WARP_VAR"] = "2"
+    K.warp_forward_levels(lv, wr, N, 10, H, H, K.ACT_RELU)
+    for bv in ("1", "2"):
+        os.environ["PTK_WARP_BWD"] = bv
         ms = timeit(lambda: K.warp_backward_levels(lv, wr, N, 10, H, H, K.ACT_RELU, True))
-        print("backward TH=%-2s (incl. zero fill)  %.4f ms  %.0f GB/s  frac %.3f" % (th, ms, alg / ms / 1e6, alg / ms / 1e6 / peak))
+        print("backward var=%s (incl. zero fill)  %.4f ms  %.0f GB/s  frac %.3f" % (bv, ms, alg / ms / 1e6, alg / ms / 1e6 / peak))
+        ms = timeit(lambda: K.warp_backward_levels(lv, wr, N, 10, H, H, K.ACT_RELU, False))
+        print("backward var=%s (no fill; dx accumulates)  %.4f ms" % (bv, ms))
+    os.environ["PTK_WARP_BWD"] = "2"
     # per-level forward times (single-level launches)
     os.environ["PTK_WARP_TH"] = "8"
     for d in lv:
