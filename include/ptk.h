@@ -158,6 +158,10 @@ int ptk_gn_bwd_apply(float* dy, const float* z, int ldz, const double* stats, co
 /* cv2.resize(INTER_LINEAR) of the f64 masks [N,K,H0,W0] to f32 [N,h,w,K] (pose_transform.py:82-87). */
 int ptk_mask_pyramid(const double* masks, int N, int K, int H0, int W0, float* out, int h, int w,
                      void* stream);
+/* the same for up to four levels in ONE launch (outs[q] = f32 [N,hs[q],ws[q],K]): what one generator pass needs
+ * (models/networks.py:205-213 call AffineTransformLayer once per warped skip level, each resizing the masks again) */
+int ptk_mask_pyramid_levels(const double* masks, int N, int K, int H0, int W0, float* const* outs, const int* hs,
+                            const int* ws, int nlevels, void* stream);
 /* y[n,y,x,c] = act(max_k m[n,y,x,k] * bilinear(x[n,:,:,c]; theta_k(y,x))).  warps = raw [N,K,8] rows
  * (first 6 used, :28).  argk = opaque record of the winning part per element (capacity N*h*w*C bytes; the layout is
  * private to the library: bytes, or 4-bit codes on the fast path).  H0,W0 = init_image_size. */

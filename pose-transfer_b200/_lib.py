@@ -51,6 +51,7 @@ SIGNATURES = {
     "ptk_gn_bwd_reduce": [vp, i32, vp, i32, i32, vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, i64, i32, vp, vp, vp],
     "ptk_gn_bwd_apply": [vp, vp, i32, vp, vp, vp, i32, i64, i32, vp, vp, vp],
     "ptk_mask_pyramid": [vp, i32, i32, i32, i32, vp, i32, i32, vp],
+    "ptk_mask_pyramid_levels": [vp, i32, i32, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(i32), ctypes.POINTER(i32), i32, vp],
     "ptk_warp_forward": [vp, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "ptk_warp_backward": [vp, i32, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "ptk_warp_forward_levels": [ctypes.POINTER(WarpLevel), i32, vp, i32, i32, i32, i32, i32, vp],

@@ -555,10 +555,12 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   // ---- tile selection.  fp32 operands make every tile L2-bandwidth bound (bytes per MAC ~ 1/M + 1/N), so the largest
   // tile that still fills the machine wins: (MH = 2, BN = 256) moves half the bytes per MAC of (1, 128).  Cost model:
   // waves x per-tile time, with a relative efficiency per tile shape and a fixed prologue/epilogue charge for the
-  // one-CTA-per-SM shapes (nothing overlaps them).  PTK_TC_TILE="mh,bn" overrides (tests / experiments).  (2, 64) is kept
-  // for the sweep test but rated below (1, 64): measured slower on every Cout = 64 layer of the network.
+  // one-CTA-per-SM shapes (nothing overlaps them) that grows with the tile's output.  PTK_TC_TILE="mh,bn" overrides (tests /
+  // experiments).  Calibrated against tools/bench_conv.py on B200 (gpurun_out r2n): with the coalescing epilogue (2, 64)
+  // beats (1, 64) on every Cout = 64 layer (stems 0.090 -> 0.067 ms); a split-K pass costs a streamed read of every
+  // partial buffer plus a launch, which makes (1, 256) un-split the better choice on the 64^2 / 32^2 encoder layers.
   struct TileCfg { int mh, bn, stages, occ; float eff; };
-  static const TileCfg kCfgs[] = {{1, 32, 4, 2, 0.20f}, {2, 32, 3, 2, 0.25f}, {1, 64, 4, 2, 0.36f}, {2, 64, 4, 1, 0.30f}, {1, 128, 3, 2, 0.50f},
+  static const TileCfg kCfgs[] = {{1, 32, 4, 2, 0.20f}, {2, 32, 3, 2, 0.25f}, {1, 64, 4, 2, 0.36f}, {2, 64, 4, 1, 0.42f}, {1, 128, 3, 2, 0.50f},
                                   {1, 256, 4, 1, 0.64f}, {2, 128, 4, 1, 0.64f}, {2, 256, 3, 1, 0.80f}};
   int forced_mh = 0, forced_bn = 0;
   if (const char* e = getenv("PTK_TC_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
@@ -593,9 +595,11 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
       while (sp > 1 && (min_kb + sp - 1) / sp * (sp - 1) >= min_kb) --sp;
     }
     if (t.occ == 1 && !forced && ctas * sp < slots / 2) continue;   // big one-CTA-per-SM shapes must fill the machine
-    const double tile_clk = (double)((min_kb + sp - 1) / sp) * t.mh * (t.bn / 128.0) * 256.0 / t.eff + (t.occ == 1 ? 6000.0 : 1500.0);
-    // combining the splits: fp32 L2 atomics (~100 floats / clk chip-wide) or one streamed pass over the partial buffers
-    const double combine = sp > 1 ? (double)out_floats * sp / (use_parts ? 1500.0 : 100.0) + (use_parts ? 3000.0 : 0.0) : 0.0;
+    const double tile_clk = (double)((min_kb + sp - 1) / sp) * t.mh * (t.bn / 128.0) * 256.0 / t.eff +
+                            (t.occ == 1 ? 3000.0 * t.mh * (t.bn / 128.0) : 1500.0);
+    // combining the splits: fp32 L2 atomics (~100 floats / clk chip-wide), or one streamed pass that reads every partial
+    // buffer and writes the result (~460 floats / clk at 3.5 TB/s) behind one more launch
+    const double combine = sp > 1 ? (use_parts ? (double)out_floats * (sp + 1) / 460.0 + 5000.0 : (double)out_floats * sp / 100.0) : 0.0;
     const double cost = (double)((ctas * sp + slots - 1) / slots) * t.occ * tile_clk + combine;
     if (forced) { best = &t; best_splits = sp; break; }
     if (!best || cost < best_cost) { best = &t; best_cost = cost; best_splits = sp; }

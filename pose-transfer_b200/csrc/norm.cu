@@ -132,8 +132,8 @@ gn_apply_kernel(const float* __restrict__ z, int ldz, const double* __restrict__
   }
 }
 
-template <int U>
-__global__ void __launch_bounds__(256)
+template <int U, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 gn_bwd_reduce_kernel(const float* __restrict__ g1, int ldg1, const float* __restrict__ a1, int lda1, int act1,
                      const float* __restrict__ g2, int ldg2, const float* __restrict__ a2, int lda2, int act2,
                      const float* __restrict__ drop, const float* __restrict__ z, int ldz,
@@ -309,8 +309,14 @@ extern "C" int ptk_gn_bwd_reduce(const float* g1, int ldg1, const float* a1, int
               "gn_bwd_reduce: strides must be multiples of 4");
   PTK_REQUIRE(!sums || (z && stats), "gn_bwd_reduce: z and stats required with sums");
   PTK_REQUIRE(C / 4 <= 4096, "gn_bwd_reduce: C too large");
-  gn_bwd_reduce_kernel<2><<<grid_walk(HW, C, N, 2), 256, 0, (cudaStream_t)stream>>>(g1, ldg1, a1, lda1, act1, g2, ldg2, a2, lda2,
-                                                                                    act2, drop, z, ldz, stats, HW, C, dy, sums);
+  // four resident CTAs per SM (64 registers, a few spilled scalars) stream the large tensors 10-15 % faster; below ~1 M
+  // elements per sample the three-CTA build wins (tools/bench_gn.py on B200)
+  if (HW * C < (1ll << 20))
+    gn_bwd_reduce_kernel<2, 3><<<grid_walk(HW, C, N, 2), 256, 0, (cudaStream_t)stream>>>(g1, ldg1, a1, lda1, act1, g2, ldg2, a2, lda2,
+                                                                                         act2, drop, z, ldz, stats, HW, C, dy, sums);
+  else
+    gn_bwd_reduce_kernel<2, 4><<<grid_walk(HW, C, N, 2), 256, 0, (cudaStream_t)stream>>>(g1, ldg1, a1, lda1, act1, g2, ldg2, a2, lda2,
+                                                                                         act2, drop, z, ldz, stats, HW, C, dy, sums);
   PTK_LAUNCH_CHECK("gn_bwd_reduce_kernel");
   return 0;
 }

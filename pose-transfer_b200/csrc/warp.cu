@@ -165,22 +165,27 @@ warp_backward_kernel(const float* __restrict__ dy, int lddy, const float* __rest
 }
 
 
-// ---------------------------------------------------------------- fast path (C % 64 == 0, K <= 15)
-// Lane mapping: G = 16 or 32 lanes own ONE pixel, lane gl holding channels [cb + 4 G q + 4 gl, +4) for q < NV, so that
-// every 128-bit request of a group is one contiguous run of 16 G bytes = whole 128-byte lines (an "8-16 channels per
-// lane" mapping touches half-used lines and doubles the L1 wavefronts per byte: ncu showed the L1/TEX pipe at 57 % busy
-// at only 0.42 of the HBM roofline).  A group carries PX = 4 / NV horizontally adjacent pixels, i.e. 16 independent
-// 128-bit loads in flight per lane and part.
-// Per row the geometry of every (pixel, part) pair is evaluated ONCE by lane gl == part (mask value, affine grid point,
-// bilinear weights incl. the mask factor, clamped tap offsets), parked in shared memory and read back as two broadcast
-// 128-bit loads, so the 16-32 lanes of a pixel do not redo the coordinate arithmetic.  Parts whose mask is zero at the
-// pixel (or whose footprint lies outside the image) are skipped: they all contribute the same candidate "0, no gradient".
+// ---------------------------------------------------------------- fast path (C = 64 / 128 / multiples of 256, K <= 15)
+// Record-staged tile kernels.  A CTA owns a tile of 32 x TH output pixels of one level and every warp a run of them:
+//   A  one LANE per pixel evaluates the geometry of that pixel's active parts once (mask value, affine grid point,
+//      bilinear weights incl. the mask factor, clamped tap offsets) and parks it in shared memory as 32-byte records plus
+//      one header word per pixel (count, the part index of each record, the position of the first "0, no gradient"
+//      candidate).  Parts whose mask is zero at the pixel (or whose footprint lies outside the image) get no record: they
+//      all contribute the same candidate "0, no gradient".
+//   B  the warp gathers (forward) or scatters (backward): G = 8 / 16 / 32 lanes own ONE pixel, lane gl holding channels
+//      [cb + 4 G q + 4 gl, +4) for q < NV, so that every 128-bit request of a group is one contiguous run of 16 G bytes
+//      (an "8-16 channels per lane" mapping touches half-used lines and doubles the L1 wavefronts per byte); per (pixel,
+//      part) the lanes read the record with two broadcast loads and do nothing but 4 NV loads, 16 NV FMAs and the
+//      running max (forward) or 4 NV vector reductions (backward).
+// History (profiles/README.md): a per-row-geometry "strip" predecessor re-did the coordinate arithmetic in the 16-32 lanes
+// of every pixel -- 160 M (forward) / 167 M (backward) warp instructions per launch, issue-bound at 0.36 / 0.14 of the
+// HBM roofline; the records cut that to 67 M and 0.55 / 0.33.
 // The winner record is packed to 4 bits per element (15 = "0, no gradient").
 constexpr int kNoPart = 15;
 
 struct WarpLevelDev {
   const float* x; const float* mask; float* y; uint8_t* argk; const float* dy; float* dx;
-  int ldx, ldy, lddy, C, h, w, TH, strips_x, strips_y, cta_begin, cfg;     // cfg: 0 = (G16,NV1) 1 = (G16,NV2) 2 = (G32,NV2) 3 = (G32,NV4)
+  int ldx, ldy, lddy, C, h, w, TH, strips_x, strips_y, cta_begin, cfg;     // cfg: 0 = C 64, 1 = C 128, 2 = C % 256 == 0, 3 = C % 512 == 0 (lane mappings in the kernels' dispatch)
 };
 struct WarpLaunchDev {
   WarpLevelDev lv[4];
@@ -222,142 +227,6 @@ __device__ __forceinline__ float warp_act(float v) {
   return v;
 }
 
-// geometry phase of one output row for the PX pixels of this lane's group: fills s_geo[(px * 16 + k) * 2 + {0, 1}] and
-// returns the per-pixel bit sets of real candidates.
-template <int G, int PX>
-__device__ __forceinline__ void row_geometry(const Theta* s_theta, const float* __restrict__ mrow, int K, int i, int j0, int h, int w,
-                                             int ld, int gl, int grp, float4* __restrict__ geo, unsigned (&bits)[PX]) {
-#pragma unroll
-  for (int px = 0; px < PX; ++px) {
-    const int j = j0 + px;
-    bool valid = false;
-    float4 wgt;
-    int4 off;
-    if (gl < K && j < w) {
-      const float m = __ldg(mrow + j * K + gl);
-      valid = part_geometry(s_theta[gl], m, i, j, h, w, ld, wgt, off);
-    }
-    if (valid) {
-      geo[(px * 16 + gl) * 2] = wgt;
-      geo[(px * 16 + gl) * 2 + 1] = make_float4(__int_as_float(off.x), __int_as_float(off.y), __int_as_float(off.z), __int_as_float(off.w));
-    }
-    const unsigned ball = __ballot_sync(0xffffffffu, valid);
-    bits[px] = (ball >> (grp * G)) & 0xffffu;
-  }
-}
-
-template <int G, int NV, int PX, int ACT>
-__device__ __forceinline__ void warp_fwd_strip(const WarpLevelDev& L, const Theta* s_theta, float4* s_geo_warp, int K, int n, int tile) {
-  constexpr int PPW = 32 / G, XW = 8 * PPW * PX, CH = 4 * G * NV;
-  constexpr bool kRelu = ACT == PTK_ACT_RELU;
-  const int sx = tile % L.strips_x, sy = tile / L.strips_x;
-  const int y_begin = sy * L.TH;
-  const int h = L.h, w = L.w, C = L.C;
-  const int rows = min(L.TH, h - y_begin);
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int gl = lane % G, grp = lane / G;
-  const int j0 = sx * XW + (wi * PPW + grp) * PX;
-  const int64_t img = (int64_t)n * h * w;
-  const float* xb = L.x + img * L.ldx + gl * 4;
-  const float* mb = L.mask + img * K;
-  float4* geo = s_geo_warp + grp * (PX * 32);
-  const unsigned kmask = (1u << K) - 1u;
-  for (int r = 0; r < rows; ++r) {
-    const int i = y_begin + r;
-    unsigned bits[PX];
-    row_geometry<G, PX>(s_theta, mb + (int64_t)i * w * K, K, i, j0, h, w, L.ldx, gl, grp, geo, bits);
-    __syncwarp();
-    // max over parts with torch.max's first-maximum rule.  ReLU epilogue: max(., 0) is the initial value.  Otherwise the
-    // first "0, no gradient" candidate takes part in the loop as a pseudo part at its own index kz.
-    unsigned uni = 0u;
-    int kz[PX];
-#pragma unroll
-    for (int px = 0; px < PX; ++px) {
-      const unsigned inactive = ~bits[px] & kmask;
-      kz[px] = (!kRelu && inactive) ? __ffs(inactive) - 1 : -1;
-      uni |= bits[px] | ((!kRelu && inactive) ? (inactive & (0u - inactive)) : 0u);
-    }
-    float* yrow = L.y + (img + (int64_t)i * w + j0) * L.ldy + gl * 4;
-    uint8_t* arow = L.argk + (((img + (int64_t)i * w + j0) * C) >> 1) + gl * 2;
-    for (int cb = 0; cb < C; cb += CH) {
-      float best[PX][NV * 4];
-      int arg[PX][NV * 4];
-#pragma unroll
-      for (int px = 0; px < PX; ++px)
-#pragma unroll
-        for (int q = 0; q < NV * 4; ++q) { best[px][q] = kRelu ? 0.f : -INFINITY; arg[px][q] = kNoPart; }
-      unsigned rem = uni;
-      while (rem) {
-        const int k = __ffs(rem) - 1;
-        rem &= rem - 1;
-        float4 wv[PX];
-        float4 v[PX][NV][4];
-#pragma unroll
-        for (int px = 0; px < PX; ++px) {
-          const bool on = (bits[px] >> k) & 1u;
-          wv[px] = make_float4(0.f, 0.f, 0.f, 0.f);
-          int4 o = make_int4(0, 0, 0, 0);
-          if (on) {
-            wv[px] = geo[(px * 16 + k) * 2];
-            const float4 of = geo[(px * 16 + k) * 2 + 1];
-            o = make_int4(__float_as_int(of.x), __float_as_int(of.y), __float_as_int(of.z), __float_as_int(of.w));
-          }
-#pragma unroll
-          for (int q = 0; q < NV; ++q) {
-            const float* p = xb + cb + q * G * 4;
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            v[px][q][0] = on ? __ldg(reinterpret_cast<const float4*>(p + o.x)) : z;
-            v[px][q][1] = on ? __ldg(reinterpret_cast<const float4*>(p + o.y)) : z;
-            v[px][q][2] = on ? __ldg(reinterpret_cast<const float4*>(p + o.z)) : z;
-            v[px][q][3] = on ? __ldg(reinterpret_cast<const float4*>(p + o.w)) : z;
-          }
-        }
-#pragma unroll
-        for (int px = 0; px < PX; ++px) {
-          const bool on = (bits[px] >> k) & 1u;
-          const bool zero = !kRelu && k == kz[px];
-          if (!on && !zero) continue;
-          const int tag = on ? k : kNoPart;
-#pragma unroll
-          for (int q = 0; q < NV; ++q) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            fma4(acc, wv[px].x, v[px][q][0]); fma4(acc, wv[px].y, v[px][q][1]);
-            fma4(acc, wv[px].z, v[px][q][2]); fma4(acc, wv[px].w, v[px][q][3]);
-            if (acc.x > best[px][4 * q + 0]) { best[px][4 * q + 0] = acc.x; arg[px][4 * q + 0] = tag; }
-            if (acc.y > best[px][4 * q + 1]) { best[px][4 * q + 1] = acc.y; arg[px][4 * q + 1] = tag; }
-            if (acc.z > best[px][4 * q + 2]) { best[px][4 * q + 2] = acc.z; arg[px][4 * q + 2] = tag; }
-            if (acc.w > best[px][4 * q + 3]) { best[px][4 * q + 3] = acc.w; arg[px][4 * q + 3] = tag; }
-          }
-        }
-      }
-#pragma unroll
-      for (int px = 0; px < PX; ++px) {
-        if (j0 + px >= w) continue;
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          *reinterpret_cast<float4*>(yrow + px * L.ldy + cb + q * G * 4) =
-              make_float4(warp_act<ACT>(best[px][4 * q]), warp_act<ACT>(best[px][4 * q + 1]), warp_act<ACT>(best[px][4 * q + 2]),
-                          warp_act<ACT>(best[px][4 * q + 3]));
-          *reinterpret_cast<uint16_t*>(arow + ((px * C + cb + q * G * 4) >> 1)) =
-              (uint16_t)(arg[px][4 * q] | (arg[px][4 * q + 1] << 4) | (arg[px][4 * q + 2] << 8) | (arg[px][4 * q + 3] << 12));
-        }
-      }
-    }
-    __syncwarp();   // the next row's geometry phase overwrites s_geo
-  }
-}
-
-
-// ---- forward, record-staged variant (the default).  ncu on the per-row-geometry kernel above: 160 M warp instructions per
-// launch set, 9 % of them FFMA -- the coordinate arithmetic re-done by the 16-32 lanes of every pixel, 64-bit address
-// arithmetic and divergence bookkeeping made it ISSUE-bound (66 % issue-active at 0.36 of the HBM roofline).  Here a CTA
-// owns a tile of 32 x 8 output pixels and works in two phases:
-//   A  one THREAD per pixel evaluates the geometry of that pixel's active parts once and parks it in shared memory as
-//      32-byte records (4 bilinear weights incl. the mask factor, 4 clamped tap offsets), plus one header word per pixel
-//      (count, the part index of each record, the position of the first "0, no gradient" candidate);
-//   B  one WARP per tile row gathers: G lanes own a pixel, two pixels per lane group in flight, every 128-bit request a
-//      run of whole lines; per (pixel, part) the lanes read the record with two broadcast loads and do nothing but
-//      4 NV loads, 16 NV FMAs and the running max.
 constexpr int kTileW = 32, kTileH = 8, kMaxRec = 6;     // records per pixel held in shared memory (more: inline slow path)
 
 struct FwdTileSmem {
@@ -714,127 +583,6 @@ warp_forward_tiles_kernel(const __grid_constant__ WarpLaunchDev P, const float* 
   }
 }
 
-// Backward of the same tiling: dx[taps of the winner] += dy * (mask * bilinear weight).  A lane's 4 channels usually
-// share their winner (the body part wins most pixels): one 128-bit vector reduction per tap; channels with other winners
-// go out as further vector reductions with the foreign channels zeroed.  ACT = ReLU / none need no look at y: "no
-// winner" (15) == zero candidate == y <= 0 == no gradient.
-template <int G, int NV, int PX>
-__device__ __forceinline__ void warp_bwd_strip(const WarpLevelDev& L, const Theta* s_theta, float4* s_geo_warp, int K, int n, int tile,
-                                               int act) {
-  constexpr int PPW = 32 / G, XW = 8 * PPW * PX, CH = 4 * G * NV;
-  const int sx = tile % L.strips_x, sy = tile / L.strips_x;
-  const int y_begin = sy * L.TH;
-  const int h = L.h, w = L.w, C = L.C;
-  const int rows = min(L.TH, h - y_begin);
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int gl = lane % G, grp = lane / G;
-  const int j0 = sx * XW + (wi * PPW + grp) * PX;
-  const int64_t img = (int64_t)n * h * w;
-  float* dxb = L.dx + img * C + gl * 4;
-  const float* mb = L.mask + img * K;
-  float4* geo = s_geo_warp + grp * (PX * 32);
-  for (int r = 0; r < rows; ++r) {
-    const int i = y_begin + r;
-    unsigned bits[PX];
-    row_geometry<G, PX>(s_theta, mb + (int64_t)i * w * K, K, i, j0, h, w, C, gl, grp, geo, bits);
-    __syncwarp();
-    const float* dyrow = L.dy + (img + (int64_t)i * w + j0) * L.lddy + gl * 4;
-    const float* yrow = L.y ? L.y + (img + (int64_t)i * w + j0) * L.ldy + gl * 4 : nullptr;
-    const uint8_t* arow = L.argk + (((img + (int64_t)i * w + j0) * C) >> 1) + gl * 2;
-    for (int cb = 0; cb < C; cb += CH) {
-      uint32_t a16[PX][NV];
-      float4 g[PX][NV];
-#pragma unroll
-      for (int px = 0; px < PX; ++px)
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          const bool live = j0 + px < w;
-          a16[px][q] = live ? *reinterpret_cast<const uint16_t*>(arow + ((px * C + cb + q * G * 4) >> 1)) : 0xffffu;
-          g[px][q] = (live && a16[px][q] != 0xffffu) ? __ldg(reinterpret_cast<const float4*>(dyrow + px * L.lddy + cb + q * G * 4))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-      for (int px = 0; px < PX; ++px)
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          const uint32_t a = a16[px][q];
-          if (a == 0xffffu) continue;
-          float4 gv = g[px][q];
-          if (act == PTK_ACT_LEAKY && yrow != nullptr) {
-            const float4 yv = __ldg(reinterpret_cast<const float4*>(yrow + px * L.ldy + cb + q * G * 4));
-            gv.x *= act_grad_from_output(yv.x, act); gv.y *= act_grad_from_output(yv.y, act);
-            gv.z *= act_grad_from_output(yv.z, act); gv.w *= act_grad_from_output(yv.w, act);
-          }
-          const int k0 = a & 15, k1 = (a >> 4) & 15, k2 = (a >> 8) & 15, k3 = (a >> 12) & 15;
-          unsigned done = 1u << kNoPart;
-          const int ks[4] = {k0, k1, k2, k3};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int kk = ks[c];
-            if ((done >> kk) & 1u) continue;
-            done |= 1u << kk;
-            const float4 gm = make_float4(k0 == kk ? gv.x : 0.f, k1 == kk ? gv.y : 0.f, k2 == kk ? gv.z : 0.f, k3 == kk ? gv.w : 0.f);
-            const float4 wv = geo[(px * 16 + kk) * 2];
-            const float4 of = geo[(px * 16 + kk) * 2 + 1];
-            float* p = dxb + cb + q * G * 4;
-            if (wv.x != 0.f) atomicAdd(reinterpret_cast<float4*>(p + __float_as_int(of.x)), make_float4(gm.x * wv.x, gm.y * wv.x, gm.z * wv.x, gm.w * wv.x));
-            if (wv.y != 0.f) atomicAdd(reinterpret_cast<float4*>(p + __float_as_int(of.y)), make_float4(gm.x * wv.y, gm.y * wv.y, gm.z * wv.y, gm.w * wv.y));
-            if (wv.z != 0.f) atomicAdd(reinterpret_cast<float4*>(p + __float_as_int(of.z)), make_float4(gm.x * wv.z, gm.y * wv.z, gm.z * wv.z, gm.w * wv.z));
-            if (wv.w != 0.f) atomicAdd(reinterpret_cast<float4*>(p + __float_as_int(of.w)), make_float4(gm.x * wv.w, gm.y * wv.w, gm.z * wv.w, gm.w * wv.w));
-          }
-        }
-    }
-    __syncwarp();
-  }
-}
-
-constexpr int kGeoPerWarp = 8 * 32;      // float4 slots: (pixels per warp <= 8) x 16 parts x 2
-
-// ONE launch for all warped levels of a generator pass: blockIdx.x enumerates the strips of every level (largest level
-// first; all strips carry the same number of bytes), blockIdx.y the image.
-// (forward through this kernel = the per-row-geometry variant, PTK_WARP_VAR=1; the backward pass uses its sibling below)
-template <int ACT, int VAR>
-__global__ void __launch_bounds__(256, 3)
-warp_forward_levels_kernel(const __grid_constant__ WarpLaunchDev P, const float* __restrict__ warps) {
-  __shared__ Theta s_theta[kMaxParts];
-  __shared__ float4 s_geo[8 * kGeoPerWarp];
-  const int n = blockIdx.y;
-  int li = 0;
-#pragma unroll
-  for (int q = 1; q < 4; ++q) if (q < P.nlevels && (int)blockIdx.x >= P.lv[q].cta_begin) li = q;
-  const WarpLevelDev& L = P.lv[li];
-  if (threadIdx.x < P.K) s_theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * P.K + threadIdx.x) * 8, L.h, L.w, P.H0, P.W0);
-  __syncthreads();
-  const int tile = blockIdx.x - L.cta_begin;
-  float4* geo = s_geo + (threadIdx.x >> 5) * kGeoPerWarp;
-  switch (L.cfg) {
-    case 0: warp_fwd_strip<16, 1, 2, ACT>(L, s_theta, geo, P.K, n, tile); break;
-    case 1: warp_fwd_strip<16, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
-    default: warp_fwd_strip<32, 2, 1, ACT>(L, s_theta, geo, P.K, n, tile); break;
-  }
-}
-
-__global__ void __launch_bounds__(256, 2)
-warp_backward_levels_kernel(const __grid_constant__ WarpLaunchDev P, const float* __restrict__ warps) {
-  __shared__ Theta s_theta[kMaxParts];
-  __shared__ float4 s_geo[8 * kGeoPerWarp];
-  const int n = blockIdx.y;
-  int li = 0;
-#pragma unroll
-  for (int q = 1; q < 4; ++q) if (q < P.nlevels && (int)blockIdx.x >= P.lv[q].cta_begin) li = q;
-  const WarpLevelDev& L = P.lv[li];
-  if (threadIdx.x < P.K) s_theta[threadIdx.x] = normalized_theta(warps + ((int64_t)n * P.K + threadIdx.x) * 8, L.h, L.w, P.H0, P.W0);
-  __syncthreads();
-  const int tile = blockIdx.x - L.cta_begin;
-  float4* geo = s_geo + (threadIdx.x >> 5) * kGeoPerWarp;
-  switch (L.cfg) {
-    case 0: warp_bwd_strip<16, 1, 4>(L, s_theta, geo, P.K, n, tile, P.act); break;
-    case 1: warp_bwd_strip<16, 2, 2>(L, s_theta, geo, P.K, n, tile, P.act); break;
-    case 2: warp_bwd_strip<32, 2, 2>(L, s_theta, geo, P.K, n, tile, P.act); break;
-    default: warp_bwd_strip<32, 4, 1>(L, s_theta, geo, P.K, n, tile, P.act); break;
-  }
-}
-
 // zero-fill of up to four buffers in one launch (the dx targets of the backward scatter)
 struct Fill4 { float4* p[4]; long long n4[4]; };
 __global__ void __launch_bounds__(256) fill4_kernel(const __grid_constant__ Fill4 f) {
@@ -845,15 +593,25 @@ __global__ void __launch_bounds__(256) fill4_kernel(const __grid_constant__ Fill
 }
 
 // cv2.resize(INTER_LINEAR) == half-pixel bilinear; computed in double like the reference (masks are f64).
-// A CTA produces 256 consecutive output pixels of one image for all K parts: the source planes are read part by part
-// (coalesced along x), the [pixel][part] rows are transposed through shared memory and written as one contiguous run.
+// ONE launch builds the pyramid of a generator pass (up to four levels): blockIdx.x enumerates 256-pixel chunks of every
+// level, blockIdx.y the image.  A CTA produces 256 consecutive output pixels for all K parts: the source planes are read
+// four parts at a time (coalesced along x, up to 16 independent loads in flight per thread), the [pixel][part] rows are
+// transposed through shared memory and written as one contiguous run.  The first level streams the f64 planes from
+// HBM; the later levels re-read a subset of them out of L2.
 constexpr int kPyrPix = 256;
+struct PyrLaunch { float* out[4]; int h[4], w[4], cta_begin[4]; int nlevels, K, H0, W0; };
+
 __global__ void __launch_bounds__(256)
-mask_pyramid_kernel(const double* __restrict__ masks, int K, int H0, int W0, float* __restrict__ out, int h, int w) {
+mask_pyramid_kernel(const double* __restrict__ masks, const __grid_constant__ PyrLaunch P) {
   extern __shared__ float s_row[];                 // [kPyrPix][K + 1]
-  const int n = blockIdx.y;
+  pdl_trigger();
+  const int n = blockIdx.y, K = P.K, H0 = P.H0, W0 = P.W0;
+  int li = 0;
+#pragma unroll
+  for (int q = 1; q < 4; ++q) if (q < P.nlevels && (int)blockIdx.x >= P.cta_begin[q]) li = q;
+  const int h = P.h[li], w = P.w[li];
   const int hw = h * w;
-  const int p0 = blockIdx.x * kPyrPix;
+  const int p0 = ((int)blockIdx.x - P.cta_begin[li]) * kPyrPix;
   const int p = p0 + threadIdx.x;
   const double sy = (double)H0 / h, sx = (double)W0 / w;
   if (p < hw) {
@@ -867,18 +625,28 @@ mask_pyramid_kernel(const double* __restrict__ masks, int K, int H0, int W0, flo
     const int y1 = y0 + 1 < H0 ? y0 + 1 : H0 - 1, x1 = x0 + 1 < W0 ? x0 + 1 : W0 - 1;
     const double ly = fy - y0, lx = fx - x0;
     const bool exact = ly == 0.0 && lx == 0.0;      // same-size level: a plain conversion
-    for (int k = 0; k < K; ++k) {
-      const double* src = masks + ((int64_t)n * K + k) * (int64_t)H0 * W0;
-      double v;
-      if (exact) v = src[(int64_t)y0 * W0 + x0];
-      else v = (1 - ly) * ((1 - lx) * src[(int64_t)y0 * W0 + x0] + lx * src[(int64_t)y0 * W0 + x1]) +
-               ly * ((1 - lx) * src[(int64_t)y1 * W0 + x0] + lx * src[(int64_t)y1 * W0 + x1]);
-      s_row[threadIdx.x * (K + 1) + k] = (float)v;
+    const int64_t plane = (int64_t)H0 * W0;
+    const double* src = masks + (int64_t)n * K * plane;
+    const int64_t o00 = (int64_t)y0 * W0 + x0, o01 = (int64_t)y0 * W0 + x1, o10 = (int64_t)y1 * W0 + x0, o11 = (int64_t)y1 * W0 + x1;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      double v00[4], v01[4], v10[4], v11[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double* sp = src + (int64_t)min(k0 + q, K - 1) * plane;
+        v00[q] = __ldg(sp + o00);
+        if (!exact) { v01[q] = __ldg(sp + o01); v10[q] = __ldg(sp + o10); v11[q] = __ldg(sp + o11); }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (k0 + q >= K) break;
+        const double v = exact ? v00[q] : (1 - ly) * ((1 - lx) * v00[q] + lx * v01[q]) + ly * ((1 - lx) * v10[q] + lx * v11[q]);
+        s_row[threadIdx.x * (K + 1) + k0 + q] = (float)v;
+      }
     }
   }
   __syncthreads();
   const int npix = min(kPyrPix, hw - p0);
-  float* dst = out + ((int64_t)n * hw + p0) * K;
+  float* dst = P.out[li] + ((int64_t)n * hw + p0) * K;
   for (int e = threadIdx.x; e < npix * K; e += 256) {
     const int pp = e / K, k = e - pp * K;
     dst[e] = s_row[pp * (K + 1) + k];
@@ -898,13 +666,27 @@ static inline dim3 warp_grid(int64_t work, int N) {
   return dim3((unsigned)b, (unsigned)N);
 }
 
-extern "C" int ptk_mask_pyramid(const double* masks, int N, int K, int H0, int W0, float* out, int h, int w,
-                                void* stream) {
-  PTK_REQUIRE(N > 0 && N <= 65535 && K > 0 && K <= 64 && h > 0 && w > 0, "mask_pyramid: bad extents");
-  dim3 grid((unsigned)(((int64_t)h * w + kPyrPix - 1) / kPyrPix), (unsigned)N);
-  mask_pyramid_kernel<<<grid, 256, kPyrPix * (K + 1) * sizeof(float), (cudaStream_t)stream>>>(masks, K, H0, W0, out, h, w);
+extern "C" int ptk_mask_pyramid_levels(const double* masks, int N, int K, int H0, int W0, float* const* outs, const int* hs,
+                                       const int* ws, int nlevels, void* stream) {
+  PTK_REQUIRE(masks && outs && hs && ws && nlevels >= 1 && nlevels <= 4, "mask_pyramid: 1..4 levels");
+  PTK_REQUIRE(N > 0 && N <= 65535 && K > 0 && K <= 64 && H0 > 0 && W0 > 0, "mask_pyramid: bad extents");
+  PyrLaunch P;
+  memset(&P, 0, sizeof(P));
+  P.nlevels = nlevels; P.K = K; P.H0 = H0; P.W0 = W0;
+  int ctas = 0;
+  for (int q = 0; q < nlevels; ++q) {
+    PTK_REQUIRE(outs[q] && hs[q] > 0 && ws[q] > 0, "mask_pyramid: bad level");
+    P.out[q] = outs[q]; P.h[q] = hs[q]; P.w[q] = ws[q]; P.cta_begin[q] = ctas;
+    ctas += (int)(((int64_t)hs[q] * ws[q] + kPyrPix - 1) / kPyrPix);
+  }
+  mask_pyramid_kernel<<<dim3((unsigned)ctas, (unsigned)N), 256, kPyrPix * (K + 1) * sizeof(float), (cudaStream_t)stream>>>(masks, P);
   PTK_LAUNCH_CHECK("mask_pyramid_kernel");
   return 0;
+}
+
+extern "C" int ptk_mask_pyramid(const double* masks, int N, int K, int H0, int W0, float* out, int h, int w,
+                                void* stream) {
+  return ptk_mask_pyramid_levels(masks, N, K, H0, W0, &out, &h, &w, 1, stream);
 }
 
 // configuration of the fast path for a level, or -1 (=> generic kernels, byte-sized winner record)
@@ -917,26 +699,7 @@ static int warp_fast_cfg(int C, int h, int w, int K, int ld_max, int align_corne
   return -1;
 }
 
-static int warp_rows_per_strip() {
-  const char* e = getenv("PTK_WARP_TH");      // (read per call: tests and sweeps switch it inside one process)
-  int th = e ? atoi(e) : 8;
-  if (th < 1 || th > 64) th = 8;
-  return th;
-}
-
 // fills the device-side launch description; returns false if some level cannot take the fast path
-// forward kernel variant: 2 = record-staged tiles (default), 1 = per-row geometry strips (PTK_WARP_VAR=1, kept for comparison)
-static int warp_variant() {
-  const char* e = getenv("PTK_WARP_VAR");
-  return (e && atoi(e) == 1) ? 1 : 2;
-}
-
-// backward kernel variant: 2 = record-staged tiles (default), 1 = per-row geometry strips (PTK_WARP_BWD=1, kept for comparison)
-static int warp_bwd_variant() {
-  const char* e = getenv("PTK_WARP_BWD");
-  return (e && atoi(e) == 1) ? 1 : 2;
-}
-
 static bool warp_plan(const ptk_warp_level* lv, int nlevels, int K, int H0, int W0, int act, bool backward, WarpLaunchDev& P) {
   memset(&P, 0, sizeof(P));
   P.nlevels = nlevels; P.K = K; P.H0 = H0; P.W0 = W0; P.act = act;
@@ -949,22 +712,10 @@ static bool warp_plan(const ptk_warp_level* lv, int nlevels, int K, int H0, int 
     WarpLevelDev& d = P.lv[q];
     d.x = s.x; d.mask = s.mask; d.y = s.y; d.argk = s.argk; d.dy = s.dy; d.dx = s.dx;
     d.ldx = s.ldx; d.ldy = s.ldy; d.lddy = s.lddy; d.C = s.C; d.h = s.h; d.w = s.w; d.cfg = cfg;
-    const int g = cfg <= 1 ? 16 : 32;
-    int xw;
-    if (backward && warp_bwd_variant() == 2) {   // warp_bwd_tile: the forward pass' tiles
-      xw = kTileW;
-      d.TH = cfg == 0 ? 8 : (cfg == 1 ? 4 : (cfg == 2 ? 2 : 1));
-    } else if (backward) {                // warp_bwd_strip<G, NV, 4 / NV>
-      const int nv = cfg == 0 ? 1 : (cfg == 3 ? 4 : 2);
-      xw = 8 * (32 / g) * (4 / nv);
-      d.TH = warp_rows_per_strip() < s.h ? warp_rows_per_strip() : s.h;
-    } else if (warp_variant() == 1) {     // warp_fwd_strip<G, NV, 2 / NV>
-      const int nv = cfg == 0 ? 1 : 2;
-      xw = 8 * (32 / g) * (2 / nv);
-      d.TH = warp_rows_per_strip() < s.h ? warp_rows_per_strip() : s.h;
-    } else {                              // warp_fwd_tile: 32 x TH pixel tiles, 64 KB of output each
-      xw = kTileW;
-      d.TH = cfg == 0 ? 8 : (cfg == 1 ? 4 : (cfg == 2 ? 2 : 1));
+    // 32 x TH pixel tiles carrying 64 KB of output each, so that the levels of a pass balance over the machine
+    const int xw = kTileW;
+    d.TH = cfg == 0 ? 8 : (cfg == 1 ? 4 : (cfg == 2 ? 2 : 1));
+    if (!backward) {
       const char* e = getenv("PTK_WARP_PF");
       P.prefetch = (e && atoi(e) == 0) ? 0 : 1;
     }
@@ -1013,11 +764,7 @@ extern "C" int ptk_warp_forward_levels(const ptk_warp_level* lv, int nlevels, co
     return 0;
   }
   dim3 grid((unsigned)P.ctas_per_image, (unsigned)N);
-  if (warp_variant() == 1) {
-    if (act == PTK_ACT_RELU) warp_forward_levels_kernel<PTK_ACT_RELU, 1><<<grid, 256, 0, st>>>(P, warps);
-    else if (act == PTK_ACT_LEAKY) warp_forward_levels_kernel<PTK_ACT_LEAKY, 1><<<grid, 256, 0, st>>>(P, warps);
-    else warp_forward_levels_kernel<PTK_ACT_NONE, 1><<<grid, 256, 0, st>>>(P, warps);
-  } else {
+  {
     const size_t smem = sizeof(FwdTileSmem);
 #define PTK_WARP_TILES(A_)                                                                                              \
   do {                                                                                                                  \
@@ -1030,7 +777,7 @@ extern "C" int ptk_warp_forward_levels(const ptk_warp_level* lv, int nlevels, co
     else PTK_WARP_TILES(PTK_ACT_NONE);
 #undef PTK_WARP_TILES
   }
-  PTK_LAUNCH_CHECK("warp_forward_levels_kernel");
+  PTK_LAUNCH_CHECK("warp_forward_tiles_kernel");
   return 0;
 }
 
@@ -1066,15 +813,13 @@ extern "C" int ptk_warp_backward_levels(const ptk_warp_level* lv, int nlevels, c
   }
   if (act != PTK_ACT_LEAKY) for (int q = 0; q < nlevels; ++q) P.lv[q].y = nullptr;   // ReLU / none: the winner record says it all
   dim3 grid((unsigned)P.ctas_per_image, (unsigned)N);
-  if (warp_bwd_variant() == 2) {
+  {
     const size_t smem = sizeof(FwdTileSmem);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(warp_backward_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     warp_backward_tiles_kernel<<<grid, 256, smem, st>>>(P, warps);
-  } else {
-    warp_backward_levels_kernel<<<grid, 256, 0, st>>>(P, warps);
   }
-  PTK_LAUNCH_CHECK("warp_backward_levels_kernel");
+  PTK_LAUNCH_CHECK("warp_backward_tiles_kernel");
   return 0;
 }
 

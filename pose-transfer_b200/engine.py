@@ -397,11 +397,9 @@ class GeneratorEngine:
             cats.append(ws.get("cat%d_%s" % (j, tag), (N, hs[i], wsz[i], width)))
 
         # mask pyramid for the 4 warped levels
-        mlv = []
-        for i in range(min(4, L) if any_warp else 0):
-            mk = ws.get("mask%d_%s" % (i, tag), (N, hs[i], wsz[i], Kp))
-            K.mask_pyramid(masks, mk)
-            mlv.append(mk)
+        mlv = [ws.get("mask%d_%s" % (i, tag), (N, hs[i], wsz[i], Kp)) for i in range(min(4, L) if any_warp else 0)]
+        if mlv:
+            K.mask_pyramid_levels(masks, mlv)
 
         sv = {"N": N, "H": H, "W": W, "hs": hs, "ws": wsz, "tag": tag, "stats": stats, "st_idx": st_idx, "drops": drops,
               "cats": cats, "mlv": mlv, "warps": warps, "K": Kp, "z": {}, "act": {}, "yraw": {}, "argk": {}, "xin": {}}

@@ -254,6 +254,18 @@ def gn_bwd_apply(dy, z, stats, sums, gamma, N, HW, C, dgamma, dbeta):
 
 
 @_timed("mask_pyramid")
+def mask_pyramid_levels(masks, outs):
+    """f64 masks [N,K,H0,W0] -> every f32 [N,h,w,K] tensor of `outs` (cv2.resize INTER_LINEAR) in one launch."""
+    import ctypes
+    N, K, H0, W0 = masks.shape
+    n = len(outs)
+    ptrs = (ctypes.c_void_p * n)(*[_p(o) for o in outs])
+    hs = (ctypes.c_int * n)(*[o.shape[1] for o in outs])
+    ws = (ctypes.c_int * n)(*[o.shape[2] for o in outs])
+    check(_lib.lib().ptk_mask_pyramid_levels(_p(masks), N, K, H0, W0, ptrs, hs, ws, n, _stream()), "ptk_mask_pyramid_levels")
+
+
+@_timed("mask_pyramid")
 def mask_pyramid(masks, out):
     """masks [N,K,H0,W0] f64 -> out [N,h,w,K] f32."""
     N, K, H0, W0 = masks.shape

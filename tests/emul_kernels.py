@@ -252,6 +252,10 @@ def install(K):
 
     saved_warp = {}
 
+    def mask_pyramid_levels(masks, outs):
+        for o in outs:
+            mask_pyramid(masks, o)
+
     def warp_forward(x, warps, mask_lvl, y, argk, N, C, h, w, Kp, H0, W0, act=0, align_corners=False):
         xs = nchw(view(x, C)).reshape(N, C, h, w).clone()
         # masks are already at level resolution: restate.mask_pyramid_level passes them through unchanged
@@ -368,7 +372,7 @@ def install(K):
                  head_wgrad_scatter=head_wgrad_scatter,
                  conv_forward=conv_forward, conv_wgrad=conv_wgrad, conv_wgrad_parts=conv_wgrad_parts,
                  bias_grad=bias_grad, gn_stats=gn_stats, gn_apply=gn_apply, gn_bwd_reduce=gn_bwd_reduce,
-                 gn_bwd_apply=gn_bwd_apply, mask_pyramid=mask_pyramid, warp_forward=warp_forward,
+                 gn_bwd_apply=gn_bwd_apply, mask_pyramid=mask_pyramid, mask_pyramid_levels=mask_pyramid_levels, warp_forward=warp_forward,
                  warp_backward=warp_backward, warp_forward_levels=warp_forward_levels, warp_backward_levels=warp_backward_levels,
                  adv_loss=adv_loss, l1_loss=l1_loss, nnloss_forward=nnloss_forward,
                  nnloss_backward=nnloss_backward, nnloss_features_forward=nnloss_features_forward,

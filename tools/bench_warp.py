@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """Micro-benchmark of the fused warp launches (forward: the BENCH line's roofline kernel; backward) at the benchmark
-geometry (256x256, P=18, batch 8: levels (64,256) (128,128) (256,64) (512,32)), sweeping the kernel variant and the rows
-per strip.  CUDA events around 20 back-to-back launch sets (each moves > 4x the L2 capacity).  Usage on the GPU box:
+geometry (256x256, P=18, batch 8: levels (64,256) (128,128) (256,64) (512,32)), forward, backward and each level alone.  CUDA events around 20 back-to-back launch sets (each moves > 4x the L2 capacity).  Usage on the GPU box:
     python tools/bench_warp.py [N]"""
 import json
 import os
@@ -50,21 +49,13 @@ def main():
         return e0.elapsed_time(e1) / iters
 
     print("algorithmic bytes per launch set: %.1f MB (N=%d); HBM peak %.0f GB/s" % (alg / 1e6, N, peak))
-    for var, th in (("1", "8"), ("2", "8")):
-        os.environ["PTK_WARP_VAR"], os.environ["PTK_WARP_TH"] = var, th
-        ms = timeit(lambda: K.warp_forward_levels(lv, wr, N, 10, H, H, K.ACT_RELU))
-        print("forward  var=%s  %.4f ms  %.0f GB/s  frac %.3f" % (var, ms, alg / ms / 1e6, alg / ms / 1e6 / peak))
-    os.environ["PTK_WARP_VAR"] = "2"
-    K.warp_forward_levels(lv, wr, N, 10, H, H, K.ACT_RELU)
-    for bv in ("1", "2"):
-        os.environ["PTK_WARP_BWD"] = bv
-        ms = timeit(lambda: K.warp_backward_levels(lv, wr, N, 10, H, H, K.ACT_RELU, True))
-        print("backward var=%s (incl. zero fill)  %.4f ms  %.0f GB/s  frac %.3f" % (bv, ms, alg / ms / 1e6, alg / ms / 1e6 / peak))
-        ms = timeit(lambda: K.warp_backward_levels(lv, wr, N, 10, H, H, K.ACT_RELU, False))
-        print("backward var=%s (no fill; dx accumulates)  %.4f ms" % (bv, ms))
-    os.environ["PTK_WARP_BWD"] = "2"
+    ms = timeit(lambda: K.warp_forward_levels(lv, wr, N, 10, H, H, K.ACT_RELU))
+    print("forward  %.4f ms  %.0f GB/s  frac %.3f" % (ms, alg / ms / 1e6, alg / ms / 1e6 / peak))
+    ms = timeit(lambda: K.warp_backward_levels(lv, wr, N, 10, H, H, K.ACT_RELU, True))
+    print("backward (incl. zero fill)  %.4f ms  %.0f GB/s  frac %.3f" % (ms, alg / ms / 1e6, alg / ms / 1e6 / peak))
+    ms = timeit(lambda: K.warp_backward_levels(lv, wr, N, 10, H, H, K.ACT_RELU, False))
+    print("backward (no fill; dx accumulates)  %.4f ms" % ms)
     # per-level forward times (single-level launches)
-    os.environ["PTK_WARP_TH"] = "8"
     for d in lv:
         ms = timeit(lambda: K.warp_forward_levels([d], wr, N, 10, H, H, K.ACT_RELU))
         a = N * d["h"] * d["w"] * (8 * d["C"] + 40)
