@@ -15,6 +15,8 @@
 //   (blockIdx.z), each a 2x2-tap stride-1 gather.
 #include <cuda.h>
 #include "common.cuh"
+#include <map>
+#include <mutex>
 #include "tc_ptx.cuh"
 
 namespace ptk {
@@ -493,6 +495,68 @@ static int encode(CUtensorMap* m, const float* base, int rank, const uint64_t* d
 static int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 static int floordiv2(int q) { return q >= 0 ? q / 2 : -((-q + 1) / 2); }
 
+// ---------------------------------------------------------------- first-use autotuning of the tile shape
+// Keyed by the layer geometry (and the call flavour); the winner of a few timed launches on the real operands is kept for
+// the life of the process.  PTK_TC_AUTOTUNE=0 keeps the static cost model (bit-reproducible tile choice across runs).
+struct TuneKey {
+  int v[20];
+  bool operator<(const TuneKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+struct TuneChoice { int mh, bn, splits, tpc; };
+
+static TuneKey tune_key(const ptk_conv_geom& c, int kind, int flags, int64_t capacity) {
+  TuneKey k;
+  memset(&k, 0, sizeof(k));
+  const int f[] = {c.N, c.H, c.W, c.Cin, c.ldx, c.OH, c.OW, c.Cout, c.ldy, c.k, c.stride, c.pad, c.transposed, kind, flags,
+                   (int)(capacity >> 20)};
+  for (size_t i = 0; i < sizeof(f) / sizeof(f[0]); ++i) k.v[i] = f[i];
+  return k;
+}
+
+static std::map<TuneKey, TuneChoice>& tune_table() { static std::map<TuneKey, TuneChoice> t; return t; }
+static std::mutex& tune_mutex() { static std::mutex m; return m; }
+
+static bool tune_lookup(const TuneKey& k, TuneChoice* out) {
+  std::lock_guard<std::mutex> lock(tune_mutex());
+  auto it = tune_table().find(k);
+  if (it == tune_table().end()) return false;
+  *out = it->second;
+  return true;
+}
+
+static void tune_store(const TuneKey& k, const TuneChoice& c) {
+  std::lock_guard<std::mutex> lock(tune_mutex());
+  tune_table()[k] = c;
+}
+
+static bool tc_autotune_enabled(cudaStream_t st) {
+  const char* e = getenv("PTK_TC_AUTOTUNE");         // (read per call: tests switch it inside one process)
+  if (e && atoi(e) == 0) return false;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return false;
+  return true;
+}
+
+// one warm-up + two timed launches of `fn` on stream st (drains the device first, blocks the host until they finish)
+template <typename F>
+static int tune_time(cudaStream_t st, F fn, float* ms) {
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return fail(3, "autotune: cudaEventCreate failed");
+  cudaDeviceSynchronize();            // the trial runs alone: work queued on other streams would distort the comparison
+  int rc = fn();
+  if (!rc) {
+    cudaEventRecord(e0, st);
+    rc = fn();
+    if (!rc) rc = fn();
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess) rc = fail(3, "autotune: %s", cudaGetErrorString(cudaGetLastError()));
+    else cudaEventElapsedTime(ms, e0, e1);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
 bool conv_tc_supported(const ptk_conv_geom& c) {
   if (c.Cin % 32 != 0 || c.Cout % 32 != 0) return false;
   if (c.ldx % 4 != 0 || c.ldy % 4 != 0) return false;
@@ -509,8 +573,6 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
               (reinterpret_cast<uintptr_t>(w_k) & 15) == 0, "conv_forward(tc): pointers must be 16-byte aligned");
   TcGeom g;
   memset(&g, 0, sizeof(g));
-  TmapSet maps;
-  memset(&maps, 0, sizeof(maps));
   g.N = c.N; g.OH = c.OH; g.OW = c.OW; g.ldy = c.ldy; g.kchunks = c.Cin / 32;
   int nphases, maxGH = 0, maxGW = 0;
   const int k = c.k, s = c.stride;
@@ -564,9 +626,10 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
                                   {1, 256, 4, 1, 0.64f}, {2, 128, 4, 1, 0.64f}, {2, 256, 3, 1, 0.80f}};
   int forced_mh = 0, forced_bn = 0;
   if (const char* e = getenv("PTK_TC_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
-  const TileCfg* best = nullptr;
-  double best_cost = 0.0;
-  int best_splits = 1;
+  struct Cand { const TileCfg* cfg; int splits; double cost; };
+  Cand cands[8];
+  int ncand = 0;
+  const Cand* forced_cand = nullptr;
   const bool can_split = c.ldy == c.Cout && bias == nullptr && act == PTK_ACT_NONE;
   const int64_t out_floats = (int64_t)c.N * c.OH * c.OW * c.Cout;
   const bool use_parts = scratch != nullptr && scratch_floats >= 2 * out_floats && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0 &&
@@ -595,16 +658,32 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
       while (sp > 1 && (min_kb + sp - 1) / sp * (sp - 1) >= min_kb) --sp;
     }
     if (t.occ == 1 && !forced && ctas * sp < slots / 2) continue;   // big one-CTA-per-SM shapes must fill the machine
-    const double tile_clk = (double)((min_kb + sp - 1) / sp) * t.mh * (t.bn / 128.0) * 256.0 / t.eff +
+    // (2, 64) pays off through its coalescing epilogue: only on short K loops (stems, Cout = 64 dgrads / ConvT); with 32+
+    // k-blocks per tile two co-resident (1, 64) CTAs hide the N = 64 MMA latency better (PatchGAN stem: 0.104 vs 0.111 ms)
+    const double eff = (t.mh == 2 && t.bn == 64 && min_kb > 16) ? 0.30 : t.eff;
+    const double tile_clk = (double)((min_kb + sp - 1) / sp) * t.mh * (t.bn / 128.0) * 256.0 / eff +
                             (t.occ == 1 ? 3000.0 * t.mh * (t.bn / 128.0) : 1500.0);
     // combining the splits: fp32 L2 atomics (~100 floats / clk chip-wide), or one streamed pass that reads every partial
     // buffer and writes the result (~460 floats / clk at 3.5 TB/s) behind one more launch
     const double combine = sp > 1 ? (use_parts ? (double)out_floats * (sp + 1) / 460.0 + 5000.0 : (double)out_floats * sp / 100.0) : 0.0;
     const double cost = (double)((ctas * sp + slots - 1) / slots) * t.occ * tile_clk + combine;
-    if (forced) { best = &t; best_splits = sp; break; }
-    if (!best || cost < best_cost) { best = &t; best_cost = cost; best_splits = sp; }
+    cands[ncand] = Cand{&t, sp, cost};
+    if (forced && !forced_cand) forced_cand = &cands[ncand];
+    ++ncand;
   }
-  PTK_REQUIRE(best != nullptr, "conv_forward(tc): no tile configuration for Cout=%d", c.Cout);
+  PTK_REQUIRE(ncand > 0, "conv_forward(tc): no tile configuration for Cout=%d", c.Cout);
+  for (int i = 1; i < ncand; ++i)            // by model cost (stable: ties keep the table order)
+    for (int j = i; j > 0 && cands[j].cost < cands[j - 1].cost; --j) { const Cand tmp = cands[j]; cands[j] = cands[j - 1]; cands[j - 1] = tmp; }
+  if (forced_cand) {                         // (the pointer was taken before the sort: find it again by shape)
+    for (int i = 0; i < ncand; ++i) if (cands[i].cfg->mh == forced_mh && cands[i].cfg->bn == forced_bn) { forced_cand = &cands[i]; break; }
+  }
+
+  // ---- everything that depends on the chosen tile: tensor maps, grid, launch (+ the split-K reduce)
+  const TcGeom g0 = g;
+  auto run = [&](const TileCfg* best, int best_splits, double* stats) -> int {
+  TcGeom g = g0;
+  TmapSet maps;
+  memset(&maps, 0, sizeof(maps));
   const int MH = best->mh, BN = best->bn, MT = 128 * MH;
   g.BW = pow2_ge(maxGW < MT ? maxGW : MT);
   g.BH = pow2_ge(maxGH < MT / g.BW ? maxGH : MT / g.BW);
@@ -726,6 +805,32 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   if (splits > 1 && stats != nullptr)   // atomic split-K: the statistics need one extra pass over a tiny tensor
     return ptk_gn_stats(y, c.ldy, c.N, (int64_t)c.OH * c.OW, c.Cout, stats, st);
   return 0;
+  };   // run
+
+  if (forced_cand) return run(forced_cand->cfg, forced_cand->splits, stats);
+  const Cand* pick = &cands[0];
+  if (ncand > 1 && tc_autotune_enabled(st)) {
+    // First use of this layer geometry: time the model's best candidates on the real operands and remember the winner
+    // (the cost model ranks tile shapes within ~15 %; wave quantisation, persistence and the ragged edges decide the rest).
+    const TuneKey key = tune_key(c, 0, (bias != nullptr) * 2 + (use_parts ? 1 : 0) + act * 4, scratch_floats);
+    TuneChoice ch;
+    if (!tune_lookup(key, &ch)) {
+      const int ntry = ncand < 4 ? ncand : 4;
+      float best_ms = 0.f;
+      int best_i = 0;
+      for (int i = 0; i < ntry; ++i) {
+        float ms = 0.f;
+        int rc = tune_time(st, [&]() { return run(cands[i].cfg, cands[i].splits, nullptr); }, &ms);
+        if (rc) return rc;
+        if (i == 0 || ms < best_ms) { best_ms = ms; best_i = i; }
+      }
+      ch.mh = cands[best_i].cfg->mh; ch.bn = cands[best_i].cfg->bn; ch.splits = cands[best_i].splits; ch.tpc = 1;
+      tune_store(key, ch);
+    }
+    for (int i = 0; i < ncand; ++i)
+      if (cands[i].cfg->mh == ch.mh && cands[i].cfg->bn == ch.bn && cands[i].splits == ch.splits) { pick = &cands[i]; break; }
+  }
+  return run(pick->cfg, pick->splits, stats);
 }
 
 
@@ -971,9 +1076,11 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
   int forced_mh = 0, forced_bn = 0;
   if (const char* e = getenv("PTK_WG_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
   const int bn_small = (Cb % 128 == 0) ? 128 : (Cb % 64 == 0 ? 64 : 32);
-  const WgCfg* best = nullptr;
-  int best_splits = 1;
-  double best_cost = 0.0;
+  struct Cand { const WgCfg* cfg; int splits; double cost; };
+  Cand cands[12];
+  int ncand = 0;
+  const Cand* forced_cand = nullptr;
+  const int64_t part_floats = (int64_t)g.ntaps * g.Ca * Cb;
   for (const WgCfg& t : kCfgs) {
     if (Cb % t.bn != 0) continue;
     if (t.bn < bn_small) continue;
@@ -985,7 +1092,6 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     const double stage_clk = t.tpc * t.mh * (t.bn / 128.0) * 256.0 / t.eff;
     int cfg_splits = 1;
     double cfg_cost = 0.0;
-    const int64_t part_floats = (int64_t)g.ntaps * g.Ca * Cb;
     for (int sp = 1; sp <= g.ntiles && sp <= 512; ++sp) {
       if (sp > 1 && (g.ntiles + sp - 1) / sp * (sp - 1) >= g.ntiles) continue;   // every split must own a pixel tile
       if (nparts != nullptr && sp > 1 && part_floats * sp > dw_capacity) break;
@@ -996,17 +1102,28 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
       const double cost = (double)((ctas + slots - 1) / slots) * t.occ * tile_clk + combine;
       if (sp == 1 || cost < cfg_cost) { cfg_cost = cost; cfg_splits = sp; }
     }
-    if (forced) { best = &t; best_splits = cfg_splits; break; }
-    if (!best || cfg_cost < best_cost) { best = &t; best_cost = cfg_cost; best_splits = cfg_splits; }
+    cands[ncand] = Cand{&t, cfg_splits, cfg_cost};
+    ++ncand;
+    if (forced) { forced_cand = &cands[ncand - 1]; break; }
   }
-  PTK_REQUIRE(best != nullptr, "conv_wgrad(tc): no tile configuration for Ca=%d Cb=%d", g.Ca, Cb);
+  PTK_REQUIRE(ncand > 0, "conv_wgrad(tc): no tile configuration for Ca=%d Cb=%d", g.Ca, Cb);
+  const Cand* pick = forced_cand;
+  if (!pick) {
+    for (int i = 1; i < ncand; ++i)          // by model cost (stable)
+      for (int j = i; j > 0 && cands[j].cost < cands[j - 1].cost; --j) { const Cand tmp = cands[j]; cands[j] = cands[j - 1]; cands[j - 1] = tmp; }
+    pick = &cands[0];
+  }
+
+  const WgTcGeom g0 = g;
+  auto run = [&](const WgCfg* best, int best_splits, bool launch) -> int {
+  WgTcGeom g = g0;
   const int BN = best->bn, MH = best->mh, TPC = best->tpc;
   const int atiles = (g.Ca + 128 * MH - 1) / (128 * MH);
   const int splits = best_splits;
   g.splits = splits;
   g.part_stride = nparts != nullptr ? (long long)g.ntaps * g.Ca * Cb : 0;
   if (nparts != nullptr) *nparts = splits;
-  if (plan_only) return 0;
+  if (!launch) return 0;
   if (splits > 1 && nparts == nullptr) {
     int rc = ptk_fill(dw, (int64_t)g.ntaps * g.Ca * Cb, 0.f, st);
     if (rc) return rc;
@@ -1031,6 +1148,34 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
 #undef PTK_WG_LAUNCH
   PTK_LAUNCH_CHECK("wgrad_tc_kernel");
   return 0;
+  };   // run
+
+  // First real launch of this geometry in partial-buffer mode: time the model's best candidates (those whose split count
+  // fits the caller's buffer) and keep the winner; plan-only calls and later launches read the remembered choice.
+  if (!forced_cand && ncand > 1 && nparts != nullptr && tc_autotune_enabled(st)) {
+    const int64_t allowed = part_floats > 0 ? dw_capacity / part_floats : 1;
+    const TuneKey key = tune_key(c, 1, 0, (allowed > 1024 ? 1024 : allowed) << 20);
+    TuneChoice ch;
+    bool have = tune_lookup(key, &ch);
+    if (!have && !plan_only) {
+      const int ntry = ncand < 4 ? ncand : 4;
+      float best_ms = 0.f;
+      int best_i = 0;
+      for (int i = 0; i < ntry; ++i) {
+        float ms = 0.f;
+        int rc = tune_time(st, [&]() { return run(cands[i].cfg, cands[i].splits, true); }, &ms);
+        if (rc) return rc;
+        if (i == 0 || ms < best_ms) { best_ms = ms; best_i = i; }
+      }
+      ch.mh = cands[best_i].cfg->mh; ch.bn = cands[best_i].cfg->bn; ch.splits = cands[best_i].splits; ch.tpc = cands[best_i].cfg->tpc;
+      tune_store(key, ch);
+      have = true;
+    }
+    if (have)
+      for (int i = 0; i < ncand; ++i)
+        if (cands[i].cfg->mh == ch.mh && cands[i].cfg->bn == ch.bn && cands[i].cfg->tpc == ch.tpc && cands[i].splits == ch.splits) { pick = &cands[i]; break; }
+  }
+  return run(pick->cfg, pick->splits, !plan_only);
 }
 
 }  // namespace ptk

@@ -273,6 +273,35 @@ class DeformablePose_GAN(nn.Module):
             vp = self._vgg_pre = VggPrefix(self.content_model, pose_utils.get_layer_ind(self.content_loss_layer), device)
         return vp
 
+    def _loss_readback_begin(self, loss, streams):
+        """Queue the device->host copy of the loss scalars on a copy stream right behind the kernels that PRODUCE them,
+        not behind the backward pass and the optimiser that follow: the update call then returns as soon as the losses
+        exist, and the host enqueues the next update while the GPU is still busy with this one (no idle gap between
+        updates).  Returns a token for _loss_readback_end, or None when streams are off / on CPU."""
+        from .. import engine as _engine
+        dev = loss.device
+        if dev.type != "cuda" or not _engine.STREAMS or os.environ.get("PTK_STREAMS", "1") == "0":
+            return None
+        cs = getattr(self, "_copy_st", None)
+        if cs is None or cs.device != dev:
+            cs = self._copy_st = torch.cuda.Stream(device=dev)
+            self._loss_pin = torch.empty(loss.numel(), dtype=loss.dtype).pin_memory()
+        for st in streams:
+            if st is not None:
+                cs.wait_stream(st)
+        with torch.cuda.stream(cs):
+            self._loss_pin.copy_(loss, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        loss.record_stream(cs)
+        return ev
+
+    def _loss_readback_end(self, token, loss):
+        if token is None:
+            return loss.tolist()                                         # single device->host sync
+        token.synchronize()
+        return self._loss_pin.tolist()
+
     def _opt_stream(self, dev):
         """Stream for the per-bucket all-reduce + Adam (None on CPU / with PTK_STREAMS=0)."""
         from .. import engine as _engine
@@ -369,6 +398,7 @@ class DeformablePose_GAN(nn.Module):
         dlog4 = self.disc.engine.dlogits_buffer(N, J)
         # ad_loss = sum_n -mean_j log(out+1e-7), * gan_penalty_weight / batch_size   (pose_gan.py:90-98,107)
         K.adv_loss(logits, N, J, N, opt['gan_penalty_weight'] / self.batch_size, loss[0:2], dlog4, dlog4.shape[1])
+        readback = self._loss_readback_begin(loss, [torch.cuda.current_stream() if dev.type == "cuda" else None, side])
         din_grad = self.disc.engine.backward(dlog4, grads=None, need_input_grad=True)
         if side is not None:
             main.wait_stream(side)
@@ -401,7 +431,7 @@ class DeformablePose_GAN(nn.Module):
         if ost is not None:
             torch.cuda.current_stream().wait_stream(ost)
         self.gen_opt.end_step()
-        host = loss.tolist()                                             # single device->host sync
+        host = self._loss_readback_end(readback, loss)
         self.gen_ad_loss, self.gen_ll_loss = host[0], host[2]
         self.gen_total_loss = float(torch.tensor(host[0]) + torch.tensor(host[2]))
         return out_gen, outputs_gen, [self.gen_total_loss, self.gen_ll_loss, self.gen_ad_loss]
@@ -434,16 +464,17 @@ class DeformablePose_GAN(nn.Module):
         dlog4 = self.disc.engine.dlogits_buffer(M, J)
         # rows < opt['batch_size'] are "true", the rest "fake"; both * gan_w / self.batch_size (pose_gan.py:140-163)
         K.adv_loss(logits, M, J, opt['batch_size'], opt['gan_penalty_weight'] / self.batch_size, loss[0:2], dlog4, dlog4.shape[1])
+        readback = self._loss_readback_begin(loss, [torch.cuda.current_stream() if dev.type == "cuda" else None])
         self.disc.engine.backward(dlog4, grads=self.disc_arena.grads, need_input_grad=False)
-        # all-reduce + Adam of the discriminator on the optimiser stream: they run while the host is blocked in the loss
-        # read-back below and sets up the next update; the compute stream re-joins (device-side dependency, no host sync)
+        # all-reduce + Adam of the discriminator on the optimiser stream: they run while the host reads the losses back
+        # and sets up the next update; the compute stream re-joins (device-side dependency, no host sync)
         ost = self._opt_stream(dev)
         if ost is not None:
             ost.wait_stream(torch.cuda.current_stream())
         with (torch.cuda.stream(ost) if ost is not None else contextlib.nullcontext()):
             self._allreduce(self.disc_arena)
             self.disc_opt.step()
-        host = loss.tolist()
+        host = self._loss_readback_end(readback, loss)
         if ost is not None:
             torch.cuda.current_stream().wait_stream(ost)
         self.dis_true_loss, self.dis_fake_loss = host[0], host[1]

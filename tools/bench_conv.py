@@ -23,6 +23,11 @@ LAYERS = [
     ("dec6 128->64 T @128", True, 4, 2, 1, 128, 64, 8, 128, 128, ["auto", "1,64", "2,64", "1,32"]),
     ("dec5 512->128 T @128", True, 4, 2, 1, 512, 128, 8, 128, 128, ["auto", "1,128", "2,128"]),
     ("D1 64->128 @127 N16", False, 4, 2, 1, 64, 128, 16, 127, 127, ["auto", "1,128", "2,128", "1,64"]),
+    ("D0 42->64 p0 @256 N16", False, 4, 2, 0, 42, 64, 16, 256, 256, ["auto", "1,64", "2,64", "1,32"]),
+    ("dec4 1024->256 T @64", True, 4, 2, 1, 1024, 256, 8, 64, 64, ["auto", "1,256", "2,256", "2,128"]),
+    ("dec3 1536->512 T @32", True, 4, 2, 1, 1536, 512, 8, 32, 32, ["auto", "1,256", "2,256", "2,128"]),
+    ("dec2 1536->512 T @16", True, 4, 2, 1, 1536, 512, 8, 16, 16, ["auto", "1,256", "2,256", "2,128", "1,128"]),
+    ("enc5 512->512 @16", False, 4, 2, 1, 512, 512, 8, 16, 16, ["auto", "1,256", "2,256", "2,128", "1,128"]),
 ]
 
 
@@ -55,7 +60,7 @@ def main():
         dx = torch.empty(N, H, W, layer.cin_pad, device="cuda")
         stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
         gflop = 2.0 * N * OH * OW * Cout * Cin * k * k / (s * s if tr else 1) / 1e9
-        for tile in tiles:
+        for tile in tiles + ["auto"]:          # "auto" again last: the first rows of a layer run at cooler clocks
             for var in ("PTK_TC_TILE", "PTK_WG_TILE"):
                 if tile == "auto":
                     os.environ.pop(var, None)
@@ -65,7 +70,11 @@ def main():
                 flush.zero_()
                 tf = timeit(lambda: layer.forward(K.Slice(x), N, H, W, K.Slice(y), K.ACT_NONE, stats, scratch=scratch))
                 td = timeit(lambda: layer.dgrad(K.Slice(dy), N, H, W, K.Slice(dx), dx_channels=layer.cin_pad, scratch=scratch))
-                print("%-24s tile %-6s fprop %.4f ms %6.1f TF/s | dgrad %.4f ms %6.1f TF/s" % (name, tile, tf, gflop / tf, td, gflop / td))
+                gw = torch.zeros(wshape, device="cuda")
+                wscratch = torch.empty(max(16 * layer.taps * layer.cin_pad * layer.cout_pad, 1 << 22), device="cuda")
+                tw = timeit(lambda: layer.wgrad(K.Slice(x), K.Slice(dy), N, H, W, wscratch, gw))
+                print("%-24s tile %-6s fprop %.4f ms %6.1f TF/s | dgrad %.4f ms %6.1f TF/s | wgrad(+unpack) %.4f ms %6.1f TF/s" %
+                      (name, tile, tf, gflop / tf, td, gflop / td, tw, gflop / tw))
             except RuntimeError as e:
                 print("%-24s tile %-6s unsupported (%s)" % (name, tile, str(e)[:60]))
         os.environ.pop("PTK_TC_TILE", None)
