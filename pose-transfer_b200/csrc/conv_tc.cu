@@ -502,7 +502,7 @@ struct TuneKey {
   int v[20];
   bool operator<(const TuneKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
 };
-struct TuneChoice { int mh, bn, splits, tpc; };
+struct TuneChoice { int mh, bn, splits, tpc, persist; };
 
 static TuneKey tune_key(const ptk_conv_geom& c, int kind, int flags, int64_t capacity) {
   TuneKey k;
@@ -537,23 +537,33 @@ static bool tc_autotune_enabled(cudaStream_t st) {
   return true;
 }
 
-// one warm-up + two timed launches of `fn` on stream st (drains the device first, blocks the host until they finish)
+// one warm-up + three individually timed launches of `fn` on stream st, minimum taken (drains the device first, blocks the
+// host until they finish)
 template <typename F>
 static int tune_time(cudaStream_t st, F fn, float* ms) {
-  cudaEvent_t e0, e1;
-  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return fail(3, "autotune: cudaEventCreate failed");
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; ++i)
+    if (cudaEventCreate(&ev[i]) != cudaSuccess) return fail(3, "autotune: cudaEventCreate failed");
   cudaDeviceSynchronize();            // the trial runs alone: work queued on other streams would distort the comparison
   int rc = fn();
-  if (!rc) {
-    cudaEventRecord(e0, st);
+  for (int i = 0; i < 3 && !rc; ++i) {
+    if (i == 0) cudaEventRecord(ev[0], st);
     rc = fn();
-    if (!rc) rc = fn();
-    cudaEventRecord(e1, st);
-    if (cudaEventSynchronize(e1) != cudaSuccess) rc = fail(3, "autotune: %s", cudaGetErrorString(cudaGetLastError()));
-    else cudaEventElapsedTime(ms, e0, e1);
+    cudaEventRecord(ev[i + 1], st);
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  if (!rc) {
+    if (cudaEventSynchronize(ev[3]) != cudaSuccess) rc = fail(3, "autotune: %s", cudaGetErrorString(cudaGetLastError()));
+    else {
+      float best = 0.f;
+      for (int i = 0; i < 3; ++i) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+        if (i == 0 || t < best) best = t;
+      }
+      *ms = best;
+    }
+  }
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
   return rc;
 }
 
@@ -626,8 +636,8 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
                                   {1, 256, 4, 1, 0.64f}, {2, 128, 4, 1, 0.64f}, {2, 256, 3, 1, 0.80f}};
   int forced_mh = 0, forced_bn = 0;
   if (const char* e = getenv("PTK_TC_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
-  struct Cand { const TileCfg* cfg; int splits; double cost; };
-  Cand cands[8];
+  struct Cand { const TileCfg* cfg; int splits; double cost; int persist; };     // persist: 1 = if the shape allows, 0 = never
+  Cand cands[40];
   int ncand = 0;
   const Cand* forced_cand = nullptr;
   const bool can_split = c.ldy == c.Cout && bias == nullptr && act == PTK_ACT_NONE;
@@ -667,20 +677,33 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     // buffer and writes the result (~460 floats / clk at 3.5 TB/s) behind one more launch
     const double combine = sp > 1 ? (use_parts ? (double)out_floats * (sp + 1) / 460.0 + 5000.0 : (double)out_floats * sp / 100.0) : 0.0;
     const double cost = (double)((ctas * sp + slots - 1) / slots) * t.occ * tile_clk + combine;
-    cands[ncand] = Cand{&t, sp, cost};
+    cands[ncand] = Cand{&t, sp, cost, 1};
     if (forced && !forced_cand) forced_cand = &cands[ncand];
     ++ncand;
+    // variants for the first-use autotuner only (rated slightly behind the model's own choice): half / double the split
+    // count, and the one-tile-per-CTA kernel where the persistent one would be picked
+    auto valid_split = [&](int q) {
+      if (q < 1 || q == sp || !can_split || q > min_kb / 4) return false;
+      if (use_parts && (int64_t)q * out_floats > scratch_floats) return false;
+      if (q > 1 && (min_kb + q - 1) / q * (q - 1) >= min_kb) return false;
+      return true;
+    };
+    if (valid_split(sp / 2)) cands[ncand++] = Cand{&t, sp / 2, cost * 1.05, 1};
+    if (sp > 1 && valid_split(1)) cands[ncand++] = Cand{&t, 1, cost * 1.10, 1};
+    if (ctas * 2 * sp <= 4 * slots && valid_split(sp * 2)) cands[ncand++] = Cand{&t, sp * 2, cost * 1.05, 1};
+    if (sp == 1 && 2 * t.mh * t.bn <= 512 && ctas > slots) cands[ncand++] = Cand{&t, 1, cost * 1.08, 0};
   }
   PTK_REQUIRE(ncand > 0, "conv_forward(tc): no tile configuration for Cout=%d", c.Cout);
   for (int i = 1; i < ncand; ++i)            // by model cost (stable: ties keep the table order)
     for (int j = i; j > 0 && cands[j].cost < cands[j - 1].cost; --j) { const Cand tmp = cands[j]; cands[j] = cands[j - 1]; cands[j - 1] = tmp; }
-  if (forced_cand) {                         // (the pointer was taken before the sort: find it again by shape)
-    for (int i = 0; i < ncand; ++i) if (cands[i].cfg->mh == forced_mh && cands[i].cfg->bn == forced_bn) { forced_cand = &cands[i]; break; }
+  if (forced_cand) {                         // (the pointer was taken before the sort: find the model's variant of that shape again)
+    for (int i = 0; i < ncand; ++i)
+      if (cands[i].cfg->mh == forced_mh && cands[i].cfg->bn == forced_bn && cands[i].persist == 1) { forced_cand = &cands[i]; break; }
   }
 
   // ---- everything that depends on the chosen tile: tensor maps, grid, launch (+ the split-K reduce)
   const TcGeom g0 = g;
-  auto run = [&](const TileCfg* best, int best_splits, double* stats) -> int {
+  auto run = [&](const TileCfg* best, int best_splits, int allow_persist, double* stats) -> int {
   TcGeom g = g0;
   TmapSet maps;
   memset(&maps, 0, sizeof(maps));
@@ -747,7 +770,7 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   const int64_t all_tiles = (int64_t)mtiles * (c.Cout / BN) * nphases;
   const int occ_ps = (size_t)best->stages * (MH * 128 * 128 + BN * 128) > 100 * 1024 ? 1 : 2;
   const int64_t slots_ps = (int64_t)num_sms() * occ_ps;
-  const bool persist = splits == 1 && !pair && 2 * MH * BN <= 512 && all_tiles < (1 << 30) &&
+  const bool persist = allow_persist && splits == 1 && !pair && 2 * MH * BN <= 512 && all_tiles < (1 << 30) &&
                        (ps_env == 2 ? all_tiles >= 2 : (ps_env >= 1 && all_tiles > (int64_t)(ps_env >= 3 ? ps_env - 2 : 1) * slots_ps));
   const unsigned grid_ps = (unsigned)(ps_env == 2 ? (all_tiles + 1) / 2 : (all_tiles < slots_ps ? all_tiles : slots_ps));
 #define PTK_TC_LAUNCH(BN_, ST_, MH_)                                                                                       \
@@ -807,30 +830,32 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   return 0;
   };   // run
 
-  if (forced_cand) return run(forced_cand->cfg, forced_cand->splits, stats);
+  if (forced_cand) return run(forced_cand->cfg, forced_cand->splits, 1, stats);
   const Cand* pick = &cands[0];
+  for (int i = 0; i < ncand; ++i) if (cands[i].persist == 1 && cands[i].cost <= pick->cost) { pick = &cands[i]; break; }   // model's choice
   if (ncand > 1 && tc_autotune_enabled(st)) {
     // First use of this layer geometry: time the model's best candidates on the real operands and remember the winner
     // (the cost model ranks tile shapes within ~15 %; wave quantisation, persistence and the ragged edges decide the rest).
     const TuneKey key = tune_key(c, 0, (bias != nullptr) * 2 + (use_parts ? 1 : 0) + act * 4, scratch_floats);
     TuneChoice ch;
     if (!tune_lookup(key, &ch)) {
-      const int ntry = ncand < 4 ? ncand : 4;
+      const int ntry = ncand < 12 ? ncand : 12;
       float best_ms = 0.f;
       int best_i = 0;
       for (int i = 0; i < ntry; ++i) {
         float ms = 0.f;
-        int rc = tune_time(st, [&]() { return run(cands[i].cfg, cands[i].splits, nullptr); }, &ms);
+        int rc = tune_time(st, [&]() { return run(cands[i].cfg, cands[i].splits, cands[i].persist, nullptr); }, &ms);
         if (rc) return rc;
         if (i == 0 || ms < best_ms) { best_ms = ms; best_i = i; }
       }
       ch.mh = cands[best_i].cfg->mh; ch.bn = cands[best_i].cfg->bn; ch.splits = cands[best_i].splits; ch.tpc = 1;
+      ch.persist = cands[best_i].persist;
       tune_store(key, ch);
     }
     for (int i = 0; i < ncand; ++i)
-      if (cands[i].cfg->mh == ch.mh && cands[i].cfg->bn == ch.bn && cands[i].splits == ch.splits) { pick = &cands[i]; break; }
+      if (cands[i].cfg->mh == ch.mh && cands[i].cfg->bn == ch.bn && cands[i].splits == ch.splits && cands[i].persist == ch.persist) { pick = &cands[i]; break; }
   }
-  return run(pick->cfg, pick->splits, stats);
+  return run(pick->cfg, pick->splits, pick->persist, stats);
 }
 
 
@@ -1077,7 +1102,7 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
   if (const char* e = getenv("PTK_WG_TILE")) sscanf(e, "%d,%d", &forced_mh, &forced_bn);
   const int bn_small = (Cb % 128 == 0) ? 128 : (Cb % 64 == 0 ? 64 : 32);
   struct Cand { const WgCfg* cfg; int splits; double cost; };
-  Cand cands[12];
+  Cand cands[32];
   int ncand = 0;
   const Cand* forced_cand = nullptr;
   const int64_t part_floats = (int64_t)g.ntaps * g.Ca * Cb;
@@ -1105,6 +1130,15 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     cands[ncand] = Cand{&t, cfg_splits, cfg_cost};
     ++ncand;
     if (forced) { forced_cand = &cands[ncand - 1]; break; }
+    // variants for the first-use autotuner: half / double the split count
+    auto valid_split = [&](int q) {
+      if (q < 1 || q == cfg_splits || q > g.ntiles || q > 512) return false;
+      if (q > 1 && (g.ntiles + q - 1) / q * (q - 1) >= g.ntiles) return false;
+      if (nparts != nullptr && q > 1 && part_floats * q > dw_capacity) return false;
+      return true;
+    };
+    if (ncand < 30 && valid_split(cfg_splits / 2)) cands[ncand++] = Cand{&t, cfg_splits / 2, cfg_cost * 1.05};
+    if (ncand < 30 && valid_split(cfg_splits * 2)) cands[ncand++] = Cand{&t, cfg_splits * 2, cfg_cost * 1.05};
   }
   PTK_REQUIRE(ncand > 0, "conv_wgrad(tc): no tile configuration for Ca=%d Cb=%d", g.Ca, Cb);
   const Cand* pick = forced_cand;
@@ -1158,7 +1192,7 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     TuneChoice ch;
     bool have = tune_lookup(key, &ch);
     if (!have && !plan_only) {
-      const int ntry = ncand < 4 ? ncand : 4;
+      const int ntry = ncand < 12 ? ncand : 12;
       float best_ms = 0.f;
       int best_i = 0;
       for (int i = 0; i < ntry; ++i) {
@@ -1168,6 +1202,7 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
         if (i == 0 || ms < best_ms) { best_ms = ms; best_i = i; }
       }
       ch.mh = cands[best_i].cfg->mh; ch.bn = cands[best_i].cfg->bn; ch.splits = cands[best_i].splits; ch.tpc = cands[best_i].cfg->tpc;
+      ch.persist = 1;
       tune_store(key, ch);
       have = true;
     }

@@ -450,3 +450,53 @@ def test_conv_tc_persistent_double_buffered(case, monkeypatch):
     assert float((outs[1][0][..., :32] - 7.0).abs().max()) == 0
     if not with_bias:
         assert rel_l2(outs[1][1], outs[0][1]) < 1e-12        # fp64 atomics: equal up to summation order
+
+
+AUTOTUNE_CASES = [
+    # name, transposed, Cin, Cout, N, H, W
+    ("enc_256to512_32", False, 256, 512, 4, 32, 32),
+    ("dec_512to128_T_32", True, 512, 128, 4, 32, 32),
+    ("enc_64to128_96", False, 64, 128, 2, 96, 96),
+]
+
+
+@pytest.mark.parametrize("case", AUTOTUNE_CASES, ids=[c[0] for c in AUTOTUNE_CASES])
+def test_conv_tc_first_use_autotune(case, monkeypatch):
+    """First-use autotuning (several tile shapes / split counts / persistent-or-not timed on the real operands, winner
+    cached per geometry): whatever it picks is correct vs torch for fprop, dgrad and wgrad, agrees with the static cost
+    model's choice up to fp32 summation order, and the cached choice is bit-reproducible from call to call."""
+    import pose_transfer_b200  # noqa: F401
+    from pose_transfer_b200 import kernels as K
+    from pose_transfer_b200.engine import ConvLayer
+    name, tr, Cin, Cout, N, H, W = case
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    wshape = (Cin, Cout, 4, 4) if tr else (Cout, Cin, 4, 4)
+    w = (torch.rand(wshape, generator=g) * 2 - 1) / (Cin * 16 / (4 if tr else 1)) ** 0.5
+    x = torch.randn(N, Cin, H, W, generator=g)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    z = F.conv_transpose2d(xr, wr, None, stride=2, padding=1) if tr else F.conv2d(xr, wr, None, stride=2, padding=1)
+    dz = torch.randn(z.shape, generator=g)
+    z.backward(dz)
+    xin, dzd = nhwc(x).cuda(), nhwc(dz).cuda()
+    res = {}
+    for mode in ("0", "1", "1"):
+        monkeypatch.setenv("PTK_TC_AUTOTUNE", mode)
+        layer = ConvLayer(torch.nn.Parameter(w.cuda()), None, tr, 4, 2, 1)
+        layer.impl = K.IMPL_TC
+        layer.pack_forward()
+        OH, OW = layer.out_hw(H, W)
+        scratch = torch.empty(1 << 24, device="cuda")
+        y = torch.empty(N, OH, OW, Cout, device="cuda")
+        stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+        layer.forward(K.Slice(xin), N, H, W, K.Slice(y), K.ACT_NONE, stats, scratch=scratch)
+        dx = torch.empty(N, H, W, Cin, device="cuda")
+        layer.dgrad(K.Slice(dzd), N, H, W, K.Slice(dx), scratch=scratch)
+        gw = torch.zeros(wshape, device="cuda")
+        layer.wgrad(K.Slice(xin), K.Slice(dzd), N, H, W, scratch, gw)
+        torch.cuda.synchronize()
+        res.setdefault(mode, []).append((y, dx, gw, stats))
+    (ym, dxm, gwm, stm), = res["0"]
+    (y1, dx1, gw1, st1), (y2, dx2, gw2, st2) = res["1"]
+    assert rel_l2(nchw(y1).cpu(), z.detach()) < TF32_TOL and rel_l2(nchw(dx1).cpu(), xr.grad) < TF32_TOL and rel_l2(gw1.cpu(), wr.grad) < TF32_TOL
+    assert rel_l2(y1, ym) < 1e-5 and rel_l2(dx1, dxm) < 1e-5 and rel_l2(gw1, gwm) < 1e-5 and rel_l2(st1, stm) < 1e-6
+    assert torch.equal(y1, y2) and torch.equal(dx1, dx2) and torch.equal(gw1, gw2), "cached tile choice must be reproducible"
