@@ -516,8 +516,31 @@ static TuneKey tune_key(const ptk_conv_geom& c, int kind, int flags, int64_t cap
 static std::map<TuneKey, TuneChoice>& tune_table() { static std::map<TuneKey, TuneChoice> t; return t; }
 static std::mutex& tune_mutex() { static std::mutex m; return m; }
 
+// PTK_TC_TUNE_FILE=<path>: the table is read from that file at first use and every new winner is appended to it, so that a
+// later process (a profiler run, a production job) makes exactly the tile choices of the process that tuned.
+static void tune_load_locked() {
+  static bool loaded = false;
+  if (loaded) return;
+  loaded = true;
+  const char* path = getenv("PTK_TC_TUNE_FILE");
+  if (!path) return;
+  FILE* f = fopen(path, "r");
+  if (!f) return;
+  for (;;) {
+    TuneKey k;
+    TuneChoice c;
+    bool ok = true;
+    for (int i = 0; i < 20 && ok; ++i) ok = fscanf(f, "%d", &k.v[i]) == 1;
+    ok = ok && fscanf(f, "%d %d %d %d %d", &c.mh, &c.bn, &c.splits, &c.tpc, &c.persist) == 5;
+    if (!ok) break;
+    tune_table()[k] = c;
+  }
+  fclose(f);
+}
+
 static bool tune_lookup(const TuneKey& k, TuneChoice* out) {
   std::lock_guard<std::mutex> lock(tune_mutex());
+  tune_load_locked();
   auto it = tune_table().find(k);
   if (it == tune_table().end()) return false;
   *out = it->second;
@@ -526,7 +549,15 @@ static bool tune_lookup(const TuneKey& k, TuneChoice* out) {
 
 static void tune_store(const TuneKey& k, const TuneChoice& c) {
   std::lock_guard<std::mutex> lock(tune_mutex());
+  tune_load_locked();
   tune_table()[k] = c;
+  if (const char* path = getenv("PTK_TC_TUNE_FILE")) {
+    if (FILE* f = fopen(path, "a")) {
+      for (int i = 0; i < 20; ++i) fprintf(f, "%d ", k.v[i]);
+      fprintf(f, "%d %d %d %d %d\n", c.mh, c.bn, c.splits, c.tpc, c.persist);
+      fclose(f);
+    }
+  }
 }
 
 static bool tc_autotune_enabled(cudaStream_t st) {
