@@ -31,6 +31,10 @@ struct TcGeom {
   int N, OH, OW, ldy, so;
   int BW, BH, BI, tiles_x, tiles_y, tiles_i;
   int kchunks;
+  int nph;         // output-parity phases of the launch (1, or 4 for transposed / dgrad-of-strided gathers)
+  int phase_fast;  // 1: the phases of one pixel tile are neighbours in the launch order, so that the input region they all read
+                   // comes from HBM once and from L2 three times (phase-slowest order: ncu showed decoder.5 reading its
+                   // 268 MB input 5x from DRAM; 0.503 -> 0.412 ms); 0: phase-slowest (CTA pairs must share the phase)
   int splits;      // split-K factor: the k-blocks of a tile are divided over `splits` CTAs
   long long part_stride;   // > 0: split z stores its partial tile into y + z * part_stride (summed in a fixed order by
                            // splitk_reduce_kernel => deterministic); 0: the splits accumulate atomically into y
@@ -65,9 +69,9 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   pdl_trigger();
-  const TcPhase ph = g.ph[blockIdx.z / g.splits];
-  const int split = blockIdx.z % g.splits;
-  int t = blockIdx.x;
+  const TcPhase ph = g.ph[g.phase_fast ? blockIdx.x % g.nph : blockIdx.z / g.splits];
+  const int split = g.phase_fast ? blockIdx.z : blockIdx.z % g.splits;
+  int t = g.phase_fast ? blockIdx.x / g.nph : blockIdx.x;
   const int tx = t % g.tiles_x; t /= g.tiles_x;
   const int ty = t % g.tiles_y;
   const int ti = t / g.tiles_y;
@@ -202,7 +206,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
 
 // ----------------------------------------------------------------------------- persistent variant
 // Same tile arithmetic as conv_tc_kernel, but a CTA stays resident and walks tiles T = blockIdx.x, + gridDim.x, ... of the
-// whole launch (pixel tile fastest, then output-channel tile, then output-parity phase).  The TMA producer and the MMA
+// whole launch (output-parity phase fastest, then pixel tile, then output-channel tile).  The TMA producer and the MMA
 // issuer run ahead across tile boundaries (one shared-memory ring for the whole CTA lifetime) and the accumulator is
 // DOUBLE-BUFFERED in tensor memory: while the four epilogue warps drain tile i (tcgen05.ld -> bias / statistics /
 // activation -> global), the MMAs of tile i + 1 already fill the other buffer.  For the layers with short K loops (stems,
@@ -253,9 +257,9 @@ conv_tc_persist_kernel(const __grid_constant__ TmapSet maps, const __grid_consta
     if (lane == 0) {
       uint32_t it = 0;                                   // k-blocks issued by this CTA so far (ring position)
       for (int T = blockIdx.x; T < ntiles; T += gridDim.x) {
-        int t = T % mtiles;
-        const int nt = (T / mtiles) % ntile_n;
-        const TcPhase& ph = g.ph[T / (mtiles * ntile_n)];
+        int t = (T / nphases) % mtiles;                  // phase fastest, then pixel tile, then output-channel tile
+        const int nt = T / (nphases * mtiles);
+        const TcPhase& ph = g.ph[T % nphases];
         const int tx = t % g.tiles_x; t /= g.tiles_x;
         const int ty = t % g.tiles_y;
         const int ti = t / g.tiles_y;
@@ -278,7 +282,7 @@ conv_tc_persist_kernel(const __grid_constant__ TmapSet maps, const __grid_consta
       constexpr uint32_t idesc = idesc_tf32(128, BLOCK_N);
       uint32_t it = 0, tile_i = 0;
       for (int T = blockIdx.x; T < ntiles; T += gridDim.x, ++tile_i) {
-        const int KB = g.ph[T / (mtiles * ntile_n)].ntaps * g.kchunks;
+        const int KB = g.ph[T % nphases].ntaps * g.kchunks;
         const uint32_t acc = tile_i & 1u, use = tile_i >> 1;          // use-th time this buffer is filled
         mbar_wait(bar_acce + 8 * acc, (use & 1u) ^ 1u);                // the epilogue has drained its previous contents
         tc_fence_after();
@@ -305,9 +309,9 @@ conv_tc_persist_kernel(const __grid_constant__ TmapSet maps, const __grid_consta
     const int lg = warp & 3;
     uint32_t tile_i = 0;
     for (int T = blockIdx.x; T < ntiles; T += gridDim.x, ++tile_i) {
-      int t = T % mtiles;
-      const int nt = (T / mtiles) % ntile_n;
-      const TcPhase& ph = g.ph[T / (mtiles * ntile_n)];
+      int t = (T / nphases) % mtiles;
+      const int nt = T / (nphases * mtiles);
+      const TcPhase& ph = g.ph[T % nphases];
       const int tx = t % g.tiles_x; t /= g.tiles_x;
       const int ty = t % g.tiles_y;
       const int ti = t / g.tiles_y;
@@ -792,7 +796,9 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     int rc = encode(&maps.b_half, w_k, 3, dims, str, boxH);
     if (rc) return rc;
   }
-  dim3 grid((unsigned)(pair ? (mtiles + 1) / 2 * 2 : mtiles), (unsigned)(c.Cout / BN), (unsigned)(nphases * splits));
+  g.nph = nphases;
+  g.phase_fast = pair ? 0 : 1;
+  dim3 grid((unsigned)(pair ? (mtiles + 1) / 2 * 2 : mtiles * nphases), (unsigned)(c.Cout / BN), (unsigned)(pair ? nphases * splits : splits));
   // Persistent CTAs with a double-buffered accumulator (conv_tc_persist_kernel) when every resident CTA gets several tiles:
   // PTK_TC_PERSIST=0 disables, =2 forces it whenever the tile shape allows (tests), =k >= 3 requires more than (k - 2) tiles
   // per resident CTA (default: more tiles than resident CTAs).

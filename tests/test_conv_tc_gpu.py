@@ -500,3 +500,4 @@ def test_conv_tc_first_use_autotune(case, monkeypatch):
     assert rel_l2(nchw(y1).cpu(), z.detach()) < TF32_TOL and rel_l2(nchw(dx1).cpu(), xr.grad) < TF32_TOL and rel_l2(gw1.cpu(), wr.grad) < TF32_TOL
     assert rel_l2(y1, ym) < 1e-5 and rel_l2(dx1, dxm) < 1e-5 and rel_l2(gw1, gwm) < 1e-5 and rel_l2(st1[:, 1], stm[:, 1]) < 1e-5   # (sum of squares: no cancellation)
     assert torch.equal(y1, y2) and torch.equal(dx1, dx2) and torch.equal(gw1, gw2), "cached tile choice must be reproducible"
+
