@@ -32,9 +32,11 @@ struct TcGeom {
   int BW, BH, BI, tiles_x, tiles_y, tiles_i;
   int kchunks;
   int nph;         // output-parity phases of the launch (1, or 4 for transposed / dgrad-of-strided gathers)
-  int phase_fast;  // 1: the phases of one pixel tile are neighbours in the launch order, so that the input region they all read
-                   // comes from HBM once and from L2 three times (phase-slowest order: ncu showed decoder.5 reading its
-                   // 268 MB input 5x from DRAM; 0.503 -> 0.412 ms); 0: phase-slowest (CTA pairs must share the phase)
+  int ntile_n;     // output-channel tiles (Cout / BLOCK_N)
+  int phase_fast;  // 1: launch order = phase fastest, then output-channel tile, then pixel tile: every CTA that reads one input
+                   // region runs at about the same time, so the region comes from HBM once and from L2 for the others (the
+                   // weights, a few MB, always sit in L2).  Pixel-tile-fastest order: ncu showed decoder.5 reading its 268 MB
+                   // input 5x from DRAM (0.503 -> 0.412 ms) and its dgrad 2x.  0: legacy order (CTA pairs share phase and weights)
   int splits;      // split-K factor: the k-blocks of a tile are divided over `splits` CTAs
   long long part_stride;   // > 0: split z stores its partial tile into y + z * part_stride (summed in a fixed order by
                            // splitk_reduce_kernel => deterministic); 0: the splits accumulate atomically into y
@@ -71,7 +73,8 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   pdl_trigger();
   const TcPhase ph = g.ph[g.phase_fast ? blockIdx.x % g.nph : blockIdx.z / g.splits];
   const int split = g.phase_fast ? blockIdx.z : blockIdx.z % g.splits;
-  int t = g.phase_fast ? blockIdx.x / g.nph : blockIdx.x;
+  const int nt = g.phase_fast ? (blockIdx.x / g.nph) % g.ntile_n : blockIdx.y;      // output-channel tile
+  int t = g.phase_fast ? blockIdx.x / (g.nph * g.ntile_n) : blockIdx.x;
   const int tx = t % g.tiles_x; t /= g.tiles_x;
   const int ty = t % g.tiles_y;
   const int ti = t / g.tiles_y;
@@ -111,9 +114,9 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
         tma_load_4d(sA + s * A_BYTES, &maps.a[ph.map[tap]], bar_full + 8 * s, c0, gx0 + ph.cx[tap], gy0 + ph.cy[tap], n0);
         if (CL == 2)
           tma_load_3d_mc(sB + s * B_BYTES + crank * (B_BYTES / 2), &maps.b_half, bar_full + 8 * s, c0,
-                         blockIdx.y * BLOCK_N + (int)crank * (BLOCK_N / 2), ph.wt[tap], (uint16_t)0x3);
+                         nt * BLOCK_N + (int)crank * (BLOCK_N / 2), ph.wt[tap], (uint16_t)0x3);
         else
-          tma_load_3d(sB + s * B_BYTES, &maps.b, bar_full + 8 * s, c0, blockIdx.y * BLOCK_N, ph.wt[tap]);
+          tma_load_3d(sB + s * B_BYTES, &maps.b, bar_full + 8 * s, c0, nt * BLOCK_N, ph.wt[tap]);
       }
     }
     __syncwarp();
@@ -155,7 +158,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
       float* dst = nullptr;
       if (valid) {
         const int oy = gy * g.so + ph.py, ox = gx * g.so + ph.px;
-        dst = y + (int64_t)split * g.part_stride + (((int64_t)n * g.OH + oy) * g.OW + ox) * g.ldy + blockIdx.y * BLOCK_N;
+        dst = y + (int64_t)split * g.part_stride + (((int64_t)n * g.OH + oy) * g.OW + ox) * g.ldy + nt * BLOCK_N;
       }
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -167,7 +170,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
           for (int q = 0; q < 32; ++q) atomicAdd(dst + c * 32 + q, v[q]);
         } else if (valid) {
           if (bias != nullptr) {
-            const float* bp = bias + blockIdx.y * BLOCK_N + c * 32;
+            const float* bp = bias + nt * BLOCK_N + c * 32;
 #pragma unroll
             for (int q = 0; q < 32; ++q) v[q] += __ldg(bp + q);
           }
@@ -206,7 +209,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
 
 // ----------------------------------------------------------------------------- persistent variant
 // Same tile arithmetic as conv_tc_kernel, but a CTA stays resident and walks tiles T = blockIdx.x, + gridDim.x, ... of the
-// whole launch (output-parity phase fastest, then pixel tile, then output-channel tile).  The TMA producer and the MMA
+// whole launch (output-parity phase fastest, then output-channel tile, then pixel tile).  The TMA producer and the MMA
 // issuer run ahead across tile boundaries (one shared-memory ring for the whole CTA lifetime) and the accumulator is
 // DOUBLE-BUFFERED in tensor memory: while the four epilogue warps drain tile i (tcgen05.ld -> bias / statistics /
 // activation -> global), the MMAs of tile i + 1 already fill the other buffer.  For the layers with short K loops (stems,
@@ -257,8 +260,8 @@ conv_tc_persist_kernel(const __grid_constant__ TmapSet maps, const __grid_consta
     if (lane == 0) {
       uint32_t it = 0;                                   // k-blocks issued by this CTA so far (ring position)
       for (int T = blockIdx.x; T < ntiles; T += gridDim.x) {
-        int t = (T / nphases) % mtiles;                  // phase fastest, then pixel tile, then output-channel tile
-        const int nt = T / (nphases * mtiles);
+        int t = T / (nphases * ntile_n);                 // phase fastest, then output-channel tile, then pixel tile
+        const int nt = (T / nphases) % ntile_n;
         const TcPhase& ph = g.ph[T % nphases];
         const int tx = t % g.tiles_x; t /= g.tiles_x;
         const int ty = t % g.tiles_y;
@@ -309,8 +312,8 @@ conv_tc_persist_kernel(const __grid_constant__ TmapSet maps, const __grid_consta
     const int lg = warp & 3;
     uint32_t tile_i = 0;
     for (int T = blockIdx.x; T < ntiles; T += gridDim.x, ++tile_i) {
-      int t = (T / nphases) % mtiles;
-      const int nt = T / (nphases * mtiles);
+      int t = T / (nphases * ntile_n);
+      const int nt = (T / nphases) % ntile_n;
       const TcPhase& ph = g.ph[T % nphases];
       const int tx = t % g.tiles_x; t /= g.tiles_x;
       const int ty = t % g.tiles_y;
@@ -797,8 +800,10 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     if (rc) return rc;
   }
   g.nph = nphases;
+  g.ntile_n = c.Cout / BN;
   g.phase_fast = pair ? 0 : 1;
-  dim3 grid((unsigned)(pair ? (mtiles + 1) / 2 * 2 : mtiles * nphases), (unsigned)(c.Cout / BN), (unsigned)(pair ? nphases * splits : splits));
+  dim3 grid((unsigned)(pair ? (mtiles + 1) / 2 * 2 : mtiles * nphases * g.ntile_n), (unsigned)(pair ? c.Cout / BN : 1),
+            (unsigned)(pair ? nphases * splits : splits));
   // Persistent CTAs with a double-buffered accumulator (conv_tc_persist_kernel) when every resident CTA gets several tiles:
   // PTK_TC_PERSIST=0 disables, =2 forces it whenever the tile shape allows (tests), =k >= 3 requires more than (k - 2) tiles
   // per resident CTA (default: more tiles than resident CTAs).
