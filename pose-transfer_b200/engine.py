@@ -35,6 +35,17 @@ def pad_in_channels(c):
     return (c + 31) // 32 * 32
 
 
+def _weights_version(module):
+    """Staleness key of a module's GEMM-layout weight packs: the manual counter bumped by whoever writes the weights through
+    raw pointers (FlatAdam's kernel, ParamArena.bind, load_state_dict) plus torch's own in-place version counters, which see
+    in-place edits of the parameters themselves (`with torch.no_grad(): p.copy_(..)`, `nn.init.*_(p)`, clipping, EMA) through
+    any view of the storage.  Edits through `p.data` bypass torch's counter: follow them with ParamArena.bump()."""
+    v = getattr(module, "_ptk_weights_version", None)
+    if v is None:
+        return None
+    return (v, sum(p._version for p in module.parameters()))
+
+
 class ConvLayer:
     """A Conv2d / ConvTranspose2d bound to its parameters.  Keeps GEMM-layout copies of the weight."""
 
@@ -308,17 +319,16 @@ class GeneratorEngine:
                 self.head_wk = torch.zeros(32 * fc.cin, device=dev)     # [32][Cin]: forward B operand
                 self.head_wd = torch.zeros(fc.cin * 32, device=dev)     # [Cin][32]: dgrad B operand
             K.head_pack_weights(fc.weight.detach().contiguous(), self.head_wk, self.head_wd)
-        self.packed_version = getattr(self.m, "_ptk_weights_version", None)
+        self.packed_version = _weights_version(self.m)
 
     def pack_weights_backward(self):
         for c in self.all_convs:
             c.pack_backward()
 
     def _need_repack(self, repack):
-        """repack=True: always; None: only if the owning module's weight version moved since the last pack
-        (bumped by FlatAdam.step / load_state_dict / ParamArena.bind)."""
+        """repack=True: always; None: only if the weights moved since the last pack (_weights_version)."""
         if repack is None:
-            v = getattr(self.m, "_ptk_weights_version", None)
+            v = _weights_version(self.m)
             return v is None or v != getattr(self, "packed_version", -1) or self.all_convs[0].w_fwd is None
         return bool(repack)
 
@@ -690,11 +700,11 @@ class DiscriminatorEngine:
     def pack_weights(self):
         for c in self.convs:
             c.pack_forward()
-        self.packed_version = getattr(self.m, "_ptk_weights_version", None)
+        self.packed_version = _weights_version(self.m)
 
     def _need_repack(self, repack):
         if repack is None:
-            v = getattr(self.m, "_ptk_weights_version", None)
+            v = _weights_version(self.m)
             return v is None or v != getattr(self, "packed_version", -1) or self.convs[0].w_fwd is None
         return bool(repack)
 

@@ -67,10 +67,16 @@ class ParamArena:
             self.lengths.append(n)
             total += n
         self.total = (total + 3) // 4 * 4
+        old_m, old_v = getattr(self, "exp_avg", None), getattr(self, "exp_avg_sq", None)
         self.flat = torch.zeros(self.total, device=dev)
         self.grad = torch.zeros(self.total, device=dev)
         self.exp_avg = torch.zeros(self.total, device=dev)
         self.exp_avg_sq = torch.zeros(self.total, device=dev)
+        if old_m is not None and old_m.numel() == self.total:
+            # re-bind after e.g. module.to(...): same parameters in the same order => same arena layout; the optimiser state
+            # moves with the weights (FlatAdam keeps its step count, so the bias correction stays consistent)
+            self.exp_avg.copy_(old_m)
+            self.exp_avg_sq.copy_(old_v)
         self.grads = {}
         with torch.no_grad():
             for p, off, n in zip(self.params, self.offsets, self.lengths):
@@ -326,6 +332,10 @@ class DeformablePose_GAN(nn.Module):
 
     def _prep(self, t, dtype=torch.float32):
         t = t.cuda() if not t.is_cuda else t
+        if t.is_cuda and t.device.index != torch.cuda.current_device():
+            # the C ABI launches on the runtime's current device with a raw stream handle: one process drives one GPU
+            raise RuntimeError("pose_transfer_b200: tensor on cuda:%d but the current device is cuda:%d -- call "
+                               "torch.cuda.set_device() first (one process per GPU)" % (t.device.index, torch.cuda.current_device()))
         return t.to(dtype).contiguous() if t.dtype != dtype else t.contiguous()
 
     # ------------------------------------------------------------------ updates

@@ -144,6 +144,25 @@ def test_trainer_schedule_deeper_content_layer(tag, content, seed):
     _steps(tag, content, 3, 0.01, 1, seed)
 
 
+def test_weight_pack_staleness_sees_in_place_edits():
+    """The engines repack their GEMM-layout weight copies when the weights moved: in-place edits of a parameter (torch's
+    version counter) and the manual bump used by the raw-pointer writers both change the staleness key."""
+    from pose_transfer_b200.engine import _weights_version
+    from pose_transfer_b200.models.networks import Deformable_Generator
+    G = Deformable_Generator(3 + 2 * 18, 18, (64, 64), (64, 128, 256, 512, 512, 512), (512, 512, 512, 256, 128, 3), "mask")
+    v0 = _weights_version(G)
+    assert v0 is not None and _weights_version(G) == v0
+    with torch.no_grad():
+        next(G.parameters()).mul_(1.0)
+    v1 = _weights_version(G)
+    assert v1 != v0
+    torch.nn.init.normal_(list(G.parameters())[3], std=0.02)
+    v2 = _weights_version(G)
+    assert v2 != v1
+    G._ptk_weights_version += 1
+    assert _weights_version(G) != v2
+
+
 def test_trainer_schedule_l1():
     _steps("64x64_p18_l1", "none", 1, 100.0, 1, 3)
 
