@@ -45,6 +45,12 @@ int ptk_nchw_to_nhwc(const float* src, int C_src, int c_src0, float* dst, int ld
 /* dst[n,c,y,x] = src[n,y,x,c_src0+c]  (NHWC slice -> dense NCHW, e.g. out_gen for the caller) */
 int ptk_nhwc_to_nchw(const float* src, int ld_src, int c_src0, float* dst, int N, int C, int H, int W,
                      void* stream);
+/* dst[n,y,x, c_dst0 + c] for c in [0, c_total) = srcs[q][n, c_src0[q] + (c - c_dst[q]), y, x] where segment q covers c, else 0:
+ * assembles NHWC rows from up to four NCHW channel ranges in one pass and writes the whole range (float4 stores of full
+ * sectors).  Replaces the per-slice copies of get_imgpose / torch.cat (utils/pose_utils.py:227-233, models/pose_gan.py:84-86,
+ * 131-136) when a buffer is filled from several tensors.  c_total, c_dst0, ld_dst multiples of 4; c_total <= 96. */
+int ptk_gather_nhwc(const float* const* srcs, const int* src_channels, const int* c_src0, const int* C, const int* c_dst,
+                    int nseg, float* dst, int ld_dst, int c_dst0, int c_total, int N, int H, int W, void* stream);
 /* Weight repack.  src is the torch layout [A][B][k][k] (Conv2d: A=Cout,B=Cin; ConvTranspose2d: A=Cin,
  * B=Cout; models/networks.py:154,156).  transpose==0: dst[tap][a][b_pad]; transpose==1: dst[tap][b][a_pad].
  * Padding entries are written as zero. */

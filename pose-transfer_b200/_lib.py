@@ -27,6 +27,8 @@ SIGNATURES = {
     "ptk_last_error": [],
     "ptk_launch_count": [],
     "ptk_nchw_to_nhwc": [vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "ptk_gather_nhwc": [ctypes.POINTER(vp), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), i32, vp, i32,
+                        i32, i32, i32, i32, i32, vp],
     "ptk_nhwc_to_nchw": [vp, i32, i32, vp, i32, i32, i32, i32, vp],
     "ptk_pack_weight": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "ptk_pack_weight_dual": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],

@@ -28,6 +28,52 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, int C_src, int c_src0, float*
   }
 }
 
+// Assembles NHWC rows from up to four NCHW channel ranges in ONE pass and writes the WHOLE range [c_dst0, c_dst0 + c_total) of
+// every pixel (channels not covered by a segment are written as zeros): 16-byte stores of full 32-byte sectors.  The
+// slice-by-slice nchw_to_nhwc above leaves partially written sectors (21 of 32 channels, 3 of 64, ...), each of which costs an
+// HBM read-modify-write: ncu showed 556 MB of DRAM reads per training step for 11 such launches (2 TB/s effective).
+constexpr int kGatherPix = 128;
+struct GatherSegs { const float* src[4]; int Cs[4], c0[4], C[4], cd[4]; int n; };
+__global__ void __launch_bounds__(256)
+gather_nhwc_kernel(const __grid_constant__ GatherSegs g, float* __restrict__ dst, int ld_dst, int c_dst0, int c_total, int64_t HW) {
+  extern __shared__ float s_tile[];                // [c_total][kGatherPix + 1]
+  pdl_trigger();
+  const int n = blockIdx.y;
+  const int64_t p0 = (int64_t)blockIdx.x * kGatherPix;
+  const int np = (int)min((int64_t)kGatherPix, HW - p0);
+  for (int e = threadIdx.x; e < c_total * (kGatherPix + 1); e += 256) s_tile[e] = 0.f;
+  __syncthreads();
+  if ((HW & 3) == 0 && np == kGatherPix) {
+    // a warp fetches one channel row of the tile per instruction (128 pixels = 32 x 16 bytes), eight rows in flight per CTA
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int q = 0; q < g.n; ++q) {
+      const float* sb = g.src[q] + ((int64_t)n * g.Cs[q] + g.c0[q]) * HW + p0 + 4 * lane;
+#pragma unroll 4
+      for (int c = w; c < g.C[q]; c += 8) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(sb + (int64_t)c * HW));
+        float* t = s_tile + (g.cd[q] + c) * (kGatherPix + 1) + 4 * lane;
+        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+      }
+    }
+  } else {
+    const int px = threadIdx.x & (kGatherPix - 1), half = threadIdx.x >> 7;
+    for (int q = 0; q < g.n; ++q) {
+      const float* sb = g.src[q] + ((int64_t)n * g.Cs[q] + g.c0[q]) * HW + p0;
+      if (px < np)
+        for (int c = half; c < g.C[q]; c += 2) s_tile[(g.cd[q] + c) * (kGatherPix + 1) + px] = __ldg(sb + (int64_t)c * HW + px);
+    }
+  }
+  __syncthreads();
+  const int c4 = c_total >> 2;
+  float* db = dst + ((int64_t)n * HW + p0) * ld_dst + c_dst0;
+  for (int e = threadIdx.x; e < np * c4; e += 256) {
+    const int p = e / c4, q = e - p * c4;
+    const float* t = s_tile + (4 * q) * (kGatherPix + 1) + p;
+    *reinterpret_cast<float4*>(db + (int64_t)p * ld_dst + 4 * q) =
+        make_float4(t[0], t[kGatherPix + 1], t[2 * (kGatherPix + 1)], t[3 * (kGatherPix + 1)]);
+  }
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int ld_src, int c_src0, float* __restrict__ dst,
                                     int C, int64_t HW) {
   __shared__ float tile[32][33];
@@ -191,6 +237,29 @@ extern "C" int ptk_nchw_to_nhwc(const float* src, int C_src, int c_src0, float* 
   dim3 grid((unsigned)((HW + kNhwcPix - 1) / kNhwcPix), (C + kNhwcCh - 1) / kNhwcCh, N);
   nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, C_src, c_src0, dst, ld_dst, c_dst0, C, HW, act);
   PTK_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return 0;
+}
+
+extern "C" int ptk_gather_nhwc(const float* const* srcs, const int* src_channels, const int* c_src0, const int* C, const int* c_dst,
+                               int nseg, float* dst, int ld_dst, int c_dst0, int c_total, int N, int H, int W, void* stream) {
+  PTK_REQUIRE(srcs && dst && nseg >= 1 && nseg <= 4 && N > 0 && N <= 65535 && H > 0 && W > 0, "gather_nhwc: 1..4 segments, N in [1,65535]");
+  PTK_REQUIRE(c_total > 0 && c_total % 4 == 0 && c_total <= 96 && c_dst0 % 4 == 0 && ld_dst % 4 == 0 && c_dst0 + c_total <= ld_dst &&
+              (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "gather_nhwc: the written channel range must be float4-aligned and inside the row");
+  ptk::GatherSegs g;
+  memset(&g, 0, sizeof(g));
+  g.n = nseg;
+  for (int q = 0; q < nseg; ++q) {
+    PTK_REQUIRE(srcs[q] && C[q] > 0 && c_src0[q] >= 0 && c_src0[q] + C[q] <= src_channels[q] && c_dst[q] >= 0 && c_dst[q] + C[q] <= c_total,
+                "gather_nhwc: segment %d outside its source or the written range", q);
+    g.src[q] = srcs[q]; g.Cs[q] = src_channels[q]; g.c0[q] = c_src0[q]; g.C[q] = C[q]; g.cd[q] = c_dst[q];
+  }
+  const int64_t HW = (int64_t)H * W;
+  const size_t smem = (size_t)c_total * (ptk::kGatherPix + 1) * sizeof(float);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(ptk::gather_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * (ptk::kGatherPix + 1) * 4); attr = true; }
+  ptk::gather_nhwc_kernel<<<dim3((unsigned)((HW + ptk::kGatherPix - 1) / ptk::kGatherPix), (unsigned)N), 256, smem, (cudaStream_t)stream>>>(
+      g, dst, ld_dst, c_dst0, c_total, HW);
+  PTK_LAUNCH_CHECK("gather_nhwc_kernel");
   return 0;
 }
 

@@ -426,12 +426,18 @@ class GeneratorEngine:
                 ck = ws.get("splitk_side" if (side is not None and e_idx == 1) else "splitk_main", (SPLITK_SCRATCH,))
                 warp_levels = []
                 xin = ws.get("xin_%s_%s" % (name, tag), (N, H, W, convs[0].cin_pad))
-                lo = 0
+                lo, segs = 0, []
                 for t, t0, tc in pieces:        # channel range [c_src0, c_src0 + cin) of the (virtual) concatenation
                     a, b = max(lo, c_src0), min(lo + tc, c_src0 + cin)
                     if a < b:
-                        K.nchw_to_nhwc(t, t0 + a - lo, b - a, Slice(xin, a - c_src0, b - a))
+                        segs.append((t, t0 + a - lo, b - a, a - c_src0))
                     lo += tc
+                for q in range(0, len(segs), 4):   # whole rows incl. the zero channel padding, four source ranges per launch
+                    if q == 0:
+                        K.gather_nhwc(segs[:4], Slice(xin, 0, xin.shape[-1]), xin.shape[-1])
+                    else:
+                        for t, ts, tcn, td in segs[q:q + 4]:
+                            K.nchw_to_nhwc(t, ts, tcn, Slice(xin, td, tcn))
                 sv["xin"][name] = xin
                 for i in range(L):
                     j = L - 1 - i

@@ -105,6 +105,21 @@ def nchw_to_nhwc(src, c_src0, C, dst, act=ACT_NONE):
           "ptk_nchw_to_nhwc")
 
 
+def gather_nhwc(segs, dst, c_total):
+    """dst slice rows [c0, c0 + c_total) <- the NCHW channel ranges segs = [(src [N,Cs,H,W], c_src0, C, c_dst_rel)], zeros in
+    between: ONE launch that writes whole sectors (see ptk_gather_nhwc)."""
+    import ctypes
+    dst = _as_slice(dst)
+    n = len(segs)
+    N, _, H, W = segs[0][0].shape
+    ptrs = (ctypes.c_void_p * n)(*[_p(s[0]) for s in segs])
+    Cs = (ctypes.c_int * n)(*[s[0].shape[1] for s in segs])
+    c0 = (ctypes.c_int * n)(*[s[1] for s in segs])
+    C = (ctypes.c_int * n)(*[s[2] for s in segs])
+    cd = (ctypes.c_int * n)(*[s[3] for s in segs])
+    check(_lib.lib().ptk_gather_nhwc(ptrs, Cs, c0, C, cd, n, dst.t.data_ptr(), dst.ld, dst.c0, c_total, N, H, W, _stream()), "ptk_gather_nhwc")
+
+
 def nhwc_to_nchw(src, dst):
     """dst [N,C,H,W] <- src slice."""
     src = _as_slice(src)

@@ -410,7 +410,7 @@ class Discriminator(nn.Module):
         from .. import kernels as K
         M, C, H, W = x.shape
         din = self.engine.input_buffer(M, H, W, x.device)
-        K.nchw_to_nhwc(x.contiguous(), 0, C, Slice(din, 0, C))
+        K.gather_nhwc([(x.contiguous(), 0, C, 0)], Slice(din, 0, din.shape[-1]), din.shape[-1])
         return self.engine.forward(din, probs=True)
 
     def forward(self, input):

@@ -325,10 +325,11 @@ class DeformablePose_GAN(nn.Module):
     def _fill_disc_input(self, din, inp, middle, P):
         """din[..., :3+P] = (img, src pose); din[..., 3+P:6+P] = middle (or left to the generator);
         din[..., 6+P:6+2P] = target pose   (pose_gan.py:84-86,131-135)."""
-        K.nchw_to_nhwc(inp, 0, 3 + P, Slice(din, 0, 3 + P))
+        segs = [(inp, 0, 3 + P, 0), (inp, 3 + P, P, 6 + P)]
         if middle is not None:
-            K.nchw_to_nhwc(middle, 0, 3, Slice(din, 3 + P, 3))
-        K.nchw_to_nhwc(inp, 3 + P, P, Slice(din, 6 + P, P))
+            segs.append((middle, 0, 3, 3 + P))
+        # one pass writing whole rows (zeros in the generator's slot and in the channel padding)
+        K.gather_nhwc(segs, Slice(din, 0, din.shape[-1]), din.shape[-1])
 
     def _prep(self, t, dtype=torch.float32):
         t = t.cuda() if not t.is_cuda else t

@@ -51,6 +51,12 @@ def install(K):
     def nchw_to_nhwc(src, c_src0, C, dst, act=0):
         view(dst, C).copy_(nhwc(_act(src[:, c_src0:c_src0 + C], act)))
 
+    def gather_nhwc(segs, dst, c_total):
+        v = view(dst, c_total)
+        v.zero_()
+        for src, c_src0, C, c_dst in segs:
+            v[..., c_dst:c_dst + C].copy_(nhwc(src[:, c_src0:c_src0 + C]))
+
     def nhwc_to_nchw(src, dst):
         dst.copy_(nchw(view(src, dst.shape[1])))
 
@@ -365,7 +371,7 @@ def install(K):
         bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
         p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
 
-    table = dict(nchw_to_nhwc=nchw_to_nhwc, nhwc_to_nchw=nhwc_to_nchw, pack_weight=pack_weight, pack_weight_dual=pack_weight_dual,
+    table = dict(nchw_to_nhwc=nchw_to_nhwc, gather_nhwc=gather_nhwc, nhwc_to_nchw=nhwc_to_nchw, pack_weight=pack_weight, pack_weight_dual=pack_weight_dual,
                  unpack_weight_grad=unpack_weight_grad, unpack_weight_grad_parts=unpack_weight_grad_parts, fill=fill,
                  transpose_weight=transpose_weight, sum_parts=sum_parts, conv_wgrad_plan=conv_wgrad_plan,
                  head_pack_weights=head_pack_weights, head_shift_add=head_shift_add, head_shift_gather=head_shift_gather,

@@ -170,6 +170,28 @@ def test_gn_identity_mode_and_act_backward(K):
     assert max_abs(nchw(dy), gu * torch.where(z > 0, 1.0, 0.2)) < 1e-7
 
 
+def test_gather_nhwc_rows(K):
+    """ptk_gather_nhwc: rows assembled from several NCHW channel ranges in one pass, zeros in the gaps and in the channel
+    padding, nothing written outside [c0, c0 + c_total); ragged pixel count (HW % 128 != 0)."""
+    g = gen(31)
+    N, H, W = 3, 19, 23
+    a = torch.randn(N, 39, H, W, generator=g)
+    b = torch.randn(N, 3, H, W, generator=g)
+    dst = torch.full((N, H, W, 72), 7.0, device="cuda")
+    segs = [(a.cuda(), 0, 21, 0), (a.cuda(), 21, 18, 24), (b.cuda(), 0, 3, 21)]
+    K.gather_nhwc(segs, K.Slice(dst, 4, 64), 64)
+    want = torch.zeros(N, H, W, 64)
+    want[..., 0:21] = nhwc(a[:, 0:21]); want[..., 24:42] = nhwc(a[:, 21:39]); want[..., 21:24] = nhwc(b)
+    assert torch.equal(dst[..., 4:68].cpu(), want)
+    assert float((dst[..., :4] - 7.0).abs().max()) == 0 and float((dst[..., 68:] - 7.0).abs().max()) == 0
+    # a hole (the generator's slot) and a single narrow segment
+    dst2 = torch.full((N, H, W, 32), 7.0, device="cuda")
+    K.gather_nhwc([(a.cuda(), 21, 18, 0)], K.Slice(dst2, 0, 32), 32)
+    want2 = torch.zeros(N, H, W, 32)
+    want2[..., :18] = nhwc(a[:, 21:39])
+    assert torch.equal(dst2.cpu(), want2)
+
+
 # ----------------------------------------------------------------------------- warp
 def _run_warp(K, x, warps, masks, H0, W0, gy=None, act=0):
     N, C, h, w = x.shape
