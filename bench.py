@@ -395,24 +395,27 @@ def run_ours(args):
     if args.diag:
         # host-bound or GPU-bound?  Time the host spends blocked in the two loss read-backs of a step: ~0 => the GPU waits
         # for the host's launches; large => the host runs ahead and only the read-back latency is exposed.
+        # (the read-back waits on an event recorded right behind the loss kernels: models/pose_gan.py::_loss_readback_end)
         wait = [0.0]
-        orig = torch.Tensor.tolist
+        orig = model._loss_readback_end
 
-        def timed_tolist(self):
+        def timed_readback(token, loss):
             t0 = time.perf_counter()
-            r = orig(self)
+            r = orig(token, loss)
             wait[0] += time.perf_counter() - t0
             return r
-        torch.Tensor.tolist = timed_tolist
+        model._loss_readback_end = timed_readback
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(10):
             step_resident()
+        t_enq = time.perf_counter() - t0
         torch.cuda.synchronize()
         total = time.perf_counter() - t0
-        torch.Tensor.tolist = orig
-        print("diag: %.2f ms/step wall, of which %.2f ms blocked in loss read-backs (host enqueue time %.2f ms/step)"
-              % (100 * total, 100 * wait[0], 100 * (total - wait[0])), file=sys.stderr)
+        del model._loss_readback_end
+        print("diag: %.2f ms/step wall; host: %.2f ms/step blocked in loss read-backs, %.2f ms/step enqueueing, %.2f ms/step of GPU "
+              "work still queued when the host finished" % (100 * total, 100 * wait[0], 100 * (t_enq - wait[0]), 100 * (total - t_enq)),
+              file=sys.stderr)
     if args.ncu_step:
         # for `ncu --profile-from-start off`: exactly one resident step inside the profiler range, nothing else
         torch.cuda.synchronize()

@@ -482,8 +482,41 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Tensor maps are pure functions of (base pointer, extents, strides, box, swizzle) and the step re-uses the same buffers
+// every iteration: descriptors are encoded once and looked up afterwards (a step needs ~500 of them).
+struct TmapKey {
+  uint64_t v[14];
+  bool operator<(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+static std::map<TmapKey, CUtensorMap>& tmap_cache() { static std::map<TmapKey, CUtensorMap> c; return c; }
+static std::mutex& tmap_mutex() { static std::mutex m; return m; }
+
+static int encode_uncached(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, CUtensorMapSwizzle swizzle);
+
 static int encode(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.v[0] = (uint64_t)reinterpret_cast<uintptr_t>(base);
+  k.v[1] = (uint64_t)rank | ((uint64_t)swizzle << 8);
+  for (int i = 0; i < rank; ++i) { k.v[2 + i] = dims[i]; k.v[10 + i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) k.v[6 + i] = strides_bytes[i];
+  {
+    std::lock_guard<std::mutex> lock(tmap_mutex());
+    auto it = tmap_cache().find(k);
+    if (it != tmap_cache().end()) { *m = it->second; return 0; }
+  }
+  int rc = encode_uncached(m, base, rank, dims, strides_bytes, box, swizzle);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(tmap_mutex());
+  if (tmap_cache().size() > 16384) tmap_cache().clear();      // (buffers of a long-gone shape: start over)
+  tmap_cache()[k] = *m;
+  return 0;
+}
+
+static int encode_uncached(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(5, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t gd[5], gs[4];
@@ -609,7 +642,7 @@ bool conv_tc_supported(const ptk_conv_geom& c) {
   if (c.Cin % 32 != 0 || c.Cout % 32 != 0) return false;
   if (c.ldx % 4 != 0 || c.ldy % 4 != 0) return false;
   if (!((c.k == 4 && c.stride == 2) || (c.k == 3 && c.stride == 1) || (c.k == 1 && c.stride == 1 && c.pad == 0 && !c.transposed))) return false;
-  if (c.H < 4 || c.W < 4 || c.OH < 4 || c.OW < 4) return false;
+  if (c.H < 1 || c.W < 1 || c.OH < 1 || c.OW < 1) return false;
   if (c.N < 1 || c.N > 4096) return false;
   return true;
 }
