@@ -133,10 +133,6 @@ def _network_layer_geometries():
         out.append(("dec256_%d" % h, True, 1, ci, co, 8, h, h))
     for i, (ci, co, h) in enumerate(((64, 128, 127), (128, 256, 63), (256, 512, 31))):
         out.append(("disc256_%d" % (i + 1), False, 1, ci, co, 4, h, h))
-    # one- and two-pixel extents (the bottleneck of a 128x64 input, the PatchGAN tail): on the tensor cores as well
-    out.append(("enc128x64_4x2to2x1", False, 1, 512, 512, 3, 4, 2))
-    out.append(("dec128x64_2x1to4x2", True, 1, 1024, 512, 3, 2, 1))
-    out.append(("disc128x64_7x3to3x1", False, 1, 256, 512, 4, 7, 3))
     return out
 
 
