@@ -174,8 +174,12 @@ __device__ __forceinline__ void nn_fwd_chunk(const NnCtx& c, float4* __restrict_
 
 constexpr int kNnFwdThreads = 416;   // >= (16 + 4)^2 halo positions in one round; threads 0..255 own the tile pixels
 constexpr int kNnBwdThreads = 352;   // >= 18^2 positions
+// Both kernels are compiled for TWO resident CTAs per SM (72 / 80 registers instead of 105 / 150, at the price of 0.5 / 1.3 KB
+// of spilled accumulators): they are latency-bound on dependent FFMA chains with 11-13 warps per CTA, and the second CTA is
+// worth more than the spills cost -- forward 0.501 -> 0.303 ms, backward 0.511 -> 0.388 ms at 8 x 256 x 256, 5 x 5 window
+// (tools/bench_nnloss.py).
 
-__global__ void __launch_bounds__(kNnFwdThreads)
+__global__ void __launch_bounds__(kNnFwdThreads, 2)
 nnloss_forward_kernel(const float* __restrict__ pred, const float* __restrict__ target, int H, int W, int area,
                       float scale_over_count, float* __restrict__ loss, uint8_t* __restrict__ argmin) {
   const int P = area / 2;
@@ -284,7 +288,7 @@ __device__ __forceinline__ void nn_bwd_chunk(const NnCtx& c, const uint8_t* __re
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kNnBwdThreads)
+__global__ void __launch_bounds__(kNnBwdThreads, 2)
 nnloss_backward_kernel(const float* __restrict__ pred, const float* __restrict__ target, const uint8_t* __restrict__ argmin,
                        int H, int W, int area, float scale_over_count, float* __restrict__ dpred) {
   const int P = area / 2;
