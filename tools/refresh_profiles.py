@@ -34,10 +34,11 @@ def main():
     head = ("# round 2 (final kernels) -- ncu --set full --clock-control none captures, tile choices pinned to those of the un-profiled bench run\n"
             "# (PTK_TC_TUNE_FILE = profiles/r2_tuned_tiles.txt); first 1..8 launches of each family in one training step at 256x256 batch 8.\n"
             "# Cold-cache, serialised replays: read shares and ratios, not absolutes.  Families not re-captured here (gn_apply, gn_bwd_apply,\n"
-            "# adam, nnloss, splitk_reduce -- kernels unchanged since) are in r2a_ncu_summary.txt.\n")
+            "# adam, splitk_reduce -- kernels unchanged since) are in r2a_ncu_summary.txt.\n")
     with open(os.path.join(pr, "r2_ncu_summary.txt"), "w") as f:
         f.write(head)
-        for k in ("warp_forward_tiles", "warp_backward_tiles", "mask_pyramid", "gn_bwd_reduce", "conv_tc_persist", "conv_tc_kernel", "wgrad_tc"):
+        for k in ("warp_forward_tiles", "warp_backward_tiles", "mask_pyramid", "nnloss_forward", "nnloss_backward", "gn_bwd_reduce",
+                  "conv_tc_persist", "conv_tc_kernel", "wgrad_tc"):
             p = os.path.join(go, "%s_full_%s.csv" % (tag, k))
             if os.path.isfile(p):
                 f.write("\n## %s\n" % k)
