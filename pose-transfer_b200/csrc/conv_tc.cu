@@ -33,10 +33,10 @@ struct TcGeom {
   int kchunks;
   int nph;         // output-parity phases of the launch (1, or 4 for transposed / dgrad-of-strided gathers)
   int ntile_n;     // output-channel tiles (Cout / BLOCK_N)
-  int phase_fast;  // 1: launch order = phase fastest, then output-channel tile, then pixel tile: every CTA that reads one input
-                   // region runs at about the same time, so the region comes from HBM once and from L2 for the others (the
-                   // weights, a few MB, always sit in L2).  Pixel-tile-fastest order: ncu showed decoder.5 reading its 268 MB
-                   // input 5x from DRAM (0.503 -> 0.412 ms) and its dgrad 2x.  0: legacy order (CTA pairs share phase and weights)
+                   // Launch order = phase fastest, then output-channel tile, then pixel tile: every CTA that reads one input region
+                   // runs at about the same time, so the region comes from HBM once and from L2 for the others (the weights, a
+                   // few MB, always sit in L2).  Pixel-tile-fastest order: ncu showed decoder.5 reading its 268 MB input 5x from
+                   // DRAM (0.503 -> 0.412 ms) and its dgrad 2x.
   int splits;      // split-K factor: the k-blocks of a tile are divided over `splits` CTAs
   long long part_stride;   // > 0: split z stores its partial tile into y + z * part_stride (summed in a fixed order by
                            // splitk_reduce_kernel => deterministic); 0: the splits accumulate atomically into y
@@ -46,17 +46,14 @@ struct TcGeom {
 struct TmapSet {
   CUtensorMap a[4];
   CUtensorMap b;
-  CUtensorMap b_half;    // box of BLOCK_N / 2 weight rows: what one CTA of a pair fetches and multicasts to both
 };
 
 // MH = number of 128-pixel halves of the CTA's M tile (1 or 2): with MH = 2 the same weight (B) stage feeds two
 // M = 128 MMAs, and BLOCK_N = 256 lets one activation (A) stage feed a twice-as-wide MMA -- both raise the MACs per
 // byte fetched from L2, which (not the tensor pipe) is what bounds fp32-operand tiles.  TMEM: MH * BLOCK_N columns.
-// CL = CTAs per cluster (1 or 2).  CL = 2: two CTAs that are neighbours along the pixel (M) dimension need the SAME weight
-// tile; each fetches half of it and multicasts it into both shared memories, so the L2 -> SM weight traffic per CTA halves
-// (fp32 operands make these kernels L2-bandwidth bound).  A stage may be refilled only when the MMAs of BOTH CTAs have
-// consumed it: the empty barriers count CL arrivals and every MMA issuer commits to its own and to its peer's barrier.
-template <int BLOCK_N, int STAGES, int MH, int CL>
+// (A CTA-pair variant that multicast the weight tile into both shared memories halved the L2 -> SM weight traffic but measured
+// 3 % slower over the conv stack -- lock-step stage recycling and two cluster barriers per CTA -- and was removed.)
+template <int BLOCK_N, int STAGES, int MH>
 __global__ void __launch_bounds__(192)
 conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcGeom g, float* __restrict__ y,
                double* __restrict__ stats, const float* __restrict__ bias, int act) {
@@ -71,10 +68,11 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   pdl_trigger();
-  const TcPhase ph = g.ph[g.phase_fast ? blockIdx.x % g.nph : blockIdx.z / g.splits];
-  const int split = g.phase_fast ? blockIdx.z : blockIdx.z % g.splits;
-  const int nt = g.phase_fast ? (blockIdx.x / g.nph) % g.ntile_n : blockIdx.y;      // output-channel tile
-  int t = g.phase_fast ? blockIdx.x / (g.nph * g.ntile_n) : blockIdx.x;
+  // launch order: output-parity phase fastest, then output-channel tile, then pixel tile (TcGeom::nph)
+  const TcPhase ph = g.ph[blockIdx.x % g.nph];
+  const int split = blockIdx.z;
+  const int nt = (blockIdx.x / g.nph) % g.ntile_n;      // output-channel tile
+  int t = blockIdx.x / (g.nph * g.ntile_n);
   const int tx = t % g.tiles_x; t /= g.tiles_x;
   const int ty = t % g.tiles_y;
   const int ti = t / g.tiles_y;
@@ -84,9 +82,8 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   const int kb0 = split * kb_per;
   const int KB = (kb0 + kb_per < KB_all ? kb0 + kb_per : KB_all) - kb0;   // k-blocks of this CTA (may be <= 0)
 
-  const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_tmem, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -97,7 +94,6 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (CL == 2) cluster_sync_all();      // the peer's barriers exist before anything is multicast into them
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_wait();      // nothing above touched global memory: the setup overlapped the previous kernel's tail
@@ -112,11 +108,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
         const int c0 = ((kb0 + kb) - tap * g.kchunks) * 32;
         mbar_expect_tx(bar_full + 8 * s, A_BYTES + B_BYTES);
         tma_load_4d(sA + s * A_BYTES, &maps.a[ph.map[tap]], bar_full + 8 * s, c0, gx0 + ph.cx[tap], gy0 + ph.cy[tap], n0);
-        if (CL == 2)
-          tma_load_3d_mc(sB + s * B_BYTES + crank * (B_BYTES / 2), &maps.b_half, bar_full + 8 * s, c0,
-                         nt * BLOCK_N + (int)crank * (BLOCK_N / 2), ph.wt[tap], (uint16_t)0x3);
-        else
-          tma_load_3d(sB + s * B_BYTES, &maps.b, bar_full + 8 * s, c0, nt * BLOCK_N, ph.wt[tap]);
+        tma_load_3d(sB + s * B_BYTES, &maps.b, bar_full + 8 * s, c0, nt * BLOCK_N, ph.wt[tap]);
       }
     }
     __syncwarp();
@@ -135,9 +127,7 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
           for (int hm = 0; hm < MH; ++hm)   // pixel rows [128 hm, 128 hm + 128) of the stage -> accumulator hm
             tc_mma_tf32(tmem_base + (uint32_t)(hm * BLOCK_N), da + (uint64_t)(hm * (16384 >> 4)) + 2 * k, db + 2 * k, idesc,
                         (kb > 0 || k > 0) ? 1u : 0u);
-        // frees the smem stage once these MMAs have read it (CL = 2: in both CTAs, the peer multicasts into this stage too)
-        if (CL == 2) tc_commit_mc(bar_empty + 8 * s, (uint16_t)0x3);
-        else tc_commit(bar_empty + 8 * s);
+        tc_commit(bar_empty + 8 * s);       // frees the smem stage once these MMAs have read it
       }
       if (KB > 0) tc_commit(bar_tmem);  // accumulator complete
     }
@@ -203,7 +193,6 @@ conv_tc_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ TcG
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
-  if (CL == 2) cluster_sync_all();      // the peer may still be arriving on this CTA's barriers
 }
 
 
@@ -451,19 +440,14 @@ static bool pdl_enabled() {
 
 // launch with programmatic stream serialization (see pdl_wait / pdl_trigger in tc_ptx.cuh)
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args... args) {
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (cluster_x > 1) {
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = (unsigned)cluster_x; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
-    cfg.numAttrs = 2;
-  }
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -820,26 +804,10 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
     int rc = ptk_fill(y, out_floats, 0.f, st);
     if (rc) return rc;
   }
-  // CTA pairs along the pixel dimension can share their weight tile through a TMA multicast (PTK_TC_CLUSTER=1).  Measured on
-  // B200 (profiles/README.md, r2f): correct, but 3 % SLOWER over the conv stack (decoder.5 0.577 -> 0.604 ms, Cout = 64
-  // dgrads 0.156 -> 0.189 ms): the pair's lock-step stage recycling and the two cluster barriers cost more than the halved
-  // weight traffic saves, so it stays opt-in.
-  static int cl_env = -1;
-  if (cl_env < 0) { const char* e = getenv("PTK_TC_CLUSTER"); cl_env = (e && atoi(e) == 1) ? 1 : 0; }
   const int mtiles = g.tiles_x * g.tiles_y * g.tiles_i;
-  const bool pair = cl_env && mtiles >= 2 && BN >= 64;
-  if (pair) {
-    const uint64_t dims[3] = {(uint64_t)c.Cin, (uint64_t)c.Cout, (uint64_t)(k * k)};
-    const uint64_t str[2] = {(uint64_t)c.Cin * 4, (uint64_t)c.Cin * c.Cout * 4};
-    const uint32_t boxH[3] = {32u, (uint32_t)(BN / 2), 1u};
-    int rc = encode(&maps.b_half, w_k, 3, dims, str, boxH);
-    if (rc) return rc;
-  }
   g.nph = nphases;
   g.ntile_n = c.Cout / BN;
-  g.phase_fast = pair ? 0 : 1;
-  dim3 grid((unsigned)(pair ? (mtiles + 1) / 2 * 2 : mtiles * nphases * g.ntile_n), (unsigned)(pair ? c.Cout / BN : 1),
-            (unsigned)(pair ? nphases * splits : splits));
+  dim3 grid((unsigned)(mtiles * nphases * g.ntile_n), 1u, (unsigned)splits);
   // Persistent CTAs with a double-buffered accumulator (conv_tc_persist_kernel) when every resident CTA gets several tiles:
   // PTK_TC_PERSIST=0 disables, =2 forces it whenever the tile shape allows (tests), =k >= 3 requires more than (k - 2) tiles
   // per resident CTA (default: more tiles than resident CTAs).
@@ -848,27 +816,22 @@ int conv_forward_tc(const ptk_conv_geom& c, const float* x, const float* w_k, co
   const int64_t all_tiles = (int64_t)mtiles * (c.Cout / BN) * nphases;
   const int occ_ps = (size_t)best->stages * (MH * 128 * 128 + BN * 128) > 100 * 1024 ? 1 : 2;
   const int64_t slots_ps = (int64_t)num_sms() * occ_ps;
-  const bool persist = allow_persist && splits == 1 && !pair && 2 * MH * BN <= 512 && all_tiles < (1 << 30) &&
+  const bool persist = allow_persist && splits == 1 && 2 * MH * BN <= 512 && all_tiles < (1 << 30) &&
                        (ps_env == 2 ? all_tiles >= 2 : (ps_env >= 1 && all_tiles > (int64_t)(ps_env >= 3 ? ps_env - 2 : 1) * slots_ps));
   const unsigned grid_ps = (unsigned)(ps_env == 2 ? (all_tiles + 1) / 2 : (all_tiles < slots_ps ? all_tiles : slots_ps));
 #define PTK_TC_LAUNCH(BN_, ST_, MH_)                                                                                       \
   do {                                                                                                                     \
     const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 16 + 1024;                                 \
     static bool attr = false;                                                                                              \
-    if (!attr) {                                                                                                           \
-      cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MH_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-      cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MH_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-      attr = true;                                                                                                         \
-    }                                                                                                                      \
-    if (pair) launch_pdl(conv_tc_kernel<BN_, ST_, MH_, 2>, grid, dim3(192), smem, st, 2, maps, g, y_kernel, stats, bias, act); \
-    else launch_pdl(conv_tc_kernel<BN_, ST_, MH_, 1>, grid, dim3(192), smem, st, 1, maps, g, y_kernel, stats, bias, act);    \
+    if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
+    launch_pdl(conv_tc_kernel<BN_, ST_, MH_>, grid, dim3(192), smem, st, maps, g, y_kernel, stats, bias, act);            \
   } while (0)
 #define PTK_TC_LAUNCH_PS(BN_, ST_, MH_, CO_)                                                                               \
   do {                                                                                                                     \
     const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + BN_ * 128) + 16 * ST_ + 64 + (CO_ ? 18432 + 1024 : 0) + 1024 + 64;  \
     static bool attr = false;                                                                                              \
     if (!attr) { cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, ST_, MH_, CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
-    launch_pdl(conv_tc_persist_kernel<BN_, ST_, MH_, CO_>, dim3(grid_ps), dim3(192), smem, st, 1, maps, g, y_kernel, stats, bias, act, \
+    launch_pdl(conv_tc_persist_kernel<BN_, ST_, MH_, CO_>, dim3(grid_ps), dim3(192), smem, st, maps, g, y_kernel, stats, bias, act, \
                c.Cout / BN_, nphases);                                                                                     \
   } while (0)
   if (persist) {
@@ -1246,7 +1209,7 @@ int conv_wgrad_tc(const ptk_conv_geom& c, const float* x, const float* dy, float
     const size_t smem = (size_t)ST_ * (MH_ * 128 * 128 + TPC_ * BN_ * 128) + 16 * ST_ + 16 + 1024;                          \
     static bool attr = false;                                                                                              \
     if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<BN_, ST_, MH_, TPC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
-    launch_pdl(wgrad_tc_kernel<BN_, ST_, MH_, TPC_>, grid, dim3(192), smem, st, 1, maps, g, dw);                                \
+    launch_pdl(wgrad_tc_kernel<BN_, ST_, MH_, TPC_>, grid, dim3(192), smem, st, maps, g, dw);                                \
   } while (0)
   if (TPC == 9) PTK_WG_LAUNCH(32, 3, 1, 9);
   else if (TPC == 4) PTK_WG_LAUNCH(64, 4, 1, 4);
