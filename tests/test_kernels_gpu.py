@@ -1,6 +1,5 @@
 """GPU parity tests, kernel level: every ptk kernel family through the C ABI vs the CPU oracle
 (torch fp32 CPU ops / oracle.restate) and vs the golden outputs of the unmodified reference."""
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -61,7 +60,7 @@ CONV_CASES = [
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv_simt_fprop_dgrad_wgrad(K, case):
-    from pose_transfer_b200.engine import ConvLayer, ceil4
+    from pose_transfer_b200.engine import ConvLayer
     name, tr, k, s, p, Cin, Cout, N, H, W, use_bias, act = case
     g = gen(hash(name) % 1000)
     wshape = (Cin, Cout, k, k) if tr else (Cout, Cin, k, k)

@@ -6,10 +6,8 @@ import argparse
 import contextlib
 import io
 
-import numpy as np
 import pytest
 import torch
-import torch.nn.functional as F
 
 from helpers import golden, max_abs, rel_l2
 
